@@ -1,0 +1,52 @@
+"""ctypes loader of csrc/libb2q.so (the C ABI in include/b2q.h).  Fails loudly: there is no fallback path."""
+import ctypes as C
+import os
+
+from ._config import B2QConfig
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libb2q.so")
+_lib = None
+
+# every symbol include/b2q.h declares: (name, restype, argtypes)
+_vp, _i, _u8p = C.c_void_p, C.c_int, C.c_void_p
+SYMBOLS = {
+    "b2q_default_config": (None, [C.POINTER(B2QConfig)]),
+    "b2q_create": (_i, [C.POINTER(B2QConfig), C.POINTER(_vp)]),
+    "b2q_destroy": (_i, [_vp]),
+    "b2q_last_error": (C.c_char_p, [_vp]),
+    "b2q_version": (C.c_char_p, []),
+    "b2q_num_envs": (_i, [_vp]),
+    "b2q_obs_dim": (_i, [_vp]),
+    "b2q_act_dim": (_i, [_vp]),
+    "b2q_info_dim": (_i, [_vp]),
+    "b2q_elem_size": (_i, [_vp]),
+    "b2q_set_dynamics": (_i, [_vp, _u8p, _vp, _vp]),
+    "b2q_reset": (_i, [_vp, _u8p, _vp, _vp, _vp, _vp]),
+    "b2q_step": (_i, [_vp, _vp, _i, _vp, _vp, _u8p, _vp, _vp]),
+    "b2q_get_state": (_i, [_vp, _vp, _vp]),
+    "b2q_set_state": (_i, [_vp, _vp, _vp]),
+    "b2q_get_step_count": (_i, [_vp, _vp, _vp]),
+    "b2q_launch_count": (C.c_int64, [_vp]),
+}
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Returns the loaded library; raises if it was not built (run `python -m paddlerobotics_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(
+            "paddlerobotics_b200: %s is missing — build it with `python -m paddlerobotics_b200.build` "
+            "(nvcc, sm_100a). There is no CPU/PyTorch fallback for this path." % _LIB_PATH)
+    lib = C.CDLL(_LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

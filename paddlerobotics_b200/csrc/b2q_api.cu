@@ -1,0 +1,275 @@
+// b2q_api.cu — sm_100a kernels and the C ABI (include/b2q.h) of the batched A1 simulator.
+//
+// Kernel map: K1 b2q_step_kernel (hot: R fused physics substeps + ETG + obs/reward pack, optional
+// in-kernel auto-reset), K2 b2q_reset_kernel (masked snapshot copy), b2q_settle_kernel (builds the snapshot), and
+// small repack kernels.  Mapping: one lane per leg, 4 lanes per robot, 8 robots per warp; SoA float4 packs in HBM
+// ([pack][env]) so that every lane's 16-byte load is part of a fully coalesced 128-byte warp transaction.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <new>
+#include <string>
+#include "b2q_host_common.h"
+
+using namespace b2q;
+
+namespace {
+
+struct WarpComm {
+  int k;
+  __device__ __forceinline__ int leg() const { return k; }
+  template <typename T>
+  __device__ __forceinline__ T sum4(T v) const {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+  }
+  template <typename T>
+  __device__ __forceinline__ T bcast(T v, int f) const { return __shfl_sync(0xffffffffu, v, f, 4); }
+};
+
+template <typename T>
+__device__ __forceinline__ const Model<T>& stage_model(const Model<T>* g, unsigned char* smem) {
+  // model constants (~1 KB) staged once per CTA in shared memory: lanes of different legs read different
+  // LegModel rows, which a __constant__ bank would serialise
+  Model<T>* s = reinterpret_cast<Model<T>*>(smem);
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(g);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(s);
+  for (int i = threadIdx.x; i < (int)(sizeof(Model<T>) / 4); i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+  return *s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) b2q_step_kernel(Cfg<T> cf, const Model<T>* __restrict__ gm, Buffers<T> B, const T* __restrict__ action, int donef,
+                                                       int auto_reset, T* __restrict__ obs, T* __restrict__ reward, uint8_t* __restrict__ done, T* __restrict__ info) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Model<T>& md = stage_model(gm, smem);
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  int env = gid >> 2;
+  bool valid = env < B.N;
+  if (!valid) env = B.N - 1;  // whole warps stay convergent for the shuffles; invalid lanes never store
+  WarpComm cm{(int)(threadIdx.x & 3)};
+  step_lane<T>(cm, cf, md, B, env, valid, action, donef, auto_reset, obs, reward, done, info);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) b2q_settle_kernel(Cfg<T> cf, const Model<T>* __restrict__ gm, Buffers<T> B, const uint8_t* __restrict__ mask) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Model<T>& md = stage_model(gm, smem);
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  int env = gid >> 2;
+  bool valid = env < B.N;
+  if (!valid) env = B.N - 1;
+  if (mask && !mask[env]) valid = false;
+  WarpComm cm{(int)(threadIdx.x & 3)};
+  settle_lane<T>(cm, cf, md, B, env, valid);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) b2q_reset_kernel(Cfg<T> cf, const Model<T>* __restrict__ gm, Buffers<T> B, const uint8_t* __restrict__ mask, T* __restrict__ obs) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Model<T>& md = stage_model(gm, smem);
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  int env = gid >> 2;
+  bool valid = env < B.N;
+  if (!valid) env = B.N - 1;
+  if (mask && !mask[env]) valid = false;
+  WarpComm cm{(int)(threadIdx.x & 3)};
+  reset_lane<T>(cm, cf, md, B, env, valid, obs ? obs + (size_t)env * OBS_DIM : (T*)nullptr);
+}
+
+template <typename T>
+__global__ void b2q_pack_param_kernel(const T* __restrict__ dyn, const T* __restrict__ def48, P4<T>* param, const uint8_t* __restrict__ mask, int N) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= N || (mask && !mask[env])) return;
+  pack_param_env<T>(dyn, def48, param, N, env);
+}
+template <typename T>
+__global__ void b2q_pack_etg_kernel(const T* __restrict__ w, const T* __restrict__ b, P4<T>* etg, const uint8_t* __restrict__ mask, int N) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= N || (mask && !mask[env])) return;
+  pack_etg_env<T>(w, b, etg, N, env);
+}
+template <typename T>
+__global__ void b2q_get_state_kernel(const P4<T>* st, T* out, int N) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env < N) get_state_env<T>(st, out, N, env);
+}
+template <typename T>
+__global__ void b2q_set_state_kernel(P4<T>* st, const T* in, int N) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env < N) set_state_env<T>(st, in, N, env);
+}
+
+thread_local std::string g_create_err;
+
+struct EnvBase {
+  B2QConfig cfg;
+  int prec;
+  std::string err;
+  int64_t launches = 0;
+  virtual ~EnvBase() {}
+  virtual int set_dynamics(const uint8_t* mask, const void* dyn, cudaStream_t s) = 0;
+  virtual int reset(const uint8_t* mask, const void* w, const void* b, void* obs, cudaStream_t s) = 0;
+  virtual int step(const void* action, int donef, void* obs, void* rew, uint8_t* done, void* info, cudaStream_t s) = 0;
+  virtual int get_state(void* out, cudaStream_t s) = 0;
+  virtual int set_state(const void* in, cudaStream_t s) = 0;
+  virtual int get_step_count(int32_t* out, cudaStream_t s) = 0;
+};
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      err = std::string(#call) + ": " + cudaGetErrorString(e_);                       \
+      return B2Q_ECUDA;                                                               \
+    }                                                                                 \
+  } while (0)
+
+template <typename T>
+struct EnvT : EnvBase {
+  Cfg<T> kc;
+  Buffers<T> B;
+  Model<T>* d_model = nullptr;
+  T* d_def48 = nullptr;
+  T* d_hf = nullptr;
+  void* d_pool = nullptr;
+  int tpb = 32;
+
+  ~EnvT() override {
+    cudaSetDevice(cfg.device);
+    if (d_pool) cudaFree(d_pool);
+    if (d_model) cudaFree(d_model);
+    if (d_def48) cudaFree(d_def48);
+    if (d_hf) cudaFree(d_hf);
+  }
+  int grid_lanes() const { return (B.N * 4 + tpb - 1) / tpb; }
+
+  int init(const B2QConfig& c) {
+    cfg = c; prec = c.precision;
+    tpb = c.threads_per_block ? c.threads_per_block : 32;
+    CK(cudaSetDevice(c.device));
+    int N = c.num_envs, Dm = c.ring_depth;
+    if (c.terrain_type == 1) {
+      size_t n = (size_t)c.hf_nx * c.hf_ny;
+      T* tmp = (T*)malloc(n * sizeof(T));
+      if (!tmp) { err = "host alloc failed"; return B2Q_ENOMEM; }
+      for (size_t i = 0; i < n; i++) tmp[i] = (T)c.hf_host[i];
+      cudaError_t e1 = cudaMalloc(&d_hf, n * sizeof(T));
+      if (e1 == cudaSuccess) e1 = cudaMemcpy(d_hf, tmp, n * sizeof(T), cudaMemcpyHostToDevice);
+      free(tmp);
+      CK(e1);
+    }
+    kc = make_cfg<T>(c, d_hf);
+    Model<T> hm; build_model_host(hm, c.foot_radius, c.etg_T, c.etg_amp, c.etg_phase0, c.etg_phase1);
+    CK(cudaMalloc(&d_model, sizeof(Model<T>)));
+    CK(cudaMemcpy(d_model, &hm, sizeof(Model<T>), cudaMemcpyHostToDevice));
+    double d48[48]; default_dyn_row(d48); T t48[48]; for (int i = 0; i < 48; i++) t48[i] = (T)d48[i];
+    CK(cudaMalloc(&d_def48, sizeof(t48)));
+    CK(cudaMemcpy(d_def48, t48, sizeof(t48), cudaMemcpyHostToDevice));
+    // one pool for the SoA env state: [state NS | snap NS | snap_obs 12 | param NP | etg NE | ring Dm*24] packs x N, + step counters
+    size_t packs = (size_t)(NS + NS + 12 + NP + NE + Dm * 24) * N;
+    size_t bytes = packs * sizeof(P4<T>) + (size_t)N * sizeof(int);
+    CK(cudaMalloc(&d_pool, bytes));
+    CK(cudaMemset(d_pool, 0, bytes));
+    P4<T>* p = (P4<T>*)d_pool;
+    B.N = N; B.Dm = Dm;
+    B.state = p; p += (size_t)NS * N; B.snap = p; p += (size_t)NS * N; B.snap_obs = p; p += (size_t)12 * N;
+    B.param = p; p += (size_t)NP * N; B.etg = p; p += (size_t)NE * N; B.ring = p; p += (size_t)Dm * 24 * N;
+    B.step_count = (int*)p;
+    int rc = set_dynamics(nullptr, nullptr, 0);
+    if (rc) return rc;
+    rc = reset(nullptr, nullptr, nullptr, nullptr, 0);
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());
+    return B2Q_OK;
+  }
+  size_t smem_bytes() const { return (sizeof(Model<T>) + 15) & ~size_t(15); }
+
+  int set_dynamics(const uint8_t* mask, const void* dyn, cudaStream_t s) override {
+    CK(cudaSetDevice(cfg.device));
+    int N = B.N;
+    b2q_pack_param_kernel<T><<<(N + 127) / 128, 128, 0, s>>>((const T*)dyn, d_def48, const_cast<P4<T>*>(B.param), mask, N);
+    b2q_settle_kernel<T><<<grid_lanes(), tpb, smem_bytes(), s>>>(kc, d_model, B, mask);
+    launches += 2;
+    CK(cudaGetLastError());
+    return B2Q_OK;
+  }
+  int reset(const uint8_t* mask, const void* w, const void* b, void* obs, cudaStream_t s) override {
+    CK(cudaSetDevice(cfg.device));
+    int N = B.N;
+    if (w || b) { b2q_pack_etg_kernel<T><<<(N + 127) / 128, 128, 0, s>>>((const T*)w, (const T*)b, const_cast<P4<T>*>(B.etg), mask, N); launches++; }
+    b2q_reset_kernel<T><<<grid_lanes(), tpb, smem_bytes(), s>>>(kc, d_model, B, mask, (T*)obs);
+    launches++;
+    CK(cudaGetLastError());
+    return B2Q_OK;
+  }
+  int step(const void* action, int donef, void* obs, void* rew, uint8_t* done, void* info, cudaStream_t s) override {
+    if (!action || !obs || !rew || !done || !info) { err = "b2q_step: null device pointer"; return B2Q_EINVAL; }
+    b2q_step_kernel<T><<<grid_lanes(), tpb, smem_bytes(), s>>>(kc, d_model, B, (const T*)action, donef, cfg.auto_reset, (T*)obs, (T*)rew, done, (T*)info);
+    launches++;
+    CK(cudaGetLastError());
+    return B2Q_OK;
+  }
+  int get_state(void* out, cudaStream_t s) override {
+    b2q_get_state_kernel<T><<<(B.N + 127) / 128, 128, 0, s>>>(B.state, (T*)out, B.N); launches++;
+    CK(cudaGetLastError());
+    return B2Q_OK;
+  }
+  int set_state(const void* in, cudaStream_t s) override {
+    b2q_set_state_kernel<T><<<(B.N + 127) / 128, 128, 0, s>>>(B.state, (const T*)in, B.N); launches++;
+    CK(cudaGetLastError());
+    return B2Q_OK;
+  }
+  int get_step_count(int32_t* out, cudaStream_t s) override {
+    CK(cudaMemcpyAsync(out, B.step_count, sizeof(int) * B.N, cudaMemcpyDeviceToDevice, s));
+    return B2Q_OK;
+  }
+};
+
+}  // namespace
+
+struct B2QEnv { EnvBase* impl; };
+
+extern "C" {
+
+void b2q_default_config(B2QConfig* cfg) { if (cfg) default_config(cfg); }
+const char* b2q_version(void) { return "b2q 0.1.0 (sm_100a)"; }
+
+int b2q_create(const B2QConfig* cfg, B2QHandle* out) {
+  if (!cfg || !out) { g_create_err = "null argument"; return B2Q_EINVAL; }
+  *out = nullptr;
+  if (const char* m = validate_config(*cfg)) { g_create_err = m; return B2Q_EINVAL; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { g_create_err = std::string("no CUDA device (no CPU fallback exists): ") + cudaGetErrorString(e); return B2Q_ECUDA; }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "device ordinal out of range"; return B2Q_EINVAL; }
+  EnvBase* impl = nullptr;
+  int rc;
+  if (cfg->precision == 0) { auto* t = new (std::nothrow) EnvT<float>(); if (!t) return B2Q_ENOMEM; rc = t->init(*cfg); impl = t; }
+  else { auto* t = new (std::nothrow) EnvT<double>(); if (!t) return B2Q_ENOMEM; rc = t->init(*cfg); impl = t; }
+  if (rc != B2Q_OK) { g_create_err = impl->err; delete impl; return rc; }
+  B2QEnv* h = new (std::nothrow) B2QEnv{impl};
+  if (!h) { delete impl; return B2Q_ENOMEM; }
+  *out = h;
+  return B2Q_OK;
+}
+int b2q_destroy(B2QHandle h) { if (!h) return B2Q_EINVAL; delete h->impl; delete h; return B2Q_OK; }
+const char* b2q_last_error(B2QHandle h) { return h ? h->impl->err.c_str() : g_create_err.c_str(); }
+int b2q_num_envs(B2QHandle h) { return h ? h->impl->cfg.num_envs : B2Q_EINVAL; }
+int b2q_obs_dim(B2QHandle h) { return h ? B2Q_OBS_DIM : B2Q_EINVAL; }
+int b2q_act_dim(B2QHandle h) { return h ? B2Q_ACT_DIM : B2Q_EINVAL; }
+int b2q_info_dim(B2QHandle h) { return h ? B2Q_INFO_DIM : B2Q_EINVAL; }
+int b2q_elem_size(B2QHandle h) { return h ? (h->impl->prec ? 8 : 4) : B2Q_EINVAL; }
+int b2q_set_dynamics(B2QHandle h, const uint8_t* m, const void* dyn, void* s) { return h ? h->impl->set_dynamics(m, dyn, (cudaStream_t)s) : B2Q_EINVAL; }
+int b2q_reset(B2QHandle h, const uint8_t* m, const void* w, const void* b, void* obs, void* s) { return h ? h->impl->reset(m, w, b, obs, (cudaStream_t)s) : B2Q_EINVAL; }
+int b2q_step(B2QHandle h, const void* a, int donef, void* obs, void* rew, uint8_t* done, void* info, void* s) {
+  return h ? h->impl->step(a, donef, obs, rew, done, info, (cudaStream_t)s) : B2Q_EINVAL;
+}
+int b2q_get_state(B2QHandle h, void* out, void* s) { return h ? h->impl->get_state(out, (cudaStream_t)s) : B2Q_EINVAL; }
+int b2q_set_state(B2QHandle h, const void* in, void* s) { return h ? h->impl->set_state(in, (cudaStream_t)s) : B2Q_EINVAL; }
+int b2q_get_step_count(B2QHandle h, int32_t* out, void* s) { return h ? h->impl->get_step_count(out, (cudaStream_t)s) : B2Q_EINVAL; }
+int64_t b2q_launch_count(B2QHandle h) { return h ? h->impl->launches : 0; }
+
+}  // extern "C"

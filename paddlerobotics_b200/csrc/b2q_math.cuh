@@ -1,0 +1,163 @@
+// b2q_math.cuh — small fixed-size algebra used by the A1 step kernels (sm_100a) and by the host SIMT
+// emulation harness in tests/emu (same source, different Comm policy).
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define B2Q_HD __host__ __device__ __forceinline__
+#define B2Q_D __device__ __forceinline__
+#else
+#define B2Q_HD inline
+#define B2Q_D inline
+#endif
+
+namespace b2q {
+
+// ---- scalar math wrappers (precise variants: no fast-math intrinsics, parity with the f64 oracle matters)
+B2Q_HD float m_sqrt(float x) { return sqrtf(x); }
+B2Q_HD double m_sqrt(double x) { return sqrt(x); }
+B2Q_HD float m_sin(float x) { return sinf(x); }
+B2Q_HD double m_sin(double x) { return sin(x); }
+B2Q_HD float m_cos(float x) { return cosf(x); }
+B2Q_HD double m_cos(double x) { return cos(x); }
+B2Q_HD float m_acos(float x) { return acosf(x); }
+B2Q_HD double m_acos(double x) { return acos(x); }
+B2Q_HD float m_asin(float x) { return asinf(x); }
+B2Q_HD double m_asin(double x) { return asin(x); }
+B2Q_HD float m_atan2(float y, float x) { return atan2f(y, x); }
+B2Q_HD double m_atan2(double y, double x) { return atan2(y, x); }
+B2Q_HD float m_exp(float x) { return expf(x); }
+B2Q_HD double m_exp(double x) { return exp(x); }
+B2Q_HD float m_tanh(float x) { return tanhf(x); }
+B2Q_HD double m_tanh(double x) { return tanh(x); }
+B2Q_HD float m_fmod(float x, float y) { return fmodf(x, y); }
+B2Q_HD double m_fmod(double x, double y) { return fmod(x, y); }
+B2Q_HD float m_abs(float x) { return fabsf(x); }
+B2Q_HD double m_abs(double x) { return fabs(x); }
+B2Q_HD float m_min(float a, float b) { return fminf(a, b); }
+B2Q_HD double m_min(double a, double b) { return fmin(a, b); }
+B2Q_HD float m_max(float a, float b) { return fmaxf(a, b); }
+B2Q_HD double m_max(double a, double b) { return fmax(a, b); }
+B2Q_HD bool m_isfinite(float x) { return (x - x) == 0.0f; }
+B2Q_HD bool m_isfinite(double x) { return (x - x) == 0.0; }
+B2Q_HD bool m_isnan(float x) { return x != x; }
+B2Q_HD bool m_isnan(double x) { return x != x; }
+
+template <typename T>
+struct V3 {
+  T x, y, z;
+};
+template <typename T> B2Q_HD V3<T> mk(T x, T y, T z) { V3<T> r; r.x = x; r.y = y; r.z = z; return r; }
+template <typename T> B2Q_HD V3<T> operator+(V3<T> a, V3<T> b) { return mk<T>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <typename T> B2Q_HD V3<T> operator-(V3<T> a, V3<T> b) { return mk<T>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <typename T> B2Q_HD V3<T> operator-(V3<T> a) { return mk<T>(-a.x, -a.y, -a.z); }
+template <typename T> B2Q_HD V3<T> operator*(V3<T> a, T s) { return mk<T>(a.x * s, a.y * s, a.z * s); }
+template <typename T> B2Q_HD V3<T> operator*(T s, V3<T> a) { return mk<T>(a.x * s, a.y * s, a.z * s); }
+template <typename T> B2Q_HD T dot(V3<T> a, V3<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename T> B2Q_HD V3<T> cross(V3<T> a, V3<T> b) { return mk<T>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+
+// symmetric 3x3
+template <typename T>
+struct S3 {
+  T xx, xy, xz, yy, yz, zz;
+};
+template <typename T> B2Q_HD V3<T> mul(const S3<T>& s, V3<T> v) {
+  return mk<T>(s.xx * v.x + s.xy * v.y + s.xz * v.z, s.xy * v.x + s.yy * v.y + s.yz * v.z, s.xz * v.x + s.yz * v.y + s.zz * v.z);
+}
+template <typename T> B2Q_HD S3<T> operator+(const S3<T>& a, const S3<T>& b) { S3<T> r = {a.xx + b.xx, a.xy + b.xy, a.xz + b.xz, a.yy + b.yy, a.yz + b.yz, a.zz + b.zz}; return r; }
+// m (|c|^2 1 - c c^T)
+template <typename T> B2Q_HD S3<T> point_inertia(T m, V3<T> c) {
+  S3<T> r = {m * (c.y * c.y + c.z * c.z), -m * c.x * c.y, -m * c.x * c.z, m * (c.x * c.x + c.z * c.z), -m * c.y * c.z, m * (c.x * c.x + c.y * c.y)};
+  return r;
+}
+
+// rotation matrix stored by columns (body->outer): v_outer = cx*v.x + cy*v.y + cz*v.z
+template <typename T>
+struct R3 {
+  V3<T> cx, cy, cz;
+};
+template <typename T> B2Q_HD V3<T> rot(const R3<T>& R, V3<T> v) { return R.cx * v.x + R.cy * v.y + R.cz * v.z; }
+template <typename T> B2Q_HD V3<T> rotT(const R3<T>& R, V3<T> v) { return mk<T>(dot(R.cx, v), dot(R.cy, v), dot(R.cz, v)); }
+template <typename T> B2Q_HD S3<T> rot_sym(const R3<T>& R, const S3<T>& I) {  // R I R^T
+  V3<T> a = R.cx * I.xx + R.cy * I.xy + R.cz * I.xz;  // (R I) column 0
+  V3<T> b = R.cx * I.xy + R.cy * I.yy + R.cz * I.yz;
+  V3<T> c = R.cx * I.xz + R.cy * I.yz + R.cz * I.zz;
+  // out = [a b c] R^T = a cx^T + b cy^T + c cz^T
+  S3<T> o;
+  o.xx = a.x * R.cx.x + b.x * R.cy.x + c.x * R.cz.x;
+  o.xy = a.x * R.cx.y + b.x * R.cy.y + c.x * R.cz.y;
+  o.xz = a.x * R.cx.z + b.x * R.cy.z + c.x * R.cz.z;
+  o.yy = a.y * R.cx.y + b.y * R.cy.y + c.y * R.cz.y;
+  o.yz = a.y * R.cx.z + b.y * R.cy.z + c.y * R.cz.z;
+  o.zz = a.z * R.cx.z + b.z * R.cy.z + c.z * R.cz.z;
+  return o;
+}
+template <typename T> B2Q_HD R3<T> quat_to_R(T x, T y, T z, T w) {  // xyzw, body->world (pybullet convention)
+  R3<T> R;
+  R.cx = mk<T>(1 - 2 * (y * y + z * z), 2 * (x * y + z * w), 2 * (x * z - y * w));
+  R.cy = mk<T>(2 * (x * y - z * w), 1 - 2 * (x * x + z * z), 2 * (y * z + x * w));
+  R.cz = mk<T>(2 * (x * z + y * w), 2 * (y * z - x * w), 1 - 2 * (x * x + y * y));
+  return R;
+}
+template <typename T> B2Q_HD V3<T> quat_to_rpy(T x, T y, T z, T w) {  // minitaur.py:613-621 (getEulerFromQuaternion)
+  T s = 2 * (w * y - z * x);
+  s = m_min(m_max(s, T(-1)), T(1));
+  return mk<T>(m_atan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y)), m_asin(s), m_atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z)));
+}
+
+// 6-vectors [ang; lin]
+template <typename T>
+struct V6 {
+  V3<T> a, l;
+};
+template <typename T> B2Q_HD V6<T> operator+(V6<T> p, V6<T> q) { V6<T> r; r.a = p.a + q.a; r.l = p.l + q.l; return r; }
+template <typename T> B2Q_HD V6<T> operator-(V6<T> p, V6<T> q) { V6<T> r; r.a = p.a - q.a; r.l = p.l - q.l; return r; }
+template <typename T> B2Q_HD V6<T> operator*(V6<T> p, T s) { V6<T> r; r.a = p.a * s; r.l = p.l * s; return r; }
+template <typename T> B2Q_HD T dot6(V6<T> p, V6<T> q) { return dot(p.a, q.a) + dot(p.l, q.l); }
+template <typename T> B2Q_HD T get6(const V6<T>& v, int i) { return i == 0 ? v.a.x : i == 1 ? v.a.y : i == 2 ? v.a.z : i == 3 ? v.l.x : i == 4 ? v.l.y : v.l.z; }
+
+// packed lower-triangular 6x6 / symmetric 6x6: index (i>=j) -> i*(i+1)/2 + j
+B2Q_HD constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+template <typename T> B2Q_HD void chol6(T* S /*21, in: sym lower; out: L lower*/) {
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    T d = S[tri(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; k++) d -= S[tri(j, k)] * S[tri(j, k)];
+    d = m_sqrt(d);
+    S[tri(j, j)] = d;
+    T inv = T(1) / d;
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) {
+      T s = S[tri(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= S[tri(i, k)] * S[tri(j, k)];
+      S[tri(i, j)] = s * inv;
+    }
+  }
+}
+// the diagonal of L is stored as is; solves use division
+template <typename T> B2Q_HD void fwd6(const T* L, T* b) {  // b <- L^-1 b
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    T s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) s -= L[tri(i, k)] * b[k];
+    b[i] = s / L[tri(i, i)];
+  }
+}
+template <typename T> B2Q_HD void bwd6(const T* L, T* b) {  // b <- L^-T b
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    T s = b[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) s -= L[tri(k, i)] * b[k];
+    b[i] = s / L[tri(i, i)];
+  }
+}
+template <typename T> B2Q_HD void v6_to_arr(const V6<T>& v, T* a) { a[0] = v.a.x; a[1] = v.a.y; a[2] = v.a.z; a[3] = v.l.x; a[4] = v.l.y; a[5] = v.l.z; }
+template <typename T> B2Q_HD V6<T> arr_to_v6(const T* a) { V6<T> v; v.a = mk<T>(a[0], a[1], a[2]); v.l = mk<T>(a[3], a[4], a[5]); return v; }
+
+}  // namespace b2q

@@ -1,0 +1,674 @@
+// b2q_sim.cuh — the A1 per-step hot path as SIMT code: one lane per LEG, four lanes per robot, eight robots
+// per warp.  Everything a leg needs (its 3 joints, link frames, composite inertias, foot contact rows) lives in
+// the lane's registers; the only cross-lane traffic is (a) 4-lane butterfly sums for quantities that meet at the
+// floating base and (b) 4-lane broadcasts inside the PGS contact sweep.  `Comm` supplies those two primitives:
+// warp shuffles on the GPU (b2q_kernels.cu), a 4-thread barrier exchange in the CPU emulation harness used by the
+// CPU-side tests (tests/emu/) — same source, so kernel logic is testable without a GPU.
+//
+// Reference path replaced: Minitaur.Step/ProcessAction/ApplyAction (minitaur.py:248-260,
+// 904-947,1384-1401), LaikagoMotorModel.convert_to_torque (laikago_motor.py:103-175), pybullet.stepSimulation
+// (minitaur.py:244; Bullet multibody ABA + PGS — restated), ReceiveObservation /
+// _GetDelayedObservation (minitaur.py:1151-1193), A1 IK (a1.py:97-110,464-497), ETG layer (rlschool, restated),
+// observation packing (EnvWrapper.py:50-109).
+//
+// Formulation (differs on purpose from the oracle's link-coordinate ABA): all quantities are expressed in the
+// base frame B; per leg a 3x3 joint-space block M_k, a 6x3 base coupling F_k and the leg's composite inertia are
+// built by the composite-rigid-body method; the four legs only couple through the base, so
+//     S = H_base - sum_k F_k M_k^-1 F_k^T   (6x6 Schur complement, = articulated inertia of the base)
+// is reduced over the 4 lanes, Cholesky-factored redundantly, and back-substituted per leg.  Contacts are solved
+// in contact space: W = J M^-1 J^T (12x12, each lane owns its foot's 3 rows) with projected Gauss-Seidel in
+// Bullet's row order (all normals, then all friction rows).
+#pragma once
+#include "b2q_math.cuh"
+
+namespace b2q {
+
+constexpr int NS = 21;    // state packs per env
+constexpr int NP = 15;    // param packs per env
+constexpr int NE = 16;    // ETG packs per env (w[3][20], b[3], pad)
+constexpr int OBS_DIM = 49;
+constexpr int INFO_DIM = 56;
+constexpr int ETG_H = 20;
+
+template <typename T>
+struct alignas(4 * sizeof(T)) P4 {
+  T x, y, z, w;
+};
+
+template <typename T>
+struct LegModel {
+  T p1[3];       // hip joint origin in the base frame (a1.py:70-73, incl. COM_OFFSET)
+  T lhip;        // signed thigh-joint y offset (a1.py:100)
+  T com[3][3];   // link COMs in link frames: hip, thigh, calf(+toe)
+  T I[3][6];     // inertia about COM, link frame: xx xy xz yy yz zz
+  T m[3];
+};
+template <typename T>
+struct Model {
+  LegModel<T> leg[4];
+  T m0, I0[6];
+  T foot_r, l_up, l_low;
+  T etg_u[ETG_H][2];
+  T base_foot[4][3];
+  T etg_mean[12], etg_std[12];
+  T pose_ori[3];
+};
+template <typename T>
+struct Cfg {
+  T dt; int R; int iters; T erp, warm, margin; int interp; T tau_limit; int settle_steps;
+  T etg_T, etg_T2, etg_sigma_sq, etg_amp, etg_ph0, etg_ph1;
+  T w_torso, w_feet, w_up, w_tau, w_stand, w_badfoot, w_footcontact, w_done, reward_p, vel_d;
+  int terrain, hf_nx, hf_ny; T hf_x0, hf_y0, hf_cell; const T* hf;
+};
+template <typename T>
+struct Buffers {
+  int N, Dm;
+  P4<T>* state;          // [NS][N]
+  P4<T>* snap;           // [NS][N] settled snapshot (K2: reset = masked copy)
+  P4<T>* snap_obs;       // [12][N]
+  const P4<T>* param;    // [NP][N]
+  const P4<T>* etg;      // [NE][N]
+  P4<T>* ring;           // [Dm][2][12][N]
+  int* step_count;       // [N]
+};
+template <typename T>
+struct LaneParam {
+  T kp[3], kd[3], iscale[3], mscale[3], m0s, I0s[3], mu, latency;
+  V3<T> g;
+};
+template <typename T>
+struct LaneState {
+  V3<T> pos; T qx, qy, qz, qw; V3<T> vlin, vang;
+  T q[3], qd[3]; T lam_n; int contact;
+};
+
+template <typename T> B2Q_HD void sincos_t(T a, T& s, T& c) { s = m_sin(a); c = m_cos(a); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// terrain: plane or bilinear height field
+template <typename T>
+B2Q_HD T terrain_height(const Cfg<T>& cf, T x, T y, V3<T>& n) {
+  if (cf.terrain == 0) { n = mk<T>(0, 0, 1); return T(0); }
+  T fx = (x - cf.hf_x0) / cf.hf_cell, fy = (y - cf.hf_y0) / cf.hf_cell;
+  fx = m_min(m_max(fx, T(0)), T(cf.hf_nx) - T(1.000001));
+  fy = m_min(m_max(fy, T(0)), T(cf.hf_ny) - T(1.000001));
+  int ix = (int)fx, iy = (int)fy;
+  T tx = fx - T(ix), ty = fy - T(iy);
+  const T* h = cf.hf; int nx = cf.hf_nx;
+  T h00 = h[iy * nx + ix], h10 = h[iy * nx + ix + 1], h01 = h[(iy + 1) * nx + ix], h11 = h[(iy + 1) * nx + ix + 1];
+  T hh = (1 - tx) * (1 - ty) * h00 + tx * (1 - ty) * h10 + (1 - tx) * ty * h01 + tx * ty * h11;
+  T dhdx = ((1 - ty) * (h10 - h00) + ty * (h11 - h01)) / cf.hf_cell;
+  T dhdy = ((1 - tx) * (h01 - h00) + tx * (h11 - h10)) / cf.hf_cell;
+  T inv = T(1) / m_sqrt(dhdx * dhdx + dhdy * dhdy + T(1));
+  n = mk<T>(-dhdx * inv, -dhdy * inv, inv);
+  return hh;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// closed-form leg kinematics in the base frame (tree-consistent with a1.py:113-129)
+template <typename T>
+struct LegKin {
+  R3<T> R1, R2, R3m;
+  V3<T> p1, p2, p3, toe, a2;
+};
+template <typename T>
+B2Q_HD void leg_kin(const Model<T>& md, const LegModel<T>& lm, const T* q, LegKin<T>& K) {
+  T s1, c1, s2, c2, s23, c23;
+  sincos_t(q[0], s1, c1); sincos_t(q[1], s2, c2); sincos_t(q[1] + q[2], s23, c23);
+  K.R1.cx = mk<T>(1, 0, 0); K.R1.cy = mk<T>(0, c1, s1); K.R1.cz = mk<T>(0, -s1, c1);
+  K.R2.cx = mk<T>(c2, s1 * s2, -c1 * s2); K.R2.cy = K.R1.cy; K.R2.cz = mk<T>(s2, -s1 * c2, c1 * c2);
+  K.R3m.cx = mk<T>(c23, s1 * s23, -c1 * s23); K.R3m.cy = K.R1.cy; K.R3m.cz = mk<T>(s23, -s1 * c23, c1 * c23);
+  K.a2 = K.R1.cy;
+  K.p1 = mk<T>(lm.p1[0], lm.p1[1], lm.p1[2]);
+  K.p2 = K.p1 + K.R1.cy * lm.lhip;
+  K.p3 = K.p2 - K.R2.cz * md.l_up;
+  K.toe = K.p3 - K.R3m.cz * md.l_low;
+}
+
+// closed-form IK, a1.py:97-110 (foot relative to the hip joint origin)
+template <typename T>
+B2Q_HD void leg_ik(const Model<T>& md, V3<T> f, T lhip, T* ang) {
+  T lu = md.l_up, ll = md.l_low;
+  T tk = -m_acos((f.x * f.x + f.y * f.y + f.z * f.z - lhip * lhip - ll * ll - lu * lu) / (2 * ll * lu));
+  T l = m_sqrt(lu * lu + ll * ll + 2 * lu * ll * m_cos(tk));
+  T th = m_asin(-f.x / l) - tk / 2;
+  T cc = m_cos(th + tk / 2);
+  T c1 = lhip * f.y - l * cc * f.z;
+  T s1 = l * cc * f.y + lhip * f.z;
+  ang[0] = m_atan2(s1, c1); ang[1] = th; ang[2] = tk;
+}
+
+// ETG open-loop reference for this lane's leg: joint offsets relative to pose_ori
+template <typename T, class Comm>
+B2Q_HD void etg_act_leg(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const P4<T>* etg, int N, int env, T t, T* act) {
+  const int k = cm.leg();
+  const T two_pi = T(6.283185307179586476925286766559);
+  T tt = (k == 0 || k == 3) ? t : t + T(0.5) * cf.etg_T2;
+  T om = two_pi / cf.etg_T;
+  T x0 = cf.etg_amp * m_sin(cf.etg_ph0 + om * tt), x1 = cf.etg_amp * m_sin(cf.etg_ph1 + om * tt);
+  T d[3] = {0, 0, 0};
+  const T* e = reinterpret_cast<const T*>(etg);  // pack p, env -> e[(p*N+env)*4 + c]
+#pragma unroll 4
+  for (int h = 0; h < ETG_H; h++) {
+    T dx = x0 - md.etg_u[h][0], dy = x1 - md.etg_u[h][1];
+    T r = m_exp(-(dx * dx + dy * dy) / cf.etg_sigma_sq);
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      int idx = a * ETG_H + h;
+      d[a] += e[((size_t)(idx >> 2) * N + env) * 4 + (idx & 3)] * r;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) { int idx = 60 + a; d[a] += e[((size_t)(idx >> 2) * N + env) * 4 + (idx & 3)]; }
+  const LegModel<T>& lm = md.leg[k];
+  T ang[3];
+  for (int tries = 0; tries < 200; tries++) {  // act_clip: shrink until IK is finite
+    V3<T> f = mk<T>(md.base_foot[k][0] + d[0] - lm.p1[0], md.base_foot[k][1] + d[1] - lm.p1[1], md.base_foot[k][2] + d[2] - lm.p1[2]);
+    leg_ik(md, f, lm.lhip, ang);
+    if (!(m_isnan(ang[0]) || m_isnan(ang[1]) || m_isnan(ang[2]))) break;
+    d[0] *= T(0.95); d[1] *= T(0.95); d[2] *= T(0.95);
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) act[a] = ang[a] - md.pose_ori[a];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// one physics substep for this lane's leg (+ redundant base)
+template <typename T, class Comm>
+B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const LaneParam<T>& pr, LaneState<T>& s,
+                    const T* target, T* tau_out) {
+  const int k = cm.leg();
+  const LegModel<T>& lm = md.leg[k];
+  const T dt = cf.dt;
+  R3<T> R = quat_to_R(s.qx, s.qy, s.qz, s.qw);
+  V3<T> wB = rotT(R, s.vang), vB = rotT(R, s.vlin), gB = rotT(R, pr.g);
+
+  // --- ApplyAction: PD on the current q, qd (pd_latency = 0), laikago_motor.py:165-173
+  T tau[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    T t = T(-1) * (pr.kp[j] * (s.q[j] - target[j])) - pr.kd[j] * (s.qd[j] - T(0));
+    if (cf.tau_limit > T(0)) t = m_min(m_max(t, -cf.tau_limit), cf.tau_limit);
+    tau[j] = t; tau_out[j] = t;
+  }
+
+  // --- kinematics in B
+  LegKin<T> K; leg_kin(md, lm, s.q, K);
+  const V3<T> a1 = mk<T>(1, 0, 0), a2 = K.a2;
+  V3<T> cL[3]; S3<T> IL[3]; T mL[3];
+  {
+    const R3<T>* Rs[3] = {&K.R1, &K.R2, &K.R3m};
+    const V3<T> ps[3] = {K.p1, K.p2, K.p3};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      cL[i] = ps[i] + rot(*Rs[i], mk<T>(lm.com[i][0], lm.com[i][1], lm.com[i][2]));
+      S3<T> Il = {lm.I[i][0], lm.I[i][1], lm.I[i][2], lm.I[i][3], lm.I[i][4], lm.I[i][5]};
+      S3<T> Ib = rot_sym(*Rs[i], Il);
+      T sc = pr.iscale[i];
+      IL[i].xx = Ib.xx * sc; IL[i].xy = Ib.xy * sc; IL[i].xz = Ib.xz * sc; IL[i].yy = Ib.yy * sc; IL[i].yz = Ib.yz * sc; IL[i].zz = Ib.zz * sc;
+      mL[i] = lm.m[i] * pr.mscale[i];
+    }
+  }
+  // --- velocities and bias accelerations (q'' = 0, base twist derivative = 0, gravity as -g fictitious accel)
+  V3<T> w1 = wB + a1 * s.qd[0], w2 = w1 + a2 * s.qd[1], w3 = w2 + a2 * s.qd[2];
+  V3<T> pdd0 = cross(wB, vB) - gB;
+  V3<T> al1 = cross(wB, a1) * s.qd[0];
+  V3<T> pdd1 = pdd0 + cross(wB, cross(wB, K.p1));
+  V3<T> al2 = al1 + cross(w1, a2) * s.qd[1];
+  V3<T> d21 = K.p2 - K.p1;
+  V3<T> pdd2 = pdd1 + cross(al1, d21) + cross(w1, cross(w1, d21));
+  V3<T> al3 = al2 + cross(w2, a2) * s.qd[2];
+  V3<T> d32 = K.p3 - K.p2;
+  V3<T> pdd3 = pdd2 + cross(al2, d32) + cross(w2, cross(w2, d32));
+  V3<T> fL[3], nL[3];
+  {
+    const V3<T> ws[3] = {w1, w2, w3}, als[3] = {al1, al2, al3}, pdds[3] = {pdd1, pdd2, pdd3}, ps[3] = {K.p1, K.p2, K.p3};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      V3<T> r = cL[i] - ps[i];
+      V3<T> cdd = pdds[i] + cross(als[i], r) + cross(ws[i], cross(ws[i], r));
+      fL[i] = cdd * mL[i];
+      nL[i] = mul(IL[i], als[i]) + cross(ws[i], mul(IL[i], ws[i]));
+    }
+  }
+  V3<T> F3 = fL[2], N3 = nL[2] + cross(cL[2] - K.p3, fL[2]);
+  V3<T> F2 = fL[1] + F3, N2 = nL[1] + cross(cL[1] - K.p2, fL[1]) + N3 + cross(d32, F3);
+  V3<T> F1 = fL[0] + F2, N1 = nL[0] + cross(cL[0] - K.p1, fL[0]) + N2 + cross(d21, F2);
+  T hj[3] = {dot(a1, N1), dot(a2, N2), dot(a2, N3)};
+  V3<T> NO = N1 + cross(K.p1, F1);  // leg bias wrench about the base origin
+
+  // --- composite inertias about the base origin and the joint-space blocks
+  T m3c = mL[2], m2c = mL[1] + m3c, m1c = mL[0] + m2c;
+  V3<T> h3c = cL[2] * mL[2], h2c = cL[1] * mL[1] + h3c, h1c = cL[0] * mL[0] + h2c;
+  S3<T> I3c = IL[2] + point_inertia(mL[2], cL[2]);
+  S3<T> I2c = IL[1] + point_inertia(mL[1], cL[1]) + I3c;
+  S3<T> I1c = IL[0] + point_inertia(mL[0], cL[0]) + I2c;
+  V3<T> v1 = cross(K.p1, a1), v2 = cross(K.p2, a2), v3 = cross(K.p3, a2);
+  V6<T> Fc[3];
+  Fc[0].a = mul(I1c, a1) + cross(h1c, v1); Fc[0].l = v1 * m1c + cross(a1, h1c);
+  Fc[1].a = mul(I2c, a2) + cross(h2c, v2); Fc[1].l = v2 * m2c + cross(a2, h2c);
+  Fc[2].a = mul(I3c, a2) + cross(h3c, v3); Fc[2].l = v3 * m3c + cross(a2, h3c);
+  T M11 = dot(a1, Fc[0].a) + dot(v1, Fc[0].l);
+  T M21 = dot(a1, Fc[1].a) + dot(v1, Fc[1].l), M22 = dot(a2, Fc[1].a) + dot(v2, Fc[1].l);
+  T M31 = dot(a1, Fc[2].a) + dot(v1, Fc[2].l), M32 = dot(a2, Fc[2].a) + dot(v2, Fc[2].l), M33 = dot(a2, Fc[2].a) + dot(v3, Fc[2].l);
+  // D = M_k^-1 (symmetric 3x3, cofactors)
+  T D[3][3];
+  {
+    T c00 = M22 * M33 - M32 * M32, c01 = M31 * M32 - M21 * M33, c02 = M21 * M32 - M31 * M22;
+    T det = M11 * c00 + M21 * c01 + M31 * c02, id = T(1) / det;
+    D[0][0] = c00 * id; D[0][1] = D[1][0] = c01 * id; D[0][2] = D[2][0] = c02 * id;
+    D[1][1] = (M11 * M33 - M31 * M31) * id; D[1][2] = D[2][1] = (M31 * M21 - M11 * M32) * id;
+    D[2][2] = (M11 * M22 - M21 * M21) * id;
+  }
+  T bj[3] = {tau[0] - hj[0], tau[1] - hj[1], tau[2] - hj[2]};
+  V6<T> FD[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) FD[j] = Fc[0] * D[0][j] + Fc[1] * D[1][j] + Fc[2] * D[2][j];
+
+  // --- leg contribution to the base Schur complement and rhs; reduce over the 4 legs
+  T S[21], r6[6];
+  {
+    T Fa[3][6], FDa[3][6];
+#pragma unroll
+    for (int j = 0; j < 3; j++) { v6_to_arr(Fc[j], Fa[j]); v6_to_arr(FD[j], FDa[j]); }
+    // composite C1 as 6x6: [[I1c, hx],[hx^T, m 1]], hx = skew(h1c)
+    T C[21];
+    C[tri(0, 0)] = I1c.xx; C[tri(1, 0)] = I1c.xy; C[tri(1, 1)] = I1c.yy; C[tri(2, 0)] = I1c.xz; C[tri(2, 1)] = I1c.yz; C[tri(2, 2)] = I1c.zz;
+    // lower-left block rows 3..5 (lin), cols 0..2 (ang) = hx^T = -skew(h): [[0,hz,-hy],[-hz,0,hx],[hy,-hx,0]]
+    C[tri(3, 0)] = 0; C[tri(3, 1)] = h1c.z; C[tri(3, 2)] = -h1c.y;
+    C[tri(4, 0)] = -h1c.z; C[tri(4, 1)] = 0; C[tri(4, 2)] = h1c.x;
+    C[tri(5, 0)] = h1c.y; C[tri(5, 1)] = -h1c.x; C[tri(5, 2)] = 0;
+    C[tri(3, 3)] = m1c; C[tri(4, 3)] = 0; C[tri(4, 4)] = m1c; C[tri(5, 3)] = 0; C[tri(5, 4)] = 0; C[tri(5, 5)] = m1c;
+    T NOa[6] = {NO.x, NO.y, NO.z, F1.x, F1.y, F1.z};
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+#pragma unroll
+      for (int j = 0; j <= i; j++) {
+        T v = C[tri(i, j)] - (FDa[0][i] * Fa[0][j] + FDa[1][i] * Fa[1][j] + FDa[2][i] * Fa[2][j]);
+        S[tri(i, j)] = cm.sum4(v);
+      }
+      T rv = -NOa[i] - (FDa[0][i] * bj[0] + FDa[1][i] * bj[1] + FDa[2][i] * bj[2]);
+      r6[i] = cm.sum4(rv);
+    }
+  }
+  {
+    // base link: inertia (per-env scaled: I'_ab = sqrt(s_a s_b) I_ab), mass, and its own bias wrench
+    T sx = m_sqrt(pr.I0s[0]), sy = m_sqrt(pr.I0s[1]), sz = m_sqrt(pr.I0s[2]);
+    S3<T> I0 = {md.I0[0] * sx * sx, md.I0[1] * sx * sy, md.I0[2] * sx * sz, md.I0[3] * sy * sy, md.I0[4] * sy * sz, md.I0[5] * sz * sz};
+    T m0 = md.m0 * pr.m0s;
+    S[tri(0, 0)] += I0.xx; S[tri(1, 0)] += I0.xy; S[tri(1, 1)] += I0.yy; S[tri(2, 0)] += I0.xz; S[tri(2, 1)] += I0.yz; S[tri(2, 2)] += I0.zz;
+    S[tri(3, 3)] += m0; S[tri(4, 4)] += m0; S[tri(5, 5)] += m0;
+    V3<T> n0 = cross(wB, mul(I0, wB)), f0 = pdd0 * m0;
+    r6[0] -= n0.x; r6[1] -= n0.y; r6[2] -= n0.z; r6[3] -= f0.x; r6[4] -= f0.y; r6[5] -= f0.z;
+  }
+  chol6(S);          // S now holds L
+  fwd6(S, r6); bwd6(S, r6);  // r6 = base twist derivative (body coordinates)
+  V6<T> nud = arr_to_v6(r6);
+  T qdd[3];
+  {
+    T t[3] = {bj[0] - dot6(Fc[0], nud), bj[1] - dot6(Fc[1], nud), bj[2] - dot6(Fc[2], nud)};
+#pragma unroll
+    for (int j = 0; j < 3; j++) qdd[j] = D[j][0] * t[0] + D[j][1] * t[1] + D[j][2] * t[2];
+  }
+  // --- unconstrained velocities (body coordinates)
+  V3<T> wBs = wB + nud.a * dt, vBs = vB + (nud.l + cross(wB, vB)) * dt;
+  T qds[3] = {s.qd[0] + dt * qdd[0], s.qd[1] + dt * qdd[1], s.qd[2] + dt * qdd[2]};
+
+  // --- contact rows of this lane's foot
+  V3<T> toe_w = s.pos + rot(R, K.toe), n_w;
+  T hgt = terrain_height(cf, toe_w.x, toe_w.y, n_w);
+  T dist = toe_w.z - hgt - md.foot_r;
+  bool act = dist < cf.margin;
+  V3<T> t1w = mk<T>(1 - n_w.x * n_w.x, -n_w.x * n_w.y, -n_w.x * n_w.z);
+  t1w = t1w * (T(1) / m_sqrt(dot(t1w, t1w)));
+  V3<T> t2w = cross(n_w, t1w);
+  V3<T> eB[3] = {rotT(R, n_w), rotT(R, t1w), rotT(R, t2w)};
+  V3<T> xc = K.toe - eB[0] * md.foot_r;
+  T Jk[3][3], u[3], Y[3][6], Wl[3][3];
+  {
+    V3<T> r1 = cross(a1, xc - K.p1), r2 = cross(a2, xc - K.p2), r3 = cross(a2, xc - K.p3);
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+      Jk[e][0] = dot(eB[e], r1); Jk[e][1] = dot(eB[e], r2); Jk[e][2] = dot(eB[e], r3);
+      V6<T> Jb; Jb.a = cross(xc, eB[e]); Jb.l = eB[e];
+      u[e] = dot(Jb.a, wBs) + dot(Jb.l, vBs) + Jk[e][0] * qds[0] + Jk[e][1] * qds[1] + Jk[e][2] * qds[2];
+      V6<T> G = Jb - (FD[0] * Jk[e][0] + FD[1] * Jk[e][1] + FD[2] * Jk[e][2]);
+      v6_to_arr(G, Y[e]);
+      fwd6(S, Y[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+      T dj[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) dj[i] = D[i][0] * Jk[e][0] + D[i][1] * Jk[e][1] + D[i][2] * Jk[e][2];
+#pragma unroll
+      for (int e2 = 0; e2 < 3; e2++) Wl[e2][e] = Jk[e2][0] * dj[0] + Jk[e2][1] * dj[1] + Jk[e2][2] * dj[2];
+    }
+  }
+  T W[3][12];
+#pragma unroll
+  for (int f = 0; f < 4; f++) {
+#pragma unroll
+    for (int e2 = 0; e2 < 3; e2++) {
+      T yf[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) yf[c] = cm.bcast(Y[e2][c], f);
+#pragma unroll
+      for (int e = 0; e < 3; e++) {
+        T w = Y[e][0] * yf[0] + Y[e][1] * yf[1] + Y[e][2] * yf[2] + Y[e][3] * yf[3] + Y[e][4] * yf[4] + Y[e][5] * yf[5];
+        if (f == k) w += Wl[e][e2];
+        W[e][3 * f + e2] = w;
+      }
+    }
+  }
+  // --- projected Gauss-Seidel, Bullet row order: normals of feet 0..3, then (t1,t2) of feet 0..3
+  T lam[3] = {act ? cf.warm * s.lam_n : T(0), T(0), T(0)};
+  T targ0 = dist > T(0) ? -dist / dt : cf.erp * (-dist) / dt;
+  T invd[3] = {T(0), T(0), T(0)};
+  // the diagonal of this lane's own block (selected without dynamic register indexing)
+#pragma unroll
+  for (int f = 0; f < 4; f++) if (f == k) { invd[0] = T(1) / W[0][3 * f]; invd[1] = T(1) / W[1][3 * f + 1]; invd[2] = T(1) / W[2][3 * f + 2]; }
+#pragma unroll
+  for (int f = 0; f < 4; f++) {
+    T l0 = cm.bcast(lam[0], f);
+    u[0] += W[0][3 * f] * l0; u[1] += W[1][3 * f] * l0; u[2] += W[2][3 * f] * l0;
+  }
+  for (int it = 0; it < cf.iters; it++) {
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      T ln = m_max(lam[0] + (targ0 - u[0]) * invd[0], T(0));
+      T dl = cm.bcast(act ? ln - lam[0] : T(0), f);
+      if (f == k) lam[0] += dl;
+      u[0] += W[0][3 * f] * dl; u[1] += W[1][3 * f] * dl; u[2] += W[2][3 * f] * dl;
+    }
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+#pragma unroll
+      for (int td = 1; td < 3; td++) {
+        T lim = pr.mu * lam[0];
+        T ln = m_min(m_max(lam[td] + (T(0) - u[td]) * invd[td], -lim), lim);
+        T dl = cm.bcast(act ? ln - lam[td] : T(0), f);
+        if (f == k) lam[td] += dl;
+        u[0] += W[0][3 * f + td] * dl; u[1] += W[1][3 * f + td] * dl; u[2] += W[2][3 * f + td] * dl;
+      }
+    }
+  }
+  s.lam_n = lam[0]; s.contact = lam[0] > T(0);
+  // --- apply impulses
+  T z[6];
+#pragma unroll
+  for (int c = 0; c < 6; c++) z[c] = cm.sum4(Y[0][c] * lam[0] + Y[1][c] * lam[1] + Y[2][c] * lam[2]);
+  bwd6(S, z);
+  V6<T> dnu = arr_to_v6(z);
+  {
+    T jl[3], t[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { jl[i] = Jk[0][i] * lam[0] + Jk[1][i] * lam[1] + Jk[2][i] * lam[2]; t[i] = jl[i] - dot6(Fc[i], dnu); }
+#pragma unroll
+    for (int j = 0; j < 3; j++) qds[j] += D[j][0] * t[0] + D[j][1] * t[1] + D[j][2] * t[2];
+  }
+  wBs = wBs + dnu.a; vBs = vBs + dnu.l;
+  // --- integrate (semi-implicit Euler; base velocity stored in the world frame as pybullet reports it)
+  s.vang = rot(R, wBs); s.vlin = rot(R, vBs);
+#pragma unroll
+  for (int j = 0; j < 3; j++) { s.qd[j] = qds[j]; s.q[j] += dt * qds[j]; }
+  s.pos = s.pos + s.vlin * dt;
+  {
+    T wx = s.vang.x, wy = s.vang.y, wz = s.vang.z, th = m_sqrt(wx * wx + wy * wy + wz * wz) * dt;
+    T kk = th < T(1e-4) ? T(0.5) - th * th / T(48) : m_sin(T(0.5) * th) / th, cw = m_cos(T(0.5) * th);
+    T dx = wx * dt * kk, dy = wy * dt * kk, dz = wz * dt * kk;
+    T ox = cw * s.qx + dx * s.qw + dy * s.qz - dz * s.qy;
+    T oy = cw * s.qy - dx * s.qz + dy * s.qw + dz * s.qx;
+    T oz = cw * s.qz + dx * s.qy - dy * s.qx + dz * s.qw;
+    T ow = cw * s.qw - dx * s.qx - dy * s.qy - dz * s.qz;
+    T nn = T(1) / m_sqrt(ox * ox + oy * oy + oz * oz + ow * ow);
+    s.qx = ox * nn; s.qy = oy * nn; s.qz = oz * nn; s.qw = ow * nn;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pack I/O
+template <typename T> B2Q_HD P4<T> ldp(const P4<T>* base, int pack, int N, int env) { return base[(size_t)pack * N + env]; }
+template <typename T> B2Q_HD void stp(P4<T>* base, int pack, int N, int env, T x, T y, T z, T w) {
+  P4<T> p; p.x = x; p.y = y; p.z = z; p.w = w; base[(size_t)pack * N + env] = p;
+}
+
+template <typename T, class Comm>
+B2Q_HD void load_param(const Comm& cm, const Buffers<T>& B, int env, LaneParam<T>& pr) {
+  const int k = cm.leg(), N = B.N;
+  P4<T> a = ldp(B.param, 0 + k, N, env), b = ldp(B.param, 4 + k, N, env), c = ldp(B.param, 8 + k, N, env);
+  P4<T> d = ldp(B.param, 12, N, env), e = ldp(B.param, 13, N, env), g = ldp(B.param, 14, N, env);
+  pr.kp[0] = a.x; pr.kp[1] = a.y; pr.kp[2] = a.z; pr.mu = a.w;
+  pr.kd[0] = b.x; pr.kd[1] = b.y; pr.kd[2] = b.z; pr.latency = b.w;
+  pr.iscale[0] = c.x; pr.iscale[1] = c.y; pr.iscale[2] = c.z;
+  pr.mscale[0] = d.x; pr.mscale[1] = d.y; pr.mscale[2] = d.z; pr.m0s = d.w;
+  pr.I0s[0] = e.x; pr.I0s[1] = e.y; pr.I0s[2] = e.z;
+  pr.g = mk<T>(g.x, g.y, g.z);
+}
+template <typename T, class Comm>
+B2Q_HD void load_state(const Comm& cm, const P4<T>* st, int N, int env, LaneState<T>& s, T* last_action, T* etg_act, int& has_last, V3<T>& rpy0) {
+  const int k = cm.leg();
+  P4<T> p0 = ldp(st, 0, N, env), p1 = ldp(st, 1, N, env), p2 = ldp(st, 2, N, env), p3 = ldp(st, 3, N, env);
+  P4<T> pq = ldp(st, 4 + k, N, env), pd = ldp(st, 8 + k, N, env), pa = ldp(st, 12 + k, N, env), pe = ldp(st, 16 + k, N, env), pr = ldp(st, 20, N, env);
+  s.pos = mk<T>(p0.x, p0.y, p0.z); s.qx = p1.x; s.qy = p1.y; s.qz = p1.z; s.qw = p1.w;
+  s.vlin = mk<T>(p2.x, p2.y, p2.z); has_last = p2.w > T(0.5);
+  s.vang = mk<T>(p3.x, p3.y, p3.z);
+  s.q[0] = pq.x; s.q[1] = pq.y; s.q[2] = pq.z; s.lam_n = pq.w;
+  s.qd[0] = pd.x; s.qd[1] = pd.y; s.qd[2] = pd.z; s.contact = pd.w > T(0.5);
+  last_action[0] = pa.x; last_action[1] = pa.y; last_action[2] = pa.z;
+  etg_act[0] = pe.x; etg_act[1] = pe.y; etg_act[2] = pe.z;
+  rpy0 = mk<T>(pr.x, pr.y, pr.z);
+}
+template <typename T, class Comm>
+B2Q_HD void store_state(const Comm& cm, P4<T>* st, int N, int env, const LaneState<T>& s, const T* last_action, const T* etg_act, int has_last, V3<T> rpy0) {
+  const int k = cm.leg();
+  if (k == 0) { stp(st, 0, N, env, s.pos.x, s.pos.y, s.pos.z, T(0)); stp(st, 20, N, env, rpy0.x, rpy0.y, rpy0.z, T(0)); }
+  if (k == 1) stp(st, 1, N, env, s.qx, s.qy, s.qz, s.qw);
+  if (k == 2) stp(st, 2, N, env, s.vlin.x, s.vlin.y, s.vlin.z, T(has_last));
+  if (k == 3) stp(st, 3, N, env, s.vang.x, s.vang.y, s.vang.z, T(0));
+  stp(st, 4 + k, N, env, s.q[0], s.q[1], s.q[2], s.lam_n);
+  stp(st, 8 + k, N, env, s.qd[0], s.qd[1], s.qd[2], T(s.contact));
+  stp(st, 12 + k, N, env, last_action[0], last_action[1], last_action[2], T(0));
+  stp(st, 16 + k, N, env, etg_act[0], etg_act[1], etg_act[2], T(0));
+}
+// observation history ring: [Dm][2][12][N]; lane k owns packs 3k..3k+2 = (q, tau0),(qd, tau1),(tau2,-,-,-)
+template <typename T>
+B2Q_HD void ring_write(const Buffers<T>& B, int slot, int ab, int k, int env, const T* q, const T* qd, const T* tau) {
+  P4<T>* base = B.ring + ((size_t)(slot * 2 + ab) * 12) * B.N;
+  stp(base, 3 * k + 0, B.N, env, q[0], q[1], q[2], tau[0]);
+  stp(base, 3 * k + 1, B.N, env, qd[0], qd[1], qd[2], tau[1]);
+  stp(base, 3 * k + 2, B.N, env, tau[2], T(0), T(0), T(0));
+}
+template <typename T>
+B2Q_HD void ring_read(const Buffers<T>& B, int slot, int ab, int k, int env, T* q, T* qd, T* tau) {
+  const P4<T>* base = B.ring + ((size_t)(slot * 2 + ab) * 12) * B.N;
+  P4<T> a = ldp(base, 3 * k + 0, B.N, env), b = ldp(base, 3 * k + 1, B.N, env), c = ldp(base, 3 * k + 2, B.N, env);
+  q[0] = a.x; q[1] = a.y; q[2] = a.z; tau[0] = a.w; qd[0] = b.x; qd[1] = b.y; qd[2] = b.z; tau[1] = b.w; tau[2] = c.x;
+}
+
+template <typename T> B2Q_HD T map_pi(T a) {  // MapToMinusPiToPi, minitaur.py:67-83
+  const T two_pi = T(6.283185307179586476925286766559), pi = T(3.1415926535897932384626433832795);
+  T m = m_fmod(a, two_pi);
+  if (m >= pi) m -= two_pi; else if (m < -pi) m += two_pi;
+  return m;
+}
+template <typename T> B2Q_HD T c_prec(T v, T t, T m) { T w = (v - t) * T(2.178272210300875) / m; return m_tanh(w * w); }  // atanh(sqrt(0.95))
+
+// observation row (EnvWrapper.py:60-109 layout; sorted sensor keys, then normalised ETG)
+template <typename T, class Comm>
+B2Q_HD void write_obs(const Comm& cm, const Model<T>& md, T* obs, bool valid, const LaneState<T>& s, V3<T> start_pos, T dtc, V3<T> rpy0,
+                      const T* dq, const T* dqd, const T* etg_act) {
+  if (!valid) return;
+  const int k = cm.leg();
+  if (k == 0) {
+    obs[0] = (s.pos.x - start_pos.x) / dtc; obs[1] = (s.pos.y - start_pos.y) / dtc; obs[2] = (s.pos.z - start_pos.z) / dtc;
+    V3<T> rpy = quat_to_rpy(s.qx, s.qy, s.qz, s.qw);
+    R3<T> R = quat_to_R(s.qx, s.qy, s.qz, s.qw);
+    V3<T> wb = rotT(R, s.vang);
+    obs[7] = (rpy.x - rpy0.x) / T(0.1); obs[8] = (rpy.y - rpy0.y) / T(0.1); obs[9] = (rpy.z - rpy0.z) / T(0.1);
+    obs[10] = wb.x / T(0.5); obs[11] = wb.y / T(0.5); obs[12] = wb.z / T(0.5);
+  }
+  obs[3 + k] = s.contact ? T(1) : T(0);
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    obs[13 + 3 * k + j] = (map_pi(dq[j]) - md.pose_ori[j]) / T(0.1);
+    obs[25 + 3 * k + j] = dqd[j] / T(1.0);
+    obs[37 + 3 * k + j] = (etg_act[j] - md.etg_mean[3 * k + j]) / md.etg_std[3 * k + j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// reset = masked copy of the settled snapshot (K2); history ring filled with the settled observation
+template <typename T, class Comm>
+B2Q_HD void reset_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const Buffers<T>& B, int env, bool valid, T* obs /*row or null*/) {
+  const int k = cm.leg(), N = B.N;
+  LaneState<T> s; T la[3], ea[3]; int hl; V3<T> rpy0;
+  load_state(cm, B.snap, N, env, s, la, ea, hl, rpy0);
+  T sq[3], sqd[3], stau[3];
+  {
+    P4<T> a = ldp(B.snap_obs, 3 * k, N, env), b = ldp(B.snap_obs, 3 * k + 1, N, env), c = ldp(B.snap_obs, 3 * k + 2, N, env);
+    sq[0] = a.x; sq[1] = a.y; sq[2] = a.z; stau[0] = a.w; sqd[0] = b.x; sqd[1] = b.y; sqd[2] = b.z; stau[1] = b.w; stau[2] = c.x;
+  }
+  s.contact = s.lam_n > T(0);
+  rpy0 = quat_to_rpy(s.qx, s.qy, s.qz, s.qw);
+  etg_act_leg(cm, cf, md, B.etg, N, env, T(0), ea);
+  la[0] = la[1] = la[2] = T(0);
+  if (valid) {
+    store_state(cm, B.state, N, env, s, la, ea, 0, rpy0);
+    for (int d = 0; d < B.Dm; d++) { ring_write(B, d, 0, k, env, sq, sqd, stau); ring_write(B, d, 1, k, env, sq, sqd, stau); }
+    if (k == 0) B.step_count[env] = 0;
+  }
+  if (obs) write_obs(cm, md, obs, valid, s, s.pos, cf.dt * T(cf.R), rpy0, sq, sqd, ea);
+}
+
+// settle: reset pose, hold INIT_MOTOR_ANGLES for settle_steps substeps (a1.py:289-304), then snapshot
+template <typename T, class Comm>
+B2Q_HD void settle_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const Buffers<T>& B, int env, bool valid) {
+  const int k = cm.leg(), N = B.N;
+  LaneParam<T> pr; load_param(cm, B, env, pr);
+  LaneState<T> s;
+  s.pos = mk<T>(0, 0, T(0.32)); s.qx = s.qy = s.qz = 0; s.qw = 1; s.vlin = mk<T>(0, 0, 0); s.vang = mk<T>(0, 0, 0);
+  T tgt[3], tau[3] = {0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < 3; j++) { s.q[j] = md.pose_ori[j]; s.qd[j] = 0; tgt[j] = md.pose_ori[j]; }
+  s.lam_n = 0; s.contact = 0;
+  for (int i = 0; i < cf.settle_steps; i++) substep(cm, cf, md, pr, s, tgt, tau);
+  if (valid) {
+    T z3[3] = {0, 0, 0};
+    store_state(cm, B.snap, N, env, s, z3, z3, 0, mk<T>(0, 0, 0));
+    stp(B.snap_obs, 3 * k + 0, N, env, s.q[0], s.q[1], s.q[2], tau[0]);
+    stp(B.snap_obs, 3 * k + 1, N, env, s.qd[0], s.qd[1], s.qd[2], tau[1]);
+    stp(B.snap_obs, 3 * k + 2, N, env, tau[2], T(0), T(0), T(0));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// one control step (= R physics substeps) for this lane: env.step() of the reference
+template <typename T, class Comm>
+B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const Buffers<T>& B, int env, bool valid,
+                      const T* action, int donef, int auto_reset, T* obs, T* reward, uint8_t* done, T* info) {
+  const int k = cm.leg(), N = B.N, R = cf.R;
+  const T dtc = cf.dt * T(R);
+  LaneParam<T> pr; load_param(cm, B, env, pr);
+  LaneState<T> s; T last_action[3], etg_act[3]; int has_last; V3<T> rpy0;
+  load_state(cm, B.state, N, env, s, last_action, etg_act, has_last, rpy0);
+  int step = B.step_count[env];
+  T target[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) target[j] = md.pose_ori[j] + etg_act[j] + action[(size_t)env * 12 + 3 * k + j];  // deployment/test.py:95-99
+  const V3<T> start_pos = s.pos;
+  T foot0_x;
+  {
+    LegKin<T> K; leg_kin(md, md.leg[k], s.q, K);
+    R3<T> Rb = quat_to_R(s.qx, s.qy, s.qz, s.qw);
+    foot0_x = s.pos.x + rot(Rb, K.toe).x;
+  }
+  // control-latency bookkeeping (minitaur.py:1172-1193): lags n and n+1 counted from the last substep
+  int n_lag = pr.latency > T(0) ? (int)(pr.latency / cf.dt) : 0;
+  T alpha = pr.latency > T(0) ? (pr.latency - T(n_lag) * cf.dt) / cf.dt : T(0);
+  int max_lag = B.Dm * R - 2; if (n_lag > max_lag) { n_lag = max_lag; alpha = T(0); }
+  int ia = ((R - 1 - n_lag) % R + R) % R, ma = (n_lag - (R - 1 - ia)) / R;
+  int ib = ((R - 2 - n_lag) % R + R) % R, mb = (n_lag + 1 - (R - 1 - ib)) / R;
+  const int slot = step % B.Dm;
+  T tau[3] = {0, 0, 0};
+  for (int i = 0; i < R; i++) {  // Minitaur.Step, minitaur.py:248-260
+    T proc[3];
+    if (cf.interp && has_last) {  // ProcessAction, minitaur.py:1384-1401
+      T lerp = T(i + 1) / T(R);
+#pragma unroll
+      for (int j = 0; j < 3; j++) proc[j] = last_action[j] + lerp * (target[j] - last_action[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 3; j++) proc[j] = target[j];
+    }
+    substep(cm, cf, md, pr, s, proc, tau);
+    if (valid && i == ia) ring_write(B, slot, 0, k, env, s.q, s.qd, tau);
+    if (valid && i == ib) ring_write(B, slot, 1, k, env, s.q, s.qd, tau);
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++) last_action[j] = target[j];
+  has_last = 1;
+  // delayed (control-latency) observation of this leg's joints
+  T dq[3], dqd[3], dtau[3];
+  {
+    T aq[3], aqd[3], at[3], bq[3], bqd[3], bt[3];
+    ring_read(B, ((step - ma) % B.Dm + B.Dm) % B.Dm, 0, k, env, aq, aqd, at);
+    ring_read(B, ((step - mb) % B.Dm + B.Dm) % B.Dm, 1, k, env, bq, bqd, bt);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      dq[j] = (T(1) - alpha) * aq[j] + alpha * bq[j];
+      dqd[j] = (T(1) - alpha) * aqd[j] + alpha * bqd[j];
+      dtau[j] = (T(1) - alpha) * at[j] + alpha * bt[j];
+    }
+  }
+  step += 1;
+  etg_act_leg(cm, cf, md, B.etg, N, env, T(step) * dtc, etg_act);
+  T* orow = obs + (size_t)env * OBS_DIM;
+  write_obs(cm, md, orow, valid, s, start_pos, dtc, rpy0, dq, dqd, etg_act);
+
+  // ---- reward / termination (this repo's definition)
+  R3<T> Rb = quat_to_R(s.qx, s.qy, s.qz, s.qw);
+  LegKin<T> K; leg_kin(md, md.leg[k], s.q, K);
+  V3<T> toe_w = s.pos + rot(Rb, K.toe), knee_w = s.pos + rot(Rb, K.p3), nrm;
+  T velx = (s.pos.x - start_pos.x) / dtc;
+  T torso = m_min(velx, cf.vel_d);
+  T feet = cm.sum4(m_min((toe_w.x - foot0_x) / dtc, cf.vel_d) / T(4));
+  V3<T> rpy = quat_to_rpy(s.qx, s.qy, s.qz, s.qw);
+  T up = T(1) - T(0.5) * (c_prec(rpy.x, T(0), T(0.25)) + c_prec(rpy.y, T(0), T(0.25)));
+  T pw = cm.sum4(dtau[0] * dqd[0] + dtau[1] * dqd[1] + dtau[2] * dqd[2]);
+  T energy = m_abs(pw) * cf.dt * T(R);  // minitaur.py:810-818
+  T kh = terrain_height(cf, knee_w.x, knee_w.y, nrm);
+  T bad = cm.sum4((knee_w.z - kh < T(0.03)) ? T(1) : T(0));
+  T nofoot = cm.sum4(s.contact ? T(0) : T(1));
+  T meanz = cm.sum4(K.toe.z / T(4));
+  T above = cm.sum4(K.toe.z > T(0) ? T(1) : T(0));
+  bool fin = m_isfinite(s.q[0]) && m_isfinite(s.q[1]) && m_isfinite(s.q[2]) && m_isfinite(s.qd[0]) && m_isfinite(s.qd[1]) && m_isfinite(s.qd[2]) &&
+             m_isfinite(s.pos.x) && m_isfinite(s.pos.y) && m_isfinite(s.pos.z) && m_isfinite(s.vlin.x) && m_isfinite(s.vlin.y) && m_isfinite(s.vlin.z);
+  T nanf = cm.sum4(fin ? T(0) : T(1));
+  bool fall = (Rb.cz.z < T(0.5)) || (meanz > T(-0.1)) || (above > T(0)) || (nanf > T(0));
+  T r_torso = cf.w_torso * torso, r_feet = cf.w_feet * feet, r_up = cf.w_up * up, r_tau = -cf.w_tau * energy;
+  T r_bad = -cf.w_badfoot * bad, r_fc = -cf.w_footcontact * (nofoot > T(2) ? nofoot - T(2) : T(0)), r_done = fall ? -cf.w_done : T(0);
+  T rew = cf.reward_p * (r_torso + r_feet + r_up + r_tau + r_bad + r_fc + r_done);
+  bool dn = fall || donef;
+  if (valid) {
+    T* irow = info + (size_t)env * INFO_DIM;
+    if (k == 0) {
+      reward[env] = rew; done[env] = dn ? 1 : 0;
+      irow[0] = velx; irow[1] = r_torso; irow[2] = r_feet; irow[3] = r_up; irow[4] = r_tau; irow[5] = 0; irow[6] = r_bad; irow[7] = r_fc; irow[8] = r_done;
+      irow[9] = nanf > T(0) ? T(1) : T(0); irow[10] = energy; irow[11] = s.pos.z;
+      V3<T> wb = rotT(Rb, s.vang);
+      irow[36] = rpy.x; irow[37] = rpy.y; irow[38] = rpy.z; irow[39] = wb.x; irow[40] = wb.y; irow[41] = wb.z;
+      irow[54] = fall ? T(1) : T(0); irow[55] = T(step);
+      B.step_count[env] = step;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) { irow[12 + 3 * k + j] = etg_act[j]; irow[24 + 3 * k + j] = target[j]; irow[42 + 3 * k + j] = s.q[j]; }
+    store_state(cm, B.state, N, env, s, last_action, etg_act, has_last, rpy0);
+  }
+  if (auto_reset) {
+    // all four lanes of a robot agree on dn; reset_lane contains exchanges only inside etg/none -> safe to branch per robot
+    if (dn) reset_lane(cm, cf, md, B, env, valid, orow);
+  }
+}
+
+}  // namespace b2q

