@@ -64,15 +64,15 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_oracle_rate(n_envs, steps, threads, w, b, seed=1234):
-    """Oracle (float64 C port of the path; pybullet/rlschool are absent) on `threads` host threads."""
+    """Oracle (float64 C port of the path; pybullet/rlschool are absent) on `threads` host threads: every thread owns a
+    contiguous slice of envs and runs `steps` control steps on it (one env per actor, as Dynamic_parallel_model.py:96-99)."""
     from oracle import oracle as O
     batch = O.OracleBatch(n_envs, etg_w=w, etg_b=b)
     rng = np.random.default_rng(seed)
-    acts = rng.uniform(-0.3, 0.3, (8, n_envs, 12))
-    batch.step(acts[0], auto_reset=True, nthreads=threads)      # warm
+    batch.rollout(rng.uniform(-0.3, 0.3, (2, n_envs, 12)), auto_reset=True, nthreads=threads)      # warm
+    acts = rng.uniform(-0.3, 0.3, (steps, n_envs, 12))
     t0 = time.perf_counter()
-    for k in range(steps):
-        batch.step(acts[k % 8], auto_reset=True, nthreads=threads)
+    batch.rollout(acts, auto_reset=True, nthreads=threads)
     dt = time.perf_counter() - t0
     return n_envs * steps / dt, dt
 
@@ -83,17 +83,15 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     w, b = etg_weights()
-    n_envs = 256                                              # bounded sample of the 4096-env workload per step
+    n_envs = max(256, 32 * threads)                           # bounded sample of the 4096-env workload per step
     W, K = max(args.warmup, 1), args.steps
     from oracle import oracle as O
     batch = O.OracleBatch(n_envs, etg_w=w, etg_b=b)
     rng = np.random.default_rng(1234)
-    acts = rng.uniform(-0.3, 0.3, (8, n_envs, 12))
-    for k in range(W):
-        batch.step(acts[k % 8], auto_reset=True, nthreads=threads)
+    batch.rollout(rng.uniform(-0.3, 0.3, (W, n_envs, 12)), auto_reset=True, nthreads=threads)
+    acts = rng.uniform(-0.3, 0.3, (K, n_envs, 12))
     t0 = time.perf_counter()
-    for k in range(K):
-        batch.step(acts[k % 8], auto_reset=True, nthreads=threads)
+    batch.rollout(acts, auto_reset=True, nthreads=threads)
     dt = time.perf_counter() - t0
     val = n_envs * K / dt
     line = {
@@ -202,11 +200,11 @@ def main():
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             rate1, _ = cpu_oracle_rate(64, 8, 1, w, b)
-            steps_c = max(4, int(12.0 * rate1 * min(threads, 64) / 512 / 1.0))          # ~12 s of CPU work at the multi-thread rate
-            steps_c = min(steps_c, 400)
-            rate, secs = cpu_oracle_rate(512, steps_c, threads, w, b)
+            n_c = max(512, 32 * threads)
+            steps_c = int(min(400, max(4, 12.0 * rate1 * threads / n_c)))                # ~12 s of CPU work at the ideal multi-thread rate
+            rate, secs = cpu_oracle_rate(n_c, steps_c, threads, w, b)
             cpu = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                   "sample": "512 envs x %d control steps (%.1f s), float64 C oracle on %d pthreads; single-thread rate %.0f env-steps/s; NOT pybullet (absent)" % (steps_c, secs, threads, rate1)}
+                   "sample": "%d envs x %d control steps (%.1f s), float64 C oracle on %d pthreads; single-thread rate %.0f env-steps/s; NOT pybullet (absent)" % (n_c, steps_c, secs, threads, rate1)}
         line = {
             "metric": "env-steps/sec (A1, 4096 envs)", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -397,7 +397,7 @@ static void dyn_delta(const Dyn* D, int body, const double f[6], const double* t
 
 void orc_forward_dynamics(const OrcConfig* c, const OrcEnv* e, const double tau[12], double qdd[12], double wdot_w[3], double vdot_w[3]) {
   (void)c;
-  Dyn* D = (Dyn*)malloc(sizeof(Dyn));
+  Dyn Dstack; Dyn* D = &Dstack;
   build_model(e->param, &D->mdl);
   dyn_kinematics(e, D);
   double a0[6]; dyn_aba(e, D, tau, qdd, a0);
@@ -405,13 +405,12 @@ void orc_forward_dynamics(const OrcConfig* c, const OrcEnv* e, const double tau[
   double wxv[3]; v3cross(D->v[0], D->v[0] + 3, wxv);
   double al[3] = {a0[3] + gB[0] + wxv[0], a0[4] + gB[1] + wxv[1], a0[5] + gB[2] + wxv[2]};
   m3v(D->R0, a0, wdot_w); m3v(D->R0, al, vdot_w);
-  free(D);
 }
 
 void orc_mass_matrix(const OrcConfig* c, const OrcEnv* e, double M[18 * 18]) {
   (void)c;
   /* columns of M^-1 via dyn_delta, then invert numerically (tests only) */
-  Dyn* D = (Dyn*)malloc(sizeof(Dyn));
+  Dyn Dstack; Dyn* D = &Dstack;
   build_model(e->param, &D->mdl);
   dyn_kinematics(e, D);
   double tau[12] = {0}, qdd[12], a0[6]; dyn_aba(e, D, tau, qdd, a0);
@@ -431,12 +430,11 @@ void orc_mass_matrix(const OrcConfig* c, const OrcEnv* e, double M[18 * 18]) {
     for (int i = 0; i < 18; i++) if (i != k) { double f = A[i][k]; if (f != 0) for (int j = 0; j < 36; j++) A[i][j] -= f * A[k][j]; }
   }
   for (int i = 0; i < 18; i++) for (int j = 0; j < 18; j++) M[18 * i + j] = A[i][18 + j];
-  free(D);
 }
 
 double orc_energy(const OrcConfig* c, const OrcEnv* e, double* kin, double* pot) {
   (void)c;
-  Dyn* D = (Dyn*)malloc(sizeof(Dyn));
+  Dyn Dstack; Dyn* D = &Dstack;
   build_model(e->param, &D->mdl);
   dyn_kinematics(e, D);
   double tau[12] = {0}, qdd[12], a0[6]; dyn_aba(e, D, tau, qdd, a0); /* fills v[] */
@@ -450,7 +448,6 @@ double orc_energy(const OrcConfig* c, const OrcEnv* e, double* kin, double* pot)
     for (int k = 0; k < 3; k++) P -= D->mdl.mass[b] * e->param[26 + k] * (p[k] + cw[k]);
   }
   if (kin) *kin = K; if (pot) *pot = P;
-  free(D);
   return K + P;
 }
 
@@ -477,10 +474,9 @@ static void toe_world(const Dyn* D, int leg, double o[3]) {
   o[0] = D->pw[i][0] + tw[0]; o[1] = D->pw[i][1] + tw[1]; o[2] = D->pw[i][2] + tw[2];
 }
 void orc_foot_world(const OrcEnv* e, double feet[4][3]) {
-  Dyn* D = (Dyn*)malloc(sizeof(Dyn));
+  Dyn Dstack; Dyn* D = &Dstack;
   build_model(e->param, &D->mdl); dyn_kinematics(e, D);
   for (int k = 0; k < 4; k++) toe_world(D, k, feet[k]);
-  free(D);
 }
 
 /* ------------------------------------------------------------------ history (minitaur.py:1142-1193) */
@@ -509,7 +505,7 @@ static void true_obs(const OrcEnv* e, double o[ORC_HIST_W]) {
 /* ------------------------------------------------------------------ one physics substep */
 void orc_substep(const OrcConfig* c, OrcEnv* e, const double target[12]) {
   const double dt = c->sim_dt;
-  Dyn* D = (Dyn*)malloc(sizeof(Dyn));
+  Dyn Dstack; Dyn* D = &Dstack;
   build_model(e->param, &D->mdl);
   dyn_kinematics(e, D);
   /* ApplyAction: PD on the *current* observation (pd_latency = 0, minitaur.py:100,1195-1199) */
@@ -608,7 +604,6 @@ void orc_substep(const OrcConfig* c, OrcEnv* e, const double target[12]) {
   }
   /* ReceiveObservation */
   double ob[ORC_HIST_W]; true_obs(e, ob); hist_push(e, ob);
-  free(D);
 }
 
 /* ------------------------------------------------------------------ env */
@@ -699,7 +694,7 @@ void orc_env_step(const OrcConfig* c, OrcEnv* e, const double action[12], int do
   /* knees (calf joint origins) */
   int bad = 0, nofoot = 0; double meanz = 0; int above = 0;
   {
-    Dyn* D = (Dyn*)malloc(sizeof(Dyn)); build_model(e->param, &D->mdl); dyn_kinematics(e, D);
+    Dyn Dstack; Dyn* D = &Dstack; build_model(e->param, &D->mdl); dyn_kinematics(e, D);
     for (int k = 0; k < 4; k++) {
       double nrm[3]; double h = terrain_height(c, D->pw[3 * k + 2][0], D->pw[3 * k + 2][1], nrm);
       if (D->pw[3 * k + 2][2] - h < 0.03) bad++;
@@ -707,8 +702,7 @@ void orc_env_step(const OrcConfig* c, OrcEnv* e, const double action[12], int do
       double fb_w[3] = {feet1[k][0] - e->pos[0], feet1[k][1] - e->pos[1], feet1[k][2] - e->pos[2]}, fb[3];
       m3tv(Rm, fb_w, fb); meanz += fb[2] / 4.0; if (fb[2] > 0) above = 1;
     }
-    free(D);
-  }
+    }
   int nanf = 0;
   for (int k = 0; k < 3; k++) if (!isfinite(e->pos[k]) || !isfinite(e->vlin[k])) nanf = 1;
   for (int j = 0; j < 12; j++) if (!isfinite(e->q[j]) || !isfinite(e->qd[j])) nanf = 1;
@@ -748,6 +742,32 @@ void orc_batch_step(const OrcConfig* c, OrcEnv* envs, int n, const double* actio
     if (t > 0) pthread_create(&th[t], NULL, job_run, &jobs[t]);
   }
   job_run(&jobs[0]);
+  for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
+}
+/* K consecutive control steps per env inside each thread (envs are independent: mirrors one-env-per-process
+ * actors, Dynamic_parallel_model.py:96-99).  actions: [K][n][12]; returns the sum of rewards in ret[n]. */
+typedef struct { const OrcConfig* c; OrcEnv* envs; int lo, hi, n, K; const double* act; int auto_reset; double* obs; double* ret; int* ndone; } RJob;
+static void* rjob_run(void* p) {
+  RJob* j = (RJob*)p;
+  for (int i = j->lo; i < j->hi; i++) {
+    double info[ORC_INFO_DIM], rew; int done; j->ret[i] = 0; j->ndone[i] = 0;
+    for (int k = 0; k < j->K; k++) {
+      orc_env_step(j->c, &j->envs[i], j->act + ((size_t)k * j->n + i) * 12, 0, j->obs + ORC_OBS_DIM * i, &rew, &done, info);
+      j->ret[i] += rew; j->ndone[i] += done;
+      if (j->auto_reset && done) orc_env_reset(j->c, &j->envs[i], NULL, NULL, j->obs + ORC_OBS_DIM * i);
+    }
+  }
+  return NULL;
+}
+void orc_batch_rollout(const OrcConfig* c, OrcEnv* envs, int n, const double* actions, int K, int auto_reset,
+                       double* obs, double* ret, int* ndone, int nthreads) {
+  if (nthreads < 1) nthreads = 1; if (nthreads > 256) nthreads = 256; if (nthreads > n) nthreads = n;
+  pthread_t th[256]; RJob jobs[256];
+  for (int t = 0; t < nthreads; t++) {
+    jobs[t] = (RJob){c, envs, (int)((long)n * t / nthreads), (int)((long)n * (t + 1) / nthreads), n, K, actions, auto_reset, obs, ret, ndone};
+    if (t > 0) pthread_create(&th[t], NULL, rjob_run, &jobs[t]);
+  }
+  rjob_run(&jobs[0]);
   for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
 }
 int orc_sizeof_env(void) { return (int)sizeof(OrcEnv); }

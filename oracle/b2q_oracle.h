@@ -95,6 +95,8 @@ void orc_env_step(const OrcConfig* c, OrcEnv* e, const double action[12], int do
 /* batch helpers (cpu baseline): nthreads pthreads over envs */
 void orc_batch_step(const OrcConfig* c, OrcEnv* envs, int n, const double* actions, int donef, int auto_reset,
                     double* obs, double* reward, int* done, double* info, int nthreads);
+void orc_batch_rollout(const OrcConfig* c, OrcEnv* envs, int n, const double* actions, int K, int auto_reset,
+                       double* obs, double* ret, int* ndone, int nthreads);
 int orc_sizeof_env(void);
 #ifdef __cplusplus
 }

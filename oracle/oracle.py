@@ -255,3 +255,14 @@ class OracleBatch:
                              self.obs.ctypes.data_as(dp), self.rew.ctypes.data_as(dp),
                              self.done.ctypes.data_as(C.POINTER(C.c_int)), self.info.ctypes.data_as(dp), C.c_int(nthreads))
         return self.obs, self.rew, self.done, self.info
+
+    def rollout(self, actions, auto_reset=True, nthreads=1):
+        """actions [K,n,12]: K control steps per env, envs distributed over pthreads (no per-step barrier)."""
+        a, ap = _d(np.asarray(actions).reshape(-1, self.n, 12))
+        K = a.shape[0]
+        ret = np.zeros(self.n)
+        nd = np.zeros(self.n, dtype=np.int32)
+        dp = C.POINTER(C.c_double)
+        lib().orc_batch_rollout(C.byref(self.cfg), self.envs, C.c_int(self.n), ap, C.c_int(K), C.c_int(int(auto_reset)),
+                                self.obs.ctypes.data_as(dp), ret.ctypes.data_as(dp), nd.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(nthreads))
+        return ret, nd
