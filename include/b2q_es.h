@@ -1,0 +1,22 @@
+/* b2q_es.h — C ABI of the ES population-fitness kernels (K4).  Device pointers, caller's stream, 0 on success.
+ *
+ * Reference interfaces replaced (QuadrupedalRobots/ETGRL):
+ *   b2q_es_accumulate  episode_reward += reward ... until done        train.py:213-249 (run_EStrain_episode)
+ *   b2q_es_fitness     fitness_list.append(episode_reward)            train.py:404-413;
+ *                      rewards gathered per individual                Dynamic_parallel_model.py:157-167
+ * Env e = individual*rollouts + r.  The cross-GPU gather of `fitness` is the caller's NCCL all-gather.
+ */
+#ifndef B2Q_ES_H
+#define B2Q_ES_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* per control step: for alive envs ret += reward, len += 1, alive &= !done.  elem_size 4 (float) or 8 (double). */
+int b2q_es_accumulate(const void* reward, const uint8_t* done, uint8_t* alive, void* ret, int32_t* len, int n, int elem_size, void* stream);
+/* fitness[i] = mean over the individual's rollouts of ret; mean_len (may be NULL) likewise for episode lengths. */
+int b2q_es_fitness(const void* ret, const int32_t* len, void* fitness, void* mean_len, int pop, int rollouts, int elem_size, void* stream);
+#ifdef __cplusplus
+}
+#endif
+#endif

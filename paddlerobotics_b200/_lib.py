@@ -27,6 +27,9 @@ SYMBOLS = {
     "b2q_set_state": (_i, [_vp, _vp, _vp]),
     "b2q_get_step_count": (_i, [_vp, _vp, _vp]),
     "b2q_launch_count": (C.c_int64, [_vp]),
+    # ES population fitness — include/b2q_es.h
+    "b2q_es_accumulate": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "b2q_es_fitness": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
 }
 
 

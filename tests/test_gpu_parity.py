@@ -168,3 +168,33 @@ def test_make_env_reference_call_shapes(torch_cuda, etg_default):
         assert np.abs(info["ETG_act"] - tab[k]).max() < 2e-6
     obs, r, d, info = env.step(np.zeros(12), donef=True)
     assert d is True
+
+
+def test_es_population_fitness_vs_oracle(torch_cuda, golden):
+    """a15: population of ETG individuals (SimpleGA.ask -> Opt_with_points), each rolled out `rollouts` times on the
+    GPU with first-done freezing; fitness vector == serial oracle evaluation (train.py:404-413 semantics)."""
+    import torch
+    from oracle import oracle as O
+    from paddlerobotics_b200.es import PopulationEvaluator, SimpleGA, solutions_to_etg
+    np.random.seed(0)
+    ga = SimpleGA(12, sigma_init=0.02, sigma_decay=0.99, sigma_limit=0.005, elite_ratio=0.25, weight_decay=0.005, popsize=4, param=np.zeros(12))
+    sol = ga.ask()
+    w, b = solutions_to_etg(sol, golden["opt_points"], golden["opt_w0"], golden["opt_b0"])
+    pop, rollouts, T = 4, 2, 45
+    ev = PopulationEvaluator(pop, rollouts, max_steps=T, precision="f64")
+    noise = np.random.default_rng(0).uniform(-0.3, 0.3, (T, pop * rollouts, 12))
+    fit, mlen = ev.evaluate(w, b, residual_noise=torch.tensor(noise, device="cuda"))
+    ref_fit, ref_len = np.zeros(pop), np.zeros(pop)
+    for i in range(pop):
+        for r in range(rollouts):
+            o = O.OracleEnv(); o.reset(w[i], b[i])
+            for k in range(T):
+                _, rew, done, _ = o.step(noise[k, i * rollouts + r])
+                ref_fit[i] += rew / rollouts; ref_len[i] += 1.0 / rollouts
+                if done:
+                    break
+    assert np.abs(_np(fit) - ref_fit).max() < 1e-6, (_np(fit), ref_fit)
+    assert np.array_equal(_np(mlen), ref_len)
+    assert (ref_len < T).any()            # some episodes ended early (falls) and were frozen
+    ga.tell(_np(fit))
+    ev.env.close()
