@@ -27,6 +27,13 @@ SYMBOLS = {
     "b2q_set_state": (_i, [_vp, _vp, _vp]),
     "b2q_get_step_count": (_i, [_vp, _vp, _vp]),
     "b2q_launch_count": (C.c_int64, [_vp]),
+    # policy / critic MLP forward on tcgen05 — include/b2q_mlp.h
+    "b2q_mlp_create": (_i, [_i, _i, _i, _i, C.POINTER(_vp)]),
+    "b2q_mlp_destroy": (_i, [_vp]),
+    "b2q_mlp_last_error": (C.c_char_p, [_vp]),
+    "b2q_mlp_set_weights": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2q_mlp_forward": (_i, [_vp, _vp, _i, _vp, _i, _i, C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
+    "b2q_mlp_launch_count": (C.c_int64, [_vp]),
     # ES population fitness — include/b2q_es.h
     "b2q_es_accumulate": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "b2q_es_fitness": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

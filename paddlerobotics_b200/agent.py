@@ -1,0 +1,153 @@
+"""PARL-surface agent (`MujocoAgent.predict / sample / restore / save`, ETGRL/model/mujoco_agent.py:20-65) on top of the
+fused tcgen05 MLP kernel (csrc/b2q_mlp.cu).  Parameters are held as float32 torch tensors under the reference's
+state-dict key names (`actor_model.{l1,l2,mean_linear,std_linear}.{weight,bias}`, `critic_model.l1..l6.*`)
+so the reference's `.pt` checkpoints load unchanged; the kernel consumes bf16 images repacked on the device.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+
+PREDICT, SAMPLE, RAW = 0, 1, 2
+LOG_SIG_MAX, LOG_SIG_MIN = 2.0, -20.0   # mujoco_model.py:21-22
+
+
+class FusedMLP:
+    """ctypes handle of one b2q_mlp object: in_dim(<=64) -> 256 -> 256 -> out_dim(<=32), `nets` weight sets."""
+
+    def __init__(self, in_dim, out_dim, nets=1, device=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("FusedMLP needs a CUDA device (tcgen05 kernel, no fallback)")
+        self.lib = _lib.load()
+        self.in_dim, self.out_dim, self.nets = in_dim, out_dim, nets
+        self.device = torch.device("cuda", int(device))
+        self.h = C.c_void_p()
+        rc = self.lib.b2q_mlp_create(int(device), in_dim, out_dim, nets, C.byref(self.h))
+        if rc != 0:
+            raise RuntimeError("b2q_mlp_create failed (%d)" % rc)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_weights(self, net, w1, b1, w2, b2, w3, b3):
+        ts = [t.detach().to(self.device, torch.float32).contiguous() for t in (w1, b1, w2, b2, w3, b3)]
+        assert ts[0].shape == (256, self.in_dim) and ts[2].shape == (256, 256) and ts[4].shape == (self.out_dim, 256)
+        rc = self.lib.b2q_mlp_set_weights(self.h, net, *[t.data_ptr() for t in ts], self._stream())
+        if rc != 0:
+            raise RuntimeError("b2q_mlp_set_weights: %s" % self.lib.b2q_mlp_last_error(self.h).decode())
+        self._keep = ts
+
+    def forward(self, in1, in2=None, mode=PREDICT, seed=0, eps=None, want_raw=False, want_logp=False):
+        in1 = in1.contiguous()
+        M, d1 = in1.shape
+        A = self.out_dim if mode == RAW else self.out_dim // 2
+        out = torch.empty(self.nets, M, A, device=self.device, dtype=torch.float32)
+        logp = torch.empty(self.nets, M, device=self.device, dtype=torch.float32) if (want_logp or mode == SAMPLE) else None
+        raw = torch.empty(self.nets, M, self.out_dim, device=self.device, dtype=torch.float32) if want_raw else None
+        p = lambda t: None if t is None else t.data_ptr()
+        if in2 is not None:
+            in2 = in2.contiguous()
+        if eps is not None:
+            eps = eps.contiguous()
+        rc = self.lib.b2q_mlp_forward(self.h, in1.data_ptr(), d1, p(in2), M, mode, C.c_uint64(seed), p(eps), out.data_ptr(), p(logp), p(raw), self._stream())
+        if rc != 0:
+            raise RuntimeError("b2q_mlp_forward: %s" % self.lib.b2q_mlp_last_error(self.h).decode())
+        return out, logp, raw
+
+    def launch_count(self):
+        return int(self.lib.b2q_mlp_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b2q_mlp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _init_linear(out_f, in_f, gen):
+    # torch.nn.Linear default init (kaiming_uniform(a=sqrt(5)) -> U(-1/sqrt(in), 1/sqrt(in)) for weight and bias)
+    bound = 1.0 / np.sqrt(in_f)
+    w = (torch.rand(out_f, in_f, generator=gen) * 2 - 1) * bound
+    b = (torch.rand(out_f, generator=gen) * 2 - 1) * bound
+    return w, b
+
+
+class MujocoAgent:
+    """Batched drop-in for the reference agent: numpy [obs_dim] in -> numpy [act_dim] out like the reference, or
+    device tensors [M, obs_dim] -> [M, act_dim] for rollouts (zero host traffic)."""
+
+    def __init__(self, obs_dim, act_dim=12, device=0, seed=0):
+        self.obs_dim, self.act_dim = obs_dim, act_dim
+        self.device = torch.device("cuda", int(device))
+        g = torch.Generator().manual_seed(seed)
+        sd = OrderedDict()
+        for name, (o, i) in (("actor_model.l1", (256, obs_dim)), ("actor_model.l2", (256, 256)), ("actor_model.mean_linear", (act_dim, 256)),
+                             ("actor_model.std_linear", (act_dim, 256)), ("critic_model.l1", (256, obs_dim + act_dim)), ("critic_model.l2", (256, 256)),
+                             ("critic_model.l3", (1, 256)), ("critic_model.l4", (256, obs_dim + act_dim)), ("critic_model.l5", (256, 256)),
+                             ("critic_model.l6", (1, 256))):
+            w, b = _init_linear(o, i, g)
+            sd[name + ".weight"], sd[name + ".bias"] = w.to(self.device), b.to(self.device)
+        self.params = sd
+        self.actor = FusedMLP(obs_dim, 2 * act_dim, nets=1, device=device)
+        self.critic = FusedMLP(obs_dim + act_dim, 1, nets=2, device=device)
+        self._sample_calls = 0
+        self.sync_weights()
+
+    # ---- checkpoint surface (PARL: agent.save -> torch.save(state_dict), agent.restore: mujoco_agent.py:61-65)
+    def state_dict(self):
+        return OrderedDict((k, v.detach().cpu()) for k, v in self.params.items())
+
+    def load_state_dict(self, sd):
+        for k in self.params:
+            if k not in sd:
+                raise KeyError("checkpoint is missing %s" % k)
+            if tuple(sd[k].shape) != tuple(self.params[k].shape):
+                raise ValueError("shape mismatch for %s: %s vs %s" % (k, tuple(sd[k].shape), tuple(self.params[k].shape)))
+            self.params[k] = sd[k].to(self.device, torch.float32).contiguous()
+        self.sync_weights()
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def restore(self, path):
+        self.load_state_dict(torch.load(path, map_location="cpu"))
+
+    def sync_weights(self):
+        p = self.params
+        self.actor.set_weights(0, p["actor_model.l1.weight"], p["actor_model.l1.bias"], p["actor_model.l2.weight"], p["actor_model.l2.bias"],
+                               torch.cat([p["actor_model.mean_linear.weight"], p["actor_model.std_linear.weight"]], 0),
+                               torch.cat([p["actor_model.mean_linear.bias"], p["actor_model.std_linear.bias"]], 0))
+        self.critic.set_weights(0, p["critic_model.l1.weight"], p["critic_model.l1.bias"], p["critic_model.l2.weight"], p["critic_model.l2.bias"],
+                                p["critic_model.l3.weight"], p["critic_model.l3.bias"])
+        self.critic.set_weights(1, p["critic_model.l4.weight"], p["critic_model.l4.bias"], p["critic_model.l5.weight"], p["critic_model.l5.bias"],
+                                p["critic_model.l6.weight"], p["critic_model.l6.bias"])
+
+    # ---- batched device API
+    def predict_batch(self, obs):
+        return self.actor.forward(obs, mode=PREDICT)[0][0]
+
+    def sample_batch(self, obs, eps=None, seed=None):
+        self._sample_calls += 1
+        out, logp, _ = self.actor.forward(obs, mode=SAMPLE, eps=eps, seed=self._sample_calls if seed is None else seed)
+        return out[0], logp[0]
+
+    def q_values(self, obs, act):
+        out, _, _ = self.critic.forward(obs, in2=act, mode=RAW)
+        return out[0, :, 0], out[1, :, 0]
+
+    # ---- reference call shapes (numpy, batch 1): mujoco_agent.py:29-41
+    def predict(self, obs):
+        o = torch.as_tensor(np.asarray(obs, dtype=np.float32).reshape(1, -1), device=self.device)
+        return self.predict_batch(o)[0].cpu().numpy().flatten()
+
+    def sample(self, obs):
+        o = torch.as_tensor(np.asarray(obs, dtype=np.float32).reshape(1, -1), device=self.device)
+        return self.sample_batch(o)[0][0].cpu().numpy().flatten()

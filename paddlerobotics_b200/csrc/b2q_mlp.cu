@@ -1,0 +1,348 @@
+// b2q_mlp.cu — K3: fused 3-layer MLP forward (in<=64 -> 256 -> 256 -> out<=32) on tcgen05 tensor cores.
+//
+// One CTA (128 threads) per 128-row tile of the batch:
+//   * weights live in HBM as ready-made shared-memory images (bf16, K-major, 128-byte swizzle, 64-column panels) and are
+//     brought in by bulk async copies (cp.async.bulk -> UBLKCP) that complete on mbarriers;
+//   * the input tile is converted f32 -> bf16 by the CTA's threads straight into the swizzled A-operand layout;
+//   * each layer is a chain of tcgen05.mma (M=128, N=256|32, K=16) issued by ONE thread, accumulating in TMEM
+//     (layer 1 -> columns 0..255, layer 2 -> 256..511, layer 3 -> 0..31); tcgen05.commit signals an mbarrier;
+//   * the epilogue warps read the accumulator with tcgen05.ld (each thread owns one row = one TMEM lane), apply
+//     bias+ReLU in f32, and write the bf16 activations back into the A-operand region for the next layer, so
+//     activations never leave the SM; the last epilogue applies tanh / clamp / sampling / log-prob and stores f32.
+// Shared memory: A 64 KB | W2 128 KB | W1 then W3 32 KB | biases 2.1 KB | barriers  = 226.2 KB (of 227 KB).
+// Reference: Actor/Critic.forward (model/mujoco_model.py:44-89), SAC.predict/sample (alg/sac.py:60-75).
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <new>
+#include <string>
+#include "../../include/b2q_mlp.h"
+
+namespace {
+
+constexpr int HID = B2Q_MLP_HIDDEN;
+constexpr int TILE_M = 128;
+constexpr uint32_t SZ_A = 65536, SZ_W2 = 131072, SZ_W13 = 32768, SZ_W1 = 32768, SZ_W3 = 16384, SZ_BIAS = (HID + HID + 32) * 4;
+constexpr uint32_t OFF_A = 0, OFF_W2 = OFF_A + SZ_A, OFF_W13 = OFF_W2 + SZ_W2, OFF_BIAS = OFF_W13 + SZ_W13, OFF_BAR = OFF_BIAS + SZ_BIAS;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 64;
+constexpr size_t IMG_W1 = 0, IMG_W2 = SZ_W1, IMG_W3 = IMG_W2 + SZ_W2, IMG_BIAS = IMG_W3 + SZ_W3, IMG_BYTES = IMG_BIAS + SZ_BIAS;
+static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
+
+// byte offset of element (row, k) inside a K-major SWIZZLE_128B operand image with `rows` rows (64-element panels)
+__host__ __device__ inline uint32_t sw128_offset(int row, int k, int rows) {
+  int p = k >> 6, kk = k & 63, c = kk >> 3, e = kk & 7;
+  return (uint32_t)p * (uint32_t)rows * 128u + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4) + (uint32_t)e * 2u;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, sm100 version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                    // leading byte offset (ignored for swizzled K-major; canonical value 1)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor kind::f16: D=f32, A=B=bf16, both K-major, M x N
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// counter-based Gaussian (Philox-4x32-10 keyed by seed, counter = (row, col)) -> Box-Muller
+__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
+  uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0, h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+  uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+  c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+}
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t row, uint32_t col) {
+  uint32_t c0 = row, c1 = col, c2 = 0x9E3779B9u, c3 = 0, k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; i++) { philox_round(c0, c1, c2, c3, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  float u1 = ((float)(c0 >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(c1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+}
+
+struct FwdArgs {
+  const float* in1; const float* in2; int in1_dim, in_dim, out_dim, M, mode; uint64_t seed; const float* eps;
+  float* out; float* logp; float* raw; const uint8_t* img; size_t img_stride;
+};
+
+__global__ void __launch_bounds__(128, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, net = blockIdx.y;
+  const int row0 = blockIdx.x * TILE_M, row = row0 + tid;
+  const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) __trap();   // SWIZZLE_128B operands need a 1024-byte aligned base
+  const uint32_t sA = sbase + OFF_A, sW2 = sbase + OFF_W2, sW13 = sbase + OFF_W13;
+  const uint32_t bar_w1 = sbase + OFF_BAR, bar_w2 = bar_w1 + 8, bar_w3 = bar_w1 + 16, bar_mma = bar_w1 + 24;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 32);
+  const float* bias = reinterpret_cast<const float*>(smem + OFF_BIAS);
+  const uint8_t* img = a.img + (size_t)net * a.img_stride;
+
+  if (tid == 0) {
+    mbar_init(bar_w1, 1); mbar_init(bar_w2, 1); mbar_init(bar_w3, 1); mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // weights: W1 (+biases) first, then W2 in 32 KB pieces
+    mbar_expect_tx(bar_w1, SZ_W1 + SZ_BIAS);
+    bulk_g2s(sW13, img + IMG_W1, SZ_W1, bar_w1);
+    bulk_g2s(sbase + OFF_BIAS, img + IMG_BIAS, SZ_BIAS, bar_w1);
+    mbar_expect_tx(bar_w2, SZ_W2);
+#pragma unroll
+    for (int i = 0; i < 4; i++) bulk_g2s(sW2 + i * 32768u, img + IMG_W2 + (size_t)i * 32768u, 32768u, bar_w2);
+  }
+  if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM by construction: 226 KB of shared memory)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(const_cast<const uint32_t*>(tmem_slot))), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // input tile: f32 [rows, in_dim] (two sources concatenated) -> bf16 swizzled panel 0 (K padded to 64 with zeros)
+  {
+    const int in2_dim = a.in_dim - a.in1_dim;
+    for (int idx = tid; idx < TILE_M * 64; idx += 128) {
+      int r = idx >> 6, k = idx & 63, gr = row0 + r;
+      float v = 0.f;
+      if (gr < a.M) {
+        if (k < a.in1_dim) v = a.in1[(size_t)gr * a.in1_dim + k];
+        else if (k < a.in_dim) v = a.in2[(size_t)gr * in2_dim + (k - a.in1_dim)];
+      }
+      *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + sw128_offset(r, k, TILE_M)) = __float2bfloat16(v);
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+
+  // ---- layer 1: [128 x 64] x [256 x 64]^T -> TMEM cols 0..255
+  if (tid == 0) {
+    mbar_wait(bar_w1, 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc(TILE_M, HID);
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) umma_f16(tmem, umma_desc(sA + ks * 32), umma_desc(sW13 + ks * 32), idesc, ks > 0);
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+  if (tid == 0) {  // W1 is consumed: reuse its region for W3
+    mbar_expect_tx(bar_w3, SZ_W3);
+    bulk_g2s(sW13, img + IMG_W3, SZ_W3, bar_w3);
+  }
+  auto epilogue_hidden = [&](uint32_t col_base, const float* b) {
+#pragma unroll 1
+    for (int cc = 0; cc < 8; cc++) {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld32(lane_addr + col_base + cc * 32, r);
+#pragma unroll
+      for (int j0 = 0; j0 < 32; j0 += 8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          float v0 = fmaxf(__uint_as_float(r[j0 + j]) + b[cc * 32 + j0 + j], 0.f);
+          float v1 = fmaxf(__uint_as_float(r[j0 + j + 1]) + b[cc * 32 + j0 + j + 1], 0.f);
+          __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(smem + OFF_A + sw128_offset(tid, cc * 32 + j0, TILE_M)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  };
+  epilogue_hidden(0, bias);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // ---- layer 2: [128 x 256] x [256 x 256]^T -> TMEM cols 256..511
+  if (tid == 0) {
+    mbar_wait(bar_w2, 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc(TILE_M, HID);
+#pragma unroll
+    for (int ks = 0; ks < 16; ks++)
+      umma_f16(tmem + 256, umma_desc(sA + (ks >> 2) * (TILE_M * 128) + (ks & 3) * 32), umma_desc(sW2 + (ks >> 2) * (HID * 128) + (ks & 3) * 32), idesc, ks > 0);
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 1);
+  tc_fence_after();
+  epilogue_hidden(256, bias + HID);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // ---- layer 3: [128 x 256] x [32 x 256]^T -> TMEM cols 0..31
+  if (tid == 0) {
+    mbar_wait(bar_w3, 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc(TILE_M, 32);
+#pragma unroll
+    for (int ks = 0; ks < 16; ks++)
+      umma_f16(tmem, umma_desc(sA + (ks >> 2) * (TILE_M * 128) + (ks & 3) * 32), umma_desc(sW13 + (ks >> 2) * (32 * 128) + (ks & 3) * 32), idesc, ks > 0);
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+  {
+    uint32_t r[32];
+    __syncwarp();
+    tmem_ld32(lane_addr, r);
+    if (row < a.M) {
+      const float* b3 = bias + 2 * HID;
+      float y[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) y[j] = __uint_as_float(r[j]) + b3[j];
+      if (a.raw) for (int j = 0; j < a.out_dim; j++) a.raw[((size_t)net * a.M + row) * a.out_dim + j] = y[j];
+      if (a.mode == B2Q_MLP_RAW) {
+        for (int j = 0; j < a.out_dim; j++) a.out[((size_t)net * a.M + row) * a.out_dim + j] = y[j];
+      } else {
+        const int A = a.out_dim >> 1;
+        float lp = 0.f;
+        for (int j = 0; j < A; j++) {
+          float mean = y[j], act;
+          if (a.mode == B2Q_MLP_PREDICT) {
+            act = tanhf(mean);                                                     // sac.py:60-63
+          } else {
+            float ls = fminf(fmaxf(y[A + j], -20.f), 2.f), sd = expf(ls);         // mujoco_model.py:21-22,59
+            float e = a.eps ? a.eps[(size_t)row * A + j] : philox_normal(a.seed, (uint32_t)row, (uint32_t)j);
+            float x = mean + sd * e;                                               // rsample
+            act = tanhf(x);
+            lp += -0.5f * e * e - ls - 0.9189385332046727f;                        // Normal.log_prob(x)
+            lp -= logf((1.f - act * act) + 1e-6f);                                 // sac.py:72
+          }
+          a.out[((size_t)net * a.M + row) * A + j] = act;
+        }
+        if (a.mode == B2Q_MLP_SAMPLE && a.logp) a.logp[(size_t)net * a.M + row] = lp;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// f32 nn.Linear weights -> bf16 swizzled operand images (+ f32 biases) in the per-net image
+__global__ void b2q_mlp_pack_kernel(uint8_t* img, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
+                                    int in_dim, int out_dim) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < HID * 64) {  // W1 [256 x 64 padded]
+    int n = i >> 6, k = i & 63;
+    *reinterpret_cast<__nv_bfloat16*>(img + IMG_W1 + sw128_offset(n, k, HID)) = __float2bfloat16(k < in_dim ? w1[(size_t)n * in_dim + k] : 0.f);
+  }
+  if (i < HID * HID) {
+    int n = i >> 8, k = i & 255;
+    *reinterpret_cast<__nv_bfloat16*>(img + IMG_W2 + sw128_offset(n, k, HID)) = __float2bfloat16(w2[(size_t)n * HID + k]);
+  }
+  if (i < 32 * HID) {
+    int n = i >> 8, k = i & 255;
+    *reinterpret_cast<__nv_bfloat16*>(img + IMG_W3 + sw128_offset(n, k, 32)) = __float2bfloat16(n < out_dim ? w3[(size_t)n * HID + k] : 0.f);
+  }
+  float* bias = reinterpret_cast<float*>(img + IMG_BIAS);
+  if (i < HID) { bias[i] = b1[i]; bias[HID + i] = b2[i]; }
+  if (i < 32) bias[2 * HID + i] = i < out_dim ? b3[i] : 0.f;
+}
+
+}  // namespace
+
+struct B2QMlp {
+  int device, in_dim, out_dim, nets;
+  uint8_t* img = nullptr;
+  std::string err;
+  int64_t launches = 0;
+};
+
+extern "C" {
+
+int b2q_mlp_create(int device, int in_dim, int out_dim, int nets, B2QMlpHandle* out) {
+  if (!out || in_dim < 1 || in_dim > B2Q_MLP_MAX_IN || out_dim < 1 || out_dim > B2Q_MLP_MAX_OUT || nets < 1 || nets > 8) return -1;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return -2;
+  B2QMlp* h = new (std::nothrow) B2QMlp();
+  if (!h) return -3;
+  h->device = device; h->in_dim = in_dim; h->out_dim = out_dim; h->nets = nets;
+  cudaSetDevice(device);
+  if (cudaMalloc(&h->img, IMG_BYTES * nets) != cudaSuccess) { delete h; return -3; }
+  cudaMemset(h->img, 0, IMG_BYTES * nets);
+  if (cudaFuncSetAttribute(b2q_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) { cudaFree(h->img); delete h; return -2; }
+  *out = h;
+  return 0;
+}
+int b2q_mlp_destroy(B2QMlpHandle h) {
+  if (!h) return -1;
+  cudaSetDevice(h->device);
+  cudaFree(h->img);
+  delete h;
+  return 0;
+}
+const char* b2q_mlp_last_error(B2QMlpHandle h) { return h ? h->err.c_str() : "null handle / create failed"; }
+int64_t b2q_mlp_launch_count(B2QMlpHandle h) { return h ? h->launches : 0; }
+
+int b2q_mlp_set_weights(B2QMlpHandle h, int net, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3, void* stream) {
+  if (!h || net < 0 || net >= h->nets || !w1 || !b1 || !w2 || !b2 || !w3 || !b3) { if (h) h->err = "b2q_mlp_set_weights: bad argument"; return -1; }
+  b2q_mlp_pack_kernel<<<(HID * HID + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->img + (size_t)net * IMG_BYTES, w1, b1, w2, b2, w3, b3, h->in_dim, h->out_dim);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return -2; }
+  return 0;
+}
+
+int b2q_mlp_forward(B2QMlpHandle h, const float* in1, int in1_dim, const float* in2, int M, int mode, uint64_t seed, const float* eps, float* out,
+                    float* logp, float* raw, void* stream) {
+  if (!h || !in1 || !out || M < 1 || in1_dim < 1 || in1_dim > h->in_dim || (in1_dim < h->in_dim && !in2) || mode < 0 || mode > 2 ||
+      (mode != B2Q_MLP_RAW && (h->out_dim & 1))) { if (h) h->err = "b2q_mlp_forward: bad argument"; return -1; }
+  FwdArgs a{in1, in2, in1_dim, h->in_dim, h->out_dim, M, mode, seed, eps, out, logp, raw, h->img, IMG_BYTES};
+  dim3 grid((M + TILE_M - 1) / TILE_M, h->nets);
+  b2q_mlp_fwd_kernel<<<grid, 128, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return -2; }
+  return 0;
+}
+
+}  // extern "C"
