@@ -17,6 +17,12 @@ namespace b2q {
 // ---- scalar math wrappers (precise variants: no fast-math intrinsics, parity with the f64 oracle matters)
 B2Q_HD float m_sqrt(float x) { return sqrtf(x); }
 B2Q_HD double m_sqrt(double x) { return sqrt(x); }
+#if defined(__CUDA_ARCH__)
+B2Q_HD float m_rsqrt(float x) { return rsqrtf(x); }
+#else
+B2Q_HD float m_rsqrt(float x) { return 1.0f / sqrtf(x); }
+#endif
+B2Q_HD double m_rsqrt(double x) { return 1.0 / sqrt(x); }
 B2Q_HD float m_sin(float x) { return sinf(x); }
 B2Q_HD double m_sin(double x) { return sin(x); }
 B2Q_HD float m_cos(float x) { return cosf(x); }
@@ -120,15 +126,17 @@ template <typename T> B2Q_HD T get6(const V6<T>& v, int i) { return i == 0 ? v.a
 // packed lower-triangular 6x6 / symmetric 6x6: index (i>=j) -> i*(i+1)/2 + j
 B2Q_HD constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
-template <typename T> B2Q_HD void chol6(T* S /*21, in: sym lower; out: L lower*/) {
+// Cholesky of a packed symmetric 6x6 (lower).  Out: L (lower, unit scaling NOT applied) and the reciprocals of its
+// diagonal in Li[6], so that the triangular solves below are multiply-only (no division on their serial chains).
+template <typename T> B2Q_HD void chol6(T* S /*21, in: sym lower; out: L lower*/, T* Li /*6*/) {
 #pragma unroll
   for (int j = 0; j < 6; j++) {
     T d = S[tri(j, j)];
 #pragma unroll
     for (int k = 0; k < j; k++) d -= S[tri(j, k)] * S[tri(j, k)];
-    d = m_sqrt(d);
-    S[tri(j, j)] = d;
-    T inv = T(1) / d;
+    T inv = m_rsqrt(d);
+    S[tri(j, j)] = d * inv;
+    Li[j] = inv;
 #pragma unroll
     for (int i = j + 1; i < 6; i++) {
       T s = S[tri(i, j)];
@@ -138,23 +146,22 @@ template <typename T> B2Q_HD void chol6(T* S /*21, in: sym lower; out: L lower*/
     }
   }
 }
-// the diagonal of L is stored as is; solves use division
-template <typename T> B2Q_HD void fwd6(const T* L, T* b) {  // b <- L^-1 b
+template <typename T> B2Q_HD void fwd6(const T* L, const T* Li, T* b) {  // b <- L^-1 b
 #pragma unroll
   for (int i = 0; i < 6; i++) {
     T s = b[i];
 #pragma unroll
     for (int k = 0; k < i; k++) s -= L[tri(i, k)] * b[k];
-    b[i] = s / L[tri(i, i)];
+    b[i] = s * Li[i];
   }
 }
-template <typename T> B2Q_HD void bwd6(const T* L, T* b) {  // b <- L^-T b
+template <typename T> B2Q_HD void bwd6(const T* L, const T* Li, T* b) {  // b <- L^-T b
 #pragma unroll
   for (int i = 5; i >= 0; i--) {
     T s = b[i];
 #pragma unroll
     for (int k = i + 1; k < 6; k++) s -= L[tri(k, i)] * b[k];
-    b[i] = s / L[tri(i, i)];
+    b[i] = s * Li[i];
   }
 }
 template <typename T> B2Q_HD void v6_to_arr(const V6<T>& v, T* a) { a[0] = v.a.x; a[1] = v.a.y; a[2] = v.a.z; a[3] = v.l.x; a[4] = v.l.y; a[5] = v.l.z; }

@@ -301,8 +301,9 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
     V3<T> n0 = cross(wB, mul(I0, wB)), f0 = pdd0 * m0;
     r6[0] -= n0.x; r6[1] -= n0.y; r6[2] -= n0.z; r6[3] -= f0.x; r6[4] -= f0.y; r6[5] -= f0.z;
   }
-  chol6(S);          // S now holds L
-  fwd6(S, r6); bwd6(S, r6);  // r6 = base twist derivative (body coordinates)
+  T Li[6];
+  chol6(S, Li);      // S now holds L, Li the reciprocal diagonal
+  fwd6(S, Li, r6); bwd6(S, Li, r6);  // r6 = base twist derivative (body coordinates)
   V6<T> nud = arr_to_v6(r6);
   T qdd[3];
   {
@@ -334,7 +335,7 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
       u[e] = dot(Jb.a, wBs) + dot(Jb.l, vBs) + Jk[e][0] * qds[0] + Jk[e][1] * qds[1] + Jk[e][2] * qds[2];
       V6<T> G = Jb - (FD[0] * Jk[e][0] + FD[1] * Jk[e][1] + FD[2] * Jk[e][2]);
       v6_to_arr(G, Y[e]);
-      fwd6(S, Y[e]);
+      fwd6(S, Li, Y[e]);
     }
 #pragma unroll
     for (int e = 0; e < 3; e++) {
@@ -345,65 +346,98 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
       for (int e2 = 0; e2 < 3; e2++) Wl[e2][e] = Jk[e2][0] * dj[0] + Jk[e2][1] * dj[1] + Jk[e2][2] * dj[2];
     }
   }
-  T W[3][12];
+  // --- gather every foot's rows on every lane (4-lane broadcasts), then the whole 12x12 contact problem is solved
+  //     REDUNDANTLY in registers by all four lanes: the Gauss-Seidel sweep below has no shuffle on its dependent chain.
+  //     Row index r = 3*foot + e (e: 0 normal, 1,2 friction).
+  T Ya[12][6], Wd[4][6], u0[12], lam[12], targn[4], actf[4];
 #pragma unroll
   for (int f = 0; f < 4; f++) {
 #pragma unroll
-    for (int e2 = 0; e2 < 3; e2++) {
-      T yf[6];
+    for (int e = 0; e < 3; e++) {
 #pragma unroll
-      for (int c = 0; c < 6; c++) yf[c] = cm.bcast(Y[e2][c], f);
+      for (int c = 0; c < 6; c++) Ya[3 * f + e][c] = cm.bcast(Y[e][c], f);
+      u0[3 * f + e] = cm.bcast(u[e], f);
+    }
+    Wd[f][0] = cm.bcast(Wl[0][0], f); Wd[f][1] = cm.bcast(Wl[1][0], f); Wd[f][2] = cm.bcast(Wl[1][1], f);
+    Wd[f][3] = cm.bcast(Wl[2][0], f); Wd[f][4] = cm.bcast(Wl[2][1], f); Wd[f][5] = cm.bcast(Wl[2][2], f);
+    targn[f] = cm.bcast(dist > T(0) ? -dist / dt : cf.erp * (-dist) / dt, f);
+    actf[f] = cm.bcast(act ? T(1) : T(0), f);
+    lam[3 * f] = cm.bcast(act ? cf.warm * s.lam_n : T(0), f);   // warm start of the normal impulse (Bullet 0.85)
+    lam[3 * f + 1] = T(0); lam[3 * f + 2] = T(0);
+  }
+  // Delassus matrix W = J M^-1 J^T  (symmetric): W_ij = Y_i . Y_j  (+ the leg-local block on the diagonal blocks)
+  T Wm[12][12];
 #pragma unroll
-      for (int e = 0; e < 3; e++) {
-        T w = Y[e][0] * yf[0] + Y[e][1] * yf[1] + Y[e][2] * yf[2] + Y[e][3] * yf[3] + Y[e][4] * yf[4] + Y[e][5] * yf[5];
-        if (f == k) w += Wl[e][e2];
-        W[e][3 * f + e2] = w;
-      }
+  for (int i = 0; i < 12; i++) {
+#pragma unroll
+    for (int j = 0; j <= i; j++) {
+      T w = Ya[i][0] * Ya[j][0] + Ya[i][1] * Ya[j][1] + Ya[i][2] * Ya[j][2] + Ya[i][3] * Ya[j][3] + Ya[i][4] * Ya[j][4] + Ya[i][5] * Ya[j][5];
+      if (i / 3 == j / 3) { const int a = i % 3, b = j % 3; w += Wd[i / 3][a * (a + 1) / 2 + b]; }
+      Wm[i][j] = w; Wm[j][i] = w;
+    }
+  }
+  // g_i = lam_i + (target_i - u_i) / W_ii is the UNCLAMPED Gauss-Seidel candidate of row i.  A row update
+  // lam_j <- clamp(g_j) changes g_i (i != j) by -(W_ij / W_ii) * dlam_j and leaves g_j itself unchanged, so the sweep
+  // carries g instead of the contact velocities.  Inactive feet: zero scale (g frozen), g_n = -BIG => lam stays 0.
+  T g[12];
+  {
+    T invd[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) invd[i] = actf[i / 3] > T(0) ? T(1) / Wm[i][i] : T(0);
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      T ui = u0[i];
+#pragma unroll
+      for (int f = 0; f < 4; f++) ui += Wm[i][3 * f] * lam[3 * f];
+      T tg = (i % 3 == 0) ? targn[i / 3] : T(0);
+      g[i] = lam[i] + (tg - ui) * invd[i];
+      if (i % 3 == 0 && !(actf[i / 3] > T(0))) g[i] = T(-1e30);
+#pragma unroll
+      for (int j = 0; j < 12; j++) Wm[i][j] = (i == j) ? T(0) : Wm[i][j] * invd[i];
     }
   }
   // --- projected Gauss-Seidel, Bullet row order: normals of feet 0..3, then (t1,t2) of feet 0..3
-  T lam[3] = {act ? cf.warm * s.lam_n : T(0), T(0), T(0)};
-  T targ0 = dist > T(0) ? -dist / dt : cf.erp * (-dist) / dt;
-  T invd[3] = {T(0), T(0), T(0)};
-  // the diagonal of this lane's own block (selected without dynamic register indexing)
-#pragma unroll
-  for (int f = 0; f < 4; f++) if (f == k) { invd[0] = T(1) / W[0][3 * f]; invd[1] = T(1) / W[1][3 * f + 1]; invd[2] = T(1) / W[2][3 * f + 2]; }
-#pragma unroll
-  for (int f = 0; f < 4; f++) {
-    T l0 = cm.bcast(lam[0], f);
-    u[0] += W[0][3 * f] * l0; u[1] += W[1][3 * f] * l0; u[2] += W[2][3 * f] * l0;
-  }
   for (int it = 0; it < cf.iters; it++) {
 #pragma unroll
     for (int f = 0; f < 4; f++) {
-      T ln = m_max(lam[0] + (targ0 - u[0]) * invd[0], T(0));
-      T dl = cm.bcast(act ? ln - lam[0] : T(0), f);
-      if (f == k) lam[0] += dl;
-      u[0] += W[0][3 * f] * dl; u[1] += W[1][3 * f] * dl; u[2] += W[2][3 * f] * dl;
+      const int r = 3 * f;
+      T ln = m_max(g[r], T(0));
+      T dl = ln - lam[r]; lam[r] = ln;
+#pragma unroll
+      for (int i = 0; i < 12; i++) if (i != r) g[i] -= Wm[i][r] * dl;
     }
 #pragma unroll
     for (int f = 0; f < 4; f++) {
 #pragma unroll
       for (int td = 1; td < 3; td++) {
-        T lim = pr.mu * lam[0];
-        T ln = m_min(m_max(lam[td] + (T(0) - u[td]) * invd[td], -lim), lim);
-        T dl = cm.bcast(act ? ln - lam[td] : T(0), f);
-        if (f == k) lam[td] += dl;
-        u[0] += W[0][3 * f + td] * dl; u[1] += W[1][3 * f + td] * dl; u[2] += W[2][3 * f + td] * dl;
+        const int r = 3 * f + td;
+        T lim = pr.mu * lam[3 * f];
+        T ln = m_min(m_max(g[r], -lim), lim);
+        T dl = ln - lam[r]; lam[r] = ln;
+#pragma unroll
+        for (int i = 0; i < 12; i++) if (i != r) g[i] -= Wm[i][r] * dl;
       }
     }
   }
-  s.lam_n = lam[0]; s.contact = lam[0] > T(0);
-  // --- apply impulses
+  T lk[3] = {T(0), T(0), T(0)};   // this lane's own impulses (selected without dynamic register indexing)
+#pragma unroll
+  for (int f = 0; f < 4; f++) if (f == k) { lk[0] = lam[3 * f]; lk[1] = lam[3 * f + 1]; lk[2] = lam[3 * f + 2]; }
+  s.lam_n = lk[0]; s.contact = lk[0] > T(0);
+  // --- apply impulses: every lane holds all rows, so sum_f Y_f lam_f needs no reduction
   T z[6];
 #pragma unroll
-  for (int c = 0; c < 6; c++) z[c] = cm.sum4(Y[0][c] * lam[0] + Y[1][c] * lam[1] + Y[2][c] * lam[2]);
-  bwd6(S, z);
+  for (int c = 0; c < 6; c++) {
+    T a = T(0);
+#pragma unroll
+    for (int i = 0; i < 12; i++) a += Ya[i][c] * lam[i];
+    z[c] = a;
+  }
+  bwd6(S, Li, z);
   V6<T> dnu = arr_to_v6(z);
   {
     T jl[3], t[3];
 #pragma unroll
-    for (int i = 0; i < 3; i++) { jl[i] = Jk[0][i] * lam[0] + Jk[1][i] * lam[1] + Jk[2][i] * lam[2]; t[i] = jl[i] - dot6(Fc[i], dnu); }
+    for (int i = 0; i < 3; i++) { jl[i] = Jk[0][i] * lk[0] + Jk[1][i] * lk[1] + Jk[2][i] * lk[2]; t[i] = jl[i] - dot6(Fc[i], dnu); }
 #pragma unroll
     for (int j = 0; j < 3; j++) qds[j] += D[j][0] * t[0] + D[j][1] * t[1] + D[j][2] * t[2];
   }
@@ -552,6 +586,7 @@ B2Q_HD void settle_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, co
 #pragma unroll
   for (int j = 0; j < 3; j++) { s.q[j] = md.pose_ori[j]; s.qd[j] = 0; tgt[j] = md.pose_ori[j]; }
   s.lam_n = 0; s.contact = 0;
+#pragma unroll 1
   for (int i = 0; i < cf.settle_steps; i++) substep(cm, cf, md, pr, s, tgt, tau);
   if (valid) {
     T z3[3] = {0, 0, 0};
@@ -591,6 +626,7 @@ B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, cons
   int ib = ((R - 2 - n_lag) % R + R) % R, mb = (n_lag + 1 - (R - 1 - ib)) / R;
   const int slot = step % B.Dm;
   T tau[3] = {0, 0, 0};
+#pragma unroll 1
   for (int i = 0; i < R; i++) {  // Minitaur.Step, minitaur.py:248-260
     T proc[3];
     if (cf.interp && has_last) {  // ProcessAction, minitaur.py:1384-1401

@@ -46,7 +46,7 @@ def test_checkpoint_known_answers(golden):
     out, _, raw = ag.actor.forward(obs, mode=PREDICT, want_raw=True)
     mean, ls = raw[0, :, :12].cpu().numpy(), np.clip(raw[0, :, 12:].cpu().numpy(), -20, 2)
     # bf16 operand rounding on the trained weights: measured max 4.1e-2 on means of magnitude ~1.5
-    tol = lambda ref: 2e-2 + 3e-2 * np.maximum(1.0, np.abs(ref))          # bf16: ~1% of the magnitude
+    tol = lambda ref: 3e-2 + 4e-2 * np.maximum(1.0, np.abs(ref))          # bf16 operands on trained weights (measured 4e-2 @ |ref|~1, 8e-2 @ 3.3)
     assert (np.abs(mean - golden["mlp_mean"]) < tol(golden["mlp_mean"])).all()
     assert (np.abs(ls - golden["mlp_logstd"]) < tol(golden["mlp_logstd"])).all()
     assert np.abs(out[0].cpu().numpy() - np.tanh(golden["mlp_mean"])).max() < 4e-2
