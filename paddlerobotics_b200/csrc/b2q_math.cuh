@@ -50,6 +50,32 @@ B2Q_HD bool m_isfinite(double x) { return (x - x) == 0.0; }
 B2Q_HD bool m_isnan(float x) { return x != x; }
 B2Q_HD bool m_isnan(double x) { return x != x; }
 
+// reciprocal: one MUFU.RCP + one Newton step on the GPU (<= 1 ulp, no slow path / branch); exact division elsewhere
+#if defined(__CUDA_ARCH__)
+B2Q_HD float m_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return fmaf(r, fmaf(-x, r, 1.0f), r); }
+#else
+B2Q_HD float m_rcp(float x) { return 1.0f / x; }
+#endif
+B2Q_HD double m_rcp(double x) { return 1.0 / x; }
+
+// sin and cos together for |a| up to a few turns (joint angles, Euler-step rotation angles): Cody-Waite reduction by
+// pi/2 (3 constants) + the classic degree-7/8 minimax kernels on [-pi/4, pi/4]; ~1 ulp, branch-free, ~30 instructions
+// (libm's sinf/cosf carry a Payne-Hanek slow path that costs >2000 instructions of code in this kernel).
+B2Q_HD void m_sincos(float a, float& s, float& c) {
+  float q = rintf(a * 0.636619772367581343f);            // nearest multiple of pi/2
+  int n = (int)q;
+  float r = fmaf(q, -1.57079601287841796875f, a);        // pi/2 split in three parts
+  r = fmaf(q, -3.1391647326017846353352069854736328125e-7f, r);
+  r = fmaf(q, -5.390302529957764765543e-15f, r);
+  float r2 = r * r;
+  float sp = fmaf(fmaf(fmaf(-1.95152959e-4f, r2, 8.33216087e-3f), r2, -1.66666546e-1f), r2 * r, r);
+  float cp = fmaf(fmaf(fmaf(fmaf(2.44331571e-5f, r2, -1.38873163e-3f), r2, 4.16666457e-2f), r2, -0.5f), r2, 1.0f);
+  float ss = (n & 1) ? cp : sp, cc = (n & 1) ? sp : cp;
+  s = (n & 2) ? -ss : ss;
+  c = ((n + 1) & 2) ? -cc : cc;
+}
+B2Q_HD void m_sincos(double a, double& s, double& c) { s = sin(a); c = cos(a); }
+
 template <typename T>
 struct V3 {
   T x, y, z;

@@ -37,7 +37,7 @@ inline void build_model_host(Model<T>& M, double foot_radius, double etg_T, doub
   for (int i = 0; i < 6; i++) M.I0[i] = (T)TRUNK_I[i];
   M.foot_r = (T)foot_radius; M.l_up = (T)A1Nominal::l_up; M.l_low = (T)A1Nominal::l_low;
   M.pose_ori[0] = (T)0.0; M.pose_ori[1] = (T)0.9; M.pose_ori[2] = (T)-1.8;
-  for (int j = 0; j < 12; j++) { M.etg_mean[j] = (T)ETG_MEAN[j]; M.etg_std[j] = (T)ETG_STD[j]; }
+  for (int j = 0; j < 12; j++) { M.etg_mean[j] = (T)ETG_MEAN[j]; M.etg_std[j] = (T)ETG_STD[j]; M.etg_istd[j] = (T)(1.0 / ETG_STD[j]); }
   for (int h = 0; h < ETG_H; h++) {  // RBF centres: forward(h*T/(H-0.9)), SURVEY App. A
     double t = h * etg_T / (ETG_H - 0.9), om = 2 * PI / etg_T;
     M.etg_u[h][0] = (T)(etg_amp * std::sin(ph0 + om * t));

@@ -50,7 +50,7 @@ struct Model {
   T foot_r, l_up, l_low;
   T etg_u[ETG_H][2];
   T base_foot[4][3];
-  T etg_mean[12], etg_std[12];
+  T etg_mean[12], etg_std[12], etg_istd[12];
   T pose_ori[3];
 };
 template <typename T>
@@ -82,7 +82,7 @@ struct LaneState {
   T q[3], qd[3]; T lam_n; int contact;
 };
 
-template <typename T> B2Q_HD void sincos_t(T a, T& s, T& c) { s = m_sin(a); c = m_cos(a); }
+template <typename T> B2Q_HD void sincos_t(T a, T& s, T& c) { m_sincos(a, s, c); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // terrain: plane or bilinear height field
@@ -147,11 +147,12 @@ B2Q_HD void etg_act_leg(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, co
   T om = two_pi / cf.etg_T;
   T x0 = cf.etg_amp * m_sin(cf.etg_ph0 + om * tt), x1 = cf.etg_amp * m_sin(cf.etg_ph1 + om * tt);
   T d[3] = {0, 0, 0};
+  const T isig = T(1) / cf.etg_sigma_sq;
   const T* e = reinterpret_cast<const T*>(etg);  // pack p, env -> e[(p*N+env)*4 + c]
 #pragma unroll 4
   for (int h = 0; h < ETG_H; h++) {
     T dx = x0 - md.etg_u[h][0], dy = x1 - md.etg_u[h][1];
-    T r = m_exp(-(dx * dx + dy * dy) / cf.etg_sigma_sq);
+    T r = m_exp(-(dx * dx + dy * dy) * isig);
 #pragma unroll
     for (int a = 0; a < 3; a++) {
       int idx = a * ETG_H + h;
@@ -179,7 +180,7 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
                     const T* target, T* tau_out) {
   const int k = cm.leg();
   const LegModel<T>& lm = md.leg[k];
-  const T dt = cf.dt;
+  const T dt = cf.dt, idt = T(1) / cf.dt;
   R3<T> R = quat_to_R(s.qx, s.qy, s.qz, s.qw);
   V3<T> wB = rotT(R, s.vang), vB = rotT(R, s.vlin), gB = rotT(R, pr.g);
 
@@ -255,7 +256,7 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
   T D[3][3];
   {
     T c00 = M22 * M33 - M32 * M32, c01 = M31 * M32 - M21 * M33, c02 = M21 * M32 - M31 * M22;
-    T det = M11 * c00 + M21 * c01 + M31 * c02, id = T(1) / det;
+    T det = M11 * c00 + M21 * c01 + M31 * c02, id = m_rcp(det);
     D[0][0] = c00 * id; D[0][1] = D[1][0] = c01 * id; D[0][2] = D[2][0] = c02 * id;
     D[1][1] = (M11 * M33 - M31 * M31) * id; D[1][2] = D[2][1] = (M31 * M21 - M11 * M32) * id;
     D[2][2] = (M11 * M22 - M21 * M21) * id;
@@ -321,7 +322,7 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
   T dist = toe_w.z - hgt - md.foot_r;
   bool act = dist < cf.margin;
   V3<T> t1w = mk<T>(1 - n_w.x * n_w.x, -n_w.x * n_w.y, -n_w.x * n_w.z);
-  t1w = t1w * (T(1) / m_sqrt(dot(t1w, t1w)));
+  t1w = t1w * m_rsqrt(dot(t1w, t1w));
   V3<T> t2w = cross(n_w, t1w);
   V3<T> eB[3] = {rotT(R, n_w), rotT(R, t1w), rotT(R, t2w)};
   V3<T> xc = K.toe - eB[0] * md.foot_r;
@@ -360,7 +361,7 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
     }
     Wd[f][0] = cm.bcast(Wl[0][0], f); Wd[f][1] = cm.bcast(Wl[1][0], f); Wd[f][2] = cm.bcast(Wl[1][1], f);
     Wd[f][3] = cm.bcast(Wl[2][0], f); Wd[f][4] = cm.bcast(Wl[2][1], f); Wd[f][5] = cm.bcast(Wl[2][2], f);
-    targn[f] = cm.bcast(dist > T(0) ? -dist / dt : cf.erp * (-dist) / dt, f);
+    targn[f] = cm.bcast(dist > T(0) ? -dist * idt : cf.erp * (-dist) * idt, f);
     actf[f] = cm.bcast(act ? T(1) : T(0), f);
     lam[3 * f] = cm.bcast(act ? cf.warm * s.lam_n : T(0), f);   // warm start of the normal impulse (Bullet 0.85)
     lam[3 * f + 1] = T(0); lam[3 * f + 2] = T(0);
@@ -383,7 +384,7 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
   {
     T invd[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) invd[i] = actf[i / 3] > T(0) ? T(1) / Wm[i][i] : T(0);
+    for (int i = 0; i < 12; i++) invd[i] = actf[i / 3] > T(0) ? m_rcp(Wm[i][i]) : T(0);
 #pragma unroll
     for (int i = 0; i < 12; i++) {
       T ui = u0[i];
@@ -449,13 +450,14 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
   s.pos = s.pos + s.vlin * dt;
   {
     T wx = s.vang.x, wy = s.vang.y, wz = s.vang.z, th = m_sqrt(wx * wx + wy * wy + wz * wz) * dt;
-    T kk = th < T(1e-4) ? T(0.5) - th * th / T(48) : m_sin(T(0.5) * th) / th, cw = m_cos(T(0.5) * th);
+    T sh, cw; sincos_t(T(0.5) * th, sh, cw);
+    T kk = th < T(1e-4) ? T(0.5) - th * th * T(1.0 / 48.0) : sh * m_rcp(th);
     T dx = wx * dt * kk, dy = wy * dt * kk, dz = wz * dt * kk;
     T ox = cw * s.qx + dx * s.qw + dy * s.qz - dz * s.qy;
     T oy = cw * s.qy - dx * s.qz + dy * s.qw + dz * s.qx;
     T oz = cw * s.qz + dx * s.qy - dy * s.qx + dz * s.qw;
     T ow = cw * s.qw - dx * s.qx - dy * s.qy - dz * s.qz;
-    T nn = T(1) / m_sqrt(ox * ox + oy * oy + oz * oz + ow * ow);
+    T nn = m_rsqrt(ox * ox + oy * oy + oz * oz + ow * ow);
     s.qx = ox * nn; s.qy = oy * nn; s.qz = oz * nn; s.qw = ow * nn;
   }
 }
@@ -535,19 +537,20 @@ B2Q_HD void write_obs(const Comm& cm, const Model<T>& md, T* obs, bool valid, co
   if (!valid) return;
   const int k = cm.leg();
   if (k == 0) {
-    obs[0] = (s.pos.x - start_pos.x) / dtc; obs[1] = (s.pos.y - start_pos.y) / dtc; obs[2] = (s.pos.z - start_pos.z) / dtc;
+    const T idtc = T(1) / dtc;
+    obs[0] = (s.pos.x - start_pos.x) * idtc; obs[1] = (s.pos.y - start_pos.y) * idtc; obs[2] = (s.pos.z - start_pos.z) * idtc;
     V3<T> rpy = quat_to_rpy(s.qx, s.qy, s.qz, s.qw);
     R3<T> R = quat_to_R(s.qx, s.qy, s.qz, s.qw);
     V3<T> wb = rotT(R, s.vang);
-    obs[7] = (rpy.x - rpy0.x) / T(0.1); obs[8] = (rpy.y - rpy0.y) / T(0.1); obs[9] = (rpy.z - rpy0.z) / T(0.1);
-    obs[10] = wb.x / T(0.5); obs[11] = wb.y / T(0.5); obs[12] = wb.z / T(0.5);
+    obs[7] = (rpy.x - rpy0.x) * T(10); obs[8] = (rpy.y - rpy0.y) * T(10); obs[9] = (rpy.z - rpy0.z) * T(10);   // /0.1, EnvWrapper.py:87
+    obs[10] = wb.x * T(2); obs[11] = wb.y * T(2); obs[12] = wb.z * T(2);                                            // /0.5, EnvWrapper.py:88
   }
   obs[3 + k] = s.contact ? T(1) : T(0);
 #pragma unroll
   for (int j = 0; j < 3; j++) {
-    obs[13 + 3 * k + j] = (map_pi(dq[j]) - md.pose_ori[j]) / T(0.1);
-    obs[25 + 3 * k + j] = dqd[j] / T(1.0);
-    obs[37 + 3 * k + j] = (etg_act[j] - md.etg_mean[3 * k + j]) / md.etg_std[3 * k + j];
+    obs[13 + 3 * k + j] = (map_pi(dq[j]) - md.pose_ori[j]) * T(10);   // /0.1, EnvWrapper.py:66
+    obs[25 + 3 * k + j] = dqd[j];                                          // /1.0, EnvWrapper.py:70
+    obs[37 + 3 * k + j] = (etg_act[j] - md.etg_mean[3 * k + j]) * md.etg_istd[3 * k + j];
   }
 }
 
@@ -666,9 +669,10 @@ B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, cons
   R3<T> Rb = quat_to_R(s.qx, s.qy, s.qz, s.qw);
   LegKin<T> K; leg_kin(md, md.leg[k], s.q, K);
   V3<T> toe_w = s.pos + rot(Rb, K.toe), knee_w = s.pos + rot(Rb, K.p3), nrm;
-  T velx = (s.pos.x - start_pos.x) / dtc;
+  const T idtc = T(1) / dtc;
+  T velx = (s.pos.x - start_pos.x) * idtc;
   T torso = m_min(velx, cf.vel_d);
-  T feet = cm.sum4(m_min((toe_w.x - foot0_x) / dtc, cf.vel_d) / T(4));
+  T feet = cm.sum4(m_min((toe_w.x - foot0_x) * idtc, cf.vel_d) * T(0.25));
   V3<T> rpy = quat_to_rpy(s.qx, s.qy, s.qz, s.qw);
   T up = T(1) - T(0.5) * (c_prec(rpy.x, T(0), T(0.25)) + c_prec(rpy.y, T(0), T(0.25)));
   T pw = cm.sum4(dtau[0] * dqd[0] + dtau[1] * dqd[1] + dtau[2] * dqd[2]);
@@ -676,7 +680,7 @@ B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, cons
   T kh = terrain_height(cf, knee_w.x, knee_w.y, nrm);
   T bad = cm.sum4((knee_w.z - kh < T(0.03)) ? T(1) : T(0));
   T nofoot = cm.sum4(s.contact ? T(0) : T(1));
-  T meanz = cm.sum4(K.toe.z / T(4));
+  T meanz = cm.sum4(K.toe.z * T(0.25));
   T above = cm.sum4(K.toe.z > T(0) ? T(1) : T(0));
   bool fin = m_isfinite(s.q[0]) && m_isfinite(s.q[1]) && m_isfinite(s.q[2]) && m_isfinite(s.qd[0]) && m_isfinite(s.qd[1]) && m_isfinite(s.qd[2]) &&
              m_isfinite(s.pos.x) && m_isfinite(s.pos.y) && m_isfinite(s.pos.z) && m_isfinite(s.vlin.x) && m_isfinite(s.vlin.y) && m_isfinite(s.vlin.z);
