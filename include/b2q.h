@@ -28,6 +28,7 @@
 #ifndef B2Q_H
 #define B2Q_H
 #include <stdint.h>
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -96,6 +97,13 @@ int b2q_set_dynamics(B2QHandle h, const uint8_t* env_mask, const void* dyn, void
 int b2q_reset(B2QHandle h, const uint8_t* env_mask, const void* etg_w, const void* etg_b, void* obs_out, void* stream);
 /* action [N,12] (already scaled by act_bound, joint-space residual). obs [N,49], reward [N], done [N] u8, info [N,56]. */
 int b2q_step(B2QHandle h, const void* action, int donef, void* obs, void* reward, uint8_t* done, void* info, void* stream);
+/* The same step with HOST buffers (the reference-facing call: numpy in / numpy out): H2D of the actions, the step
+ * kernel, D2H of obs / reward / done (and info if non-NULL), then a stream synchronise.  Use page-locked host memory
+ * (b2q_host_alloc or cudaHostAlloc / torch pin_memory) so the copies are true async DMA. */
+int b2q_step_host(B2QHandle h, const void* action_host, int donef, void* obs_host, void* reward_host, uint8_t* done_host,
+                  void* info_host, void* stream);
+void* b2q_host_alloc(size_t bytes);   /* page-locked host memory, NULL on failure */
+void b2q_host_free(void* p);
 /* tests / checkpointing */
 int b2q_get_state(B2QHandle h, void* state_out /*[N,37]*/, void* stream);
 int b2q_set_state(B2QHandle h, const void* state_in /*[N,37]*/, void* stream);

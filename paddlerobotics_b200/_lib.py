@@ -23,6 +23,9 @@ SYMBOLS = {
     "b2q_set_dynamics": (_i, [_vp, _u8p, _vp, _vp]),
     "b2q_reset": (_i, [_vp, _u8p, _vp, _vp, _vp, _vp]),
     "b2q_step": (_i, [_vp, _vp, _i, _vp, _vp, _u8p, _vp, _vp]),
+    "b2q_step_host": (_i, [_vp, _vp, _i, _vp, _vp, _u8p, _vp, _vp]),
+    "b2q_host_alloc": (_vp, [C.c_size_t]),
+    "b2q_host_free": (None, [_vp]),
     "b2q_get_state": (_i, [_vp, _vp, _vp]),
     "b2q_set_state": (_i, [_vp, _vp, _vp]),
     "b2q_get_step_count": (_i, [_vp, _vp, _vp]),

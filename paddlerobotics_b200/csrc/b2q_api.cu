@@ -113,6 +113,7 @@ struct EnvBase {
   virtual int set_dynamics(const uint8_t* mask, const void* dyn, cudaStream_t s) = 0;
   virtual int reset(const uint8_t* mask, const void* w, const void* b, void* obs, cudaStream_t s) = 0;
   virtual int step(const void* action, int donef, void* obs, void* rew, uint8_t* done, void* info, cudaStream_t s) = 0;
+  virtual int step_host(const void* a, int donef, void* obs, void* rew, uint8_t* done, void* info, cudaStream_t s) = 0;
   virtual int get_state(void* out, cudaStream_t s) = 0;
   virtual int set_state(const void* in, cudaStream_t s) = 0;
   virtual int get_step_count(int32_t* out, cudaStream_t s) = 0;
@@ -143,6 +144,7 @@ struct EnvT : EnvBase {
     if (d_model) cudaFree(d_model);
     if (d_def48) cudaFree(d_def48);
     if (d_hf) cudaFree(d_hf);
+    if (st_act) cudaFree(st_act);
   }
   int grid_lanes() const { return (B.N * 4 + tpb - 1) / tpb; }
 
@@ -212,6 +214,28 @@ struct EnvT : EnvBase {
     CK(cudaGetLastError());
     return B2Q_OK;
   }
+  // device staging for the host-buffer API (allocated on first use)
+  T* st_act = nullptr; T* st_obs = nullptr; T* st_rew = nullptr; uint8_t* st_done = nullptr; T* st_info = nullptr;
+  int step_host(const void* a, int donef, void* obs, void* rew, uint8_t* done, void* info, cudaStream_t s) override {
+    if (!a || !obs || !rew || !done) { err = "b2q_step_host: null host pointer"; return B2Q_EINVAL; }
+    CK(cudaSetDevice(cfg.device));
+    const size_t N = (size_t)B.N;
+    if (!st_act) {
+      size_t bytes = N * (12 + OBS_DIM + 1 + INFO_DIM) * sizeof(T) + N;
+      void* p = nullptr;
+      CK(cudaMalloc(&p, bytes));
+      st_act = (T*)p; st_obs = st_act + N * 12; st_rew = st_obs + N * OBS_DIM; st_info = st_rew + N; st_done = (uint8_t*)(st_info + N * INFO_DIM);
+    }
+    CK(cudaMemcpyAsync(st_act, a, N * 12 * sizeof(T), cudaMemcpyHostToDevice, s));
+    int rc = step(st_act, donef, st_obs, st_rew, st_done, st_info, s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(obs, st_obs, N * OBS_DIM * sizeof(T), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(rew, st_rew, N * sizeof(T), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(done, st_done, N, cudaMemcpyDeviceToHost, s));
+    if (info) CK(cudaMemcpyAsync(info, st_info, N * INFO_DIM * sizeof(T), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return B2Q_OK;
+  }
   int get_state(void* out, cudaStream_t s) override {
     b2q_get_state_kernel<T><<<(B.N + 127) / 128, 128, 0, s>>>(B.state, (T*)out, B.N); launches++;
     CK(cudaGetLastError());
@@ -267,6 +291,11 @@ int b2q_reset(B2QHandle h, const uint8_t* m, const void* w, const void* b, void*
 int b2q_step(B2QHandle h, const void* a, int donef, void* obs, void* rew, uint8_t* done, void* info, void* s) {
   return h ? h->impl->step(a, donef, obs, rew, done, info, (cudaStream_t)s) : B2Q_EINVAL;
 }
+int b2q_step_host(B2QHandle h, const void* a, int donef, void* obs, void* rew, uint8_t* done, void* info, void* s) {
+  return h ? h->impl->step_host(a, donef, obs, rew, done, info, (cudaStream_t)s) : B2Q_EINVAL;
+}
+void* b2q_host_alloc(size_t bytes) { void* p = nullptr; return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
+void b2q_host_free(void* p) { if (p) cudaFreeHost(p); }
 int b2q_get_state(B2QHandle h, void* out, void* s) { return h ? h->impl->get_state(out, (cudaStream_t)s) : B2Q_EINVAL; }
 int b2q_set_state(B2QHandle h, const void* in, void* s) { return h ? h->impl->set_state(in, (cudaStream_t)s) : B2Q_EINVAL; }
 int b2q_get_step_count(B2QHandle h, int32_t* out, void* s) { return h ? h->impl->get_step_count(out, (cudaStream_t)s) : B2Q_EINVAL; }

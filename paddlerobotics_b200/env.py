@@ -116,22 +116,21 @@ class VecQuadrupedalEnv:
         if self._h_act is None:
             n, npdt = self.num_envs, self.dtype
             self._h_act = torch.empty(n, ACT_DIM, dtype=npdt).pin_memory()
-            self._d_act = torch.empty(n, ACT_DIM, dtype=npdt, device=self.device)
             self._h_obs = torch.empty(n, OBS_DIM, dtype=npdt).pin_memory()
             self._h_rew = torch.empty(n, dtype=npdt).pin_memory()
             self._h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+            self._np_act, self._np_obs, self._np_rew, self._np_done = self._h_act.numpy(), self._h_obs.numpy(), self._h_rew.numpy(), self._h_done.numpy()
 
     def step_host(self, action_np, donef=False):
-        """The reference-facing call with HOST buffers: H2D of the actions, one step, D2H of obs/reward/done."""
+        """The reference-facing call with HOST buffers (numpy in / numpy out), one C call: pinned H2D of the actions, the
+        step kernel, D2H of obs/reward/done, stream sync (b2q_step_host)."""
         self._host_bufs()
-        self._h_act.copy_(torch.from_numpy(np.asarray(action_np)).reshape(self.num_envs, ACT_DIM))
-        self._d_act.copy_(self._h_act, non_blocking=True)
-        self.step(self._d_act, donef)
-        self._h_obs.copy_(self.obs, non_blocking=True)
-        self._h_rew.copy_(self.reward, non_blocking=True)
-        self._h_done.copy_(self.done, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return self._h_obs.numpy(), self._h_rew.numpy(), self._h_done.numpy()
+        np.copyto(self._np_act, np.asarray(action_np).reshape(self.num_envs, ACT_DIM), casting="same_kind")
+        rc = self.lib.b2q_step_host(self.h, self._h_act.data_ptr(), int(bool(donef)), self._h_obs.data_ptr(), self._h_rew.data_ptr(),
+                                    self._h_done.data_ptr(), None, self._stream())
+        if rc != 0:
+            _check(self.lib, self.h, rc, "b2q_step_host")
+        return self._np_obs, self._np_rew, self._np_done
 
     def h2d_bytes_per_step(self):
         return self.num_envs * ACT_DIM * self.obs.element_size()

@@ -198,3 +198,19 @@ def test_es_population_fitness_vs_oracle(torch_cuda, golden):
     assert (ref_len < T).any()            # some episodes ended early (falls) and were frozen
     ga.tell(_np(fit))
     ev.env.close()
+
+
+def test_host_buffer_api_equals_device_api(torch_cuda, etg_default):
+    """b2q_step_host (numpy in/out through pinned buffers, the reference-facing call) == b2q_step on device tensors."""
+    import torch
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    w, b = etg_default
+    a = VecQuadrupedalEnv(256, auto_reset=True); c = VecQuadrupedalEnv(256, auto_reset=True)
+    a.reset(w, b); c.reset(w, b)
+    rng = np.random.default_rng(0)
+    for k in range(40):
+        act = rng.uniform(-0.3, 0.3, (256, 12)).astype(np.float32)
+        o1, r1, d1, _ = a.step(torch.tensor(act, device="cuda"))
+        o2, r2, d2 = c.step_host(act)
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(d1.cpu().numpy(), d2)
+    a.close(); c.close()
