@@ -37,6 +37,19 @@ SYMBOLS = {
     "b2q_mlp_set_weights": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2q_mlp_forward": (_i, [_vp, _vp, _i, _vp, _i, _i, C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
     "b2q_mlp_launch_count": (C.c_int64, [_vp]),
+    # SAC learner — include/b2q_sac.h
+    "b2q_sac_create": (_i, [_i, _i, _i, _i, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(_vp)]),
+    "b2q_sac_destroy": (_i, [_vp]),
+    "b2q_sac_last_error": (C.c_char_p, [_vp]),
+    "b2q_sac_param_count": (_i, [_vp, _i]),
+    "b2q_sac_set_params": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "b2q_sac_get_params": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "b2q_sac_get_grads": (_i, [_vp, _vp, _vp, _vp]),
+    "b2q_sac_learn": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp]),
+    "b2q_sac_phase": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint64, _vp]),
+    "b2q_sac_grad_ptr": (_vp, [_vp, _i]),
+    "b2q_sac_loss_ptr": (_vp, [_vp]),
+    "b2q_sac_launch_count": (C.c_int64, [_vp]),
     # ES population fitness — include/b2q_es.h
     "b2q_es_accumulate": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "b2q_es_fitness": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -151,3 +151,133 @@ class MujocoAgent:
     def sample(self, obs):
         o = torch.as_tensor(np.asarray(obs, dtype=np.float32).reshape(1, -1), device=self.device)
         return self.sample_batch(o)[0][0].cpu().numpy().flatten()
+
+
+ACTOR_KEYS = ("actor_model.l1", "actor_model.l2")
+CRITIC_NETS = (("critic_model.l1", "critic_model.l2", "critic_model.l3"), ("critic_model.l4", "critic_model.l5", "critic_model.l6"))
+
+
+def flatten_params(p):
+    """state-dict tensors -> the learner's flat vectors: actor [W1|b1|W2|b2|W3|b3] (W3 = cat(mean_linear, std_linear)), twin critic [2][...]."""
+    a = torch.cat([p["actor_model.l1.weight"].reshape(-1), p["actor_model.l1.bias"], p["actor_model.l2.weight"].reshape(-1), p["actor_model.l2.bias"],
+                   p["actor_model.mean_linear.weight"].reshape(-1), p["actor_model.std_linear.weight"].reshape(-1),
+                   p["actor_model.mean_linear.bias"], p["actor_model.std_linear.bias"]])
+    c = torch.cat([torch.cat([p[k + ".weight"].reshape(-1) if j == 0 else p[k + ".bias"] for k in net for j in (0, 1)]) for net in CRITIC_NETS])
+    return a.contiguous(), c.contiguous()
+
+
+def unflatten_params(p, a, c, obs_dim, act_dim):
+    """inverse of flatten_params, writing into the state dict `p` (shapes taken from it)."""
+    def take(vec, off, shape):
+        n = int(np.prod(shape))
+        return vec[off:off + n].reshape(shape).clone(), off + n
+    off = 0
+    for k in ("actor_model.l1", "actor_model.l2"):
+        p[k + ".weight"], off = take(a, off, p[k + ".weight"].shape)
+        p[k + ".bias"], off = take(a, off, p[k + ".bias"].shape)
+    p["actor_model.mean_linear.weight"], off = take(a, off, p["actor_model.mean_linear.weight"].shape)
+    p["actor_model.std_linear.weight"], off = take(a, off, p["actor_model.std_linear.weight"].shape)
+    p["actor_model.mean_linear.bias"], off = take(a, off, p["actor_model.mean_linear.bias"].shape)
+    p["actor_model.std_linear.bias"], off = take(a, off, p["actor_model.std_linear.bias"].shape)
+    off = 0
+    for net in CRITIC_NETS:
+        for k in net:
+            p[k + ".weight"], off = take(c, off, p[k + ".weight"].shape)
+            p[k + ".bias"], off = take(c, off, p[k + ".bias"].shape)
+
+
+class SACLearner:
+    """SAC.learn on the device (csrc/b2q_sac.cu): same hyper-parameters and update order as ETGRL/alg/sac.py:30-118.
+    `world`>1: data-parallel learner, gradient buckets all-reduced (NCCL) between the gradient and optimiser phases."""
+
+    def __init__(self, agent, batch, gamma=0.99, tau=0.005, alpha=0.2, actor_lr=3e-4, critic_lr=3e-4, world=1):
+        self.lib = _lib.load()
+        self.agent, self.batch, self.world = agent, batch, world
+        self.h = C.c_void_p()
+        rc = self.lib.b2q_sac_create(agent.device.index or 0, agent.obs_dim, agent.act_dim, batch, gamma, tau, alpha, actor_lr, critic_lr, C.byref(self.h))
+        if rc != 0:
+            raise RuntimeError("b2q_sac_create failed (%d)" % rc)
+        self.na, self.nc = self.lib.b2q_sac_param_count(self.h, 0), self.lib.b2q_sac_param_count(self.h, 1)
+        self.losses = torch.zeros(2, device=agent.device)
+        self.steps = 0
+        self.push()
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.agent.device).cuda_stream)
+
+    def push(self):
+        a, c = flatten_params(self.agent.params)
+        assert a.numel() == self.na and c.numel() == self.nc
+        rc = self.lib.b2q_sac_set_params(self.h, a.data_ptr(), c.data_ptr(), None, self._stream())
+        assert rc == 0
+        self._keep = (a, c)
+
+    def pull(self):
+        a = torch.empty(self.na, device=self.agent.device); c = torch.empty(self.nc, device=self.agent.device)
+        assert self.lib.b2q_sac_get_params(self.h, a.data_ptr(), c.data_ptr(), None, self._stream()) == 0
+        unflatten_params(self.agent.params, a, c, self.agent.obs_dim, self.agent.act_dim)
+        self.agent.sync_weights()
+
+    def grads(self):
+        a = torch.empty(self.na, device=self.agent.device); c = torch.empty(self.nc, device=self.agent.device)
+        assert self.lib.b2q_sac_get_grads(self.h, a.data_ptr(), c.data_ptr(), self._stream()) == 0
+        return a, c
+
+    def _grad_view(self, which, n):
+        # wrap the device bucket without copying (for in-place NCCL all-reduce)
+        return torch.as_tensor(_CudaBuf(self.lib.b2q_sac_grad_ptr(self.h, which), n), device=self.agent.device)
+
+    def learn(self, obs, act, rew, next_obs, term, eps_next=None, eps_cur=None, pull=True):
+        dev = self.agent.device
+        t = lambda x: torch.as_tensor(x, dtype=torch.float32, device=dev).contiguous()
+        obs, act, rew, next_obs, term = t(obs), t(act), t(rew).reshape(-1), t(next_obs), t(term).reshape(-1)
+        assert obs.shape[0] == self.batch
+        if eps_next is None:
+            eps_next = torch.randn(self.batch, self.agent.act_dim, device=dev)
+        if eps_cur is None:
+            eps_cur = torch.randn(self.batch, self.agent.act_dim, device=dev)
+        eps_next, eps_cur = t(eps_next), t(eps_cur)
+        self.steps += 1
+        args = (obs.data_ptr(), act.data_ptr(), rew.data_ptr(), next_obs.data_ptr(), term.data_ptr(), eps_next.data_ptr(), eps_cur.data_ptr(), C.c_uint64(self.steps))
+        if self.world == 1:
+            rc = self.lib.b2q_sac_learn(self.h, *args, self.losses.data_ptr(), self._stream())
+            if rc != 0:
+                raise RuntimeError("b2q_sac_learn: %d %s" % (rc, self.lib.b2q_sac_last_error(self.h).decode()))
+        else:
+            import torch.distributed as dist
+            for ph in range(4):
+                rc = self.lib.b2q_sac_phase(self.h, ph, *args, self._stream())
+                if rc != 0:
+                    raise RuntimeError("b2q_sac_phase %d: %d" % (ph, rc))
+                if ph in (0, 2):   # one flat bucket per optimiser: all-reduce(mean) then the fused Adam kernel consumes it
+                    g = self._grad_view(0 if ph == 2 else 1, self.na if ph == 2 else self.nc)
+                    dist.all_reduce(g, op=dist.ReduceOp.SUM)
+                    g.mul_(1.0 / self.world)
+            self.losses.copy_(torch.as_tensor(_CudaBuf(self.lib.b2q_sac_loss_ptr(self.h), 2), device=dev))
+        if pull:
+            self.pull()
+        return self.losses
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b2q_sac_destroy(self.h)
+            self.h = None
+
+
+class _CudaBuf:
+    """Minimal __cuda_array_interface__ wrapper of a raw device float32 buffer (zero-copy view for torch.as_tensor)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+
+
+def _agent_learn(self, obs, action, reward, next_obs, terminal):
+    """MujocoAgent.learn(obs, act, reward, next_obs, terminal) -> (critic_loss, actor_loss), mujoco_agent.py:43-54."""
+    n = np.asarray(obs).shape[0] if not isinstance(obs, torch.Tensor) else obs.shape[0]
+    if getattr(self, "_learner", None) is None or self._learner.batch != n:
+        self._learner = SACLearner(self, n)
+    l = self._learner.learn(obs, action, reward, next_obs, terminal)
+    return float(l[0]), float(l[1])
+
+
+MujocoAgent.learn = _agent_learn

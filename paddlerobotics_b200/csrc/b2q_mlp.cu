@@ -17,6 +17,10 @@
 #include <new>
 #include <string>
 #include "../../include/b2q_mlp.h"
+#include "b2q_tc.cuh"
+#include "b2q_mlp_internal.h"
+
+using namespace b2q_tc;
 
 namespace {
 
@@ -27,66 +31,6 @@ constexpr uint32_t OFF_A = 0, OFF_W2 = OFF_A + SZ_A, OFF_W13 = OFF_W2 + SZ_W2, O
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 64;
 constexpr size_t IMG_W1 = 0, IMG_W2 = SZ_W1, IMG_W3 = IMG_W2 + SZ_W2, IMG_BIAS = IMG_W3 + SZ_W3, IMG_BYTES = IMG_BIAS + SZ_BIAS;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
-
-// byte offset of element (row, k) inside a K-major SWIZZLE_128B operand image with `rows` rows (64-element panels)
-__host__ __device__ inline uint32_t sw128_offset(int row, int k, int rows) {
-  int p = k >> 6, kk = k & 63, c = kk >> 3, e = kk & 7;
-  return (uint32_t)p * (uint32_t)rows * 128u + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4) + (uint32_t)e * 2u;
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, sm100 version 1)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;                    // leading byte offset (ignored for swizzled K-major; canonical value 1)
-  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
-  return d;
-}
-// instruction descriptor kind::f16: D=f32, A=B=bf16, both K-major, M x N
-__device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // counter-based Gaussian (Philox-4x32-10 keyed by seed, counter = (row, col)) -> Box-Muller
 __device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
@@ -105,6 +49,7 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t row, uint
 struct FwdArgs {
   const float* in1; const float* in2; int in1_dim, in_dim, out_dim, M, mode; uint64_t seed; const float* eps;
   float* out; float* logp; float* raw; const uint8_t* img; size_t img_stride;
+  B2QMlpSaves sv; int save;
 };
 
 __global__ void __launch_bounds__(128, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
@@ -144,7 +89,9 @@ __global__ void __launch_bounds__(128, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
         if (k < a.in1_dim) v = a.in1[(size_t)gr * a.in1_dim + k];
         else if (k < a.in_dim) v = a.in2[(size_t)gr * in2_dim + (k - a.in1_dim)];
       }
-      *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + sw128_offset(r, k, TILE_M)) = __float2bfloat16(v);
+      __nv_bfloat16 vb = __float2bfloat16(v);
+      *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + sw128_offset(r, k, TILE_M)) = vb;
+      if (a.save && net == 0 && gr < a.M) { a.sv.x_rm[(size_t)gr * 64 + k] = vb; a.sv.x_t[(size_t)k * a.M + gr] = vb; }
     }
   }
   fence_async_smem();
@@ -170,7 +117,7 @@ __global__ void __launch_bounds__(128, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
     mbar_expect_tx(bar_w3, SZ_W3);
     bulk_g2s(sW13, img + IMG_W3, SZ_W3, bar_w3);
   }
-  auto epilogue_hidden = [&](uint32_t col_base, const float* b) {
+  auto epilogue_hidden = [&](uint32_t col_base, const float* b, __nv_bfloat16* d_rm, __nv_bfloat16* d_t) {
 #pragma unroll 1
     for (int cc = 0; cc < 8; cc++) {
       uint32_t r[32];
@@ -187,10 +134,17 @@ __global__ void __launch_bounds__(128, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
           pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
         *reinterpret_cast<uint4*>(smem + OFF_A + sw128_offset(tid, cc * 32 + j0, TILE_M)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (d_rm && row < a.M) {
+          const int col = cc * 32 + j0;
+          *reinterpret_cast<uint4*>(d_rm + ((size_t)net * a.M + row) * HID + col) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(pk);
+#pragma unroll
+          for (int j = 0; j < 8; j++) d_t[((size_t)net * HID + col + j) * a.M + row] = hv[j];
+        }
       }
     }
   };
-  epilogue_hidden(0, bias);
+  epilogue_hidden(0, bias, a.save ? a.sv.h1_rm : nullptr, a.save ? a.sv.h1_t : nullptr);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -209,7 +163,7 @@ __global__ void __launch_bounds__(128, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
   __syncwarp();
   mbar_wait(bar_mma, 1);
   tc_fence_after();
-  epilogue_hidden(256, bias + HID);
+  epilogue_hidden(256, bias + HID, a.save ? a.sv.h2_rm : nullptr, a.save ? a.sv.h2_t : nullptr);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -332,17 +286,22 @@ int b2q_mlp_set_weights(B2QMlpHandle h, int net, const float* w1, const float* b
   return 0;
 }
 
-int b2q_mlp_forward(B2QMlpHandle h, const float* in1, int in1_dim, const float* in2, int M, int mode, uint64_t seed, const float* eps, float* out,
-                    float* logp, float* raw, void* stream) {
+int b2q_mlp_forward_ex(B2QMlpHandle h, const float* in1, int in1_dim, const float* in2, int M, int mode, uint64_t seed, const float* eps, float* out,
+                       float* logp, float* raw, const B2QMlpSaves* saves, void* stream) {
   if (!h || !in1 || !out || M < 1 || in1_dim < 1 || in1_dim > h->in_dim || (in1_dim < h->in_dim && !in2) || mode < 0 || mode > 2 ||
       (mode != B2Q_MLP_RAW && (h->out_dim & 1))) { if (h) h->err = "b2q_mlp_forward: bad argument"; return -1; }
-  FwdArgs a{in1, in2, in1_dim, h->in_dim, h->out_dim, M, mode, seed, eps, out, logp, raw, h->img, IMG_BYTES};
+  FwdArgs a{in1, in2, in1_dim, h->in_dim, h->out_dim, M, mode, seed, eps, out, logp, raw, h->img, IMG_BYTES, B2QMlpSaves{}, 0};
+  if (saves) { a.sv = *saves; a.save = 1; }
   dim3 grid((M + TILE_M - 1) / TILE_M, h->nets);
   b2q_mlp_fwd_kernel<<<grid, 128, SMEM_BYTES, (cudaStream_t)stream>>>(a);
   h->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return -2; }
   return 0;
+}
+int b2q_mlp_forward(B2QMlpHandle h, const float* in1, int in1_dim, const float* in2, int M, int mode, uint64_t seed, const float* eps, float* out,
+                    float* logp, float* raw, void* stream) {
+  return b2q_mlp_forward_ex(h, in1, in1_dim, in2, M, mode, seed, eps, out, logp, raw, nullptr, stream);
 }
 
 }  // extern "C"

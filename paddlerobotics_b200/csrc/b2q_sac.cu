@@ -1,0 +1,491 @@
+// b2q_sac.cu — K5/K6: SAC update on the GPU (include/b2q_sac.h): critic + actor forward (fused tcgen05 MLP kernel of
+// b2q_mlp.cu with activation dumps), backward GEMMs on tcgen05 tensor cores, fused elementwise epilogues, Adam and Polyak.
+// Reference: SAC.learn / _critic_learn / _actor_learn / sync_target, ETGRL/alg/sac.py:77-118; torch.optim.Adam :55-58.
+//
+// Every backward product is phrased as C[MxN] (+)= A[MxK] . B[NxK]^T with both operands K-major bf16 (the layout the
+// tcgen05 descriptors of b2q_tc.cuh address): weight gradients contract over the batch (K = batch, split-K across CTAs,
+// f32 atomics), data gradients contract over the hidden width.  Activations are therefore kept in two bf16 layouts
+// ([batch x width] and [width x batch]) written by the forward kernel's epilogue, and each weight matrix has a transposed
+// bf16 copy refreshed by the optimiser kernel.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+#include "../../include/b2q_sac.h"
+#include "b2q_mlp_internal.h"
+#include "b2q_tc.cuh"
+
+using namespace b2q_tc;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+constexpr int H = 256;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// generic tensor-core GEMM  C[M x N] (+)= A[M x K] . B[N x K]^T   (bf16 K-major operands, f32 result), N <= 256
+struct GemmArgs {
+  const bf16* A; int lda; const bf16* B; int ldb; float* C; int ldc;
+  int M, N, K, BN, chunks_per_split, atomic;
+};
+constexpr uint32_t G_STAGE_A = 128 * 128, G_STAGE_B = 256 * 128, G_STAGE = G_STAGE_A + G_STAGE_B;
+constexpr uint32_t G_SMEM = 2 * G_STAGE + 64;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  uint32_t sz = valid ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void load_panel(uint32_t dst, const bf16* src, int ld, int row0, int rows_valid, int rows_tile, int k0, int K, int tid) {
+  for (int i = tid; i < rows_tile * 8; i += 128) {
+    int r = i >> 3, c = i & 7, k = k0 + c * 8;
+    bool ok = (row0 + r < rows_valid) && (k < K);
+    const bf16* p = ok ? src + (size_t)(row0 + r) * ld + k : src;
+    cp_async16(dst + r * 128 + ((c ^ (r & 7)) << 4), p, ok);
+  }
+}
+
+__global__ void __launch_bounds__(128) b2q_gemm_kernel(GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) __trap();
+  const uint32_t bar_free0 = sbase + 2 * G_STAGE, bar_done = bar_free0 + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 2 * G_STAGE + 32);
+  const int row0 = blockIdx.x * 128;
+  const int nk_total = (g.K + 63) / 64;
+  const int kc0 = blockIdx.z * g.chunks_per_split, kc1 = min(nk_total, kc0 + g.chunks_per_split), nk = kc1 - kc0;
+  const uint32_t tm_cols = g.BN <= 32 ? 32u : (g.BN <= 64 ? 64u : (g.BN <= 128 ? 128u : 256u));
+  if (tid == 0) {
+    mbar_init(bar_free0, 1); mbar_init(bar_free0 + 8, 1); mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(const_cast<const uint32_t*>(tmem_slot))), "r"(tm_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (nk > 0) {
+    load_panel(sbase, g.A, g.lda, row0, g.M, 128, kc0 * 64, g.K, tid);
+    load_panel(sbase + G_STAGE_A, g.B, g.ldb, 0, g.N, g.BN, kc0 * 64, g.K, tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const uint32_t idesc = umma_idesc(128, g.BN);
+    for (int kc = 0; kc < nk; kc++) {
+      if (kc + 1 < nk) {
+        const int s1 = (kc + 1) & 1;
+        if (kc + 1 >= 2) mbar_wait(bar_free0 + 8 * s1, (uint32_t)(((kc + 1) / 2 - 1) & 1));
+        load_panel(sbase + s1 * G_STAGE, g.A, g.lda, row0, g.M, 128, (kc0 + kc + 1) * 64, g.K, tid);
+        load_panel(sbase + s1 * G_STAGE + G_STAGE_A, g.B, g.ldb, 0, g.N, g.BN, (kc0 + kc + 1) * 64, g.K, tid);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t sa = sbase + (kc & 1) * G_STAGE, sb = sa + G_STAGE_A;
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) umma_f16(tmem, umma_desc(sa + ks * 32), umma_desc(sb + ks * 32), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(bar_free0 + 8 * (kc & 1));
+        if (kc == nk - 1) umma_commit(bar_done);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const int row = row0 + tid;
+    for (int cc = 0; cc < (g.BN + 31) / 32; cc++) {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld32(lane_addr + cc * 32, r);
+      if (row < g.M) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          int col = cc * 32 + j;
+          if (col < g.N) {
+            float* c = g.C + (size_t)row * g.ldc + col;
+            if (g.atomic) atomicAdd(c, __uint_as_float(r[j])); else *c = __uint_as_float(r[j]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tm_cols) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// elementwise / reduction kernels
+__global__ void k_target_q(const float* rew, const float* term, const float* q1n, const float* q2n, const float* logpn, float gamma, float alpha, float* tq, int B) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) tq[b] = rew[b] + gamma * term[b] * (fminf(q1n[b], q2n[b]) - alpha * logpn[b]);   // sac.py:88-91
+}
+// critic head backward for both nets: dq = 2 (q - tq)/B; loss += (q-tq)^2/B; db3 += dq   (mse_loss mean reduction, sac.py:94-95)
+__global__ void k_critic_dq(const float* q /*[2][B]*/, const float* tq, float* dq /*[2][B]*/, float* loss, int B) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x, net = blockIdx.y;
+  float l = 0.f;
+  if (b < B) { float e = q[net * B + b] - tq[b]; dq[net * B + b] = 2.f * e / (float)B; l = e * e / (float)B; }
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(loss, l);
+}
+// dh2[b,:] = dy[b,:] . W3 (out_dim x 256), masked by relu(h2) > 0 -> bf16 row-major + transposed; dW3 += dy^T h2 (tiny N: done here)
+__global__ void k_head_bwd(const float* dy /*[B][od]*/, int od, const float* W3 /*[od][256]*/, const bf16* h2 /*[B][256]*/, bf16* dh_rm, bf16* dh_t,
+                           float* dW3 /*[od][256]*/, int B) {
+  // block: 256 threads = hidden columns; grid.x over batch tiles of 32 rows
+  int col = threadIdx.x, b0 = blockIdx.x * 32;
+  float w[24];
+  for (int o = 0; o < od; o++) w[o] = W3[o * H + col];
+  float acc[24];
+  for (int o = 0; o < od; o++) acc[o] = 0.f;
+  for (int r = 0; r < 32; r++) {
+    int b = b0 + r;
+    if (b >= B) break;
+    float hv = __bfloat162float(h2[(size_t)b * H + col]);
+    float g = 0.f;
+    for (int o = 0; o < od; o++) { float d = dy[(size_t)b * od + o]; g += d * w[o]; acc[o] += d * hv; }
+    g = hv > 0.f ? g : 0.f;
+    bf16 gb = __float2bfloat16(g);
+    dh_rm[(size_t)b * H + col] = gb;
+    dh_t[(size_t)col * B + b] = gb;
+  }
+  for (int o = 0; o < od; o++) atomicAdd(dW3 + o * H + col, acc[o]);
+}
+// dh = G (f32 [B][256]) masked by h>0 -> bf16 row-major + transposed
+__global__ void k_relu_mask(const float* G, const bf16* h, bf16* dh_rm, bf16* dh_t, int B) {
+  int col = threadIdx.x, b0 = blockIdx.x * 32;
+  for (int r = 0; r < 32; r++) {
+    int b = b0 + r;
+    if (b >= B) break;
+    float v = __bfloat162float(h[(size_t)b * H + col]) > 0.f ? G[(size_t)b * H + col] : 0.f;
+    bf16 vb = __float2bfloat16(v);
+    dh_rm[(size_t)b * H + col] = vb;
+    dh_t[(size_t)col * B + b] = vb;
+  }
+}
+// db[col] = sum_b dh_t[col][b]  (one warp per column)
+__global__ void k_rowsum_bf16(const bf16* dh_t, float* db, int B) {
+  int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (col >= H) return;
+  float s = 0.f;
+  for (int b = lane; b < B; b += 32) s += __bfloat162float(dh_t[(size_t)col * B + b]);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) db[col] = s;
+}
+__global__ void k_colsum_f32(const float* dy, int od, float* db, int B) {   // db[o] = sum_b dy[b][o]
+  int o = blockIdx.x, lane = threadIdx.x;
+  float s = 0.f;
+  for (int b = lane; b < B; b += blockDim.x) s += dy[(size_t)b * od + o];
+  for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+  __shared__ float sh[8];
+  if ((lane & 31) == 0) sh[lane >> 5] = s;
+  __syncthreads();
+  if (lane == 0) { float t = 0.f; for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += sh[i]; db[o] = t; }
+}
+// actor head: from raw y=[mean|raw_ls], eps, da_c (critic gradient wrt action, already includes -1/B routing) build dy and the loss
+__global__ void k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const float* act /*[B][A] tanh(x)*/, const float* logp, const float* q /*[2][B]*/,
+                           const float* da_c /*[B][16] (cols 0..A-1)*/, float alpha, float* dy /*[B][2A]*/, float* loss, int B, int A) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  float l = 0.f;
+  if (b < B) {
+    l = (alpha * logp[b] - fminf(q[b], q[B + b])) / (float)B;                     // sac.py:105-106
+    for (int j = 0; j < A; j++) {
+      float a = act[(size_t)b * A + j], rl = raw[(size_t)b * 2 * A + A + j];
+      float ls = fminf(fmaxf(rl, -20.f), 2.f), sd = expf(ls), e = eps[(size_t)b * A + j];
+      float ga = da_c[(size_t)b * 16 + j] + (alpha / (float)B) * (2.f * a / ((1.f - a * a) + 1e-6f));
+      float gx = ga * (1.f - a * a);
+      float gls = gx * sd * e - alpha / (float)B;
+      dy[(size_t)b * 2 * A + j] = gx;
+      dy[(size_t)b * 2 * A + A + j] = (rl > -20.f && rl < 2.f) ? gls : 0.f;        // torch.clamp gradient
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(loss, l);
+}
+// dq routing for the actor loss: d(-min(q1,q2))/dq_i /B
+__global__ void k_minq_dq(const float* q /*[2][B]*/, float* dq /*[2][B]*/, int B) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) { bool first = q[b] <= q[B + b]; dq[b] = first ? -1.f / (float)B : 0.f; dq[B + b] = first ? 0.f : -1.f / (float)B; }   // torch.min picks the first on ties
+}
+__global__ void k_add_f32(float* dst, const float* src, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) dst[i] += src[i]; }
+__global__ void k_cast_pad(const float* src, int rows, int cols, bf16* dst, int ld) {   // dst [rows][ld] zero padded
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * ld) { int r = i / ld, c = i % ld; dst[i] = __float2bfloat16(c < cols ? src[(size_t)r * cols + c] : 0.f); }
+}
+// Adam (torch.optim.Adam defaults: betas 0.9/0.999, eps 1e-8, no weight decay), sac.py:55-58
+__global__ void k_adam(float* p, const float* g, float* m, float* v, int n, float lr, float b1, float b2, float eps, float bc1, float bc2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float gi = g[i], mi = b1 * m[i] + (1.f - b1) * gi, vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+  }
+}
+__global__ void k_polyak(float* tgt, const float* src, int n, float tau) {   // sync_target, sac.py:112-118: target = tau*param + (1-tau)*target
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tgt[i] = tau * src[i] + (1.f - tau) * tgt[i];
+}
+// bf16 helper copies of one net's weights for the backward GEMMs: W2T [256][256], W3T64 [256][64] (k = output index, zero padded),
+// W1A [16][256] (rows = action columns of W1, for d/da)
+__global__ void k_make_bwd_weights(const float* W1, int in_dim, int a_off, int a_dim, const float* W2, const float* W3, int od, bf16* W2T, bf16* W3T, bf16* W1A) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < H * H) { int n = i / H, k = i % H; W2T[i] = __float2bfloat16(W2[(size_t)k * H + n]); }
+  if (i < H * 64) { int n = i / 64, k = i % 64; W3T[i] = __float2bfloat16(k < od ? W3[(size_t)k * H + n] : 0.f); }
+  if (i < 16 * H) { int n = i / H, k = i % H; W1A[i] = __float2bfloat16((a_dim > 0 && n < a_dim) ? W1[(size_t)k * in_dim + a_off + n] : 0.f); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct Net {            // one 3-layer MLP: flat f32 params [W1|b1|W2|b2|W3|b3]
+  int in_dim, od;
+  size_t oW1, ob1, oW2, ob2, oW3, ob3, n;
+  void layout(int in, int o) { in_dim = in; od = o; oW1 = 0; ob1 = oW1 + (size_t)H * in; oW2 = ob1 + H; ob2 = oW2 + (size_t)H * H; oW3 = ob2 + H; ob3 = oW3 + (size_t)o * H; n = ob3 + o; }
+};
+
+}  // namespace
+
+struct B2QSac {
+  int device, D, A, B;
+  float gamma, tau, alpha, lr_a, lr_c;
+  Net an, cn;
+  // params: actor [an.n], critic [2][cn.n], target critic [2][cn.n]; grads, adam m/v
+  float *p_actor = nullptr, *p_critic = nullptr, *p_target = nullptr, *g_actor = nullptr, *g_critic = nullptr, *m_a = nullptr, *v_a = nullptr, *m_c = nullptr, *v_c = nullptr;
+  B2QMlpHandle mlp_actor = nullptr, mlp_critic = nullptr, mlp_target = nullptr;
+  // bf16 backward weights per net (0 actor, 1 c1, 2 c2)
+  bf16 *W2T[3] = {0, 0, 0}, *W3T[3] = {0, 0, 0}, *W1A[3] = {0, 0, 0};
+  // activation dumps: critic (2 nets) and actor
+  bf16 *xc_rm = nullptr, *xc_t = nullptr, *hc1_rm = nullptr, *hc1_t = nullptr, *hc2_rm = nullptr, *hc2_t = nullptr;
+  bf16 *xa_rm = nullptr, *xa_t = nullptr, *ha1_rm = nullptr, *ha1_t = nullptr, *ha2_rm = nullptr, *ha2_t = nullptr;
+  bf16 *dh_rm = nullptr, *dh_t = nullptr, *dy_bf = nullptr;
+  float *G = nullptr, *tq = nullptr, *q = nullptr, *qn = nullptr, *dq = nullptr, *next_a = nullptr, *next_logp = nullptr, *cur_a = nullptr, *cur_logp = nullptr, *raw_a = nullptr,
+        *da_c = nullptr, *dy = nullptr, *losses = nullptr;
+  std::vector<void*> allocs;
+  long long step = 0;
+  int64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+template <typename T> bool dalloc(B2QSac* s, T** p, size_t count) {
+  void* v = nullptr;
+  if (cudaMalloc(&v, count * sizeof(T)) != cudaSuccess) return false;
+  cudaMemset(v, 0, count * sizeof(T));
+  s->allocs.push_back(v);
+  *p = (T*)v;
+  return true;
+}
+
+int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int ldb, float* C, int ldc, int M, int N, int K, bool splitk) {
+  GemmArgs g; g.A = A; g.lda = lda; g.B = Bm; g.ldb = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  g.BN = ((N + 15) / 16) * 16;
+  int nk = (K + 63) / 64, splits = 1;
+  if (splitk) { splits = nk / 8; if (splits < 1) splits = 1; if (splits > 64) splits = 64; }
+  g.chunks_per_split = (nk + splits - 1) / splits;
+  splits = (nk + g.chunks_per_split - 1) / g.chunks_per_split;
+  g.atomic = splits > 1 ? 1 : 0;
+  if (g.atomic) cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st);
+  dim3 grid((M + 127) / 128, 1, splits);
+  b2q_gemm_kernel<<<grid, 128, G_SMEM, st>>>(g);
+  s->launches++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+void sync_net_weights(B2QSac* s, cudaStream_t st) {
+  // forward images + bf16 backward copies after a parameter change
+  const Net& a = s->an; const Net& c = s->cn;
+  b2q_mlp_set_weights(s->mlp_actor, 0, s->p_actor + a.oW1, s->p_actor + a.ob1, s->p_actor + a.oW2, s->p_actor + a.ob2, s->p_actor + a.oW3, s->p_actor + a.ob3, st);
+  k_make_bwd_weights<<<(H * H + 255) / 256, 256, 0, st>>>(s->p_actor + a.oW1, a.in_dim, 0, 0, s->p_actor + a.oW2, s->p_actor + a.oW3, a.od, s->W2T[0], s->W3T[0], s->W1A[0]);
+  for (int i = 0; i < 2; i++) {
+    float* p = s->p_critic + (size_t)i * c.n; float* t = s->p_target + (size_t)i * c.n;
+    b2q_mlp_set_weights(s->mlp_critic, i, p + c.oW1, p + c.ob1, p + c.oW2, p + c.ob2, p + c.oW3, p + c.ob3, st);
+    b2q_mlp_set_weights(s->mlp_target, i, t + c.oW1, t + c.ob1, t + c.oW2, t + c.ob2, t + c.oW3, t + c.ob3, st);
+    k_make_bwd_weights<<<(H * H + 255) / 256, 256, 0, st>>>(p + c.oW1, c.in_dim, s->D, s->A, p + c.oW2, p + c.oW3, c.od, s->W2T[1 + i], s->W3T[1 + i], s->W1A[1 + i]);
+  }
+  s->launches += 9;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2q_sac_create(int device, int obs_dim, int act_dim, int batch, float gamma, float tau, float alpha, float actor_lr, float critic_lr, B2QSacHandle* out) {
+  if (!out || obs_dim < 1 || act_dim < 1 || act_dim > 12 || obs_dim + act_dim > 64 || batch < 128 || batch % 128 != 0) return -1;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return -2;
+  cudaSetDevice(device);
+  B2QSac* s = new (std::nothrow) B2QSac();
+  if (!s) return -3;
+  s->device = device; s->D = obs_dim; s->A = act_dim; s->B = batch; s->gamma = gamma; s->tau = tau; s->alpha = alpha; s->lr_a = actor_lr; s->lr_c = critic_lr;
+  s->an.layout(obs_dim, 2 * act_dim); s->cn.layout(obs_dim + act_dim, 1);
+  const size_t Bz = batch;
+  bool ok = dalloc(s, &s->p_actor, s->an.n) && dalloc(s, &s->g_actor, s->an.n) && dalloc(s, &s->m_a, s->an.n) && dalloc(s, &s->v_a, s->an.n) &&
+            dalloc(s, &s->p_critic, 2 * s->cn.n) && dalloc(s, &s->p_target, 2 * s->cn.n) && dalloc(s, &s->g_critic, 2 * s->cn.n) && dalloc(s, &s->m_c, 2 * s->cn.n) && dalloc(s, &s->v_c, 2 * s->cn.n);
+  for (int i = 0; i < 3 && ok; i++) ok = dalloc(s, &s->W2T[i], (size_t)H * H) && dalloc(s, &s->W3T[i], (size_t)H * 64) && dalloc(s, &s->W1A[i], (size_t)16 * H);
+  ok = ok && dalloc(s, &s->xc_rm, Bz * 64) && dalloc(s, &s->xc_t, 64 * Bz) && dalloc(s, &s->hc1_rm, 2 * Bz * H) && dalloc(s, &s->hc1_t, 2 * Bz * H) && dalloc(s, &s->hc2_rm, 2 * Bz * H) &&
+       dalloc(s, &s->hc2_t, 2 * Bz * H) && dalloc(s, &s->xa_rm, Bz * 64) && dalloc(s, &s->xa_t, 64 * Bz) && dalloc(s, &s->ha1_rm, Bz * H) && dalloc(s, &s->ha1_t, Bz * H) &&
+       dalloc(s, &s->ha2_rm, Bz * H) && dalloc(s, &s->ha2_t, Bz * H) && dalloc(s, &s->dh_rm, Bz * H) && dalloc(s, &s->dh_t, Bz * H) && dalloc(s, &s->dy_bf, Bz * 64) &&
+       dalloc(s, &s->G, Bz * H) && dalloc(s, &s->tq, Bz) && dalloc(s, &s->q, 2 * Bz) && dalloc(s, &s->qn, 2 * Bz) && dalloc(s, &s->dq, 2 * Bz) && dalloc(s, &s->next_a, Bz * 12) &&
+       dalloc(s, &s->next_logp, Bz) && dalloc(s, &s->cur_a, Bz * 12) && dalloc(s, &s->cur_logp, Bz) && dalloc(s, &s->raw_a, Bz * 24) && dalloc(s, &s->da_c, Bz * 16) &&
+       dalloc(s, &s->dy, Bz * 24) && dalloc(s, &s->losses, 4);
+  ok = ok && b2q_mlp_create(device, obs_dim, 2 * act_dim, 1, &s->mlp_actor) == 0 && b2q_mlp_create(device, obs_dim + act_dim, 1, 2, &s->mlp_critic) == 0 &&
+       b2q_mlp_create(device, obs_dim + act_dim, 1, 2, &s->mlp_target) == 0;
+  ok = ok && cudaFuncSetAttribute(b2q_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM) == cudaSuccess;
+  if (!ok) { b2q_sac_destroy(s); return -3; }
+  *out = s;
+  return 0;
+}
+
+int b2q_sac_destroy(B2QSacHandle s) {
+  if (!s) return -1;
+  cudaSetDevice(s->device);
+  for (void* p : s->allocs) cudaFree(p);
+  if (s->mlp_actor) b2q_mlp_destroy(s->mlp_actor);
+  if (s->mlp_critic) b2q_mlp_destroy(s->mlp_critic);
+  if (s->mlp_target) b2q_mlp_destroy(s->mlp_target);
+  delete s;
+  return 0;
+}
+const char* b2q_sac_last_error(B2QSacHandle s) { return s ? s->err.c_str() : "null handle"; }
+int64_t b2q_sac_launch_count(B2QSacHandle s) { return s ? s->launches : 0; }
+int b2q_sac_param_count(B2QSacHandle s, int which) { return !s ? -1 : (which == 0 ? (int)s->an.n : (int)(2 * s->cn.n)); }
+
+int b2q_sac_set_params(B2QSacHandle s, const float* actor, const float* critic, const float* target, void* stream) {
+  if (!s) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (actor) cudaMemcpyAsync(s->p_actor, actor, s->an.n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (critic) cudaMemcpyAsync(s->p_critic, critic, 2 * s->cn.n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (target) cudaMemcpyAsync(s->p_target, target, 2 * s->cn.n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  else if (critic) cudaMemcpyAsync(s->p_target, critic, 2 * s->cn.n * sizeof(float), cudaMemcpyDeviceToDevice, st);   // MujocoAgent: sync_target(decay=0)
+  sync_net_weights(s, st);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+int b2q_sac_get_params(B2QSacHandle s, float* actor, float* critic, float* target, void* stream) {
+  if (!s) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (actor) cudaMemcpyAsync(actor, s->p_actor, s->an.n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (critic) cudaMemcpyAsync(critic, s->p_critic, 2 * s->cn.n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (target) cudaMemcpyAsync(target, s->p_target, 2 * s->cn.n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  return 0;
+}
+int b2q_sac_get_grads(B2QSacHandle s, float* actor, float* critic, void* stream) {
+  if (!s) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (actor) cudaMemcpyAsync(actor, s->g_actor, s->an.n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (critic) cudaMemcpyAsync(critic, s->g_critic, 2 * s->cn.n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  return 0;
+}
+
+// phase 0: critic gradients (g_critic, losses[0]); phase 1: Adam on the critic; phase 2: actor gradients (g_actor, losses[1]);
+// phase 3: Adam on the actor + Polyak.  b2q_sac_learn runs 0..3; the data-parallel learner all-reduces g_* between phases.
+int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act, const float* rew, const float* next_obs, const float* term,
+                  const float* eps_next, const float* eps_cur, uint64_t seed, void* stream) {
+  if (!s) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = s->B, A = s->A, D = s->D;
+  const Net& an = s->an; const Net& cn = s->cn;
+  const int TB = 256, NB = (B + TB - 1) / TB;
+  if (phase == 0) {
+    if (!obs || !act || !rew || !next_obs || !term) return -1;
+    cudaMemsetAsync(s->losses, 0, 4 * sizeof(float), st);
+    cudaMemsetAsync(s->g_critic, 0, 2 * cn.n * sizeof(float), st);
+    // target: next action ~ pi(next_obs), twin target Q (sac.py:85-91)
+    if (b2q_mlp_forward(s->mlp_actor, next_obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2 + 1, eps_next, s->next_a, s->next_logp, nullptr, st)) return -2;
+    if (b2q_mlp_forward(s->mlp_target, next_obs, D, s->next_a, B, B2Q_MLP_RAW, 0, nullptr, s->qn, nullptr, nullptr, st)) return -2;
+    k_target_q<<<NB, TB, 0, st>>>(rew, term, s->qn, s->qn + B, s->next_logp, s->gamma, s->alpha, s->tq, B);
+    // current Q with activation dumps
+    B2QMlpSaves sv = {s->xc_rm, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
+    if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, act, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, st)) return -2;
+    k_critic_dq<<<dim3(NB, 2), TB, 0, st>>>(s->q, s->tq, s->dq, s->losses + 0, B);
+    s->launches += 5;
+    for (int i = 0; i < 2; i++) {
+      float* g = s->g_critic + (size_t)i * cn.n; const float* p = s->p_critic + (size_t)i * cn.n;
+      const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h1t = s->hc1_t + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H, *h2t = s->hc2_t + (size_t)i * B * H;
+      k_colsum_f32<<<1, 256, 0, st>>>(s->dq + (size_t)i * B, 1, g + cn.ob3, B);                               // db3
+      k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dq + (size_t)i * B, 1, p + cn.oW3, h2, s->dh_rm, s->dh_t, g + cn.oW3, B);   // dh2, dW3
+      k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + cn.ob2, B);                                            // db2
+      if (gemm(s, st, s->dh_t, B, h1t, B, g + cn.oW2, H, H, H, B, true)) return -2;                            // dW2 = dh2^T h1
+      if (gemm(s, st, s->dh_rm, H, s->W2T[1 + i], H, s->G, H, B, H, H, false)) return -2;                      // dh1 = dh2 W2
+      k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(s->G, h1, s->dh_rm, s->dh_t, B);
+      k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + cn.ob1, B);                                            // db1
+      if (gemm(s, st, s->dh_t, B, s->xc_t, B, g + cn.oW1, cn.in_dim, H, cn.in_dim, B, true)) return -2;        // dW1 = dh1^T x
+      s->launches += 5;
+    }
+  } else if (phase == 1 || phase == 3) {
+    s->step += (phase == 1);
+    const float b1 = 0.9f, b2 = 0.999f, bc1 = 1.f - powf(b1, (float)s->step), bc2 = 1.f - powf(b2, (float)s->step);
+    if (phase == 1) {
+      int n = (int)(2 * cn.n);
+      k_adam<<<(n + 255) / 256, 256, 0, st>>>(s->p_critic, s->g_critic, s->m_c, s->v_c, n, s->lr_c, b1, b2, 1e-8f, bc1, bc2);
+    } else {
+      int n = (int)an.n, nc = (int)(2 * cn.n);
+      k_adam<<<(n + 255) / 256, 256, 0, st>>>(s->p_actor, s->g_actor, s->m_a, s->v_a, n, s->lr_a, b1, b2, 1e-8f, bc1, bc2);
+      k_polyak<<<(nc + 255) / 256, 256, 0, st>>>(s->p_target, s->p_critic, nc, s->tau);
+      s->launches++;
+    }
+    s->launches++;
+    sync_net_weights(s, st);
+  } else if (phase == 2) {
+    if (!obs) return -1;
+    cudaMemsetAsync(s->g_actor, 0, an.n * sizeof(float), st);
+    cudaMemsetAsync(s->da_c, 0, (size_t)B * 16 * sizeof(float), st);
+    // a ~ pi(obs) with dumps; Q(obs, a) with dumps (sac.py:102-106)
+    B2QMlpSaves sa = {s->xa_rm, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
+    if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2, eps_cur, s->cur_a, s->cur_logp, s->raw_a, &sa, st)) return -2;
+    B2QMlpSaves sv = {s->xc_rm, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
+    if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, st)) return -2;
+    k_minq_dq<<<NB, TB, 0, st>>>(s->q, s->dq, B);
+    s->launches += 3;
+    // d(-min q)/da through both critics (no critic weight gradients: only the actor optimiser steps here)
+    for (int i = 0; i < 2; i++) {
+      const float* p = s->p_critic + (size_t)i * cn.n;
+      const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
+      k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dq + (size_t)i * B, 1, p + cn.oW3, h2, s->dh_rm, s->dh_t, s->G /*scratch dW3*/, B);
+      if (gemm(s, st, s->dh_rm, H, s->W2T[1 + i], H, s->G, H, B, H, H, false)) return -2;
+      k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(s->G, h1, s->dh_rm, s->dh_t, B);
+      if (gemm(s, st, s->dh_rm, H, s->W1A[1 + i], H, s->G, 16, B, 16, H, false)) return -2;                    // da_i [B][16]
+      k_add_f32<<<(B * 16 + 255) / 256, 256, 0, st>>>(s->da_c, s->G, B * 16);
+      s->launches += 3;
+    }
+    if (!eps_cur) return -1;   // the explicit-noise path is required for the backward pass
+    k_actor_dy<<<NB, TB, 0, st>>>(s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->alpha, s->dy, s->losses + 1, B, A);
+    float* g = s->g_actor;
+    k_colsum_f32<<<2 * A, 256, 0, st>>>(s->dy, 2 * A, g + an.ob3, B);                                           // db3
+    k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dy, 2 * A, s->p_actor + an.oW3, s->ha2_rm, s->dh_rm, s->dh_t, g + an.oW3, B);   // dh2, dW3
+    k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + an.ob2, B);
+    if (gemm(s, st, s->dh_t, B, s->ha1_t, B, g + an.oW2, H, H, H, B, true)) return -2;
+    if (gemm(s, st, s->dh_rm, H, s->W2T[0], H, s->G, H, B, H, H, false)) return -2;
+    k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(s->G, s->ha1_rm, s->dh_rm, s->dh_t, B);
+    k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + an.ob1, B);
+    if (gemm(s, st, s->dh_t, B, s->xa_t, B, g + an.oW1, an.in_dim, H, an.in_dim, B, true)) return -2;
+    s->launches += 6;
+  } else {
+    return -1;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { s->err = cudaGetErrorString(e); return -2; }
+  return 0;
+}
+
+int b2q_sac_learn(B2QSacHandle s, const float* obs, const float* act, const float* rew, const float* next_obs, const float* term, const float* eps_next,
+                  const float* eps_cur, uint64_t seed, float* losses_out /*device [2]: critic, actor*/, void* stream) {
+  for (int ph = 0; ph < 4; ph++) {
+    int rc = b2q_sac_phase(s, ph, obs, act, rew, next_obs, term, eps_next, eps_cur, seed, stream);
+    if (rc) return rc;
+  }
+  if (losses_out) cudaMemcpyAsync(losses_out, s->losses, 2 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  return 0;
+}
+float* b2q_sac_grad_ptr(B2QSacHandle s, int which) { return !s ? nullptr : (which == 0 ? s->g_actor : s->g_critic); }
+float* b2q_sac_loss_ptr(B2QSacHandle s) { return s ? s->losses : nullptr; }
+
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+"""K5/K6: SAC.learn on the device vs a plain PyTorch fp32 restatement of ETGRL/alg/sac.py:77-118 (same minibatch, same
+N(0,1) draws for both rsample() calls).  Forward/backward GEMMs run in bf16 on tcgen05 with f32 accumulation, so the
+tolerance is the bf16 one: losses within 2 %, gradient buckets within 5 % relative L2 error and cosine >= 0.995."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_sac_step(p, tgt, obs, act, rew, nobs, term, eps_next, eps_cur, gamma, alpha):
+    """Returns critic_loss, actor_loss and gradients w.r.t. every parameter (critic grads from the critic loss, actor
+    grads from the actor loss evaluated AFTER the critic update is skipped — i.e. both at the same parameters)."""
+    import torch
+    import torch.nn.functional as F
+
+    def actor(pp, o):
+        x = F.relu(F.linear(o, pp["actor_model.l1.weight"], pp["actor_model.l1.bias"]))
+        x = F.relu(F.linear(x, pp["actor_model.l2.weight"], pp["actor_model.l2.bias"]))
+        mean = F.linear(x, pp["actor_model.mean_linear.weight"], pp["actor_model.mean_linear.bias"])
+        ls = torch.clamp(F.linear(x, pp["actor_model.std_linear.weight"], pp["actor_model.std_linear.bias"]), -20.0, 2.0)
+        return mean, ls
+
+    def critic(pp, o, a):
+        x = torch.cat([o, a], 1)
+        out = []
+        for l1, l2, l3 in (("l1", "l2", "l3"), ("l4", "l5", "l6")):
+            h = F.relu(F.linear(x, pp["critic_model.%s.weight" % l1], pp["critic_model.%s.bias" % l1]))
+            h = F.relu(F.linear(h, pp["critic_model.%s.weight" % l2], pp["critic_model.%s.bias" % l2]))
+            out.append(F.linear(h, pp["critic_model.%s.weight" % l3], pp["critic_model.%s.bias" % l3]))
+        return out
+
+    def sample(pp, o, eps):
+        mean, ls = actor(pp, o)
+        std = ls.exp()
+        x_t = mean + std * eps                                              # rsample with a fixed draw
+        a = torch.tanh(x_t)
+        logp = torch.distributions.Normal(mean, std).log_prob(x_t) - torch.log((1 - a.pow(2)) + 1e-6)
+        return a, logp.sum(1, keepdim=True)
+
+    with torch.no_grad():
+        na, nlp = sample(p, nobs, eps_next)
+        q1n, q2n = critic(tgt, nobs, na)
+        target_q = rew[:, None] + gamma * term[:, None] * (torch.min(q1n, q2n) - alpha * nlp)
+    q1, q2 = critic(p, obs, act)
+    critic_loss = F.mse_loss(q1, target_q) + F.mse_loss(q2, target_q)
+    a, lp = sample(p, obs, eps_cur)
+    q1p, q2p = critic(p, obs, a)
+    actor_loss = (alpha * lp - torch.min(q1p, q2p)).mean()
+    return critic_loss, actor_loss
+
+
+@pytest.mark.parametrize("B", [256, 1024])
+def test_sac_gradients_and_losses_vs_torch(B):
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from paddlerobotics_b200.agent import MujocoAgent, SACLearner, flatten_params
+    torch.manual_seed(B)
+    ag = MujocoAgent(49, 12, seed=5)
+    gamma, alpha = 0.99, 0.2
+    L = SACLearner(ag, B, gamma=gamma, tau=0.005, alpha=alpha, actor_lr=3e-4, critic_lr=3e-4)
+    dev = ag.device
+    obs, nobs = torch.randn(B, 49, device=dev), torch.randn(B, 49, device=dev)
+    act = torch.rand(B, 12, device=dev) * 2 - 1
+    rew, term = torch.randn(B, device=dev), (torch.rand(B, device=dev) > 0.1).float()
+    e1, e2 = torch.randn(B, 12, device=dev), torch.randn(B, 12, device=dev)
+    p = {k: v.clone().requires_grad_(True) for k, v in ag.params.items()}
+    tgt = {k: v.clone() for k, v in ag.params.items()}
+    cl, al = _torch_sac_step(p, tgt, obs, act, rew, nobs, term, e1, e2, gamma, alpha)
+    gc = torch.autograd.grad(cl, [p[k] for k in p if k.startswith("critic")], retain_graph=True)
+    ga = torch.autograd.grad(al, [p[k] for k in p if k.startswith("actor")])
+    gp = {k: g for k, g in zip([k for k in p if k.startswith("critic")], gc)}
+    gp.update({k: g for k, g in zip([k for k in p if k.startswith("actor")], ga)})
+    ref_a, ref_c = flatten_params(gp)
+    # device: gradient phases only (0 and 2), no optimiser step in between, so both are taken at the same parameters
+    lib, h, st = L.lib, L.h, L._stream()
+    args = (obs.data_ptr(), act.data_ptr(), rew.data_ptr(), nobs.data_ptr(), term.data_ptr(), e1.data_ptr(), e2.data_ptr(), 1)
+    assert lib.b2q_sac_phase(h, 0, *args, st) == 0
+    assert lib.b2q_sac_phase(h, 2, *args, st) == 0
+    ga_d, gc_d = L.grads()
+    losses = torch.as_tensor(__import__("paddlerobotics_b200.agent", fromlist=["_CudaBuf"])._CudaBuf(lib.b2q_sac_loss_ptr(h), 2), device=dev).clone()
+    torch.cuda.synchronize()
+    assert abs(float(losses[0]) - float(cl)) < 0.02 * abs(float(cl)) + 1e-3, (float(losses[0]), float(cl))
+    assert abs(float(losses[1]) - float(al)) < 0.02 * abs(float(al)) + 2e-2, (float(losses[1]), float(al))
+    for name, d, r in (("critic", gc_d, ref_c), ("actor", ga_d, ref_a)):
+        rel = float((d - r).norm() / r.norm())
+        cos = float(torch.dot(d, r) / (d.norm() * r.norm()))
+        print(name, "grad rel L2 err %.4f cos %.5f" % (rel, cos))
+        assert rel < 0.05 and cos > 0.995, (name, rel, cos)
+
+
+def test_sac_learn_three_steps_tracks_torch_adam():
+    """Full learn() (critic Adam -> actor grads at the UPDATED critic -> actor Adam -> Polyak), 3 steps, vs torch.optim.Adam."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from paddlerobotics_b200.agent import MujocoAgent, SACLearner, flatten_params
+    B, gamma, alpha, tau = 256, 0.99, 0.2, 0.005
+    torch.manual_seed(0)
+    ag = MujocoAgent(49, 12, seed=9)
+    L = SACLearner(ag, B, gamma=gamma, tau=tau, alpha=alpha, actor_lr=3e-4, critic_lr=3e-4)
+    dev = ag.device
+    p = {k: v.clone().requires_grad_(True) for k, v in ag.params.items()}
+    tgt = {k: v.clone() for k, v in ag.params.items()}
+    opt_a = torch.optim.Adam([p[k] for k in p if k.startswith("actor")], lr=3e-4)
+    opt_c = torch.optim.Adam([p[k] for k in p if k.startswith("critic")], lr=3e-4)
+    a0, c0 = flatten_params(ag.params)
+    for step in range(3):
+        obs, nobs = torch.randn(B, 49, device=dev), torch.randn(B, 49, device=dev)
+        act = torch.rand(B, 12, device=dev) * 2 - 1
+        rew, term = torch.randn(B, device=dev), (torch.rand(B, device=dev) > 0.1).float()
+        e1, e2 = torch.randn(B, 12, device=dev), torch.randn(B, 12, device=dev)
+        cl, _ = _torch_sac_step(p, tgt, obs, act, rew, nobs, term, e1, e2, gamma, alpha)
+        opt_c.zero_grad(); cl.backward(); opt_c.step()
+        _, al = _torch_sac_step(p, tgt, obs, act, rew, nobs, term, e1, e2, gamma, alpha)
+        opt_a.zero_grad(); al.backward(); opt_a.step()
+        with torch.no_grad():
+            for k in tgt:
+                tgt[k].copy_(tau * p[k] + (1 - tau) * tgt[k])
+        losses = L.learn(obs, act, rew, nobs, term, eps_next=e1, eps_cur=e2)
+        assert abs(float(losses[0]) - float(cl)) < 0.03 * abs(float(cl)) + 1e-3
+        assert abs(float(losses[1]) - float(al)) < 0.03 * abs(float(al)) + 3e-2
+    a1, c1 = flatten_params(ag.params)            # pulled back from the learner
+    ra, rc = flatten_params({k: v.detach() for k, v in p.items()})
+    # the 3-step parameter displacement agrees in direction and size (Adam's sign-like update amplifies tiny gradient noise
+    # on near-zero gradients, so compare displacements, not parameters)
+    for name, d, r, z in (("actor", a1, ra, a0), ("critic", c1, rc, c0)):
+        dd, rr = d - z, r - z
+        cos = float(torch.dot(dd, rr) / (dd.norm() * rr.norm()))
+        print(name, "3-step displacement cos %.4f, |d| %.4g vs %.4g" % (cos, float(dd.norm()), float(rr.norm())))
+        assert cos > 0.9 and 0.8 < float(dd.norm() / rr.norm()) < 1.25
+    # agent.learn surface (numpy in, floats out)
+    c_l, a_l = ag.learn(obs.cpu().numpy(), act.cpu().numpy(), rew.cpu().numpy(), nobs.cpu().numpy(), term.cpu().numpy())
+    assert isinstance(c_l, float) and isinstance(a_l, float) and np.isfinite(c_l) and np.isfinite(a_l)
