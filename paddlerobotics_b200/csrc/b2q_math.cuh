@@ -76,6 +76,21 @@ B2Q_HD void m_sincos(float a, float& s, float& c) {
 }
 B2Q_HD void m_sincos(double a, double& s, double& c) { s = sin(a); c = cos(a); }
 
+// two-wide value for the packed FP32 FMA of sm_100 (FFMA2: two f32 FMAs per instruction on a 64-bit register pair)
+template <typename T>
+struct P2 {
+  T x, y;
+};
+B2Q_HD P2<float> p2fma(P2<float> a, P2<float> b, P2<float> c) {
+#if defined(__CUDA_ARCH__)
+  float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+  P2<float> o; o.x = r.x; o.y = r.y; return o;
+#else
+  P2<float> o; o.x = fmaf(a.x, b.x, c.x); o.y = fmaf(a.y, b.y, c.y); return o;
+#endif
+}
+B2Q_HD P2<double> p2fma(P2<double> a, P2<double> b, P2<double> c) { P2<double> o; o.x = fma(a.x, b.x, c.x); o.y = fma(a.y, b.y, c.y); return o; }
+
 template <typename T>
 struct V3 {
   T x, y, z;

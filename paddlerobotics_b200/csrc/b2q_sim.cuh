@@ -380,9 +380,11 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
   // g_i = lam_i + (target_i - u_i) / W_ii is the UNCLAMPED Gauss-Seidel candidate of row i.  A row update
   // lam_j <- clamp(g_j) changes g_i (i != j) by -(W_ij / W_ii) * dlam_j and leaves g_j itself unchanged, so the sweep
   // carries g instead of the contact velocities.  Inactive feet: zero scale (g frozen), g_n = -BIG => lam stays 0.
-  T g[12];
+  // The sweep is FMA-pipe bound on one warp per scheduler, so g and the scaled columns of W are kept as PAIRS of rows and
+  // updated with the packed FP32 FMA of sm_100 (FFMA2): 6 instructions per row update instead of 11.
+  P2<T> g2[6], Wc[12][6];   // Wc[r][p] = (W'[2p][r], W'[2p+1][r]), W'_ij = W_ij / W_ii with a zero diagonal
   {
-    T invd[12];
+    T invd[12], g[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) invd[i] = actf[i / 3] > T(0) ? m_rcp(Wm[i][i]) : T(0);
 #pragma unroll
@@ -393,8 +395,15 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
       T tg = (i % 3 == 0) ? targn[i / 3] : T(0);
       g[i] = lam[i] + (tg - ui) * invd[i];
       if (i % 3 == 0 && !(actf[i / 3] > T(0))) g[i] = T(-1e30);
+    }
 #pragma unroll
-      for (int j = 0; j < 12; j++) Wm[i][j] = (i == j) ? T(0) : Wm[i][j] * invd[i];
+    for (int p = 0; p < 6; p++) {
+      g2[p].x = g[2 * p]; g2[p].y = g[2 * p + 1];
+#pragma unroll
+      for (int r = 0; r < 12; r++) {
+        Wc[r][p].x = (2 * p == r) ? T(0) : Wm[2 * p][r] * invd[2 * p];
+        Wc[r][p].y = (2 * p + 1 == r) ? T(0) : Wm[2 * p + 1][r] * invd[2 * p + 1];
+      }
     }
   }
   // --- projected Gauss-Seidel, Bullet row order: normals of feet 0..3, then (t1,t2) of feet 0..3
@@ -402,21 +411,25 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
 #pragma unroll
     for (int f = 0; f < 4; f++) {
       const int r = 3 * f;
-      T ln = m_max(g[r], T(0));
-      T dl = ln - lam[r]; lam[r] = ln;
+      T gr = (r & 1) ? g2[r >> 1].y : g2[r >> 1].x;
+      T ln = m_max(gr, T(0));
+      T dl = lam[r] - ln; lam[r] = ln;          // dl = -(delta lambda)
+      P2<T> d2; d2.x = dl; d2.y = dl;
 #pragma unroll
-      for (int i = 0; i < 12; i++) if (i != r) g[i] -= Wm[i][r] * dl;
+      for (int p = 0; p < 6; p++) g2[p] = p2fma(Wc[r][p], d2, g2[p]);
     }
 #pragma unroll
     for (int f = 0; f < 4; f++) {
 #pragma unroll
       for (int td = 1; td < 3; td++) {
         const int r = 3 * f + td;
+        T gr = (r & 1) ? g2[r >> 1].y : g2[r >> 1].x;
         T lim = pr.mu * lam[3 * f];
-        T ln = m_min(m_max(g[r], -lim), lim);
-        T dl = ln - lam[r]; lam[r] = ln;
+        T ln = m_min(m_max(gr, -lim), lim);
+        T dl = lam[r] - ln; lam[r] = ln;
+        P2<T> d2; d2.x = dl; d2.y = dl;
 #pragma unroll
-        for (int i = 0; i < 12; i++) if (i != r) g[i] -= Wm[i][r] * dl;
+        for (int p = 0; p < 6; p++) g2[p] = p2fma(Wc[r][p], d2, g2[p]);
       }
     }
   }
