@@ -53,6 +53,8 @@ def main():
         o, no, ac, r, t, e1, e2 = d(B, 49), d(B, 49), torch.rand(B, 12, device="cuda") * 2 - 1, d(B), torch.ones(B, device="cuda"), d(B, 12), d(B, 12)
         ms = timed(lambda: L.learn(o, ac, r, no, t, eps_next=e1, eps_cur=e2, pull=False), 50, 5)
         out.append({"what": "SAC learn (critic+actor fwd/bwd, Adam, Polyak) batch %d" % B, "ms": ms, "samples_per_s": B / ms * 1e3})
+        ms = timed(lambda: L.learn(o, ac, r, no, t, eps_next=e1, eps_cur=e2, pull=False, graph=True), 50, 5)
+        out.append({"what": "SAC learn from a CUDA graph, batch %d" % B, "ms": ms, "samples_per_s": B / ms * 1e3})
         L.close()
     # config 3 (one GPU's share at G=8): 32 individuals x 16 rollouts x 400 steps
     ev = PopulationEvaluator(32, 16, max_steps=400)

@@ -16,6 +16,11 @@ extern "C" {
 int b2q_es_accumulate(const void* reward, const uint8_t* done, uint8_t* alive, void* ret, int32_t* len, int n, int elem_size, void* stream);
 /* fitness[i] = mean over the individual's rollouts of ret; mean_len (may be NULL) likewise for episode lengths. */
 int b2q_es_fitness(const void* ret, const int32_t* len, void* fitness, void* mean_len, int pop, int rollouts, int elem_size, void* stream);
+/* Batched ETG fit: for each individual i, points = prior_points + solutions[i].reshape(6,2) and
+ * (w,b) = Opt_with_points(points=points, w0=w0, b0=b0) -- train.py:81-110,405-407 -- in float64 on the device.
+ * obs6x20 = ETG_layer.update(t) at ts = [0.5T+0.1, 0, 0.05, 0.1, 0.15, 0.2] (row-major 6x20). w_out [pop,3,20], b_out [pop,3]. */
+int b2q_etg_fit(const double* obs6x20, const double* prior_points, const double* solutions, const double* w0, const double* b0, double lamb,
+                double precision, double* w_out, double* b_out, int pop, void* stream);
 #ifdef __cplusplus
 }
 #endif

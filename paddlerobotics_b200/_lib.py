@@ -53,6 +53,10 @@ SYMBOLS = {
     # ES population fitness — include/b2q_es.h
     "b2q_es_accumulate": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "b2q_es_fitness": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b2q_etg_fit": (_i, [_vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp, _vp, _i, _vp]),
+    # device replay memory — include/b2q_rpm.h
+    "b2q_rpm_append": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b2q_rpm_sample": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.c_uint64, _vp]),
 }
 
 

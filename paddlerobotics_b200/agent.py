@@ -200,6 +200,7 @@ class SACLearner:
         self.na, self.nc = self.lib.b2q_sac_param_count(self.h, 0), self.lib.b2q_sac_param_count(self.h, 1)
         self.losses = torch.zeros(2, device=agent.device)
         self.steps = 0
+        self._graph = None
         self.push()
 
     def _stream(self):
@@ -227,7 +228,7 @@ class SACLearner:
         # wrap the device bucket without copying (for in-place NCCL all-reduce)
         return torch.as_tensor(_CudaBuf(self.lib.b2q_sac_grad_ptr(self.h, which), n), device=self.agent.device)
 
-    def learn(self, obs, act, rew, next_obs, term, eps_next=None, eps_cur=None, pull=True):
+    def learn(self, obs, act, rew, next_obs, term, eps_next=None, eps_cur=None, pull=True, graph=False):
         dev = self.agent.device
         t = lambda x: torch.as_tensor(x, dtype=torch.float32, device=dev).contiguous()
         obs, act, rew, next_obs, term = t(obs), t(act), t(rew).reshape(-1), t(next_obs), t(term).reshape(-1)
@@ -239,7 +240,24 @@ class SACLearner:
         eps_next, eps_cur = t(eps_next), t(eps_cur)
         self.steps += 1
         args = (obs.data_ptr(), act.data_ptr(), rew.data_ptr(), next_obs.data_ptr(), term.data_ptr(), eps_next.data_ptr(), eps_cur.data_ptr(), C.c_uint64(self.steps))
-        if self.world == 1:
+        if self.world == 1 and graph:
+            # the ~70 launches of one learner step replayed from a CUDA graph (static input buffers)
+            ins = (obs, act, rew, next_obs, term, eps_next, eps_cur)
+            if self._graph is None:
+                self._static = [torch.empty_like(x) for x in ins]
+                sargs = tuple(x.data_ptr() for x in self._static) + (C.c_uint64(0),)
+                for x, sx in zip(ins, self._static):
+                    sx.copy_(x)
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph, stream=side):
+                    rc = self.lib.b2q_sac_learn(self.h, *sargs, self.losses.data_ptr(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+                    assert rc == 0, rc
+            for x, sx in zip(ins, self._static):
+                sx.copy_(x)
+            self._graph.replay()
+        elif self.world == 1:
             rc = self.lib.b2q_sac_learn(self.h, *args, self.losses.data_ptr(), self._stream())
             if rc != 0:
                 raise RuntimeError("b2q_sac_learn: %d %s" % (rc, self.lib.b2q_sac_last_error(self.h).decode()))

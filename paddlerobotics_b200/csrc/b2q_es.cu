@@ -55,3 +55,54 @@ int b2q_es_fitness(const void* ret, const int32_t* len, void* fitness, void* mea
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// §8f-1: batched ETG weight fit on the device.  One thread per ES individual restates Opt_with_points + LS_sol
+// (train.py:59-110): two gradient-descent least-squares solves (<= 1000 iterations, step 0.05, Tikhonov pull towards w0)
+// of a 6x20 system, in float64 like the NumPy reference.  obs6x20 = ETG features at the six control-point times.
+namespace {
+__device__ void ls_sol_dev(const double* A /*6x20*/, const double* bvec /*6*/, const double* w0 /*20*/, double lamb, double precision, double alpha, double* x /*20 out*/) {
+  double AtA[20][20], Atb[20];
+  for (int i = 0; i < 20; i++) {
+    double s = 0; for (int r = 0; r < 6; r++) s += A[r * 20 + i] * bvec[r];
+    Atb[i] = s;
+    for (int j = 0; j < 20; j++) { double t = 0; for (int r = 0; r < 6; r++) t += A[r * 20 + i] * A[r * 20 + j]; AtA[i][j] = t; }
+  }
+  for (int i = 0; i < 20; i++) x[i] = w0[i];
+  auto sqerr = [&]() { double e = 0; for (int r = 0; r < 6; r++) { double s = -bvec[r]; for (int i = 0; i < 20; i++) s += A[r * 20 + i] * x[i]; e += s * s; } return e; };
+  double err = sqerr();
+  int it = 0;
+  while (err > precision && it < 1000) {
+    double dx[20];
+    for (int i = 0; i < 20; i++) { double s = -Atb[i]; for (int j = 0; j < 20; j++) s += AtA[i][j] * x[j]; dx[i] = s + lamb * (x[i] - w0[i]); }
+    for (int i = 0; i < 20; i++) x[i] -= alpha * dx[i];
+    err = sqerr();
+    it++;
+  }
+}
+__global__ void etg_fit_kernel(const double* __restrict__ obs6x20, const double* __restrict__ prior_points /*6x2*/, const double* __restrict__ solutions /*[pop][12]*/,
+                               const double* __restrict__ w0 /*3x20*/, const double* __restrict__ b0 /*3*/, double lamb, double precision,
+                               double* __restrict__ w_out /*[pop][3][20]*/, double* __restrict__ b_out /*[pop][3]*/, int pop) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pop) return;
+  double A[120];
+  for (int k = 0; k < 120; k++) A[k] = obs6x20[k];
+  double bx = b0[0], bz = b0[2], px[6], pz[6];
+  for (int r = 0; r < 6; r++) {   // points = prior_points + solution.reshape(-1,2); points_t = points - b   (train.py:405-406,97)
+    px[r] = prior_points[2 * r] + solutions[(size_t)i * 12 + 2 * r] - bx;
+    pz[r] = prior_points[2 * r + 1] + solutions[(size_t)i * 12 + 2 * r + 1] - bz;
+  }
+  double x1[20], x2[20];
+  ls_sol_dev(A, px, w0, lamb, precision, 0.05, x1);
+  ls_sol_dev(A, pz, w0 + 40, lamb, precision, 0.05, x2);
+  for (int h = 0; h < 20; h++) { w_out[(size_t)i * 60 + h] = x1[h]; w_out[(size_t)i * 60 + 20 + h] = 0.0; w_out[(size_t)i * 60 + 40 + h] = x2[h]; }
+  b_out[(size_t)i * 3] = bx; b_out[(size_t)i * 3 + 1] = 0.0; b_out[(size_t)i * 3 + 2] = bz;
+}
+}  // namespace
+
+extern "C" int b2q_etg_fit(const double* obs6x20, const double* prior_points, const double* solutions, const double* w0, const double* b0, double lamb,
+                           double precision, double* w_out, double* b_out, int pop, void* stream) {
+  if (!obs6x20 || !prior_points || !solutions || !w0 || !b0 || !w_out || !b_out || pop < 1) return -1;
+  etg_fit_kernel<<<(pop + 31) / 32, 32, 0, (cudaStream_t)stream>>>(obs6x20, prior_points, solutions, w0, b0, lamb, precision, w_out, b_out, pop);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}

@@ -216,14 +216,13 @@ __global__ void k_minq_dq(const float* q /*[2][B]*/, float* dq /*[2][B]*/, int B
   if (b < B) { bool first = q[b] <= q[B + b]; dq[b] = first ? -1.f / (float)B : 0.f; dq[B + b] = first ? 0.f : -1.f / (float)B; }   // torch.min picks the first on ties
 }
 __global__ void k_add_f32(float* dst, const float* src, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) dst[i] += src[i]; }
-__global__ void k_cast_pad(const float* src, int rows, int cols, bf16* dst, int ld) {   // dst [rows][ld] zero padded
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < rows * ld) { int r = i / ld, c = i % ld; dst[i] = __float2bfloat16(c < cols ? src[(size_t)r * cols + c] : 0.f); }
-}
 // Adam (torch.optim.Adam defaults: betas 0.9/0.999, eps 1e-8, no weight decay), sac.py:55-58
-__global__ void k_adam(float* p, const float* g, float* m, float* v, int n, float lr, float b1, float b2, float eps, float bc1, float bc2) {
+__global__ void k_step_inc(int* step) { *step += 1; }
+// the step counter lives on the device so that the whole learn() can be replayed from a CUDA graph
+__global__ void k_adam(float* p, const float* g, float* m, float* v, int n, float lr, float b1, float b2, float eps, const int* step) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
+    const float t = (float)(*step), bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
     float gi = g[i], mi = b1 * m[i] + (1.f - b1) * gi, vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi; v[i] = vi;
     p[i] -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
@@ -267,7 +266,7 @@ struct B2QSac {
   float *G = nullptr, *tq = nullptr, *q = nullptr, *qn = nullptr, *dq = nullptr, *next_a = nullptr, *next_logp = nullptr, *cur_a = nullptr, *cur_logp = nullptr, *raw_a = nullptr,
         *da_c = nullptr, *dy = nullptr, *losses = nullptr;
   std::vector<void*> allocs;
-  long long step = 0;
+  int* d_step = nullptr;
   int64_t launches = 0;
   std::string err;
 };
@@ -335,7 +334,7 @@ int b2q_sac_create(int device, int obs_dim, int act_dim, int batch, float gamma,
        dalloc(s, &s->ha2_rm, Bz * H) && dalloc(s, &s->ha2_t, Bz * H) && dalloc(s, &s->dh_rm, Bz * H) && dalloc(s, &s->dh_t, Bz * H) && dalloc(s, &s->dy_bf, Bz * 64) &&
        dalloc(s, &s->G, Bz * H) && dalloc(s, &s->tq, Bz) && dalloc(s, &s->q, 2 * Bz) && dalloc(s, &s->qn, 2 * Bz) && dalloc(s, &s->dq, 2 * Bz) && dalloc(s, &s->next_a, Bz * 12) &&
        dalloc(s, &s->next_logp, Bz) && dalloc(s, &s->cur_a, Bz * 12) && dalloc(s, &s->cur_logp, Bz) && dalloc(s, &s->raw_a, Bz * 24) && dalloc(s, &s->da_c, Bz * 16) &&
-       dalloc(s, &s->dy, Bz * 24) && dalloc(s, &s->losses, 4);
+       dalloc(s, &s->dy, Bz * 24) && dalloc(s, &s->losses, 4) && dalloc(s, &s->d_step, 1);
   ok = ok && b2q_mlp_create(device, obs_dim, 2 * act_dim, 1, &s->mlp_actor) == 0 && b2q_mlp_create(device, obs_dim + act_dim, 1, 2, &s->mlp_critic) == 0 &&
        b2q_mlp_create(device, obs_dim + act_dim, 1, 2, &s->mlp_target) == 0;
   ok = ok && cudaFuncSetAttribute(b2q_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM) == cudaSuccess;
@@ -408,7 +407,7 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     s->launches += 5;
     for (int i = 0; i < 2; i++) {
       float* g = s->g_critic + (size_t)i * cn.n; const float* p = s->p_critic + (size_t)i * cn.n;
-      const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h1t = s->hc1_t + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H, *h2t = s->hc2_t + (size_t)i * B * H;
+      const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h1t = s->hc1_t + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
       k_colsum_f32<<<1, 256, 0, st>>>(s->dq + (size_t)i * B, 1, g + cn.ob3, B);                               // db3
       k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dq + (size_t)i * B, 1, p + cn.oW3, h2, s->dh_rm, s->dh_t, g + cn.oW3, B);   // dh2, dW3
       k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + cn.ob2, B);                                            // db2
@@ -420,14 +419,14 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
       s->launches += 5;
     }
   } else if (phase == 1 || phase == 3) {
-    s->step += (phase == 1);
-    const float b1 = 0.9f, b2 = 0.999f, bc1 = 1.f - powf(b1, (float)s->step), bc2 = 1.f - powf(b2, (float)s->step);
+    const float b1 = 0.9f, b2 = 0.999f;
     if (phase == 1) {
       int n = (int)(2 * cn.n);
-      k_adam<<<(n + 255) / 256, 256, 0, st>>>(s->p_critic, s->g_critic, s->m_c, s->v_c, n, s->lr_c, b1, b2, 1e-8f, bc1, bc2);
+      k_step_inc<<<1, 1, 0, st>>>(s->d_step);
+      k_adam<<<(n + 255) / 256, 256, 0, st>>>(s->p_critic, s->g_critic, s->m_c, s->v_c, n, s->lr_c, b1, b2, 1e-8f, s->d_step);
     } else {
       int n = (int)an.n, nc = (int)(2 * cn.n);
-      k_adam<<<(n + 255) / 256, 256, 0, st>>>(s->p_actor, s->g_actor, s->m_a, s->v_a, n, s->lr_a, b1, b2, 1e-8f, bc1, bc2);
+      k_adam<<<(n + 255) / 256, 256, 0, st>>>(s->p_actor, s->g_actor, s->m_a, s->v_a, n, s->lr_a, b1, b2, 1e-8f, s->d_step);
       k_polyak<<<(nc + 255) / 256, 256, 0, st>>>(s->p_target, s->p_critic, nc, s->tau);
       s->launches++;
     }

@@ -114,6 +114,27 @@ def solutions_to_etg(solutions, prior_points, w0, b0, ETG_T=0.5, etg_layer=None)
     return np.array(ws), np.array(bs)
 
 
+def solutions_to_etg_device(solutions, prior_points, w0, b0, ETG_T=0.5, device=0, lamb=0.5, precision=1e-4):
+    """Same as solutions_to_etg but batched on the GPU (b2q_etg_fit): one thread per individual, float64."""
+    import torch
+    from . import _lib
+    lib = _lib.load()
+    layer = ETG_layer(ETG_T, 0.026, 20, 0.04, np.array([-np.pi / 2, 0]), 0.2, ETG_T)
+    ts = [0.5 * ETG_T + 0.1, 0, 0.05, 0.1, 0.15, 0.2]
+    obs = np.array([layer.update(t) for t in ts]).reshape(6, 20)
+    dev = torch.device("cuda", int(device))
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=dev)
+    sol = t(np.asarray(solutions).reshape(-1, 12))
+    pop = sol.shape[0]
+    o, pp, w0t, b0t = t(obs), t(np.asarray(prior_points).reshape(6, 2)), t(np.asarray(w0).reshape(3, 20)), t(np.asarray(b0).reshape(3))
+    w = torch.empty(pop, 3, 20, dtype=torch.float64, device=dev)
+    b = torch.empty(pop, 3, dtype=torch.float64, device=dev)
+    rc = lib.b2q_etg_fit(o.data_ptr(), pp.data_ptr(), sol.data_ptr(), w0t.data_ptr(), b0t.data_ptr(), float(lamb), float(precision), w.data_ptr(), b.data_ptr(), pop,
+                         C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    assert rc == 0, rc
+    return w, b
+
+
 def all_gather_concat(local, world, rank, group=None):
     """One all-gather of equally sized shards; returns the concatenation on every rank (torch.distributed)."""
     import torch

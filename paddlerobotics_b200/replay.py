@@ -1,0 +1,49 @@
+"""Device-resident replay memory with the call surface of parl.utils.ReplayMemory as the reference uses it
+(`rpm.append(obs, action, reward, next_obs, terminal)`, `rpm.sample_batch(B)`, `rpm.size()`: ETGRL/train.py:159,164,142),
+batched over envs: append() takes [N, ...] device tensors (one transition per env per control step)."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+class ReplayMemory:
+    def __init__(self, max_size, obs_dim, act_dim, device=0):
+        self.lib = _lib.load()
+        self.max_size, self.obs_dim, self.act_dim = int(max_size), obs_dim, act_dim
+        self.device = torch.device("cuda", int(device))
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)
+        self.obs, self.next_obs = z(self.max_size, obs_dim), z(self.max_size, obs_dim)
+        self.action, self.reward, self.terminal = z(self.max_size, act_dim), z(self.max_size), z(self.max_size)
+        self._curr_size, self._curr_pos, self._samples = 0, 0, 0
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def size(self):
+        return self._curr_size
+
+    def __len__(self):
+        return self._curr_size
+
+    def append(self, obs, act, reward, next_obs, terminal):
+        t = lambda x: torch.as_tensor(x, dtype=torch.float32, device=self.device).contiguous()
+        obs, act, reward, next_obs, terminal = t(obs).reshape(-1, self.obs_dim), t(act).reshape(-1, self.act_dim), t(reward).reshape(-1), t(next_obs).reshape(-1, self.obs_dim), t(terminal).reshape(-1)
+        n = obs.shape[0]
+        rc = self.lib.b2q_rpm_append(self.obs.data_ptr(), self.action.data_ptr(), self.reward.data_ptr(), self.next_obs.data_ptr(), self.terminal.data_ptr(),
+                                     obs.data_ptr(), act.data_ptr(), reward.data_ptr(), next_obs.data_ptr(), terminal.data_ptr(), None,
+                                     n, self.obs_dim, self.act_dim, self._curr_pos, self.max_size, self._stream())
+        assert rc == 0, rc
+        self._curr_pos = (self._curr_pos + n) % self.max_size
+        self._curr_size = min(self._curr_size + n, self.max_size)
+
+    def sample_batch(self, batch_size, seed=None):
+        self._samples += 1
+        z = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
+        obs, nobs, act, rew, term = z(batch_size, self.obs_dim), z(batch_size, self.obs_dim), z(batch_size, self.act_dim), z(batch_size), z(batch_size)
+        rc = self.lib.b2q_rpm_sample(self.obs.data_ptr(), self.action.data_ptr(), self.reward.data_ptr(), self.next_obs.data_ptr(), self.terminal.data_ptr(),
+                                     obs.data_ptr(), act.data_ptr(), rew.data_ptr(), nobs.data_ptr(), term.data_ptr(), batch_size, self.obs_dim, self.act_dim,
+                                     self._curr_size, C.c_uint64(self._samples if seed is None else seed), self._stream())
+        assert rc == 0, rc
+        return obs, act, rew, nobs, term

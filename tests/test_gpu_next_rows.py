@@ -1,0 +1,74 @@
+"""SURVEY §8f "next" rows: on-device ETG fit (f-1) and device replay memory feeding the SAC kernels (f-2)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_etg_fit_on_device_matches_reference_host_fit(golden):
+    """b2q_etg_fit == Opt_with_points(points=prior+solution, w0, b0) of train.py:81-110,405-407 (float64)."""
+    from paddlerobotics_b200.es import SimpleGA, solutions_to_etg, solutions_to_etg_device
+    np.random.seed(0)
+    ga = SimpleGA(12, sigma_init=0.02, sigma_decay=0.99, sigma_limit=0.005, elite_ratio=0.1, weight_decay=0.005, popsize=64, param=np.zeros(12))
+    sol = ga.ask()
+    w_h, b_h = solutions_to_etg(sol, golden["opt_points"], golden["opt_w0"], golden["opt_b0"])
+    w_d, b_d = solutions_to_etg_device(sol, golden["opt_points"], golden["opt_w0"], golden["opt_b0"])
+    assert np.abs(w_d.cpu().numpy() - w_h).max() < 1e-9 and np.abs(b_d.cpu().numpy() - b_h).max() < 1e-12
+    # and against the vector made by the reference's own function
+    w1, b1 = solutions_to_etg_device(golden["opt_sol"][None, :], golden["opt_points"], golden["opt_w0"], golden["opt_b0"])
+    assert np.abs(w1[0].cpu().numpy() - golden["opt_w1"]).max() < 1e-9 and np.abs(b1[0].cpu().numpy() - golden["opt_b1"]).max() < 1e-12
+
+
+def test_device_replay_memory_append_wrap_and_sample():
+    import torch
+    from paddlerobotics_b200.replay import ReplayMemory
+    rpm = ReplayMemory(1000, 49, 12)
+    ref = {k: [] for k in "o a r n t".split()}
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    for step in range(5):                       # 5 x 256 = 1280 > capacity: wraps
+        o, n = torch.randn(256, 49, device="cuda", generator=g), torch.randn(256, 49, device="cuda", generator=g)
+        a, r, t = torch.rand(256, 12, device="cuda", generator=g), torch.randn(256, device="cuda", generator=g), (torch.rand(256, device="cuda", generator=g) > 0.5).float()
+        rpm.append(o, a, r, n, t)
+        for k, v in zip("o a r n t".split(), (o, a, r, n, t)):
+            ref[k].append(v)
+    assert rpm.size() == 1000
+    allo = torch.cat(ref["o"]); alln = torch.cat(ref["n"]); allr = torch.cat(ref["r"])
+    # ring content: slot s holds transition index i with i % 1000 == s, the latest such i
+    for s in (0, 279, 280, 999):
+        i = s + 1000 if s + 1000 < 1280 else s
+        assert torch.equal(rpm.obs[s], allo[i]) and torch.equal(rpm.next_obs[s], alln[i]) and rpm.reward[s] == allr[i]
+    o, a, r, n, t = rpm.sample_batch(4096, seed=3)
+    # every sampled row is a stored row, consistent across the five arrays
+    idx = (o[:, None, 0] == rpm.obs[None, :, 0]).float().argmax(1)
+    assert torch.equal(o, rpm.obs[idx]) and torch.equal(n, rpm.next_obs[idx]) and torch.equal(a, rpm.action[idx]) and torch.equal(r, rpm.reward[idx]) and torch.equal(t, rpm.terminal[idx])
+    # roughly uniform over the ring
+    hist = torch.bincount(idx, minlength=1000).float()
+    assert hist.max() < 20 and (hist > 0).float().mean() > 0.95
+    o2 = rpm.sample_batch(4096, seed=3)[0]
+    assert torch.equal(o, o2)
+
+
+def test_on_device_training_loop_smoke(etg_default):
+    """rollout (sampled policy) -> device replay -> SAC learn from a CUDA graph, nothing crosses PCIe inside the loop
+    (the reference's run_train_episode, train.py:129-178, batched)."""
+    import torch
+    from paddlerobotics_b200.agent import MujocoAgent, SACLearner
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    from paddlerobotics_b200.replay import ReplayMemory
+    w, b = etg_default
+    n, B = 512, 256
+    env = VecQuadrupedalEnv(n, auto_reset=True)
+    ag = MujocoAgent(49, 12, seed=0)
+    L = SACLearner(ag, B)
+    rpm = ReplayMemory(20000, 49, 12)
+    obs = env.reset(w, b).clone()
+    losses = []
+    for k in range(30):
+        act, _ = ag.sample_batch(obs)
+        nobs, rew, done, info = env.step(act * 0.3)
+        rpm.append(obs, act, rew, nobs, 1.0 - done.float())
+        obs = nobs.clone()
+        if rpm.size() >= 2048:
+            losses.append(L.learn(*rpm.sample_batch(B), graph=True).clone())
+    assert len(losses) > 20 and all(torch.isfinite(l).all() for l in losses)
+    env.close()

@@ -130,3 +130,25 @@ def test_sac_learn_three_steps_tracks_torch_adam():
     # agent.learn surface (numpy in, floats out)
     c_l, a_l = ag.learn(obs.cpu().numpy(), act.cpu().numpy(), rew.cpu().numpy(), nobs.cpu().numpy(), term.cpu().numpy())
     assert isinstance(c_l, float) and isinstance(a_l, float) and np.isfinite(c_l) and np.isfinite(a_l)
+
+
+def test_sac_learn_cuda_graph_replay_equals_eager():
+    """learn() replayed from a CUDA graph (device-side Adam step counter) == the eager sequence of launches."""
+    import torch
+    from paddlerobotics_b200.agent import MujocoAgent, SACLearner, flatten_params
+    B = 256
+    torch.manual_seed(1)
+    res = []
+    for use_graph in (False, True):
+        ag = MujocoAgent(49, 12, seed=11)
+        L = SACLearner(ag, B)
+        g = torch.Generator(device="cuda"); g.manual_seed(5)
+        for step in range(4):
+            r = lambda *s: torch.randn(*s, device="cuda", generator=g)
+            obs, nobs, act, rew, term, e1, e2 = r(B, 49), r(B, 49), torch.rand(B, 12, device="cuda", generator=g) * 2 - 1, r(B), torch.ones(B, device="cuda"), r(B, 12), r(B, 12)
+            L.learn(obs, act, rew, nobs, term, eps_next=e1, eps_cur=e2, graph=use_graph)
+        res.append(flatten_params(ag.params))
+        L.close()
+    for x, y in zip(res[0], res[1]):
+        d = (x - y).abs().max()
+        assert d < 2e-5, float(d)      # split-K f32 atomics reorder sums run to run; otherwise identical
