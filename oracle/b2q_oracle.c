@@ -93,7 +93,7 @@ static double map_pi(double a) { /* MapToMinusPiToPi minitaur.py:67-83 */
 void orc_default_config(OrcConfig* c) {
   memset(c, 0, sizeof *c);
   c->sim_dt = 0.002; c->action_repeat = 13; c->solver_iters = 23; c->erp = 0.2; c->warmstart = 0.85; c->contact_margin = 0.02;
-  c->action_interp = 0; c->torque_limit = 0; c->settle_steps = 500;
+  c->action_interp = 0; c->torque_limit = 0; c->settle_steps = 500; c->action_filter = 0; c->filter_highcut = 4.0;
   c->etg_T = 0.5; c->etg_T2 = 0.5; c->etg_sigma_sq = 0.04; c->etg_amp = 0.2; c->etg_phase[0] = -M_PI / 2; c->etg_phase[1] = 0; /* train.py:296-297 */
   c->w_torso = 1.5; c->w_feet = 0.3; c->w_up = 0.6; c->w_tau = 0.07; c->w_stand = 0; c->w_badfoot = 0.1; c->w_footcontact = 0.1; c->w_done = 1; /* train.py:478-484 */
   c->reward_p = 5; c->vel_d = 0.5; c->foot_radius = 0.02; c->terrain_type = 0;
@@ -174,6 +174,18 @@ void orc_motor_torque(const double* kp, const double* kd, const double* target, 
     if (limit > 0) { if (t > limit) t = limit; if (t < -limit) t = -limit; }
     tau[j] = t;
   }
+}
+
+/* 2nd-order Butterworth low-pass through the bilinear transform (what scipy.signal.butter(2, Wn) returns), and one step
+ * of ActionFilter.filter (action_filter.py:111-120): y = b0 x + b1 x1 + b2 x2 - a1 y1 - a2 y2, then shift the histories */
+void orc_butter2(double highcut, double fs, double b[3], double a[3]) {
+  double K = tan(M_PI * highcut / fs), n = 1.0 / (1.0 + sqrt(2.0) * K + K * K);
+  b[0] = K * K * n; b[1] = 2 * b[0]; b[2] = b[0];
+  a[0] = 1.0; a[1] = 2.0 * (K * K - 1.0) * n; a[2] = (1.0 - sqrt(2.0) * K + K * K) * n;
+}
+void orc_filter_step(const double b[3], const double a[3], double x, double* x1, double* x2, double* y1, double* y2, double* y) {
+  double yy = b[0] * x + b[1] * *x1 + b[2] * *x2 - a[1] * *y1 - a[2] * *y2;
+  *x2 = *x1; *x1 = x; *y2 = *y1; *y1 = yy; *y = yy;
 }
 
 /* ------------------------------------------------------------------ spatial algebra ([ang;lin]) */
@@ -653,6 +665,7 @@ void orc_env_reset(const OrcConfig* c, OrcEnv* e, const double* w, const double*
   for (int k = 0; k < ORC_HIST; k++) memcpy(e->hist[k], e->snap_obs, sizeof e->snap_obs);
   e->hist_len = 100; e->hist_head = 0;
   e->has_last = 0; e->step_count = 0;
+  for (int j = 0; j < 12; j++) e->fx1[j] = e->fx2[j] = e->fy1[j] = e->fy2[j] = e->snap_obs[j]; /* init_history(GetMotorAngles()) at step 0 */
   for (int k = 0; k < 4; k++) e->contact[k] = e->lam_warm[k] > 0;
   if (w) memcpy(e->etg_w, w, sizeof e->etg_w);
   if (b) memcpy(e->etg_b, b, sizeof e->etg_b);
@@ -668,6 +681,10 @@ void orc_env_step(const OrcConfig* c, OrcEnv* e, const double action[12], int do
   const int R = c->action_repeat; const double dtc = c->sim_dt * R;
   double target[12], start_pos[3], feet0[4][3], feet1[4][3];
   for (int j = 0; j < 12; j++) target[j] = POSE_ORI[j] + e->etg_act[j] + action[j]; /* deployment/test.py:95-99 */
+  if (c->action_filter) { /* Minitaur.Step: action = _FilterAction(action), minitaur.py:250-251 */
+    double fb[3], fa[3]; orc_butter2(c->filter_highcut, 1.0 / dtc, fb, fa);
+    for (int j = 0; j < 12; j++) orc_filter_step(fb, fa, target[j], &e->fx1[j], &e->fx2[j], &e->fy1[j], &e->fy2[j], &target[j]);
+  }
   memcpy(start_pos, e->pos, sizeof start_pos);
   orc_foot_world(e, feet0);
   for (int i = 0; i < R; i++) { /* minitaur.py:248-260 */

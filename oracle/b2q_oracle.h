@@ -45,6 +45,8 @@ typedef struct {
   int action_interp;        /* minitaur.py:1384-1401 */
   double torque_limit;      /* <=0: off (laikago_motor.py:168-173) */
   int settle_steps;         /* a1.py:294-297: 500 */
+  int action_filter;        /* Butterworth low-pass on the joint targets, minitaur.py:248-251,1403-1422 */
+  double filter_highcut;    /* 4 Hz, action_filter.py:42-44 */
   double etg_T, etg_T2, etg_sigma_sq, etg_amp, etg_phase[2];
   double w_torso, w_feet, w_up, w_tau, w_stand, w_badfoot, w_footcontact, w_done;
   double reward_p, vel_d;
@@ -66,6 +68,7 @@ typedef struct {
   double hist[ORC_HIST][ORC_HIST_W]; int hist_len, hist_head; /* hist_head = most recent */
   int contact[4];
   double last_tau[12];
+  double fx1[12], fx2[12], fy1[12], fy2[12]; /* action-filter history (order 2) */
   /* snapshot for reset */
   double snap[37]; double snap_obs[ORC_HIST_W]; double snap_lam[4];
 } OrcEnv;
@@ -80,6 +83,8 @@ void orc_fk_leg(const double ang[3], int l_hip_sign, double foot[3]);
 void orc_leg_jacobian(const double ang[3], int leg_id, double J[9]);
 void orc_motor_torque(const double* kp, const double* kd, const double* target, const double* q, const double* qd, double limit, double* tau);
 void orc_quat_to_rpy(const double q[4], double rpy[3]);
+void orc_butter2(double highcut, double fs, double b[3], double a[3]);   /* scipy.signal.butter(2, highcut/(fs/2)) closed form */
+void orc_filter_step(const double b[3], const double a[3], double x, double* x1, double* x2, double* y1, double* y2, double* y);
 /* dynamics */
 void orc_forward_dynamics(const OrcConfig* c, const OrcEnv* e, const double tau[12], double qdd[12], double wdot_w[3], double vdot_w[3]);
 void orc_mass_matrix(const OrcConfig* c, const OrcEnv* e, double M[18*18]);   /* via unit-response of ABA; for tests */

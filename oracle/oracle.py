@@ -26,6 +26,7 @@ class Config(C.Structure):
         ("sim_dt", C.c_double), ("action_repeat", C.c_int), ("solver_iters", C.c_int),
         ("erp", C.c_double), ("warmstart", C.c_double), ("contact_margin", C.c_double),
         ("action_interp", C.c_int), ("torque_limit", C.c_double), ("settle_steps", C.c_int),
+        ("action_filter", C.c_int), ("filter_highcut", C.c_double),
         ("etg_T", C.c_double), ("etg_T2", C.c_double), ("etg_sigma_sq", C.c_double), ("etg_amp", C.c_double),
         ("etg_phase", C.c_double * 2),
         ("w_torso", C.c_double), ("w_feet", C.c_double), ("w_up", C.c_double), ("w_tau", C.c_double),
@@ -46,6 +47,7 @@ class Env(C.Structure):
         ("param", C.c_double * NPARAM),
         ("hist", (C.c_double * HIST_W) * HIST), ("hist_len", C.c_int), ("hist_head", C.c_int),
         ("contact", C.c_int * 4), ("last_tau", C.c_double * 12),
+        ("fx1", C.c_double * 12), ("fx2", C.c_double * 12), ("fy1", C.c_double * 12), ("fy2", C.c_double * 12),
         ("snap", C.c_double * 37), ("snap_obs", C.c_double * HIST_W), ("snap_lam", C.c_double * 4),
     ]
 
@@ -139,6 +141,28 @@ def motor_torque(kp, kd, target, q, qd, limit=0.0):
     tau = np.zeros(12)
     lib().orc_motor_torque(a, b, c, d, e, C.c_double(limit), tau.ctypes.data_as(C.POINTER(C.c_double)))
     return tau
+
+
+def butter2(highcut, fs):
+    b, a = np.zeros(3), np.zeros(3)
+    dp = C.POINTER(C.c_double)
+    lib().orc_butter2(C.c_double(highcut), C.c_double(fs), b.ctypes.data_as(dp), a.ctypes.data_as(dp))
+    return b, a
+
+
+def filter_sequence(b, a, xs, init):
+    """ActionFilter.init_history(init) then filter(x) for every row of xs (one joint per column)."""
+    xs = np.asarray(xs, dtype=np.float64)
+    ys = np.zeros_like(xs)
+    dp = C.POINTER(C.c_double)
+    b, a = np.ascontiguousarray(b, dtype=np.float64), np.ascontiguousarray(a, dtype=np.float64)
+    for j in range(xs.shape[1]):
+        h = [C.c_double(float(init[j])) for _ in range(4)]
+        for k in range(xs.shape[0]):
+            y = C.c_double()
+            lib().orc_filter_step(b.ctypes.data_as(dp), a.ctypes.data_as(dp), C.c_double(float(xs[k, j])), C.byref(h[0]), C.byref(h[1]), C.byref(h[2]), C.byref(h[3]), C.byref(y))
+            ys[k, j] = y.value
+    return ys
 
 
 def quat_to_rpy(q):

@@ -23,7 +23,7 @@
 
 namespace b2q {
 
-constexpr int NS = 21;    // state packs per env
+constexpr int NS = 37;    // state packs per env (21 + 16 action-filter history packs, touched only when the filter is on)
 constexpr int NP = 15;    // param packs per env
 constexpr int NE = 16;    // ETG packs per env (w[3][20], b[3], pad)
 constexpr int OBS_DIM = 49;
@@ -56,6 +56,7 @@ struct Model {
 template <typename T>
 struct Cfg {
   T dt; int R; int iters; T erp, warm, margin; int interp; T tau_limit; int settle_steps;
+  int filter; T fb0, fb1, fb2, fa1, fa2;
   T etg_T, etg_T2, etg_sigma_sq, etg_amp, etg_ph0, etg_ph1;
   T w_torso, w_feet, w_up, w_tau, w_stand, w_badfoot, w_footcontact, w_done, reward_p, vel_d;
   int terrain, hf_nx, hf_ny; T hf_x0, hf_y0, hf_cell; const T* hf;
@@ -587,6 +588,7 @@ B2Q_HD void reset_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, con
     store_state(cm, B.state, N, env, s, la, ea, 0, rpy0);
     for (int d = 0; d < B.Dm; d++) { ring_write(B, d, 0, k, env, sq, sqd, stau); ring_write(B, d, 1, k, env, sq, sqd, stau); }
     if (k == 0) B.step_count[env] = 0;
+    if (cf.filter) for (int hslot = 0; hslot < 4; hslot++) stp(B.state, 21 + 4 * k + hslot, N, env, sq[0], sq[1], sq[2], T(0));   // init_history(GetMotorAngles()), minitaur.py:1417-1419
   }
   if (obs) write_obs(cm, md, obs, valid, s, s.pos, cf.dt * T(cf.R), rpy0, sq, sqd, ea);
 }
@@ -627,6 +629,18 @@ B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, cons
   T target[3];
 #pragma unroll
   for (int j = 0; j < 3; j++) target[j] = md.pose_ori[j] + etg_act[j] + action[(size_t)env * 12 + 3 * k + j];  // deployment/test.py:95-99
+  if (cf.filter) {  // Minitaur.Step: action = _FilterAction(action) (minitaur.py:250-251); y = b.x_hist - a.y_hist (action_filter.py:111-120)
+    P4<T> x1 = ldp(B.state, 21 + 4 * k, N, env), x2 = ldp(B.state, 22 + 4 * k, N, env), y1 = ldp(B.state, 23 + 4 * k, N, env), y2 = ldp(B.state, 24 + 4 * k, N, env);
+    T ax1[3] = {x1.x, x1.y, x1.z}, ax2[3] = {x2.x, x2.y, x2.z}, ay1[3] = {y1.x, y1.y, y1.z}, ay2[3] = {y2.x, y2.y, y2.z}, yy[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) yy[j] = cf.fb0 * target[j] + cf.fb1 * ax1[j] + cf.fb2 * ax2[j] - cf.fa1 * ay1[j] - cf.fa2 * ay2[j];
+    if (valid) {
+      stp(B.state, 21 + 4 * k, N, env, target[0], target[1], target[2], T(0)); stp(B.state, 22 + 4 * k, N, env, ax1[0], ax1[1], ax1[2], T(0));
+      stp(B.state, 23 + 4 * k, N, env, yy[0], yy[1], yy[2], T(0)); stp(B.state, 24 + 4 * k, N, env, ay1[0], ay1[1], ay1[2], T(0));
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) target[j] = yy[j];
+  }
   const V3<T> start_pos = s.pos;
   T foot0_x;
   {

@@ -13,7 +13,7 @@ from oracle import oracle as O  # noqa: E402
 
 
 def _pair(precision, w, b, n=1, **kw):
-    ocfg = O.default_config(**{k: v for k, v in kw.items() if k in ("action_interp", "torque_limit", "solver_iters", "action_repeat")})
+    ocfg = O.default_config(**{k: v for k, v in kw.items() if k in ("action_interp", "torque_limit", "solver_iters", "action_repeat", "action_filter")})
     e = emu.EmuEnv(n, precision, **kw)
     o = O.OracleEnv(ocfg)
     return e, o, e.reset(w, b), o.reset(w, b)
@@ -68,6 +68,18 @@ def test_f64_options_interp_torque_limit_latency(etg_stable):
         a = rng.uniform(-0.3, 0.3, 12)
         ob, rw, dn, inf = o.step(a); ob2, rw2, dn2, inf2 = e.step(a)
         assert np.abs(ob2[0] - ob).max() < 1e-8
+    e.close()
+    # Butterworth action filter (minitaur.py:250-251, action_filter.py:111-216) incl. history init at reset and auto-reset
+    e, o, _, _ = _pair(1, w, b, action_filter=1)
+    for k in range(15):
+        a = rng.uniform(-0.3, 0.3, 12)
+        ob, rw, dn, inf = o.step(a); ob2, rw2, dn2, inf2 = e.step(a)
+        assert np.abs(ob2[0] - ob).max() < 1e-8 and np.abs(inf2[0] - inf).max() < 1e-8, k
+    e.reset(); o.reset()
+    for k in range(5):
+        a = rng.uniform(-0.3, 0.3, 12)
+        ob, rw, dn, inf = o.step(a); ob2, rw2, dn2, inf2 = e.step(a)
+        assert np.abs(inf2[0] - inf).max() < 1e-8
     e.close()
     # control latency across control-step boundaries (minitaur.py:1172-1193): 0.0305 s = 15.25 substeps, ring depth 3
     p = O.default_param(); p[25] = 0.0305
