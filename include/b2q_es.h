@@ -21,6 +21,11 @@ int b2q_es_fitness(const void* ret, const int32_t* len, void* fitness, void* mea
  * obs6x20 = ETG_layer.update(t) at ts = [0.5T+0.1, 0, 0.05, 0.1, 0.15, 0.2] (row-major 6x20). w_out [pop,3,20], b_out [pop,3]. */
 int b2q_etg_fit(const double* obs6x20, const double* prior_points, const double* solutions, const double* w0, const double* b0, double lamb,
                 double precision, double* w_out, double* b_out, int pop, void* stream);
+/* Dynamics identification: loss_func of model/Dynamic_parallel_model.py:29-41 accumulated on the device.
+ * info [n,56] is the step kernel's info output; mean15/std15 = recorded {motor12, drpy3} statistics of THIS control step;
+ * acc [n,15] running sums (zero it before an episode); reward[n] = 30 - (max_j mean_t motor_j + max_k mean_t drpy_k)/2. */
+int b2q_dyn_accumulate(const void* info, const void* mean15, const void* std15, void* acc, int n, int elem_size, void* stream);
+int b2q_dyn_finish(const void* acc, int steps, void* reward, int n, int elem_size, void* stream);
 #ifdef __cplusplus
 }
 #endif

@@ -93,7 +93,7 @@ static double map_pi(double a) { /* MapToMinusPiToPi minitaur.py:67-83 */
 void orc_default_config(OrcConfig* c) {
   memset(c, 0, sizeof *c);
   c->sim_dt = 0.002; c->action_repeat = 13; c->solver_iters = 23; c->erp = 0.2; c->warmstart = 0.85; c->contact_margin = 0.02;
-  c->action_interp = 0; c->torque_limit = 0; c->settle_steps = 500; c->action_filter = 0; c->filter_highcut = 4.0;
+  c->action_interp = 0; c->torque_limit = 0; c->settle_steps = 500; c->action_filter = 0; c->filter_highcut = 4.0; c->etg_enabled = 1;
   c->etg_T = 0.5; c->etg_T2 = 0.5; c->etg_sigma_sq = 0.04; c->etg_amp = 0.2; c->etg_phase[0] = -M_PI / 2; c->etg_phase[1] = 0; /* train.py:296-297 */
   c->w_torso = 1.5; c->w_feet = 0.3; c->w_up = 0.6; c->w_tau = 0.07; c->w_stand = 0; c->w_badfoot = 0.1; c->w_footcontact = 0.1; c->w_done = 1; /* train.py:478-484 */
   c->reward_p = 5; c->vel_d = 0.5; c->foot_radius = 0.02; c->terrain_type = 0;
@@ -147,6 +147,7 @@ void orc_leg_jacobian(const double a[3], int leg_id, double J[9]) { /* a1.py:132
   J[8] = L_LOW * L_UP * sin(t3) * cos(t1) * cos(te) / le + le * sin(te) * cos(t1) / 2;
 }
 void orc_etg_act(const OrcConfig* c, const double w[3][ORC_ETG_H], const double b[3], double t, double* act, double* foot_out) {
+  if (!c->etg_enabled) { for (int j = 0; j < 12; j++) { act[j] = 0; if (foot_out) foot_out[j] = 0; } return; }
   double r1[ORC_ETG_H], r2[ORC_ETG_H];
   orc_etg_features(c, t, r1);
   orc_etg_features(c, t + 0.5 * c->etg_T2, r2);

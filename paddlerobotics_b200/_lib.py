@@ -53,6 +53,8 @@ SYMBOLS = {
     # ES population fitness — include/b2q_es.h
     "b2q_es_accumulate": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "b2q_es_fitness": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b2q_dyn_accumulate": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "b2q_dyn_finish": (_i, [_vp, _i, _vp, _i, _i, _vp]),
     "b2q_etg_fit": (_i, [_vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp, _vp, _i, _vp]),
     # device replay memory — include/b2q_rpm.h
     "b2q_rpm_append": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -106,3 +106,47 @@ extern "C" int b2q_etg_fit(const double* obs6x20, const double* prior_points, co
   etg_fit_kernel<<<(pop + 31) / 32, 32, 0, (cudaStream_t)stream>>>(obs6x20, prior_points, solutions, w0, b0, lamb, precision, w_out, b_out, pop);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// §8f-4: dynamics-identification fitness (model/Dynamic_parallel_model.py:29-41,53-68).  Per env and control step the
+// squared, std-normalised deviation of the 12 joint angles and 3 body rates from the recorded real-robot statistics is
+// accumulated; the episode reward is 30 - (max_j mean_t motor + max_k mean_t drpy) / 2.
+namespace {
+template <typename T>
+__global__ void dyn_accum_kernel(const T* __restrict__ info /*[N][56]*/, const T* __restrict__ mean15 /*motor12|drpy3 at this step*/, const T* __restrict__ std15,
+                                 T* __restrict__ acc /*[N][15]*/, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 15) return;
+  int e = i / 15, c = i % 15;
+  T x = c < 12 ? info[(size_t)e * 56 + 42 + c] : info[(size_t)e * 56 + 39 + (c - 12)];   // joint_angle | obs-IMU[3:] (info columns, include/b2q.h)
+  T d = x - mean15[c], s = std15[c];
+  acc[i] += d * d / (s * s);
+}
+template <typename T>
+__global__ void dyn_finish_kernel(const T* __restrict__ acc, int steps, T* __restrict__ reward, int n) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  T lm = acc[(size_t)e * 15], ld = acc[(size_t)e * 15 + 12];
+  for (int c = 1; c < 12; c++) lm = fmax(lm, acc[(size_t)e * 15 + c]);
+  for (int c = 13; c < 15; c++) ld = fmax(ld, acc[(size_t)e * 15 + c]);
+  reward[e] = T(30) - (lm / T(steps) + ld / T(steps)) / T(2);
+}
+}  // namespace
+
+extern "C" {
+int b2q_dyn_accumulate(const void* info, const void* mean15, const void* std15, void* acc, int n, int elem_size, void* stream) {
+  if (!info || !mean15 || !std15 || !acc || n < 1 || (elem_size != 4 && elem_size != 8)) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  int blocks = (n * 15 + 255) / 256;
+  if (elem_size == 4) dyn_accum_kernel<float><<<blocks, 256, 0, s>>>((const float*)info, (const float*)mean15, (const float*)std15, (float*)acc, n);
+  else dyn_accum_kernel<double><<<blocks, 256, 0, s>>>((const double*)info, (const double*)mean15, (const double*)std15, (double*)acc, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+int b2q_dyn_finish(const void* acc, int steps, void* reward, int n, int elem_size, void* stream) {
+  if (!acc || !reward || n < 1 || steps < 1 || (elem_size != 4 && elem_size != 8)) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (elem_size == 4) dyn_finish_kernel<float><<<(n + 255) / 256, 256, 0, s>>>((const float*)acc, steps, (float*)reward, n);
+  else dyn_finish_kernel<double><<<(n + 255) / 256, 256, 0, s>>>((const double*)acc, steps, (double*)reward, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+}

@@ -12,7 +12,7 @@ inline Cfg<T> make_cfg(const B2QConfig& c, const T* hf_dev) {
   Cfg<T> k;
   k.dt = (T)c.sim_dt; k.R = c.action_repeat; k.iters = c.solver_iters; k.erp = (T)c.erp; k.warm = (T)c.warmstart; k.margin = (T)c.contact_margin;
   k.interp = c.action_interp; k.tau_limit = (T)c.torque_limit; k.settle_steps = c.settle_steps;
-  k.filter = c.action_filter;
+  k.filter = c.action_filter; k.etg = c.etg_enabled;
   {  // scipy.signal.butter(2, highcut / (fs/2)) in closed form (bilinear transform), fs = 1 / control period
     const double PI = 3.14159265358979323846, fs = 1.0 / (c.sim_dt * c.action_repeat);
     const double K = std::tan(PI * c.filter_highcut / fs), n = 1.0 / (1.0 + std::sqrt(2.0) * K + K * K);
@@ -30,7 +30,7 @@ inline void default_config(B2QConfig* c) {
   std::memset(c, 0, sizeof(*c));
   c->num_envs = 1; c->device = 0; c->precision = 0; c->threads_per_block = 0;
   c->sim_dt = 0.002; c->action_repeat = 13; c->solver_iters = 23; c->erp = 0.2; c->warmstart = 0.85; c->contact_margin = 0.02;
-  c->action_interp = 0; c->torque_limit = 0; c->settle_steps = 500; c->action_filter = 0; c->filter_highcut = 4.0;
+  c->action_interp = 0; c->torque_limit = 0; c->settle_steps = 500; c->action_filter = 0; c->filter_highcut = 4.0; c->etg_enabled = 1;
   c->etg_T = 0.5; c->etg_T2 = 0.5; c->etg_sigma_sq = 0.04; c->etg_amp = 0.2; c->etg_phase0 = -3.14159265358979323846 / 2; c->etg_phase1 = 0;
   c->w_torso = 1.5; c->w_feet = 0.3; c->w_up = 0.6; c->w_tau = 0.07; c->w_stand = 0; c->w_badfoot = 0.1; c->w_footcontact = 0.1; c->w_done = 1;
   c->reward_p = 5; c->vel_d = 0.5; c->foot_radius = 0.02; c->ring_depth = 1; c->auto_reset = 0; c->terrain_type = 0;

@@ -56,7 +56,7 @@ struct Model {
 template <typename T>
 struct Cfg {
   T dt; int R; int iters; T erp, warm, margin; int interp; T tau_limit; int settle_steps;
-  int filter; T fb0, fb1, fb2, fa1, fa2;
+  int filter; T fb0, fb1, fb2, fa1, fa2; int etg;
   T etg_T, etg_T2, etg_sigma_sq, etg_amp, etg_ph0, etg_ph1;
   T w_torso, w_feet, w_up, w_tau, w_stand, w_badfoot, w_footcontact, w_done, reward_p, vel_d;
   int terrain, hf_nx, hf_ny; T hf_x0, hf_y0, hf_cell; const T* hf;
@@ -143,6 +143,7 @@ B2Q_HD void leg_ik(const Model<T>& md, V3<T> f, T lhip, T* ang) {
 template <typename T, class Comm>
 B2Q_HD void etg_act_leg(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const P4<T>* etg, int N, int env, T t, T* act) {
   const int k = cm.leg();
+  if (!cf.etg) { act[0] = act[1] = act[2] = T(0); return; }   // make_env(ETG=0)
   const T two_pi = T(6.283185307179586476925286766559);
   T tt = (k == 0 || k == 3) ? t : t + T(0.5) * cf.etg_T2;
   T om = two_pi / cf.etg_T;

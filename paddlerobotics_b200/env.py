@@ -178,7 +178,8 @@ class QuadrupedalEnv:
             raise ValueError("ETG_H must be %d" % ETG_H_CONST)
         if task not in ("ground", "plane"):
             raise ValueError("task %r: only flat terrain is wired into make_env; pass heightfield= to VecQuadrupedalEnv for others" % (task,))
-        cfg = dict(etg_T=float(ETG_T), etg_T2=float(ETG_T), reward_p=float(reward_p), vel_d=float(vel_d))
+        cfg = dict(etg_T=float(ETG_T), etg_T2=float(ETG_T), reward_p=float(reward_p), vel_d=float(vel_d), etg_enabled=int(bool(ETG)),
+                   action_filter=int(bool(enable_action_filter)))
         for k_ref, k_cfg in (("torso", "w_torso"), ("feet", "w_feet"), ("up", "w_up"), ("tau", "w_tau"), ("stand", "w_stand"),
                              ("badfoot", "w_badfoot"), ("footcontact", "w_footcontact"), ("done", "w_done")):
             if reward_param and k_ref in reward_param:

@@ -201,3 +201,53 @@ class PopulationEvaluator:
         fit = all_gather_concat(self.fitness, self.world, self.rank)
         ml = all_gather_concat(self.mean_len, self.world, self.rank)
         return fit, ml
+
+
+class DynamicsEvaluator:
+    """Sim-to-real dynamics identification on the GPU: the population of 48-vectors is mapped through
+    param2dynamic_dict to per-env dynamics rows; every individual replays the recorded gait tables (ETG off, action =
+    table - pose_ori) for `steps` control steps and is scored against the recorded real-robot statistics with the
+    reference's loss (RemoteESAgent.sample_episode / batch_sample_episodes, Dynamic_parallel_model.py:53-77).  Individuals
+    are sharded over ranks exactly like the xparl actors (`solutions[i*K:(i+1)*K]`, :157-159) and the rewards all-gathered."""
+
+    def __init__(self, popsize, gait, mean_dict, keys=("exp", "ori"), steps=100, rank=0, world=1, device=0, precision="f32", ring_depth=4, **env_cfg):
+        import torch
+        from . import _lib
+        from .env import VecQuadrupedalEnv
+        if popsize % world != 0:
+            raise ValueError("popsize must be divisible by the number of ranks")
+        self.popsize, self.keys, self.steps, self.rank, self.world = popsize, tuple(keys), steps, rank, world
+        self.lo, self.hi = shard_range(popsize, rank, world)
+        self.pop_local = self.hi - self.lo
+        self.n = self.pop_local * len(self.keys)          # env index = key * pop_local + individual
+        self.env = VecQuadrupedalEnv(self.n, device=device, precision=precision, etg_enabled=0, ring_depth=ring_depth, **env_cfg)
+        self.lib = _lib.load()
+        dev, dt = self.env.device, self.env.dtype
+        pose = np.array([0, 0.9, -1.8] * 4)
+        # per-step action table [steps, n, 12] and statistics [steps, keys, 15]
+        act = np.stack([np.repeat((np.asarray(gait[k])[:steps] - pose)[:, None, :], self.pop_local, axis=1) for k in self.keys], axis=1).reshape(steps, self.n, 12)
+        self.actions = torch.as_tensor(act, dtype=dt, device=dev)
+        self.mean = [torch.as_tensor(np.concatenate([mean_dict[k + "_motor_mean"][:steps], mean_dict[k + "_drpy_mean"][:steps]], 1), dtype=dt, device=dev) for k in self.keys]
+        self.std = [torch.as_tensor(np.concatenate([mean_dict[k + "_motor_std"][:steps], mean_dict[k + "_drpy_std"][:steps]], 1), dtype=dt, device=dev) for k in self.keys]
+        self.acc = torch.zeros(self.n, 15, dtype=dt, device=dev)
+        self.reward = torch.zeros(self.n, dtype=dt, device=dev)
+
+    def evaluate(self, solutions):
+        """solutions [pop,48] in [-1,1] (identical on every rank) -> reward [pop] = mean over the gait keys (identical on every rank)."""
+        import torch
+        from .etg import dynamic_dict_to_row, param2dynamic_dict
+        rows = np.array([dynamic_dict_to_row(param2dynamic_dict(np.asarray(s))) for s in np.asarray(solutions)[self.lo:self.hi]])
+        env = self.env
+        env.set_dynamics(np.tile(rows, (len(self.keys), 1)))          # env.reset(hardset=False, dynamic_param=...) :55
+        env.reset()
+        self.acc.zero_()
+        es, stream, pl = env.obs.element_size(), env._stream(), self.pop_local
+        for t in range(self.steps):
+            _, _, _, info = env.step(self.actions[t], donef=False)
+            for ki in range(len(self.keys)):
+                sl = slice(ki * pl, (ki + 1) * pl)
+                rc = self.lib.b2q_dyn_accumulate(info[sl].data_ptr(), self.mean[ki][t].data_ptr(), self.std[ki][t].data_ptr(), self.acc[sl].data_ptr(), pl, es, stream)
+                assert rc == 0
+        assert self.lib.b2q_dyn_finish(self.acc.data_ptr(), self.steps, self.reward.data_ptr(), self.n, es, stream) == 0
+        local = self.reward.reshape(len(self.keys), pl).mean(0)        # (reward1 + reward2) / 2, :73
+        return all_gather_concat(local.contiguous(), self.world, self.rank)

@@ -87,6 +87,21 @@ def main():
         q1, q2 = model.value(obs, act)
     out["mlp_obs"], out["mlp_act"] = obs.numpy(), act.numpy()
     out["mlp_mean"], out["mlp_logstd"], out["mlp_q1"], out["mlp_q2"] = mean.numpy(), logstd.numpy(), q1.numpy(), q2.numpy()
+    # --- dynamics-identification loss (model/Dynamic_parallel_model.py:29-41), ast-extracted (the module imports rlschool)
+    import ast
+    src = open(ns.REF + "/model/Dynamic_parallel_model.py").read()
+    env = {"np": np}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == "loss_func":
+            exec(compile(ast.Module([node], []), "Dynamic_parallel_model.py", "exec"), env)
+    T = 100
+    md = {"exp_motor_mean": rng.normal(0, 0.3, (T, 12)), "exp_motor_std": rng.uniform(0.05, 0.2, (T, 12)),
+          "exp_drpy_mean": rng.normal(0, 0.5, (T, 3)), "exp_drpy_std": rng.uniform(0.2, 0.6, (T, 3))}
+    drpy, motor = rng.normal(0, 0.6, (T, 3)), rng.normal(0, 0.35, (T, 12))
+    out["dynloss_drpy"], out["dynloss_motor"] = drpy, motor
+    for k, v in md.items():
+        out["dynloss_" + k] = v
+    out["dynloss_value"] = np.array(env["loss_func"](drpy, motor, md, "exp"))
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     # reference's own golden artefacts (data)
     shutil.copy(ns.REF + "/gait_action_list_ETG_exp.npy", os.path.join(HERE, "gait_action_list_ETG_exp.npy"))

@@ -72,3 +72,45 @@ def test_on_device_training_loop_smoke(etg_default):
             losses.append(L.learn(*rpm.sample_batch(B), graph=True).clone())
     assert len(losses) > 20 and all(torch.isfinite(l).all() for l in losses)
     env.close()
+
+
+def test_dynamics_identification_evaluator_vs_oracle(golden):
+    """f-4: 48-parameter dynamics individuals replay a recorded gait table (ETG off) and are scored with the reference's
+    loss_func; GPU rewards == oracle rollouts + numpy restatement; the loss itself is pinned to the reference function."""
+    import os
+    import torch
+    from oracle import oracle as O
+    from paddlerobotics_b200.es import DynamicsEvaluator
+    from paddlerobotics_b200.etg import dynamic_dict_to_row, param2dynamic_dict
+
+    def loss_np(drpy, motor, md, key):          # numpy restatement of Dynamic_parallel_model.py:29-41
+        lm = np.max(np.mean((motor - md[key + "_motor_mean"]) ** 2 / md[key + "_motor_std"] ** 2, axis=0))
+        ld = np.max(np.mean((drpy - md[key + "_drpy_mean"]) ** 2 / md[key + "_drpy_std"] ** 2, axis=0))
+        return (ld + lm) / 2.0
+    md_g = {k[len("dynloss_"):]: golden[k] for k in golden.files if k.startswith("dynloss_exp")}
+    assert np.isclose(loss_np(golden["dynloss_drpy"], golden["dynloss_motor"], md_g, "exp"), float(golden["dynloss_value"]), rtol=1e-12)
+
+    T = 30
+    gait_tab = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gait_action_list_CPG_stairstair7_12_3.npy")) + np.array([0, 0.9, -1.8] * 4)
+    gait = {"exp": gait_tab[:T] , "ori": gait_tab[100:100 + T]}
+    rng = np.random.default_rng(0)
+    md = {}
+    for k in ("exp", "ori"):
+        md[k + "_motor_mean"] = gait[k] + rng.normal(0, 0.02, (T, 12)); md[k + "_motor_std"] = rng.uniform(0.05, 0.1, (T, 12))
+        md[k + "_drpy_mean"] = rng.normal(0, 0.2, (T, 3)); md[k + "_drpy_std"] = rng.uniform(0.3, 0.6, (T, 3))
+    sols = rng.uniform(-0.25, 0.25, (4, 48))
+    ev = DynamicsEvaluator(4, gait, md, steps=T, precision="f64", ring_depth=5)
+    rew = ev.evaluate(sols).cpu().numpy()
+    ref = np.zeros(4)
+    pose = np.array([0, 0.9, -1.8] * 4)
+    for i in range(4):
+        row = dynamic_dict_to_row(param2dynamic_dict(sols[i]))
+        for k in ("exp", "ori"):
+            o = O.OracleEnv(O.default_config(etg_enabled=0), row); o.reset()
+            motor, drpy = [], []
+            for t in range(T):
+                _, _, _, info = o.step(gait[k][t] - pose)
+                motor.append(info[42:54]); drpy.append(info[39:42])
+            ref[i] += (30 - loss_np(np.array(drpy), np.array(motor), md, k)) / 2.0
+    assert np.abs(rew - ref).max() < 1e-6, (rew, ref)
+    ev.env.close()
