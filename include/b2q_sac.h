@@ -12,6 +12,7 @@
 #ifndef B2Q_SAC_H
 #define B2Q_SAC_H
 #include <stdint.h>
+#include "b2q_mlp.h"
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -34,6 +35,11 @@ int b2q_sac_learn(B2QSacHandle h, const float* obs, const float* act, const floa
 /* phase 0: critic grads; 1: Adam(critic); 2: actor grads; 3: Adam(actor) + Polyak. */
 int b2q_sac_phase(B2QSacHandle h, int phase, const float* obs, const float* act, const float* rew, const float* next_obs, const float* term,
                   const float* eps_next, const float* eps_cur, uint64_t seed, void* stream);
+/* Behaviour cloning step (BC.BClearn, alg/BC.py:53-72; BCtrain.py:123-138): the student (this handle, obs_dim may be
+ * the partial observation obs[3:]) imitates an expert given as two MLP handles evaluated on ref_obs [B,ref_obs_dim].
+ * eps [B,act_dim]: the N(0,1) draw of the student's sample().  losses_out device float[2] = {critic_loss, actor_loss}. */
+int b2q_sac_bc_learn(B2QSacHandle h, const float* obs, const float* ref_obs, int ref_obs_dim, B2QMlpHandle expert_actor, B2QMlpHandle expert_critic,
+                     const float* eps, float* losses_out, void* stream);
 float* b2q_sac_grad_ptr(B2QSacHandle h, int which);   /* device gradient bucket (for ncclAllReduce in place) */
 float* b2q_sac_loss_ptr(B2QSacHandle h);
 int64_t b2q_sac_launch_count(B2QSacHandle h);

@@ -276,6 +276,20 @@ class SACLearner:
             self.pull()
         return self.losses
 
+    def bc_learn(self, obs, ref_obs, ref_agent, eps=None, pull=True):
+        """MujocoAgent.BClearn(obs, ref_obs, ref_agent) -> (critic_loss, actor_loss): mujoco_agent.py:56-60, alg/BC.py:53-72."""
+        dev = self.agent.device
+        t = lambda x: torch.as_tensor(x, dtype=torch.float32, device=dev).contiguous()
+        obs, ref_obs = t(obs), t(ref_obs)
+        eps = torch.randn(self.batch, self.agent.act_dim, device=dev) if eps is None else t(eps)
+        rc = self.lib.b2q_sac_bc_learn(self.h, obs.data_ptr(), ref_obs.data_ptr(), ref_obs.shape[1], ref_agent.actor.h, ref_agent.critic.h, eps.data_ptr(),
+                                       self.losses.data_ptr(), self._stream())
+        if rc != 0:
+            raise RuntimeError("b2q_sac_bc_learn: %d" % rc)
+        if pull:
+            self.pull()
+        return self.losses
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.b2q_sac_destroy(self.h)
@@ -299,3 +313,14 @@ def _agent_learn(self, obs, action, reward, next_obs, terminal):
 
 
 MujocoAgent.learn = _agent_learn
+
+
+def _agent_bclearn(self, obs, ref_obs, ref_agent, actor_lr=3e-4, critic_lr=3e-4):
+    n = obs.shape[0]
+    if getattr(self, "_bc_learner", None) is None or self._bc_learner.batch != n:
+        self._bc_learner = SACLearner(self, n, actor_lr=actor_lr, critic_lr=critic_lr)
+    l = self._bc_learner.bc_learn(obs, ref_obs, ref_agent)
+    return float(l[0]), float(l[1])
+
+
+MujocoAgent.BClearn = _agent_bclearn

@@ -130,10 +130,10 @@ __global__ void k_target_q(const float* rew, const float* term, const float* q1n
   if (b < B) tq[b] = rew[b] + gamma * term[b] * (fminf(q1n[b], q2n[b]) - alpha * logpn[b]);   // sac.py:88-91
 }
 // critic head backward for both nets: dq = 2 (q - tq)/B; loss += (q-tq)^2/B; db3 += dq   (mse_loss mean reduction, sac.py:94-95)
-__global__ void k_critic_dq(const float* q /*[2][B]*/, const float* tq, float* dq /*[2][B]*/, float* loss, int B) {
+__global__ void k_critic_dq(const float* q /*[2][B]*/, const float* tq /*[B] or [2][B]*/, int tq_stride, float* dq /*[2][B]*/, float* loss, int B) {
   int b = blockIdx.x * blockDim.x + threadIdx.x, net = blockIdx.y;
   float l = 0.f;
-  if (b < B) { float e = q[net * B + b] - tq[b]; dq[net * B + b] = 2.f * e / (float)B; l = e * e / (float)B; }
+  if (b < B) { float e = q[net * B + b] - tq[net * tq_stride + b]; dq[net * B + b] = 2.f * e / (float)B; l = e * e / (float)B; }
   for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
   if ((threadIdx.x & 31) == 0) atomicAdd(loss, l);
 }
@@ -205,6 +205,23 @@ __global__ void k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const
       float gls = gx * sd * e - alpha / (float)B;
       dy[(size_t)b * 2 * A + j] = gx;
       dy[(size_t)b * 2 * A + A + j] = (rl > -20.f && rl < 2.f) ? gls : 0.f;        // torch.clamp gradient
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(loss, l);
+}
+// behaviour cloning head (alg/BC.py:53-59): loss = -mean_{b,j} log N(ref | mean, exp(ls)); dy = dloss/d[mean | raw_ls]
+__global__ void k_bc_dy(const float* raw /*[B][2A]*/, const float* ref /*[B][A]*/, float* dy, float* loss, int B, int A) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  float l = 0.f;
+  const float inv = 1.f / (float)(B * A);
+  if (b < B) {
+    for (int j = 0; j < A; j++) {
+      float mu = raw[(size_t)b * 2 * A + j], rl = raw[(size_t)b * 2 * A + A + j], ls = fminf(fmaxf(rl, -20.f), 2.f);
+      float d = ref[(size_t)b * A + j] - mu, iv = expf(-2.f * ls);
+      l -= (-0.5f * d * d * iv - ls - 0.9189385332046727f) * inv;
+      dy[(size_t)b * 2 * A + j] = -(d * iv) * inv;
+      dy[(size_t)b * 2 * A + A + j] = (rl > -20.f && rl < 2.f) ? -(d * d * iv - 1.f) * inv : 0.f;
     }
   }
   for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
@@ -313,6 +330,42 @@ void sync_net_weights(B2QSac* s, cudaStream_t st) {
 
 }  // namespace
 
+namespace {
+// weight gradients of both critics from dq [2][B] and the activation dumps of the last critic forward
+int critic_backward(B2QSac* s, cudaStream_t st) {
+  const int B = s->B; const Net& cn = s->cn;
+  for (int i = 0; i < 2; i++) {
+    float* g = s->g_critic + (size_t)i * cn.n; const float* p = s->p_critic + (size_t)i * cn.n;
+    const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h1t = s->hc1_t + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
+    k_colsum_f32<<<1, 256, 0, st>>>(s->dq + (size_t)i * B, 1, g + cn.ob3, B);
+    k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dq + (size_t)i * B, 1, p + cn.oW3, h2, s->dh_rm, s->dh_t, g + cn.oW3, B);
+    k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + cn.ob2, B);
+    if (gemm(s, st, s->dh_t, B, h1t, B, g + cn.oW2, H, H, H, B, true)) return -2;
+    if (gemm(s, st, s->dh_rm, H, s->W2T[1 + i], H, s->G, H, B, H, H, false)) return -2;
+    k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(s->G, h1, s->dh_rm, s->dh_t, B);
+    k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + cn.ob1, B);
+    if (gemm(s, st, s->dh_t, B, s->xc_t, B, g + cn.oW1, cn.in_dim, H, cn.in_dim, B, true)) return -2;
+    s->launches += 5;
+  }
+  return 0;
+}
+// actor weight gradients from dy [B][2A] and the activation dumps of the last actor forward
+int actor_backward(B2QSac* s, cudaStream_t st) {
+  const int B = s->B, A = s->A; const Net& an = s->an;
+  float* g = s->g_actor;
+  k_colsum_f32<<<2 * A, 256, 0, st>>>(s->dy, 2 * A, g + an.ob3, B);
+  k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dy, 2 * A, s->p_actor + an.oW3, s->ha2_rm, s->dh_rm, s->dh_t, g + an.oW3, B);
+  k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + an.ob2, B);
+  if (gemm(s, st, s->dh_t, B, s->ha1_t, B, g + an.oW2, H, H, H, B, true)) return -2;
+  if (gemm(s, st, s->dh_rm, H, s->W2T[0], H, s->G, H, B, H, H, false)) return -2;
+  k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(s->G, s->ha1_rm, s->dh_rm, s->dh_t, B);
+  k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + an.ob1, B);
+  if (gemm(s, st, s->dh_t, B, s->xa_t, B, g + an.oW1, an.in_dim, H, an.in_dim, B, true)) return -2;
+  s->launches += 5;
+  return 0;
+}
+}  // namespace
+
 extern "C" {
 
 int b2q_sac_create(int device, int obs_dim, int act_dim, int batch, float gamma, float tau, float alpha, float actor_lr, float critic_lr, B2QSacHandle* out) {
@@ -403,21 +456,9 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     // current Q with activation dumps
     B2QMlpSaves sv = {s->xc_rm, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
     if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, act, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, st)) return -2;
-    k_critic_dq<<<dim3(NB, 2), TB, 0, st>>>(s->q, s->tq, s->dq, s->losses + 0, B);
+    k_critic_dq<<<dim3(NB, 2), TB, 0, st>>>(s->q, s->tq, 0, s->dq, s->losses + 0, B);
     s->launches += 5;
-    for (int i = 0; i < 2; i++) {
-      float* g = s->g_critic + (size_t)i * cn.n; const float* p = s->p_critic + (size_t)i * cn.n;
-      const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h1t = s->hc1_t + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
-      k_colsum_f32<<<1, 256, 0, st>>>(s->dq + (size_t)i * B, 1, g + cn.ob3, B);                               // db3
-      k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dq + (size_t)i * B, 1, p + cn.oW3, h2, s->dh_rm, s->dh_t, g + cn.oW3, B);   // dh2, dW3
-      k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + cn.ob2, B);                                            // db2
-      if (gemm(s, st, s->dh_t, B, h1t, B, g + cn.oW2, H, H, H, B, true)) return -2;                            // dW2 = dh2^T h1
-      if (gemm(s, st, s->dh_rm, H, s->W2T[1 + i], H, s->G, H, B, H, H, false)) return -2;                      // dh1 = dh2 W2
-      k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(s->G, h1, s->dh_rm, s->dh_t, B);
-      k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + cn.ob1, B);                                            // db1
-      if (gemm(s, st, s->dh_t, B, s->xc_t, B, g + cn.oW1, cn.in_dim, H, cn.in_dim, B, true)) return -2;        // dW1 = dh1^T x
-      s->launches += 5;
-    }
+    if (critic_backward(s, st)) return -2;
   } else if (phase == 1 || phase == 3) {
     const float b1 = 0.9f, b2 = 0.999f;
     if (phase == 1) {
@@ -456,16 +497,7 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     }
     if (!eps_cur) return -1;   // the explicit-noise path is required for the backward pass
     k_actor_dy<<<NB, TB, 0, st>>>(s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->alpha, s->dy, s->losses + 1, B, A);
-    float* g = s->g_actor;
-    k_colsum_f32<<<2 * A, 256, 0, st>>>(s->dy, 2 * A, g + an.ob3, B);                                           // db3
-    k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dy, 2 * A, s->p_actor + an.oW3, s->ha2_rm, s->dh_rm, s->dh_t, g + an.oW3, B);   // dh2, dW3
-    k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + an.ob2, B);
-    if (gemm(s, st, s->dh_t, B, s->ha1_t, B, g + an.oW2, H, H, H, B, true)) return -2;
-    if (gemm(s, st, s->dh_rm, H, s->W2T[0], H, s->G, H, B, H, H, false)) return -2;
-    k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(s->G, s->ha1_rm, s->dh_rm, s->dh_t, B);
-    k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + an.ob1, B);
-    if (gemm(s, st, s->dh_t, B, s->xa_t, B, g + an.oW1, an.in_dim, H, an.in_dim, B, true)) return -2;
-    s->launches += 6;
+    if (actor_backward(s, st)) return -2;
   } else {
     return -1;
   }
@@ -481,6 +513,41 @@ int b2q_sac_learn(B2QSacHandle s, const float* obs, const float* act, const floa
     if (rc) return rc;
   }
   if (losses_out) cudaMemcpyAsync(losses_out, s->losses, 2 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  return 0;
+}
+// Behaviour cloning of a (partial-observation) student from an expert (BC.BClearn, alg/BC.py:53-72): actor step on
+// -mean log N(expert_action | mean, std), then critic regression onto the expert's twin Q at the student's fresh sample.
+int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int ref_obs_dim, B2QMlpHandle expert_actor, B2QMlpHandle expert_critic,
+                     const float* eps, float* losses_out, void* stream) {
+  if (!s || !obs || !ref_obs || !expert_actor || !expert_critic || !eps) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = s->B, A = s->A, D = s->D, TB = 256, NB = (B + TB - 1) / TB;
+  const Net& an = s->an; const Net& cn = s->cn;
+  cudaMemsetAsync(s->losses, 0, 4 * sizeof(float), st);
+  cudaMemsetAsync(s->g_actor, 0, an.n * sizeof(float), st);
+  cudaMemsetAsync(s->g_critic, 0, 2 * cn.n * sizeof(float), st);
+  // --- actor
+  if (b2q_mlp_forward(expert_actor, ref_obs, ref_obs_dim, nullptr, B, B2Q_MLP_PREDICT, 0, nullptr, s->next_a /*ref action*/, nullptr, nullptr, st)) return -2;
+  B2QMlpSaves sa = {s->xa_rm, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
+  if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_RAW, 0, nullptr, s->raw_a, nullptr, nullptr, &sa, st)) return -2;
+  k_bc_dy<<<NB, TB, 0, st>>>(s->raw_a, s->next_a, s->dy, s->losses + 1, B, A);
+  if (actor_backward(s, st)) return -2;
+  k_step_inc<<<1, 1, 0, st>>>(s->d_step);
+  k_adam<<<((int)an.n + 255) / 256, 256, 0, st>>>(s->p_actor, s->g_actor, s->m_a, s->v_a, (int)an.n, s->lr_a, 0.9f, 0.999f, 1e-8f, s->d_step);
+  sync_net_weights(s, st);
+  // --- critic: a_now ~ pi_student(obs) (no grad); targets = expert Q(ref_obs, a_now)
+  if (b2q_mlp_forward(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_SAMPLE, 0, eps, s->cur_a, s->cur_logp, nullptr, st)) return -2;
+  if (b2q_mlp_forward(expert_critic, ref_obs, ref_obs_dim, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->qn, nullptr, nullptr, st)) return -2;
+  B2QMlpSaves sv = {s->xc_rm, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
+  if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, st)) return -2;
+  k_critic_dq<<<dim3(NB, 2), TB, 0, st>>>(s->q, s->qn, B, s->dq, s->losses + 0, B);
+  if (critic_backward(s, st)) return -2;
+  k_adam<<<((int)(2 * cn.n) + 255) / 256, 256, 0, st>>>(s->p_critic, s->g_critic, s->m_c, s->v_c, (int)(2 * cn.n), s->lr_c, 0.9f, 0.999f, 1e-8f, s->d_step);
+  sync_net_weights(s, st);
+  s->launches += 12;
+  if (losses_out) cudaMemcpyAsync(losses_out, s->losses, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { s->err = cudaGetErrorString(e); return -2; }
   return 0;
 }
 float* b2q_sac_grad_ptr(B2QSacHandle s, int which) { return !s ? nullptr : (which == 0 ? s->g_actor : s->g_critic); }

@@ -152,3 +152,63 @@ def test_sac_learn_cuda_graph_replay_equals_eager():
     for x, y in zip(res[0], res[1]):
         d = (x - y).abs().max()
         assert d < 2e-5, float(d)      # split-K f32 atomics reorder sums run to run; otherwise identical
+
+
+def test_bc_learn_vs_torch():
+    """f-3: BC.BClearn (alg/BC.py:53-72) — partial-observation student (obs[3:], BCtrain.py:77-81) cloned from an expert:
+    actor NLL step then critic regression onto the expert's twin Q, vs a torch fp32 restatement with the same eps."""
+    import torch
+    import torch.nn.functional as F
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from paddlerobotics_b200.agent import MujocoAgent, SACLearner, flatten_params
+    B = 256
+    torch.manual_seed(2)
+    expert, student = MujocoAgent(49, 12, seed=21), MujocoAgent(46, 12, seed=22)
+    L = SACLearner(student, B, actor_lr=3e-4, critic_lr=3e-4)
+    dev = student.device
+    ref_obs = torch.randn(B, 49, device=dev)
+    obs = ref_obs[:, 3:].contiguous()
+    eps = torch.randn(B, 12, device=dev)
+    p = {k: v.clone().requires_grad_(True) for k, v in student.params.items()}
+    pe = expert.params
+    a0, c0 = flatten_params(student.params)
+
+    def actor(pp, o):
+        x = F.relu(F.linear(o, pp["actor_model.l1.weight"], pp["actor_model.l1.bias"]))
+        x = F.relu(F.linear(x, pp["actor_model.l2.weight"], pp["actor_model.l2.bias"]))
+        return F.linear(x, pp["actor_model.mean_linear.weight"], pp["actor_model.mean_linear.bias"]), \
+            torch.clamp(F.linear(x, pp["actor_model.std_linear.weight"], pp["actor_model.std_linear.bias"]), -20.0, 2.0)
+
+    def critic(pp, o, a):
+        x = torch.cat([o, a], 1); out = []
+        for l1, l2, l3 in (("l1", "l2", "l3"), ("l4", "l5", "l6")):
+            h = F.relu(F.linear(x, pp["critic_model.%s.weight" % l1], pp["critic_model.%s.bias" % l1]))
+            h = F.relu(F.linear(h, pp["critic_model.%s.weight" % l2], pp["critic_model.%s.bias" % l2]))
+            out.append(F.linear(h, pp["critic_model.%s.weight" % l3], pp["critic_model.%s.bias" % l3]))
+        return out
+    opt_a = torch.optim.Adam([p[k] for k in p if k.startswith("actor")], lr=3e-4)
+    opt_c = torch.optim.Adam([p[k] for k in p if k.startswith("critic")], lr=3e-4)
+    mean, ls = actor(p, obs)
+    with torch.no_grad():
+        ref_action = torch.tanh(actor(pe, ref_obs)[0])
+    actor_loss = -torch.distributions.Normal(mean, ls.exp()).log_prob(ref_action).mean()
+    opt_a.zero_grad(); actor_loss.backward(); opt_a.step()
+    with torch.no_grad():
+        m2, l2 = actor(p, obs)
+        a_now = torch.tanh(m2 + l2.exp() * eps)
+        rq1, rq2 = critic(pe, ref_obs, a_now)
+    q1, q2 = critic(p, obs, a_now)
+    critic_loss = F.mse_loss(q1, rq1) + F.mse_loss(q2, rq2)
+    opt_c.zero_grad(); critic_loss.backward(); opt_c.step()
+    losses = L.bc_learn(obs, ref_obs, expert, eps=eps)
+    assert abs(float(losses[1]) - float(actor_loss)) < 0.02 * abs(float(actor_loss)) + 1e-2
+    assert abs(float(losses[0]) - float(critic_loss)) < 0.03 * abs(float(critic_loss)) + 1e-3
+    a1, c1 = flatten_params(student.params)
+    ra, rc = flatten_params({k: v.detach() for k, v in p.items()})
+    for name, d, r, z in (("actor", a1, ra, a0), ("critic", c1, rc, c0)):
+        dd, rr = d - z, r - z
+        cos = float(torch.dot(dd, rr) / (dd.norm() * rr.norm()))
+        print(name, "BC displacement cos %.4f |d| %.4g vs %.4g" % (cos, float(dd.norm()), float(rr.norm())))
+        assert cos > 0.95 and 0.9 < float(dd.norm() / rr.norm()) < 1.1
+    c_l, a_l = student.BClearn(obs, ref_obs, expert)
+    assert np.isfinite(c_l) and np.isfinite(a_l)
