@@ -221,17 +221,24 @@ struct EnvT : EnvBase {
     CK(cudaSetDevice(cfg.device));
     const size_t N = (size_t)B.N;
     if (!st_act) {
-      size_t bytes = N * (12 + OBS_DIM + 1 + INFO_DIM) * sizeof(T) + N;
+      size_t bytes = N * (12 + OBS_DIM + 1 + INFO_DIM) * sizeof(T) + N + 512;
       void* p = nullptr;
       CK(cudaMalloc(&p, bytes));
-      st_act = (T*)p; st_obs = st_act + N * 12; st_rew = st_obs + N * OBS_DIM; st_info = st_rew + N; st_done = (uint8_t*)(st_info + N * INFO_DIM);
+      // layout: act | obs | rew | done (bytes) | pad | info  — obs/rew/done contiguous so one D2H can serve all three
+      st_act = (T*)p; st_obs = st_act + N * 12; st_rew = st_obs + N * OBS_DIM; st_done = (uint8_t*)(st_rew + N);
+      st_info = (T*)((uint8_t*)p + ((N * (12 + OBS_DIM + 1) * sizeof(T) + N + 255) / 256) * 256);
     }
     CK(cudaMemcpyAsync(st_act, a, N * 12 * sizeof(T), cudaMemcpyHostToDevice, s));
     int rc = step(st_act, donef, st_obs, st_rew, st_done, st_info, s);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(obs, st_obs, N * OBS_DIM * sizeof(T), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(rew, st_rew, N * sizeof(T), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(done, st_done, N, cudaMemcpyDeviceToHost, s));
+    const size_t b_obs = N * OBS_DIM * sizeof(T), b_rew = N * sizeof(T);
+    if ((uint8_t*)rew == (uint8_t*)obs + b_obs && done == (uint8_t*)rew + b_rew) {
+      CK(cudaMemcpyAsync(obs, st_obs, b_obs + b_rew + N, cudaMemcpyDeviceToHost, s));      // caller's host buffers are contiguous too
+    } else {
+      CK(cudaMemcpyAsync(obs, st_obs, b_obs, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(rew, st_rew, b_rew, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(done, st_done, N, cudaMemcpyDeviceToHost, s));
+    }
     if (info) CK(cudaMemcpyAsync(info, st_info, N * INFO_DIM * sizeof(T), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return B2Q_OK;

@@ -116,9 +116,11 @@ class VecQuadrupedalEnv:
         if self._h_act is None:
             n, npdt = self.num_envs, self.dtype
             self._h_act = torch.empty(n, ACT_DIM, dtype=npdt).pin_memory()
-            self._h_obs = torch.empty(n, OBS_DIM, dtype=npdt).pin_memory()
-            self._h_rew = torch.empty(n, dtype=npdt).pin_memory()
-            self._h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+            es = self.obs.element_size()
+            self._h_out = torch.empty(n * (OBS_DIM + 1) * es + n, dtype=torch.uint8).pin_memory()     # obs | rew | done contiguous: one D2H
+            self._h_obs = self._h_out[: n * OBS_DIM * es].view(npdt).reshape(n, OBS_DIM)
+            self._h_rew = self._h_out[n * OBS_DIM * es: n * (OBS_DIM + 1) * es].view(npdt)
+            self._h_done = self._h_out[n * (OBS_DIM + 1) * es:]
             self._np_act, self._np_obs, self._np_rew, self._np_done = self._h_act.numpy(), self._h_obs.numpy(), self._h_rew.numpy(), self._h_done.numpy()
 
     def step_host(self, action_np, donef=False):
