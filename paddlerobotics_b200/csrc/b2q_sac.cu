@@ -137,58 +137,55 @@ __global__ void k_critic_dq(const float* q /*[2][B]*/, const float* tq /*[B] or 
   for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
   if ((threadIdx.x & 31) == 0) atomicAdd(loss, l);
 }
-// dh2[b,:] = dy[b,:] . W3 (out_dim x 256), masked by relu(h2) > 0 -> bf16 row-major + transposed; dW3 += dy^T h2 (tiny N: done here)
-__global__ void k_head_bwd(const float* dy /*[B][od]*/, int od, const float* W3 /*[od][256]*/, const bf16* h2 /*[B][256]*/, bf16* dh_rm, bf16* dh_t,
-                           float* dW3 /*[od][256]*/, int B) {
-  // block: 256 threads = hidden columns; grid.x over batch tiles of 32 rows
-  int col = threadIdx.x, b0 = blockIdx.x * 32;
-  float w[24];
-  for (int o = 0; o < od; o++) w[o] = W3[o * H + col];
-  float acc[24];
-  for (int o = 0; o < od; o++) acc[o] = 0.f;
-  for (int r = 0; r < 32; r++) {
-    int b = b0 + r;
-    if (b >= B) break;
-    float hv = __bfloat162float(h2[(size_t)b * H + col]);
-    float g = 0.f;
-    for (int o = 0; o < od; o++) { float d = dy[(size_t)b * od + o]; g += d * w[o]; acc[o] += d * hv; }
+// Both kernels below process a tile of 32 batch rows x 256 hidden columns per block (thread = column): the row-major
+// gradient is stored directly (coalesced), the [width x batch] copy goes through a shared-memory transpose so that it is
+// written as 64-byte row segments, and the bias gradient (column sums) is accumulated on the fly (one atomic per column
+// per block) -- no separate reduction launches.
+//
+// dh2[b,:] = dy[b,:] . W3 (out_dim x 256), masked by relu(h2) > 0; dW3 += dy^T h2; db3 += sum_b dy; db2 += sum_b dh2
+__global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ dy /*[B][od]*/, int od, const float* __restrict__ W3 /*[od][256]*/,
+                                                  const bf16* __restrict__ h2 /*[B][256]*/, bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t,
+                                                  float* dW3 /*[od][256]*/, float* db3 /*[od] or null*/, float* db2 /*[256] or null*/, int B) {
+  __shared__ bf16 tile[32][H + 2];
+  __shared__ float sdy[32][24];
+  const int col = threadIdx.x, b0 = blockIdx.x * 32, nr = min(32, B - b0);
+  for (int i = threadIdx.x; i < nr * od; i += blockDim.x) sdy[i / od][i % od] = dy[(size_t)b0 * od + i];
+  __syncthreads();
+  float w[24], acc[24], colsum = 0.f;
+  for (int o = 0; o < od; o++) { w[o] = W3[o * H + col]; acc[o] = 0.f; }
+  for (int r = 0; r < nr; r++) {
+    const int b = b0 + r;
+    float hv = __bfloat162float(h2[(size_t)b * H + col]), g = 0.f;
+    for (int o = 0; o < od; o++) { float d = sdy[r][o]; g += d * w[o]; acc[o] += d * hv; }
     g = hv > 0.f ? g : 0.f;
     bf16 gb = __float2bfloat16(g);
+    colsum += __bfloat162float(gb);
     dh_rm[(size_t)b * H + col] = gb;
-    dh_t[(size_t)col * B + b] = gb;
+    tile[r][col] = gb;
   }
   for (int o = 0; o < od; o++) atomicAdd(dW3 + o * H + col, acc[o]);
+  if (db2) atomicAdd(db2 + col, colsum);
+  if (db3 && col < od) { float sd = 0.f; for (int r = 0; r < nr; r++) sd += sdy[r][col]; atomicAdd(db3 + col, sd); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * 32; i += blockDim.x) { int c = i >> 5, r = i & 31; if (r < nr) dh_t[(size_t)c * B + b0 + r] = tile[r][c]; }
 }
-// dh = G (f32 [B][256]) masked by h>0 -> bf16 row-major + transposed
-__global__ void k_relu_mask(const float* G, const bf16* h, bf16* dh_rm, bf16* dh_t, int B) {
-  int col = threadIdx.x, b0 = blockIdx.x * 32;
-  for (int r = 0; r < 32; r++) {
-    int b = b0 + r;
-    if (b >= B) break;
+// dh = G (f32 [B][256]) masked by h>0 -> bf16 row-major + transposed; db += column sums
+__global__ void __launch_bounds__(256) k_relu_mask(const float* __restrict__ G, const bf16* __restrict__ h, bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t,
+                                                   float* db /*[256] or null*/, int B) {
+  __shared__ bf16 tile[32][H + 2];
+  const int col = threadIdx.x, b0 = blockIdx.x * 32, nr = min(32, B - b0);
+  float colsum = 0.f;
+  for (int r = 0; r < nr; r++) {
+    const int b = b0 + r;
     float v = __bfloat162float(h[(size_t)b * H + col]) > 0.f ? G[(size_t)b * H + col] : 0.f;
     bf16 vb = __float2bfloat16(v);
+    colsum += __bfloat162float(vb);
     dh_rm[(size_t)b * H + col] = vb;
-    dh_t[(size_t)col * B + b] = vb;
+    tile[r][col] = vb;
   }
-}
-// db[col] = sum_b dh_t[col][b]  (one warp per column)
-__global__ void k_rowsum_bf16(const bf16* dh_t, float* db, int B) {
-  int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (col >= H) return;
-  float s = 0.f;
-  for (int b = lane; b < B; b += 32) s += __bfloat162float(dh_t[(size_t)col * B + b]);
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) db[col] = s;
-}
-__global__ void k_colsum_f32(const float* dy, int od, float* db, int B) {   // db[o] = sum_b dy[b][o]
-  int o = blockIdx.x, lane = threadIdx.x;
-  float s = 0.f;
-  for (int b = lane; b < B; b += blockDim.x) s += dy[(size_t)b * od + o];
-  for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
-  __shared__ float sh[8];
-  if ((lane & 31) == 0) sh[lane >> 5] = s;
+  if (db) atomicAdd(db + col, colsum);
   __syncthreads();
-  if (lane == 0) { float t = 0.f; for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += sh[i]; db[o] = t; }
+  for (int i = threadIdx.x; i < H * 32; i += blockDim.x) { int c = i >> 5, r = i & 31; if (r < nr) dh_t[(size_t)c * B + b0 + r] = tile[r][c]; }
 }
 // actor head: from raw y=[mean|raw_ls], eps, da_c (critic gradient wrt action, already includes -1/B routing) build dy and the loss
 __global__ void k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const float* act /*[B][A] tanh(x)*/, const float* logp, const float* q /*[2][B]*/,
@@ -337,13 +334,10 @@ int critic_backward(B2QSac* s, cudaStream_t st) {
   for (int i = 0; i < 2; i++) {
     float* g = s->g_critic + (size_t)i * cn.n; const float* p = s->p_critic + (size_t)i * cn.n;
     const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h1t = s->hc1_t + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
-    k_colsum_f32<<<1, 256, 0, st>>>(s->dq + (size_t)i * B, 1, g + cn.ob3, B);
-    k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dq + (size_t)i * B, 1, p + cn.oW3, h2, s->dh_rm, s->dh_t, g + cn.oW3, B);
-    k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + cn.ob2, B);
+    k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dq + (size_t)i * B, 1, p + cn.oW3, h2, s->dh_rm, s->dh_t, g + cn.oW3, g + cn.ob3, g + cn.ob2, B);   // dh2, dW3, db3, db2
     if (gemm(s, st, s->dh_t, B, h1t, B, g + cn.oW2, H, H, H, B, true)) return -2;
     if (gemm(s, st, s->dh_rm, H, s->W2T[1 + i], H, s->G, H, B, H, H, false)) return -2;
-    k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(s->G, h1, s->dh_rm, s->dh_t, B);
-    k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + cn.ob1, B);
+    k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(s->G, h1, s->dh_rm, s->dh_t, g + cn.ob1, B);                                                      // dh1, db1
     if (gemm(s, st, s->dh_t, B, s->xc_t, B, g + cn.oW1, cn.in_dim, H, cn.in_dim, B, true)) return -2;
     s->launches += 5;
   }
@@ -353,13 +347,10 @@ int critic_backward(B2QSac* s, cudaStream_t st) {
 int actor_backward(B2QSac* s, cudaStream_t st) {
   const int B = s->B, A = s->A; const Net& an = s->an;
   float* g = s->g_actor;
-  k_colsum_f32<<<2 * A, 256, 0, st>>>(s->dy, 2 * A, g + an.ob3, B);
-  k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dy, 2 * A, s->p_actor + an.oW3, s->ha2_rm, s->dh_rm, s->dh_t, g + an.oW3, B);
-  k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + an.ob2, B);
+  k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dy, 2 * A, s->p_actor + an.oW3, s->ha2_rm, s->dh_rm, s->dh_t, g + an.oW3, g + an.ob3, g + an.ob2, B);
   if (gemm(s, st, s->dh_t, B, s->ha1_t, B, g + an.oW2, H, H, H, B, true)) return -2;
   if (gemm(s, st, s->dh_rm, H, s->W2T[0], H, s->G, H, B, H, H, false)) return -2;
-  k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(s->G, s->ha1_rm, s->dh_rm, s->dh_t, B);
-  k_rowsum_bf16<<<H / 8, 256, 0, st>>>(s->dh_t, g + an.ob1, B);
+  k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(s->G, s->ha1_rm, s->dh_rm, s->dh_t, g + an.ob1, B);
   if (gemm(s, st, s->dh_t, B, s->xa_t, B, g + an.oW1, an.in_dim, H, an.in_dim, B, true)) return -2;
   s->launches += 5;
   return 0;
@@ -488,9 +479,9 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     for (int i = 0; i < 2; i++) {
       const float* p = s->p_critic + (size_t)i * cn.n;
       const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
-      k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dq + (size_t)i * B, 1, p + cn.oW3, h2, s->dh_rm, s->dh_t, s->G /*scratch dW3*/, B);
+      k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dq + (size_t)i * B, 1, p + cn.oW3, h2, s->dh_rm, s->dh_t, s->G /*scratch dW3*/, nullptr, nullptr, B);
       if (gemm(s, st, s->dh_rm, H, s->W2T[1 + i], H, s->G, H, B, H, H, false)) return -2;
-      k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(s->G, h1, s->dh_rm, s->dh_t, B);
+      k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(s->G, h1, s->dh_rm, s->dh_t, nullptr, B);
       if (gemm(s, st, s->dh_rm, H, s->W1A[1 + i], H, s->G, 16, B, 16, H, false)) return -2;                    // da_i [B][16]
       k_add_f32<<<(B * 16 + 255) / 256, 256, 0, st>>>(s->da_c, s->G, B * 16);
       s->launches += 3;
