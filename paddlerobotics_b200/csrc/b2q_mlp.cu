@@ -82,16 +82,27 @@ __global__ void __launch_bounds__(128, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
   // input tile: f32 [rows, in_dim] (two sources concatenated) -> bf16 swizzled panel 0 (K padded to 64 with zeros)
   {
     const int in2_dim = a.in_dim - a.in1_dim;
-    for (int idx = tid; idx < TILE_M * 64; idx += 128) {
-      int r = idx >> 6, k = idx & 63, gr = row0 + r;
-      float v = 0.f;
-      if (gr < a.M) {
-        if (k < a.in1_dim) v = a.in1[(size_t)gr * a.in1_dim + k];
-        else if (k < a.in_dim) v = a.in2[(size_t)gr * in2_dim + (k - a.in1_dim)];
+    // 64 elements per thread in batches of 16 independent loads (all loads of a batch are in flight before the first use)
+#pragma unroll 1
+    for (int j0 = 0; j0 < 64; j0 += 16) {
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const int idx = tid + 128 * (j0 + j), r = idx >> 6, k = idx & 63, gr = row0 + r;
+        float x = 0.f;
+        if (gr < a.M) {
+          if (k < a.in1_dim) x = __ldg(a.in1 + (size_t)gr * a.in1_dim + k);
+          else if (k < a.in_dim) x = __ldg(a.in2 + (size_t)gr * in2_dim + (k - a.in1_dim));
+        }
+        v[j] = x;
       }
-      __nv_bfloat16 vb = __float2bfloat16(v);
-      *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + sw128_offset(r, k, TILE_M)) = vb;
-      if (a.save && net == 0 && gr < a.M) { a.sv.x_rm[(size_t)gr * 64 + k] = vb; a.sv.x_t[(size_t)k * a.M + gr] = vb; }
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const int idx = tid + 128 * (j0 + j), r = idx >> 6, k = idx & 63, gr = row0 + r;
+        __nv_bfloat16 vb = __float2bfloat16(v[j]);
+        *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + sw128_offset(r, k, TILE_M)) = vb;
+        if (a.save && net == 0 && gr < a.M) { a.sv.x_rm[(size_t)gr * 64 + k] = vb; a.sv.x_t[(size_t)k * a.M + gr] = vb; }
+      }
     }
   }
   fence_async_smem();
