@@ -67,6 +67,7 @@ typedef struct B2QConfig {
   int32_t action_interp;     /* Minitaur.ProcessAction, minitaur.py:1384-1401 */
   double torque_limit;       /* <=0 off */
   int32_t settle_steps;      /* a1.py:294-297 */
+  int32_t max_episode_steps; /* >0: done also when an env's own step counter reaches it (per-env form of donef=(steps>max_step), train.py:147) */
   int32_t etg_enabled;       /* 1; 0 = make_env(ETG=0): action is the joint offset itself (Dynamic_parallel_model.py:49,59-60) */
   int32_t action_filter;     /* 2nd-order Butterworth low-pass on the joint targets (minitaur.py:250-251, action_filter.py:111-216) */
   double filter_highcut;     /* Hz; 4.0 (action_filter.py:44) */

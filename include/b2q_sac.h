@@ -40,6 +40,9 @@ int b2q_sac_phase(B2QSacHandle h, int phase, const float* obs, const float* act,
  * eps [B,act_dim]: the N(0,1) draw of the student's sample().  losses_out device float[2] = {critic_loss, actor_loss}. */
 int b2q_sac_bc_learn(B2QSacHandle h, const float* obs, const float* ref_obs, int ref_obs_dim, B2QMlpHandle expert_actor, B2QMlpHandle expert_critic,
                      const float* eps, float* losses_out, void* stream);
+/* the learner's own forward objects (0 actor, 1 twin critic, 2 target critic): always up to date with the parameters, so a
+ * rollout can sample from the policy being trained without copying weights.  Owned by the learner. */
+B2QMlpHandle b2q_sac_mlp(B2QSacHandle h, int which);
 float* b2q_sac_grad_ptr(B2QSacHandle h, int which);   /* device gradient bucket (for ncclAllReduce in place) */
 float* b2q_sac_loss_ptr(B2QSacHandle h);
 int64_t b2q_sac_launch_count(B2QSacHandle h);

@@ -728,7 +728,7 @@ void orc_env_step(const OrcConfig* c, OrcEnv* e, const double action[12], int do
   double r_torso = c->w_torso * torso, r_feet = c->w_feet * feet, r_up = c->w_up * up, r_tau = -c->w_tau * energy;
   double r_bad = -c->w_badfoot * bad, r_fc = -c->w_footcontact * (nofoot > 2 ? nofoot - 2 : 0), r_done = fall ? -c->w_done : 0.0;
   *reward = c->reward_p * (r_torso + r_feet + r_up + r_tau + r_bad + r_fc + r_done);
-  *done = fall || donef;
+  *done = fall || donef || (c->max_episode_steps > 0 && e->step_count >= c->max_episode_steps);
   if (info) {
     memset(info, 0, sizeof(double) * ORC_INFO_DIM);
     info[0] = velx; info[1] = r_torso; info[2] = r_feet; info[3] = r_up; info[4] = r_tau; info[5] = 0; info[6] = r_bad; info[7] = r_fc; info[8] = r_done;

@@ -45,6 +45,7 @@ typedef struct {
   int action_interp;        /* minitaur.py:1384-1401 */
   double torque_limit;      /* <=0: off (laikago_motor.py:168-173) */
   int settle_steps;         /* a1.py:294-297: 500 */
+  int max_episode_steps;    /* >0: done also when the env's own step counter reaches it (donef=(steps>max_step), train.py:147) */
   int etg_enabled;          /* make_env(ETG=0): no open-loop reference, action = joint offsets (Dynamic_parallel_model.py:49,59-60) */
   int action_filter;        /* Butterworth low-pass on the joint targets, minitaur.py:248-251,1403-1422 */
   double filter_highcut;    /* 4 Hz, action_filter.py:42-44 */

@@ -26,7 +26,7 @@ class Config(C.Structure):
         ("sim_dt", C.c_double), ("action_repeat", C.c_int), ("solver_iters", C.c_int),
         ("erp", C.c_double), ("warmstart", C.c_double), ("contact_margin", C.c_double),
         ("action_interp", C.c_int), ("torque_limit", C.c_double), ("settle_steps", C.c_int),
-        ("etg_enabled", C.c_int), ("action_filter", C.c_int), ("filter_highcut", C.c_double),
+        ("max_episode_steps", C.c_int), ("etg_enabled", C.c_int), ("action_filter", C.c_int), ("filter_highcut", C.c_double),
         ("etg_T", C.c_double), ("etg_T2", C.c_double), ("etg_sigma_sq", C.c_double), ("etg_amp", C.c_double),
         ("etg_phase", C.c_double * 2),
         ("w_torso", C.c_double), ("w_feet", C.c_double), ("w_up", C.c_double), ("w_tau", C.c_double),

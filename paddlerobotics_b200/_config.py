@@ -14,7 +14,7 @@ class B2QConfig(C.Structure):
         ("sim_dt", C.c_double), ("action_repeat", C.c_int32), ("solver_iters", C.c_int32),
         ("erp", C.c_double), ("warmstart", C.c_double), ("contact_margin", C.c_double),
         ("action_interp", C.c_int32), ("torque_limit", C.c_double), ("settle_steps", C.c_int32),
-        ("etg_enabled", C.c_int32), ("action_filter", C.c_int32), ("filter_highcut", C.c_double),
+        ("max_episode_steps", C.c_int32), ("etg_enabled", C.c_int32), ("action_filter", C.c_int32), ("filter_highcut", C.c_double),
         ("etg_T", C.c_double), ("etg_T2", C.c_double), ("etg_sigma_sq", C.c_double), ("etg_amp", C.c_double),
         ("etg_phase0", C.c_double), ("etg_phase1", C.c_double),
         ("w_torso", C.c_double), ("w_feet", C.c_double), ("w_up", C.c_double), ("w_tau", C.c_double), ("w_stand", C.c_double),

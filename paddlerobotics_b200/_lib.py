@@ -48,6 +48,7 @@ SYMBOLS = {
     "b2q_sac_learn": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp]),
     "b2q_sac_phase": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint64, _vp]),
     "b2q_sac_bc_learn": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "b2q_sac_mlp": (_vp, [_vp, _i]),
     "b2q_sac_grad_ptr": (_vp, [_vp, _i]),
     "b2q_sac_loss_ptr": (_vp, [_vp]),
     "b2q_sac_launch_count": (C.c_int64, [_vp]),

@@ -18,12 +18,16 @@ LOG_SIG_MAX, LOG_SIG_MIN = 2.0, -20.0   # mujoco_model.py:21-22
 class FusedMLP:
     """ctypes handle of one b2q_mlp object: in_dim(<=64) -> 256 -> 256 -> out_dim(<=32), `nets` weight sets."""
 
-    def __init__(self, in_dim, out_dim, nets=1, device=0):
+    def __init__(self, in_dim, out_dim, nets=1, device=0, borrowed=None):
+        self._owned = borrowed is None
         if not torch.cuda.is_available():
             raise RuntimeError("FusedMLP needs a CUDA device (tcgen05 kernel, no fallback)")
         self.lib = _lib.load()
         self.in_dim, self.out_dim, self.nets = in_dim, out_dim, nets
         self.device = torch.device("cuda", int(device))
+        if borrowed is not None:
+            self.h = C.c_void_p(borrowed)
+            return
         self.h = C.c_void_p()
         rc = self.lib.b2q_mlp_create(int(device), in_dim, out_dim, nets, C.byref(self.h))
         if rc != 0:
@@ -62,7 +66,8 @@ class FusedMLP:
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.b2q_mlp_destroy(self.h)
+            if self._owned:
+                self.lib.b2q_mlp_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -202,6 +207,9 @@ class SACLearner:
         self.steps = 0
         self._graph = None
         self.push()
+        # forward objects that always see the parameters being trained (no weight copies during a rollout)
+        self.actor = FusedMLP(agent.obs_dim, 2 * agent.act_dim, 1, agent.device.index or 0, borrowed=self.lib.b2q_sac_mlp(self.h, 0))
+        self.critic = FusedMLP(agent.obs_dim + agent.act_dim, 1, 2, agent.device.index or 0, borrowed=self.lib.b2q_sac_mlp(self.h, 1))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.agent.device).cuda_stream)

@@ -12,7 +12,7 @@ inline Cfg<T> make_cfg(const B2QConfig& c, const T* hf_dev) {
   Cfg<T> k;
   k.dt = (T)c.sim_dt; k.R = c.action_repeat; k.iters = c.solver_iters; k.erp = (T)c.erp; k.warm = (T)c.warmstart; k.margin = (T)c.contact_margin;
   k.interp = c.action_interp; k.tau_limit = (T)c.torque_limit; k.settle_steps = c.settle_steps;
-  k.filter = c.action_filter; k.etg = c.etg_enabled;
+  k.filter = c.action_filter; k.etg = c.etg_enabled; k.max_steps = c.max_episode_steps;
   {  // scipy.signal.butter(2, highcut / (fs/2)) in closed form (bilinear transform), fs = 1 / control period
     const double PI = 3.14159265358979323846, fs = 1.0 / (c.sim_dt * c.action_repeat);
     const double K = std::tan(PI * c.filter_highcut / fs), n = 1.0 / (1.0 + std::sqrt(2.0) * K + K * K);

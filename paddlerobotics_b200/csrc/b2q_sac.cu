@@ -541,6 +541,7 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   if (e != cudaSuccess) { s->err = cudaGetErrorString(e); return -2; }
   return 0;
 }
+B2QMlpHandle b2q_sac_mlp(B2QSacHandle s, int which) { return !s ? nullptr : (which == 0 ? s->mlp_actor : (which == 1 ? s->mlp_critic : s->mlp_target)); }
 float* b2q_sac_grad_ptr(B2QSacHandle s, int which) { return !s ? nullptr : (which == 0 ? s->g_actor : s->g_critic); }
 float* b2q_sac_loss_ptr(B2QSacHandle s) { return s ? s->losses : nullptr; }
 

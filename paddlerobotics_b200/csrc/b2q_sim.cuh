@@ -56,7 +56,7 @@ struct Model {
 template <typename T>
 struct Cfg {
   T dt; int R; int iters; T erp, warm, margin; int interp; T tau_limit; int settle_steps;
-  int filter; T fb0, fb1, fb2, fa1, fa2; int etg;
+  int filter; T fb0, fb1, fb2, fa1, fa2; int etg; int max_steps;
   T etg_T, etg_T2, etg_sigma_sq, etg_amp, etg_ph0, etg_ph1;
   T w_torso, w_feet, w_up, w_tau, w_stand, w_badfoot, w_footcontact, w_done, reward_p, vel_d;
   int terrain, hf_nx, hf_ny; T hf_x0, hf_y0, hf_cell; const T* hf;
@@ -717,7 +717,7 @@ B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, cons
   T r_torso = cf.w_torso * torso, r_feet = cf.w_feet * feet, r_up = cf.w_up * up, r_tau = -cf.w_tau * energy;
   T r_bad = -cf.w_badfoot * bad, r_fc = -cf.w_footcontact * (nofoot > T(2) ? nofoot - T(2) : T(0)), r_done = fall ? -cf.w_done : T(0);
   T rew = cf.reward_p * (r_torso + r_feet + r_up + r_tau + r_bad + r_fc + r_done);
-  bool dn = fall || donef;
+  bool dn = fall || donef || (cf.max_steps > 0 && step >= cf.max_steps);
   if (valid) {
     T* irow = info + (size_t)env * INFO_DIM;
     if (k == 0) {

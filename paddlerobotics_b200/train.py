@@ -1,0 +1,111 @@
+"""ETG-RL training loop on the GPU engine — the batched counterpart of ETGRL/train.py:252-449 (same phases, same flag names
+where they exist): SAC episodes with one learner step per control step (train.py:163-169) over N parallel envs, and every
+`ES_EVERY_STEPS` env steps an ES phase of `ES_TRAIN_STEPS` generations over the ETG control points (train.py:392-437).
+Everything per-step stays on the device: obs -> fused MLP (tcgen05) -> step kernel -> device replay -> SAC learn (CUDA graph).
+
+    python -m paddlerobotics_b200.train --num_envs 4096 --max_steps 2000000 --ES 1
+"""
+import argparse
+import json
+import time
+
+import numpy as np
+import torch
+
+from .agent import MujocoAgent, SACLearner
+from .env import VecQuadrupedalEnv
+from .es import PopulationEvaluator, SimpleGA, solutions_to_etg_device
+from .etg import ETG_layer, Opt_with_points
+from .replay import ReplayMemory
+
+GAMMA, TAU, ALPHA, ACTOR_LR, CRITIC_LR = 0.99, 0.005, 0.2, 3e-4, 3e-4     # train.py:43-47
+
+
+def main(argv=None):
+    p = argparse.ArgumentParser()
+    p.add_argument("--num_envs", type=int, default=4096)
+    p.add_argument("--max_steps", type=int, default=400000, help="total env steps (all envs)")
+    p.add_argument("--batch", type=int, default=4096)
+    p.add_argument("--warmup_steps", type=int, default=40960)          # WARMUP_STEPS = 1e4 per env-step in the reference
+    p.add_argument("--memory", type=int, default=1000000)              # MEMORY_SIZE, train.py:41
+    p.add_argument("--e_step", type=int, default=400)                  # train.py:476
+    p.add_argument("--act_bound", type=float, default=0.3)             # train.py:488
+    p.add_argument("--ETG_T", type=float, default=0.5)
+    p.add_argument("--footheight", type=float, default=0.1)
+    p.add_argument("--steplen", type=float, default=0.05)
+    p.add_argument("--ES", type=int, default=1)
+    p.add_argument("--popsize", type=int, default=40)
+    p.add_argument("--es_rollouts", type=int, default=4)
+    p.add_argument("--es_every_steps", type=int, default=200000)       # ES_EVERY_STEPS = 5e4 per env in the reference
+    p.add_argument("--es_train_steps", type=int, default=3)            # ES_TRAIN_STEPS = 10
+    p.add_argument("--sigma", type=float, default=0.02)
+    p.add_argument("--sigma_decay", type=float, default=0.99)
+    p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--log_every", type=int, default=50)
+    p.add_argument("--torso", type=float, default=1.5); p.add_argument("--feet", type=float, default=0.3); p.add_argument("--up", type=float, default=0.6)
+    p.add_argument("--tau", type=float, default=0.07); p.add_argument("--badfoot", type=float, default=0.1); p.add_argument("--footcontact", type=float, default=0.1)
+    args = p.parse_args(argv)
+    torch.manual_seed(args.seed); np.random.seed(args.seed)
+    n = args.num_envs
+    layer = ETG_layer(args.ETG_T, 0.026, 20, 0.04, np.array([-np.pi / 2, 0]), 0.2, args.ETG_T)
+    w0, b0, prior_points = Opt_with_points(ETG=layer, ETG_T=args.ETG_T, Footheight=args.footheight, Steplength=args.steplen)     # train.py:298-299
+    w, b = w0, b0
+    env = VecQuadrupedalEnv(n, auto_reset=True, max_episode_steps=args.e_step, w_torso=args.torso, w_feet=args.feet, w_up=args.up, w_tau=args.tau,
+                            w_badfoot=args.badfoot, w_footcontact=args.footcontact)
+    agent = MujocoAgent(49, 12, seed=args.seed)
+    learner = SACLearner(agent, args.batch, gamma=GAMMA, tau=TAU, alpha=ALPHA, actor_lr=ACTOR_LR, critic_lr=CRITIC_LR)
+    rpm = ReplayMemory(args.memory, 49, 12)
+    solver = SimpleGA(12, sigma_init=args.sigma, sigma_decay=args.sigma_decay, sigma_limit=0.005, elite_ratio=0.1, weight_decay=0.005,
+                      popsize=args.popsize, param=np.zeros(12))                                                                  # train.py:288-295
+    evaluator = PopulationEvaluator(args.popsize, args.es_rollouts, max_steps=args.e_step, policy=lambda o: learner.actor.forward(o)[0][0],
+                                    act_bound=args.act_bound) if args.ES else None
+    obs = env.reset(w, b).clone()
+    total, it, last_es, t0 = 0, 0, 0, time.perf_counter()
+    ret_acc = torch.zeros(n, device=env.device); ep_rets = []
+    log = []
+    while total < args.max_steps:
+        if rpm.size() < args.warmup_steps:
+            act = torch.rand(n, 12, device=env.device) * 2 - 1                         # train.py:141-142
+        else:
+            act = learner.actor.forward(obs, mode=1, seed=it + 1)[0][0]               # agent.sample(obs)
+        nobs, rew, done, info = env.step(act * args.act_bound)
+        rpm.append(obs, act, rew, nobs, 1.0 - done.float())                            # terminal = 1 - done, train.py:148-149,159
+        ret_acc += rew
+        fin = done.bool()
+        if it % args.log_every == 0 and bool(fin.any()):
+            ep_rets.append(float(ret_acc[fin].mean()))
+        ret_acc = torch.where(fin, torch.zeros_like(ret_acc), ret_acc)
+        obs.copy_(nobs)
+        total += n; it += 1
+        if rpm.size() >= args.warmup_steps:
+            losses = learner.learn(*rpm.sample_batch(args.batch), graph=True, pull=False)   # one update per control step, train.py:163-169
+        if it % args.log_every == 0:
+            torch.cuda.synchronize()
+            el = time.perf_counter() - t0
+            rec = {"env_steps": total, "iters": it, "env_steps_per_s": total / el, "mean_step_reward": float(rew.mean()), "done_frac": float(done.float().mean()),
+                   "episode_return": ep_rets[-1] if ep_rets else None,
+                   "critic_loss": float(losses[0]) if rpm.size() >= args.warmup_steps else None, "actor_loss": float(losses[1]) if rpm.size() >= args.warmup_steps else None}
+            log.append(rec); print(json.dumps(rec), flush=True)
+        if evaluator is not None and total - last_es >= args.es_every_steps and rpm.size() >= args.warmup_steps:
+            last_es = total
+            best_fit, best_param = -1e9, None
+            for gen in range(args.es_train_steps):                                     # train.py:397-418
+                sol = solver.ask()
+                ws, bs = solutions_to_etg_device(sol, prior_points, w0, b0, ETG_T=args.ETG_T)
+                fit, mlen = evaluator.evaluate(ws.cpu().numpy(), bs.cpu().numpy())
+                fit_np = fit.double().cpu().numpy()
+                solver.tell(fit_np)
+                if fit_np.max() > best_fit:
+                    best_fit, best_param = float(fit_np.max()), sol[int(fit_np.argmax())]
+                print(json.dumps({"ES_gen": gen, "fitness_max": float(fit_np.max()), "fitness_mean": float(fit_np.mean()), "mean_len": float(mlen.mean())}), flush=True)
+            pts = prior_points + best_param.reshape(-1, 2)                              # train.py:433-437
+            w, b, _ = Opt_with_points(ETG=layer, ETG_T=args.ETG_T, w0=w0, b0=b0, points=pts)
+            solver.reset(best_param)
+            obs = env.reset(w, b).clone(); ret_acc.zero_()
+    torch.cuda.synchronize()
+    learner.pull()
+    return log
+
+
+if __name__ == "__main__":
+    main()

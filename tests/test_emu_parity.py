@@ -13,7 +13,7 @@ from oracle import oracle as O  # noqa: E402
 
 
 def _pair(precision, w, b, n=1, **kw):
-    ocfg = O.default_config(**{k: v for k, v in kw.items() if k in ("action_interp", "torque_limit", "solver_iters", "action_repeat", "action_filter")})
+    ocfg = O.default_config(**{k: v for k, v in kw.items() if k in ("action_interp", "torque_limit", "solver_iters", "action_repeat", "action_filter", "max_episode_steps")})
     e = emu.EmuEnv(n, precision, **kw)
     o = O.OracleEnv(ocfg)
     return e, o, e.reset(w, b), o.reset(w, b)
@@ -80,6 +80,13 @@ def test_f64_options_interp_torque_limit_latency(etg_stable):
         a = rng.uniform(-0.3, 0.3, 12)
         ob, rw, dn, inf = o.step(a); ob2, rw2, dn2, inf2 = e.step(a)
         assert np.abs(inf2[0] - inf).max() < 1e-8
+    e.close()
+    # per-env episode truncation (per-env form of donef=(steps>max_step), train.py:147)
+    e, o, _, _ = _pair(1, w, b, max_episode_steps=7)
+    for k in range(9):
+        a = rng.uniform(-0.1, 0.1, 12)
+        ob, rw, dn, inf = o.step(a); ob2, rw2, dn2, inf2 = e.step(a)
+        assert bool(dn2[0]) == dn == (k >= 6), k
     e.close()
     # control latency across control-step boundaries (minitaur.py:1172-1193): 0.0305 s = 15.25 substeps, ring depth 3
     p = O.default_param(); p[25] = 0.0305
