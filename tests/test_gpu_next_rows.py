@@ -114,3 +114,15 @@ def test_dynamics_identification_evaluator_vs_oracle(golden):
             ref[i] += (30 - loss_np(np.array(drpy), np.array(motor), md, k)) / 2.0
     assert np.abs(rew - ref).max() < 1e-6, (rew, ref)
     ev.env.close()
+
+
+def test_train_loop_runs_and_reward_improves():
+    """The batched ETG-RL loop (paddlerobotics_b200/train.py ~ ETGRL/train.py:252-449): SAC + one ES phase; the mean step
+    reward under the learned residual policy must beat the random-action warm-up phase."""
+    from paddlerobotics_b200 import train
+    log = train.main(["--num_envs", "1024", "--max_steps", "1300000", "--batch", "1024", "--warmup_steps", "20480", "--log_every", "100",
+                      "--es_every_steps", "700000", "--es_train_steps", "1", "--popsize", "8", "--es_rollouts", "2", "--e_step", "200"])
+    assert len(log) >= 10
+    early = np.mean([r["mean_step_reward"] for r in log[:2]])
+    late = np.mean([r["mean_step_reward"] for r in log[-3:]])
+    assert np.isfinite(late) and late > early + 0.5, (early, late)
