@@ -63,6 +63,18 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+def host_threads():
+    """Usable host threads: the scheduler affinity, capped by the cgroup CPU quota when one is set."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_oracle_rate(n_envs, steps, threads, w, b, seed=1234):
     """Oracle (float64 C port of the path; pybullet/rlschool are absent) on `threads` host threads: every thread owns a
     contiguous slice of envs and runs `steps` control steps on it (one env per actor, as Dynamic_parallel_model.py:96-99)."""
@@ -81,7 +93,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     w, b = etg_weights()
     n_envs = max(256, 32 * threads)                           # bounded sample of the 4096-env workload per step
     W, K = max(args.warmup, 1), args.steps
@@ -198,7 +210,7 @@ def main():
             pass
         cpu = None
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = host_threads()
             rate1, _ = cpu_oracle_rate(64, 8, 1, w, b)
             n_c = max(512, 32 * threads)
             steps_c = int(min(400, max(4, 12.0 * rate1 * threads / n_c)))                # ~12 s of CPU work at the ideal multi-thread rate
