@@ -439,15 +439,11 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
 #pragma unroll
   for (int f = 0; f < 4; f++) if (f == k) { lk[0] = lam[3 * f]; lk[1] = lam[3 * f + 1]; lk[2] = lam[3 * f + 2]; }
   s.lam_n = lk[0]; s.contact = lk[0] > T(0);
-  // --- apply impulses: every lane holds all rows, so sum_f Y_f lam_f needs no reduction
+  // --- apply impulses: sum over feet of Y_f lam_f by a 4-lane butterfly of each lane's own rows (keeps the gathered rows
+  //     of the other feet dead after the Delassus matrix is built: 72 fewer live registers across the sweep)
   T z[6];
 #pragma unroll
-  for (int c = 0; c < 6; c++) {
-    T a = T(0);
-#pragma unroll
-    for (int i = 0; i < 12; i++) a += Ya[i][c] * lam[i];
-    z[c] = a;
-  }
+  for (int c = 0; c < 6; c++) z[c] = cm.sum4(Y[0][c] * lk[0] + Y[1][c] * lk[1] + Y[2][c] * lk[2]);
   bwd6(S, Li, z);
   V6<T> dnu = arr_to_v6(z);
   {
