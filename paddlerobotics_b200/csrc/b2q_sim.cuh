@@ -369,16 +369,17 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
     lam[3 * f + 1] = T(0); lam[3 * f + 2] = T(0);
   }
   // Delassus matrix W = J M^-1 J^T  (symmetric): W_ij = Y_i . Y_j  (+ the leg-local block on the diagonal blocks)
-  T Wm[12][12];
+  T Ws[78];   // lower triangle, packed: index i*(i+1)/2 + j  (i >= j)
 #pragma unroll
   for (int i = 0; i < 12; i++) {
 #pragma unroll
     for (int j = 0; j <= i; j++) {
       T w = Ya[i][0] * Ya[j][0] + Ya[i][1] * Ya[j][1] + Ya[i][2] * Ya[j][2] + Ya[i][3] * Ya[j][3] + Ya[i][4] * Ya[j][4] + Ya[i][5] * Ya[j][5];
       if (i / 3 == j / 3) { const int a = i % 3, b = j % 3; w += Wd[i / 3][a * (a + 1) / 2 + b]; }
-      Wm[i][j] = w; Wm[j][i] = w;
+      Ws[i * (i + 1) / 2 + j] = w;
     }
   }
+#define WM(i, j) Ws[((i) >= (j)) ? ((i) * ((i) + 1) / 2 + (j)) : ((j) * ((j) + 1) / 2 + (i))]
   // g_i = lam_i + (target_i - u_i) / W_ii is the UNCLAMPED Gauss-Seidel candidate of row i.  A row update
   // lam_j <- clamp(g_j) changes g_i (i != j) by -(W_ij / W_ii) * dlam_j and leaves g_j itself unchanged, so the sweep
   // carries g instead of the contact velocities.  Inactive feet: zero scale (g frozen), g_n = -BIG => lam stays 0.
@@ -388,12 +389,12 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
   {
     T invd[12], g[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) invd[i] = actf[i / 3] > T(0) ? m_rcp(Wm[i][i]) : T(0);
+    for (int i = 0; i < 12; i++) invd[i] = actf[i / 3] > T(0) ? m_rcp(WM(i, i)) : T(0);
 #pragma unroll
     for (int i = 0; i < 12; i++) {
       T ui = u0[i];
 #pragma unroll
-      for (int f = 0; f < 4; f++) ui += Wm[i][3 * f] * lam[3 * f];
+      for (int f = 0; f < 4; f++) ui += WM(i, 3 * f) * lam[3 * f];
       T tg = (i % 3 == 0) ? targn[i / 3] : T(0);
       g[i] = lam[i] + (tg - ui) * invd[i];
       if (i % 3 == 0 && !(actf[i / 3] > T(0))) g[i] = T(-1e30);
@@ -403,11 +404,12 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
       g2[p].x = g[2 * p]; g2[p].y = g[2 * p + 1];
 #pragma unroll
       for (int r = 0; r < 12; r++) {
-        Wc[r][p].x = (2 * p == r) ? T(0) : Wm[2 * p][r] * invd[2 * p];
-        Wc[r][p].y = (2 * p + 1 == r) ? T(0) : Wm[2 * p + 1][r] * invd[2 * p + 1];
+        Wc[r][p].x = (2 * p == r) ? T(0) : WM(2 * p, r) * invd[2 * p];
+        Wc[r][p].y = (2 * p + 1 == r) ? T(0) : WM(2 * p + 1, r) * invd[2 * p + 1];
       }
     }
   }
+#undef WM
   // --- projected Gauss-Seidel, Bullet row order: normals of feet 0..3, then (t1,t2) of feet 0..3
   for (int it = 0; it < cf.iters; it++) {
 #pragma unroll
