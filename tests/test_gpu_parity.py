@@ -214,3 +214,47 @@ def test_host_buffer_api_equals_device_api(torch_cuda, etg_default):
         o2, r2, d2 = c.step_host(act)
         assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(d1.cpu().numpy(), d2)
     a.close(); c.close()
+
+
+@pytest.mark.parametrize("n", [1, 13])
+def test_ragged_batch_sizes_vs_oracle(torch_cuda, etg_stable, n):
+    """Batch sizes that do not fill a warp (8 robots) — the masked lanes must neither store nor disturb the shuffles."""
+    from oracle import oracle as O
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    w, b = etg_stable
+    env = VecQuadrupedalEnv(n, precision="f64")
+    env.reset(w, b)
+    os_ = [O.OracleEnv() for _ in range(n)]
+    for o in os_:
+        o.reset(w, b)
+    rng = np.random.default_rng(n)
+    for k in range(12):
+        a = rng.uniform(-0.2, 0.2, (n, 12))
+        ob, rw, dn, inf = env.step(a)
+        for i in range(n):
+            oo, ro, do, io = os_[i].step(a[i])
+            assert np.abs(_np(ob)[i] - oo).max() < 1e-8 and abs(float(rw[i]) - ro) < 1e-8
+    env.close()
+
+
+def test_large_batch_and_error_paths(torch_cuda, etg_default):
+    """65536 envs (16 x the benchmark batch): finite, duplicated envs identical; C ABI error codes instead of crashes."""
+    import ctypes as C
+    import torch
+    from paddlerobotics_b200 import _lib
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    w, b = etg_default
+    env = VecQuadrupedalEnv(65536, auto_reset=True)
+    env.reset(w, b)
+    a = (torch.rand(8, 12, device="cuda") * 0.6 - 0.3).repeat(8192, 1)
+    for k in range(10):
+        ob, rw, dn, inf = env.step(a)
+    assert torch.isfinite(ob).all() and torch.equal(ob[:8], ob[8:16]) and torch.equal(ob[:8], ob[-8:])
+    lib = _lib.load()
+    assert lib.b2q_step(env.h, None, 0, env.obs.data_ptr(), env.reward.data_ptr(), env.done.data_ptr(), env.info.data_ptr(), None) == -1
+    assert b"null" in lib.b2q_last_error(env.h)
+    assert lib.b2q_step(None, None, 0, None, None, None, None, None) == -1
+    h = C.c_void_p()
+    assert lib.b2q_sac_create(0, 49, 12, 100, 0.99, 0.005, 0.2, 3e-4, 3e-4, C.byref(h)) == -1      # batch not a multiple of 128
+    assert lib.b2q_mlp_create(0, 80, 12, 1, C.byref(h)) == -1                                    # in_dim > 64
+    env.close()
