@@ -121,7 +121,7 @@ def test_train_loop_runs_and_reward_improves():
     reward under the learned residual policy must beat the random-action warm-up phase."""
     from paddlerobotics_b200 import train
     log = train.main(["--num_envs", "1024", "--max_steps", "1300000", "--batch", "1024", "--warmup_steps", "20480", "--log_every", "100",
-                      "--es_every_steps", "700000", "--es_train_steps", "1", "--popsize", "8", "--es_rollouts", "2", "--e_step", "200"])
+                      "--es_every_steps", "700000", "--es_train_steps", "1", "--popsize", "10", "--es_rollouts", "2", "--e_step", "200"])
     assert len(log) >= 10
     early = np.mean([r["mean_step_reward"] for r in log[:2]])
     late = np.mean([r["mean_step_reward"] for r in log[-3:]])
