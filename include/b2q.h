@@ -101,9 +101,12 @@ int b2q_set_dynamics(B2QHandle h, const uint8_t* env_mask, const void* dyn, void
 int b2q_reset(B2QHandle h, const uint8_t* env_mask, const void* etg_w, const void* etg_b, void* obs_out, void* stream);
 /* action [N,12] (already scaled by act_bound, joint-space residual). obs [N,49], reward [N], done [N] u8, info [N,56]. */
 int b2q_step(B2QHandle h, const void* action, int donef, void* obs, void* reward, uint8_t* done, void* info, void* stream);
-/* The same step with HOST buffers (the reference-facing call: numpy in / numpy out): H2D of the actions, the step
- * kernel, D2H of obs / reward / done (and info if non-NULL), then a stream synchronise.  Use page-locked host memory
- * (b2q_host_alloc or cudaHostAlloc / torch pin_memory) so the copies are true async DMA. */
+/* The same step with HOST buffers (the reference-facing call: numpy in / numpy out), synchronous: on return obs / reward /
+ * done (and info if non-NULL) hold this step's results.  With page-locked host memory (b2q_host_alloc, cudaHostAlloc,
+ * torch pin_memory) the step kernel reads the action rows from and stores its coalesced observation block to the host
+ * buffers directly over PCIe (no separate copies; info still goes through a device staging area + one D2H).  Pageable
+ * buffers are staged through device memory with cudaMemcpyAsync.  Environment variable B2Q_HOST_IO (read at b2q_create)
+ * selects 0 = always memcpy, 1 = zero-copy actions only, 2 = zero-copy actions and outputs (default). */
 int b2q_step_host(B2QHandle h, const void* action_host, int donef, void* obs_host, void* reward_host, uint8_t* done_host,
                   void* info_host, void* stream);
 void* b2q_host_alloc(size_t bytes);   /* page-locked host memory, NULL on failure */

@@ -45,12 +45,23 @@ __global__ void __launch_bounds__(128) b2q_step_kernel(Cfg<T> cf, const Model<T>
                                                        int auto_reset, T* __restrict__ obs, T* __restrict__ reward, uint8_t* __restrict__ done, T* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Model<T>& md = stage_model(gm, smem);
+  // the CTA's observation rows are contiguous in [N][OBS_DIM]: stage them in shared memory and store the block with
+  // full-width coalesced stores (the lanes produce the row in 3-element pieces; `obs` may be pinned HOST memory, where
+  // piecewise stores would each become a small PCIe write)
+  T* stage = reinterpret_cast<T*>(smem + ((sizeof(Model<T>) + 15) & ~size_t(15)));
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = gid >> 2;
+  const int env0 = (blockIdx.x * blockDim.x) >> 2, per_cta = blockDim.x >> 2;
   bool valid = env < B.N;
   if (!valid) env = B.N - 1;  // whole warps stay convergent for the shuffles; invalid lanes never store
   WarpComm cm{(int)(threadIdx.x & 3)};
-  step_lane<T>(cm, cf, md, B, env, valid, action, donef, auto_reset, obs, reward, done, info);
+  const bool staged = env0 + per_cta <= B.N;   // a ragged last CTA (clamped envs) writes its rows directly
+  step_lane<T>(cm, cf, md, B, env, valid, action, donef, auto_reset, staged ? stage : obs, reward, done, info, staged ? env0 : 0);
+  if (staged) {
+    __syncthreads();
+    T* dst = obs + (size_t)env0 * OBS_DIM;
+    for (int i = threadIdx.x; i < per_cta * OBS_DIM; i += blockDim.x) dst[i] = stage[i];
+  }
 }
 
 template <typename T>
@@ -151,6 +162,7 @@ struct EnvT : EnvBase {
   int init(const B2QConfig& c) {
     cfg = c; prec = c.precision;
     tpb = c.threads_per_block ? c.threads_per_block : 32;
+    if (const char* e = std::getenv("B2Q_HOST_IO")) host_io = std::atoi(e);   // 0: memcpy both ways, 1: zero-copy actions, 2: + zero-copy outputs
     CK(cudaSetDevice(c.device));
     int N = c.num_envs, Dm = c.ring_depth;
     if (c.terrain_type == 1) {
@@ -187,7 +199,7 @@ struct EnvT : EnvBase {
     CK(cudaDeviceSynchronize());
     return B2Q_OK;
   }
-  size_t smem_bytes() const { return (sizeof(Model<T>) + 15) & ~size_t(15); }
+  size_t smem_bytes() const { return ((sizeof(Model<T>) + 15) & ~size_t(15)) + (size_t)(tpb / 4) * OBS_DIM * sizeof(T); }
 
   int set_dynamics(const uint8_t* mask, const void* dyn, cudaStream_t s) override {
     CK(cudaSetDevice(cfg.device));
@@ -229,11 +241,21 @@ struct EnvT : EnvBase {
       st_act = (T*)p; st_obs = st_act + N * 12; st_rew = st_obs + N * OBS_DIM; st_done = (uint8_t*)(st_rew + N);
       st_info = (T*)((uint8_t*)p + ((N * (12 + OBS_DIM + 1) * sizeof(T) + N + 255) / 256) * 256);
     }
-    CK(cudaMemcpyAsync(st_act, a, N * 12 * sizeof(T), cudaMemcpyHostToDevice, s));
-    int rc = step(st_act, donef, st_obs, st_rew, st_done, st_info, s);
+    // Pinned (page-locked) host buffers are device-addressable under unified addressing: the kernel then reads the actions
+    // straight from host memory (one coalesced 12-float row per robot, read once) instead of waiting for a separate H2D copy,
+    // and — host_io >= 2 — stores its staged, coalesced observation block plus reward/done straight to host memory.
+    // Pageable buffers, and the scattered info rows, go through the device staging area and cudaMemcpyAsync.
+    const T* act_dev = st_act;
+    if (host_io >= 1 && (act_dev = (const T*)mapped(a)) == nullptr) act_dev = st_act;
+    if (act_dev == st_act) CK(cudaMemcpyAsync(st_act, a, N * 12 * sizeof(T), cudaMemcpyHostToDevice, s));
+    T* obs_dev = nullptr; T* rew_dev = nullptr; uint8_t* done_dev = nullptr;
+    if (host_io >= 2) { obs_dev = (T*)mapped(obs); rew_dev = (T*)mapped(rew); done_dev = (uint8_t*)mapped(done); }
+    const bool direct = obs_dev && rew_dev && done_dev;
+    int rc = direct ? step(act_dev, donef, obs_dev, rew_dev, done_dev, st_info, s) : step(act_dev, donef, st_obs, st_rew, st_done, st_info, s);
     if (rc) return rc;
     const size_t b_obs = N * OBS_DIM * sizeof(T), b_rew = N * sizeof(T);
-    if ((uint8_t*)rew == (uint8_t*)obs + b_obs && done == (uint8_t*)rew + b_rew) {
+    if (direct) {
+    } else if ((uint8_t*)rew == (uint8_t*)obs + b_obs && done == (uint8_t*)rew + b_rew) {
       CK(cudaMemcpyAsync(obs, st_obs, b_obs + b_rew + N, cudaMemcpyDeviceToHost, s));      // caller's host buffers are contiguous too
     } else {
       CK(cudaMemcpyAsync(obs, st_obs, b_obs, cudaMemcpyDeviceToHost, s));
@@ -243,6 +265,15 @@ struct EnvT : EnvBase {
     if (info) CK(cudaMemcpyAsync(info, st_info, N * INFO_DIM * sizeof(T), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return B2Q_OK;
+  }
+  // device alias of a pinned host pointer (nullptr for pageable memory); queried every call — a cached answer could go
+  // stale if the caller frees the pinned block and the address is reused by pageable memory
+  int host_io = 2;
+  void* mapped(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
+    cudaGetLastError();
+    return nullptr;
   }
   int get_state(void* out, cudaStream_t s) override {
     b2q_get_state_kernel<T><<<(B.N + 127) / 128, 128, 0, s>>>(B.state, (T*)out, B.N); launches++;

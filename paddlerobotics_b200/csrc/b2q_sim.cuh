@@ -618,7 +618,8 @@ B2Q_HD void settle_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, co
 // one control step (= R physics substeps) for this lane: env.step() of the reference
 template <typename T, class Comm>
 B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const Buffers<T>& B, int env, bool valid,
-                      const T* action, int donef, int auto_reset, T* obs, T* reward, uint8_t* done, T* info) {
+                      const T* action, int donef, int auto_reset, T* obs, T* reward, uint8_t* done, T* info, int obs_env0 = 0) {
+  // `obs` is the row block starting at env `obs_env0`: the whole [N][OBS_DIM] array (obs_env0 = 0) or a CTA-local staging block
   const int k = cm.leg(), N = B.N, R = cf.R;
   const T dtc = cf.dt * T(R);
   LaneParam<T> pr; load_param(cm, B, env, pr);
@@ -688,7 +689,7 @@ B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, cons
   }
   step += 1;
   etg_act_leg(cm, cf, md, B.etg, N, env, T(step) * dtc, etg_act);
-  T* orow = obs + (size_t)env * OBS_DIM;
+  T* orow = obs + (size_t)(env - obs_env0) * OBS_DIM;
   write_obs(cm, md, orow, valid, s, start_pos, dtc, rpy0, dq, dqd, etg_act);
 
   // ---- reward / termination (this repo's definition)

@@ -258,3 +258,34 @@ def test_large_batch_and_error_paths(torch_cuda, etg_default):
     assert lib.b2q_sac_create(0, 49, 12, 100, 0.99, 0.005, 0.2, 3e-4, 3e-4, C.byref(h)) == -1      # batch not a multiple of 128
     assert lib.b2q_mlp_create(0, 80, 12, 1, C.byref(h)) == -1                                    # in_dim > 64
     env.close()
+
+
+@pytest.mark.parametrize("n", [13, 64])
+def test_step_host_io_modes_identical(torch_cuda, etg_stable, n, monkeypatch):
+    """b2q_step_host: zero-copy pinned buffers (B2Q_HOST_IO=2, default), zero-copy actions only (1), memcpy staging (0) and
+    PAGEABLE numpy buffers all return bit-identical obs / reward / done / info; n=13 exercises the ragged last CTA."""
+    import ctypes as C
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    w, b = etg_stable
+    rng = np.random.default_rng(7)
+    acts = rng.uniform(-0.3, 0.3, (6, n, 12)).astype(np.float32)
+    results = []
+    for mode in ("2", "1", "0", "pageable"):
+        monkeypatch.setenv("B2Q_HOST_IO", "2" if mode == "pageable" else mode)
+        env = VecQuadrupedalEnv(n)
+        env.reset(w, b)
+        outs = []
+        for a in acts:
+            if mode == "pageable":
+                o = np.empty((n, 49), np.float32); r = np.empty(n, np.float32); d = np.empty(n, np.uint8); inf = np.empty((n, 56), np.float32)
+                rc = env.lib.b2q_step_host(env.h, a.ctypes.data_as(C.c_void_p), 0, o.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p),
+                                           d.ctypes.data_as(C.c_void_p), inf.ctypes.data_as(C.c_void_p), None)
+                assert rc == 0
+            else:
+                o, r, d = env.step_host(a)
+            outs.append((o.copy(), r.copy(), d.copy()))
+        results.append(outs)
+        env.close()
+    for other in results[1:]:
+        for (o0, r0, d0), (o1, r1, d1) in zip(results[0], other):
+            assert np.array_equal(o0, o1) and np.array_equal(r0, r1) and np.array_equal(d0, d1)
