@@ -90,6 +90,26 @@ B2Q_HD P2<float> p2fma(P2<float> a, P2<float> b, P2<float> c) {
 #endif
 }
 B2Q_HD P2<double> p2fma(P2<double> a, P2<double> b, P2<double> c) { P2<double> o; o.x = fma(a.x, b.x, c.x); o.y = fma(a.y, b.y, c.y); return o; }
+B2Q_HD P2<float> p2mul(P2<float> a, P2<float> b) {
+#if defined(__CUDA_ARCH__)
+  float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  P2<float> o; o.x = r.x; o.y = r.y; return o;
+#else
+  P2<float> o; o.x = a.x * b.x; o.y = a.y * b.y; return o;
+#endif
+}
+B2Q_HD P2<double> p2mul(P2<double> a, P2<double> b) { P2<double> o; o.x = a.x * b.x; o.y = a.y * b.y; return o; }
+B2Q_HD P2<float> p2add(P2<float> a, P2<float> b) {
+#if defined(__CUDA_ARCH__)
+  float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  P2<float> o; o.x = r.x; o.y = r.y; return o;
+#else
+  P2<float> o; o.x = a.x + b.x; o.y = a.y + b.y; return o;
+#endif
+}
+B2Q_HD P2<double> p2add(P2<double> a, P2<double> b) { P2<double> o; o.x = a.x + b.x; o.y = a.y + b.y; return o; }
+template <typename T> B2Q_HD P2<T> p2s(T s) { P2<T> o; o.x = s; o.y = s; return o; }   // scalar broadcast (an operand form of FFMA2, no instruction)
+template <typename T> B2Q_HD P2<T> p2mk(T x, T y) { P2<T> o; o.x = x; o.y = y; return o; }
 
 template <typename T>
 struct V3 {

@@ -368,48 +368,72 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
     lam[3 * f] = cm.bcast(act ? cf.warm * s.lam_n : T(0), f);   // warm start of the normal impulse (Bullet 0.85)
     lam[3 * f + 1] = T(0); lam[3 * f + 2] = T(0);
   }
-  // Delassus matrix W = J M^-1 J^T  (symmetric): W_ij = Y_i . Y_j  (+ the leg-local block on the diagonal blocks)
-  T Ws[78];   // lower triangle, packed: index i*(i+1)/2 + j  (i >= j)
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-#pragma unroll
-    for (int j = 0; j <= i; j++) {
-      T w = Ya[i][0] * Ya[j][0] + Ya[i][1] * Ya[j][1] + Ya[i][2] * Ya[j][2] + Ya[i][3] * Ya[j][3] + Ya[i][4] * Ya[j][4] + Ya[i][5] * Ya[j][5];
-      if (i / 3 == j / 3) { const int a = i % 3, b = j % 3; w += Wd[i / 3][a * (a + 1) / 2 + b]; }
-      Ws[i * (i + 1) / 2 + j] = w;
-    }
-  }
-#define WM(i, j) Ws[((i) >= (j)) ? ((i) * ((i) + 1) / 2 + (j)) : ((j) * ((j) + 1) / 2 + (i))]
-  // g_i = lam_i + (target_i - u_i) / W_ii is the UNCLAMPED Gauss-Seidel candidate of row i.  A row update
-  // lam_j <- clamp(g_j) changes g_i (i != j) by -(W_ij / W_ii) * dlam_j and leaves g_j itself unchanged, so the sweep
-  // carries g instead of the contact velocities.  Inactive feet: zero scale (g frozen), g_n = -BIG => lam stays 0.
-  // The sweep is FMA-pipe bound on one warp per scheduler, so g and the scaled columns of W are kept as PAIRS of rows and
-  // updated with the packed FP32 FMA of sm_100 (FFMA2): 6 instructions per row update instead of 11.
-  P2<T> g2[6], Wc[12][6];   // Wc[r][p] = (W'[2p][r], W'[2p+1][r]), W'_ij = W_ij / W_ii with a zero diagonal
+  // Delassus matrix W = J M^-1 J^T (symmetric): W_ij = Y_i . Y_j (+ the leg-local 3x3 block on the diagonal blocks), built
+  // directly in the layout the sweep consumes — PAIRS of adjacent rows — with the packed FP32 FMA of sm_100 (FFMA2, scalar
+  // broadcast operand): WR[r][p] = (W[2p][r], W[2p+1][r]).  Only the pairs at or below the diagonal are computed (42 x 6
+  // packed FMAs instead of 78 x 6 scalar ones); the rest are re-paired from them by symmetry.  The substep body is
+  // instruction-FETCH bound (57 KB of straight-line code per substep), so instruction count is what matters.
+  P2<T> WR[12][6];
   {
-    T invd[12], g[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) invd[i] = actf[i / 3] > T(0) ? m_rcp(WM(i, i)) : T(0);
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-      T ui = u0[i];
-#pragma unroll
-      for (int f = 0; f < 4; f++) ui += WM(i, 3 * f) * lam[3 * f];
-      T tg = (i % 3 == 0) ? targn[i / 3] : T(0);
-      g[i] = lam[i] + (tg - ui) * invd[i];
-      if (i % 3 == 0 && !(actf[i / 3] > T(0))) g[i] = T(-1e30);
-    }
+    P2<T> YP[6][6];
 #pragma unroll
     for (int p = 0; p < 6; p++) {
-      g2[p].x = g[2 * p]; g2[p].y = g[2 * p + 1];
 #pragma unroll
-      for (int r = 0; r < 12; r++) {
-        Wc[r][p].x = (2 * p == r) ? T(0) : WM(2 * p, r) * invd[2 * p];
-        Wc[r][p].y = (2 * p + 1 == r) ? T(0) : WM(2 * p + 1, r) * invd[2 * p + 1];
+      for (int c = 0; c < 6; c++) YP[p][c] = p2mk(Ya[2 * p][c], Ya[2 * p + 1][c]);
+    }
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+#pragma unroll
+      for (int p = 0; p <= r / 2; p++) {
+        P2<T> acc = p2mul(YP[p][0], p2s(Ya[r][0]));
+#pragma unroll
+        for (int c = 1; c < 6; c++) acc = p2fma(YP[p][c], p2s(Ya[r][c]), acc);
+        const int f = r / 3, a = r % 3;
+        if ((2 * p) / 3 == f) { const int bb = (2 * p) % 3; acc.x += Wd[f][a >= bb ? a * (a + 1) / 2 + bb : bb * (bb + 1) / 2 + a]; }
+        if ((2 * p + 1) / 3 == f) { const int bb = (2 * p + 1) % 3; acc.y += Wd[f][a >= bb ? a * (a + 1) / 2 + bb : bb * (bb + 1) / 2 + a]; }
+        WR[r][p] = acc;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+#pragma unroll
+      for (int p = r / 2 + 1; p < 6; p++) {   // rows 2p, 2p+1 > r: W[2p][r] = W[r][2p] lives in WR[2p][r/2]
+        WR[r][p].x = (r & 1) ? WR[2 * p][r / 2].y : WR[2 * p][r / 2].x;
+        WR[r][p].y = (r & 1) ? WR[2 * p + 1][r / 2].y : WR[2 * p + 1][r / 2].x;
       }
     }
   }
-#undef WM
+  // g_i = lam_i + (target_i - u_i) / W_ii is the UNCLAMPED Gauss-Seidel candidate of row i.  A row update
+  // lam_j <- clamp(g_j) changes g_i (i != j) by -(W_ij / W_ii) * dlam_j and leaves g_j itself unchanged, so the sweep
+  // carries g instead of the contact velocities.  Inactive feet: zero scale (g frozen), g_n = -BIG => lam stays 0.
+  P2<T> g2[6], Wc[12][6];   // Wc[r][p] = (W'[2p][r], W'[2p+1][r]), W'_ij = W_ij / W_ii with a zero diagonal
+  {
+    P2<T> invd[6], uu[6];
+#pragma unroll
+    for (int p = 0; p < 6; p++) {
+      const int i0 = 2 * p, i1 = 2 * p + 1;
+      T d0 = (i0 & 1) ? WR[i0][i0 / 2].y : WR[i0][i0 / 2].x, d1 = (i1 & 1) ? WR[i1][i1 / 2].y : WR[i1][i1 / 2].x;
+      invd[p].x = actf[i0 / 3] > T(0) ? m_rcp(d0) : T(0);
+      invd[p].y = actf[i1 / 3] > T(0) ? m_rcp(d1) : T(0);
+      uu[p] = p2mk(u0[i0], u0[i1]);
+#pragma unroll
+      for (int f = 0; f < 4; f++) uu[p] = p2fma(WR[3 * f][p], p2s(lam[3 * f]), uu[p]);
+      P2<T> tg = p2mk((i0 % 3 == 0) ? targn[i0 / 3] : T(0), (i1 % 3 == 0) ? targn[i1 / 3] : T(0));
+      P2<T> res = p2mk(tg.x - uu[p].x, tg.y - uu[p].y);
+      g2[p] = p2fma(res, invd[p], p2mk(lam[i0], lam[i1]));
+      if (i0 % 3 == 0 && !(actf[i0 / 3] > T(0))) g2[p].x = T(-1e30);
+      if (i1 % 3 == 0 && !(actf[i1 / 3] > T(0))) g2[p].y = T(-1e30);
+    }
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+#pragma unroll
+      for (int p = 0; p < 6; p++) {
+        Wc[r][p] = p2mul(WR[r][p], invd[p]);
+        if (2 * p == r) Wc[r][p].x = T(0);
+        if (2 * p + 1 == r) Wc[r][p].y = T(0);
+      }
+    }
+  }
   // --- projected Gauss-Seidel, Bullet row order: normals of feet 0..3, then (t1,t2) of feet 0..3
   for (int it = 0; it < cf.iters; it++) {
 #pragma unroll
