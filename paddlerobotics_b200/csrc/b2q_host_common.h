@@ -22,7 +22,7 @@ inline Cfg<T> make_cfg(const B2QConfig& c, const T* hf_dev) {
   k.etg_T = (T)c.etg_T; k.etg_T2 = (T)c.etg_T2; k.etg_sigma_sq = (T)c.etg_sigma_sq; k.etg_amp = (T)c.etg_amp; k.etg_ph0 = (T)c.etg_phase0; k.etg_ph1 = (T)c.etg_phase1;
   k.w_torso = (T)c.w_torso; k.w_feet = (T)c.w_feet; k.w_up = (T)c.w_up; k.w_tau = (T)c.w_tau; k.w_stand = (T)c.w_stand; k.w_badfoot = (T)c.w_badfoot;
   k.w_footcontact = (T)c.w_footcontact; k.w_done = (T)c.w_done; k.reward_p = (T)c.reward_p; k.vel_d = (T)c.vel_d;
-  k.terrain = c.terrain_type; k.hf_nx = c.hf_nx; k.hf_ny = c.hf_ny; k.hf_x0 = (T)c.hf_x0; k.hf_y0 = (T)c.hf_y0; k.hf_cell = (T)c.hf_cell; k.hf = hf_dev;
+  k.terrain = c.terrain_type; k.hf_nx = c.hf_nx; k.hf_ny = c.hf_ny; k.hf_x0 = (T)c.hf_x0; k.hf_y0 = (T)c.hf_y0; k.hf_cell = (T)c.hf_cell; k.hf_icell = (T)(c.hf_cell > 0 ? 1.0 / c.hf_cell : 0.0); k.idt = (T)(1.0 / c.sim_dt); k.hf = hf_dev;
   return k;
 }
 

@@ -45,6 +45,8 @@ B2Q_HD float m_min(float a, float b) { return fminf(a, b); }
 B2Q_HD double m_min(double a, double b) { return fmin(a, b); }
 B2Q_HD float m_max(float a, float b) { return fmaxf(a, b); }
 B2Q_HD double m_max(double a, double b) { return fmax(a, b); }
+B2Q_HD float m_fma(float a, float b, float c) { return fmaf(a, b, c); }
+B2Q_HD double m_fma(double a, double b, double c) { return fma(a, b, c); }
 B2Q_HD bool m_isfinite(float x) { return (x - x) == 0.0f; }
 B2Q_HD bool m_isfinite(double x) { return (x - x) == 0.0; }
 B2Q_HD bool m_isnan(float x) { return x != x; }

@@ -59,7 +59,7 @@ struct Cfg {
   int filter; T fb0, fb1, fb2, fa1, fa2; int etg; int max_steps;
   T etg_T, etg_T2, etg_sigma_sq, etg_amp, etg_ph0, etg_ph1;
   T w_torso, w_feet, w_up, w_tau, w_stand, w_badfoot, w_footcontact, w_done, reward_p, vel_d;
-  int terrain, hf_nx, hf_ny; T hf_x0, hf_y0, hf_cell; const T* hf;
+  int terrain, hf_nx, hf_ny; T hf_x0, hf_y0, hf_cell, hf_icell, idt; const T* hf;
 };
 template <typename T>
 struct Buffers {
@@ -90,7 +90,7 @@ template <typename T> B2Q_HD void sincos_t(T a, T& s, T& c) { m_sincos(a, s, c);
 template <typename T>
 B2Q_HD T terrain_height(const Cfg<T>& cf, T x, T y, V3<T>& n) {
   if (cf.terrain == 0) { n = mk<T>(0, 0, 1); return T(0); }
-  T fx = (x - cf.hf_x0) / cf.hf_cell, fy = (y - cf.hf_y0) / cf.hf_cell;
+  T fx = (x - cf.hf_x0) * cf.hf_icell, fy = (y - cf.hf_y0) * cf.hf_icell;
   fx = m_min(m_max(fx, T(0)), T(cf.hf_nx) - T(1.000001));
   fy = m_min(m_max(fy, T(0)), T(cf.hf_ny) - T(1.000001));
   int ix = (int)fx, iy = (int)fy;
@@ -98,9 +98,9 @@ B2Q_HD T terrain_height(const Cfg<T>& cf, T x, T y, V3<T>& n) {
   const T* h = cf.hf; int nx = cf.hf_nx;
   T h00 = h[iy * nx + ix], h10 = h[iy * nx + ix + 1], h01 = h[(iy + 1) * nx + ix], h11 = h[(iy + 1) * nx + ix + 1];
   T hh = (1 - tx) * (1 - ty) * h00 + tx * (1 - ty) * h10 + (1 - tx) * ty * h01 + tx * ty * h11;
-  T dhdx = ((1 - ty) * (h10 - h00) + ty * (h11 - h01)) / cf.hf_cell;
-  T dhdy = ((1 - tx) * (h01 - h00) + tx * (h11 - h10)) / cf.hf_cell;
-  T inv = T(1) / m_sqrt(dhdx * dhdx + dhdy * dhdy + T(1));
+  T dhdx = ((1 - ty) * (h10 - h00) + ty * (h11 - h01)) * cf.hf_icell;
+  T dhdy = ((1 - tx) * (h01 - h00) + tx * (h11 - h10)) * cf.hf_icell;
+  T inv = m_rsqrt(dhdx * dhdx + dhdy * dhdy + T(1));
   n = mk<T>(-dhdx * inv, -dhdy * inv, inv);
   return hh;
 }
@@ -182,7 +182,7 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
                     const T* target, T* tau_out) {
   const int k = cm.leg();
   const LegModel<T>& lm = md.leg[k];
-  const T dt = cf.dt, idt = T(1) / cf.dt;
+  const T dt = cf.dt, idt = cf.idt;
   R3<T> R = quat_to_R(s.qx, s.qy, s.qz, s.qw);
   V3<T> wB = rotT(R, s.vang), vB = rotT(R, s.vlin), gB = rotT(R, pr.g);
 
@@ -434,7 +434,10 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
       }
     }
   }
-  // --- projected Gauss-Seidel, Bullet row order: normals of feet 0..3, then (t1,t2) of feet 0..3
+  // --- projected Gauss-Seidel, Bullet row order: normals of feet 0..3, then (t1,t2) of feet 0..3.
+  //     Row update = clamp -> delta -> 11 independent scalar FFMAs (W'_rr = 0: the row's own candidate is unchanged).
+  //     Plain FFMAs on purpose: the packed FFMA2 issues at half rate for a single warp and lengthens the serial chain
+  //     clamp(r) -> g(r+1) -> clamp(r+1) (microbenchmark scripts/ubench/ffma2.cu: 17.0 vs 22.8 cycles per row).
   for (int it = 0; it < cf.iters; it++) {
 #pragma unroll
     for (int f = 0; f < 4; f++) {
@@ -442,9 +445,11 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
       T gr = (r & 1) ? g2[r >> 1].y : g2[r >> 1].x;
       T ln = m_max(gr, T(0));
       T dl = lam[r] - ln; lam[r] = ln;          // dl = -(delta lambda)
-      P2<T> d2; d2.x = dl; d2.y = dl;
 #pragma unroll
-      for (int p = 0; p < 6; p++) g2[p] = p2fma(Wc[r][p], d2, g2[p]);
+      for (int p = 0; p < 6; p++) {
+        if (2 * p != r) g2[p].x = m_fma(Wc[r][p].x, dl, g2[p].x);
+        if (2 * p + 1 != r) g2[p].y = m_fma(Wc[r][p].y, dl, g2[p].y);
+      }
     }
 #pragma unroll
     for (int f = 0; f < 4; f++) {
@@ -455,9 +460,11 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
         T lim = pr.mu * lam[3 * f];
         T ln = m_min(m_max(gr, -lim), lim);
         T dl = lam[r] - ln; lam[r] = ln;
-        P2<T> d2; d2.x = dl; d2.y = dl;
 #pragma unroll
-        for (int p = 0; p < 6; p++) g2[p] = p2fma(Wc[r][p], d2, g2[p]);
+        for (int p = 0; p < 6; p++) {
+          if (2 * p != r) g2[p].x = m_fma(Wc[r][p].x, dl, g2[p].x);
+          if (2 * p + 1 != r) g2[p].y = m_fma(Wc[r][p].y, dl, g2[p].y);
+        }
       }
     }
   }
