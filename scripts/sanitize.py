@@ -1,0 +1,44 @@
+"""Small invocation of every kernel in libb2q.so for compute-sanitizer (memcheck / racecheck / initcheck):
+    compute-sanitizer --tool memcheck  python scripts/sanitize.py
+    compute-sanitizer --tool racecheck python scripts/sanitize.py
+"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from paddlerobotics_b200.env import VecQuadrupedalEnv
+from paddlerobotics_b200.etg import ETG_layer, Opt_with_points
+from paddlerobotics_b200.agent import MujocoAgent, SACLearner
+from paddlerobotics_b200.replay import ReplayMemory
+from paddlerobotics_b200.es import PopulationEvaluator
+
+layer = ETG_layer(0.5, 0.026, 20, 0.04, np.array([-np.pi / 2, 0]), 0.2, 0.5)
+w, b, _ = Opt_with_points(ETG=layer, ETG_T=0.5, Footheight=0.1, Steplength=0.05)
+rng = np.random.default_rng(0)
+hf = (rng.random((32, 32)) * 0.03).astype(np.float64)
+for kw in (dict(num_envs=13), dict(num_envs=16, precision="f64"), dict(num_envs=24, auto_reset=True, action_filter=1, max_episode_steps=3),
+           dict(num_envs=8, heightfield=(hf, -1.0, -1.0, 0.1)), dict(num_envs=40, threads_per_block=128)):
+    env = VecQuadrupedalEnv(**kw)
+    n = env.num_envs
+    env.reset(w, b)
+    a = (rng.random((n, 12)) * 0.6 - 0.3)
+    for _ in range(4):
+        env.step(torch.as_tensor(a, device="cuda", dtype=env.dtype))
+    env.step_host(a.astype(np.float32 if env.dtype == torch.float32 else np.float64))
+    s = env.get_state(); env.set_state(s)
+    env.reset(w, b, env_mask=(np.arange(n) % 2 == 0))
+    torch.cuda.synchronize(); env.close()
+
+agent = MujocoAgent(49, 12, seed=0)
+obs = torch.randn(200, 49, device="cuda")
+agent.predict(np.zeros(49, np.float32)); agent.sample(np.zeros(49, np.float32))
+learner = SACLearner(agent, 256)
+learner.actor.forward(obs, mode=1, seed=3)
+rpm = ReplayMemory(4096, 49, 12)
+for _ in range(3):
+    rpm.append(torch.randn(512, 49, device="cuda"), torch.rand(512, 12, device="cuda") * 2 - 1, torch.randn(512, device="cuda"), torch.randn(512, 49, device="cuda"), torch.ones(512, device="cuda"))
+for _ in range(2):
+    learner.learn(*rpm.sample_batch(256), graph=False)
+ev = PopulationEvaluator(4, 2, max_steps=5)
+ev.evaluate(np.repeat(w[None], 4, 0), np.repeat(b[None], 4, 0))
+torch.cuda.synchronize()
+print("sanitizer script done")
