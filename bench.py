@@ -208,6 +208,18 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json"))).get("dram_bytes_per_launch")
         except Exception:
             pass
+        # secondary (the bound that actually applies): warp-instruction issue slots.  Instructions per launch are the
+        # ncu count of the committed capture (profiles/step_kernel_r01d_ncu_full.csv); duration and SM clock are this run's.
+        issue = None
+        try:
+            prof = dict(l.split(",")[0::2] for l in open(os.path.join(ROOT, "profiles", "step_kernel_r01d_ncu_full.csv")).read().splitlines()[2:] if l.count(",") == 2)
+            inst = float(prof["smsp__inst_executed.sum"]) * n / 4096.0
+            mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            slots = ms_per_step * 1e-3 * mhz * 1e6 * 148 * 4
+            issue = {"warp_instructions_per_launch": inst, "issue_slot_frac": inst / slots, "fma_pipe_pct_ncu": float(prof["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]),
+                     "warps_per_sm_ncu": float(prof["sm__warps_active.avg.per_cycle_active"]), "source": "profiles/step_kernel_r01d_ncu_full.csv"}
+        except Exception:
+            pass
         cpu = None
         if not args.no_cpu_baseline:
             threads = host_threads()
@@ -227,7 +239,7 @@ def main():
                     "transport": "numpy action -> pinned buffer -> step kernel reads it over PCIe and stores obs|reward|done to pinned host memory (b2q_step_host, B2Q_HOST_IO=2), stream sync every step"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "b2q_step_kernel<float>", "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP,
+                         "peak_source": peak_src, "kernel": "b2q_step_kernel<float>", "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP, "issue": issue,
                          "note": "latency/FP32-issue bound by construction (13 substeps x 23 PGS sweeps per launch on ~2.4 KB of state): HBM fraction is structurally tiny, see DESIGN.md §5"},
             "cpu_baseline": cpu,
             "clocks": clocks,
