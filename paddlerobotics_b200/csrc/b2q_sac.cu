@@ -8,6 +8,7 @@
 // ([batch x width] and [width x batch]) written by the forward kernel's epilogue, and each weight matrix has a transposed
 // bf16 copy refreshed by the optimiser kernel.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cstdint>
 #include <cstring>
@@ -153,15 +154,24 @@ __global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ dy /
   __syncthreads();
   float w[24], acc[24], colsum = 0.f;
   for (int o = 0; o < od; o++) { w[o] = W3[o * H + col]; acc[o] = 0.f; }
-  for (int r = 0; r < nr; r++) {
-    const int b = b0 + r;
-    float hv = __bfloat162float(h2[(size_t)b * H + col]), g = 0.f;
-    for (int o = 0; o < od; o++) { float d = sdy[r][o]; g += d * w[o]; acc[o] += d * hv; }
-    g = hv > 0.f ? g : 0.f;
-    bf16 gb = __float2bfloat16(g);
-    colsum += __bfloat162float(gb);
-    dh_rm[(size_t)b * H + col] = gb;
-    tile[r][col] = gb;
+  // rows in groups of 8 with the activation loads issued together (a serial row loop is bound by the load latency)
+  for (int r8 = 0; r8 < nr; r8 += 8) {
+    float hv[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) hv[u] = (r8 + u < nr) ? __bfloat162float(h2[(size_t)(b0 + r8 + u) * H + col]) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int r = r8 + u;
+      if (r < nr) {
+        float g = 0.f;
+        for (int o = 0; o < od; o++) { float d = sdy[r][o]; g += d * w[o]; acc[o] += d * hv[u]; }
+        g = hv[u] > 0.f ? g : 0.f;
+        bf16 gb = __float2bfloat16(g);
+        colsum += __bfloat162float(gb);
+        dh_rm[(size_t)(b0 + r) * H + col] = gb;
+        tile[r][col] = gb;
+      }
+    }
   }
   for (int o = 0; o < od; o++) atomicAdd(dW3 + o * H + col, acc[o]);
   if (db2) atomicAdd(db2 + col, colsum);
@@ -175,13 +185,24 @@ __global__ void __launch_bounds__(256) k_relu_mask(const float* __restrict__ G, 
   __shared__ bf16 tile[32][H + 2];
   const int col = threadIdx.x, b0 = blockIdx.x * 32, nr = min(32, B - b0);
   float colsum = 0.f;
-  for (int r = 0; r < nr; r++) {
-    const int b = b0 + r;
-    float v = __bfloat162float(h[(size_t)b * H + col]) > 0.f ? G[(size_t)b * H + col] : 0.f;
-    bf16 vb = __float2bfloat16(v);
-    colsum += __bfloat162float(vb);
-    dh_rm[(size_t)b * H + col] = vb;
-    tile[r][col] = vb;
+  for (int r8 = 0; r8 < nr; r8 += 8) {
+    float hv[8], gv[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const bool ok = r8 + u < nr;
+      hv[u] = ok ? __bfloat162float(h[(size_t)(b0 + r8 + u) * H + col]) : 0.f;
+      gv[u] = ok ? G[(size_t)(b0 + r8 + u) * H + col] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int r = r8 + u;
+      if (r < nr) {
+        bf16 vb = __float2bfloat16(hv[u] > 0.f ? gv[u] : 0.f);
+        colsum += __bfloat162float(vb);
+        dh_rm[(size_t)(b0 + r) * H + col] = vb;
+        tile[r][col] = vb;
+      }
+    }
   }
   if (db) atomicAdd(db + col, colsum);
   __syncthreads();
@@ -300,7 +321,8 @@ int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int
   GemmArgs g; g.A = A; g.lda = lda; g.B = Bm; g.ldb = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
   g.BN = ((N + 15) / 16) * 16;
   int nk = (K + 63) / 64, splits = 1;
-  if (splitk) { splits = nk / 8; if (splits < 1) splits = 1; if (splits > 64) splits = 64; }
+  static const int split_div = [] { const char* e = std::getenv("B2Q_GEMM_SPLIT_DIV"); int v = e ? std::atoi(e) : 8; return v < 1 ? 1 : v; }();   // K chunks (of 64) per split-K CTA
+  if (splitk) { splits = nk / split_div; if (splits < 1) splits = 1; if (splits > 64) splits = 64; }
   g.chunks_per_split = (nk + splits - 1) / splits;
   splits = (nk + g.chunks_per_split - 1) / g.chunks_per_split;
   g.atomic = splits > 1 ? 1 : 0;
@@ -311,18 +333,23 @@ int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-void sync_net_weights(B2QSac* s, cudaStream_t st) {
-  // forward images + bf16 backward copies after a parameter change
+// forward images + bf16 backward copies after a parameter change; `which`: bit 0 actor, bit 1 critics, bit 2 target critics
+void sync_net_weights(B2QSac* s, cudaStream_t st, int which = 7) {
   const Net& a = s->an; const Net& c = s->cn;
-  b2q_mlp_set_weights(s->mlp_actor, 0, s->p_actor + a.oW1, s->p_actor + a.ob1, s->p_actor + a.oW2, s->p_actor + a.ob2, s->p_actor + a.oW3, s->p_actor + a.ob3, st);
-  k_make_bwd_weights<<<(H * H + 255) / 256, 256, 0, st>>>(s->p_actor + a.oW1, a.in_dim, 0, 0, s->p_actor + a.oW2, s->p_actor + a.oW3, a.od, s->W2T[0], s->W3T[0], s->W1A[0]);
+  if (which & 1) {
+    b2q_mlp_set_weights(s->mlp_actor, 0, s->p_actor + a.oW1, s->p_actor + a.ob1, s->p_actor + a.oW2, s->p_actor + a.ob2, s->p_actor + a.oW3, s->p_actor + a.ob3, st);
+    k_make_bwd_weights<<<(H * H + 255) / 256, 256, 0, st>>>(s->p_actor + a.oW1, a.in_dim, 0, 0, s->p_actor + a.oW2, s->p_actor + a.oW3, a.od, s->W2T[0], s->W3T[0], s->W1A[0]);
+    s->launches += 2;
+  }
   for (int i = 0; i < 2; i++) {
     float* p = s->p_critic + (size_t)i * c.n; float* t = s->p_target + (size_t)i * c.n;
-    b2q_mlp_set_weights(s->mlp_critic, i, p + c.oW1, p + c.ob1, p + c.oW2, p + c.ob2, p + c.oW3, p + c.ob3, st);
-    b2q_mlp_set_weights(s->mlp_target, i, t + c.oW1, t + c.ob1, t + c.oW2, t + c.ob2, t + c.oW3, t + c.ob3, st);
-    k_make_bwd_weights<<<(H * H + 255) / 256, 256, 0, st>>>(p + c.oW1, c.in_dim, s->D, s->A, p + c.oW2, p + c.oW3, c.od, s->W2T[1 + i], s->W3T[1 + i], s->W1A[1 + i]);
+    if (which & 2) {
+      b2q_mlp_set_weights(s->mlp_critic, i, p + c.oW1, p + c.ob1, p + c.oW2, p + c.ob2, p + c.oW3, p + c.ob3, st);
+      k_make_bwd_weights<<<(H * H + 255) / 256, 256, 0, st>>>(p + c.oW1, c.in_dim, s->D, s->A, p + c.oW2, p + c.oW3, c.od, s->W2T[1 + i], s->W3T[1 + i], s->W1A[1 + i]);
+      s->launches += 2;
+    }
+    if (which & 4) { b2q_mlp_set_weights(s->mlp_target, i, t + c.oW1, t + c.ob1, t + c.oW2, t + c.ob2, t + c.oW3, t + c.ob3, st); s->launches++; }
   }
-  s->launches += 9;
 }
 
 }  // namespace
@@ -463,7 +490,7 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
       s->launches++;
     }
     s->launches++;
-    sync_net_weights(s, st);
+    sync_net_weights(s, st, phase == 1 ? 2 : (1 | 4));   // phase 1 changed the critics; phase 3 the actor and (Polyak) the targets
   } else if (phase == 2) {
     if (!obs) return -1;
     cudaMemsetAsync(s->g_actor, 0, an.n * sizeof(float), st);
@@ -525,7 +552,7 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   if (actor_backward(s, st)) return -2;
   k_step_inc<<<1, 1, 0, st>>>(s->d_step);
   k_adam<<<((int)an.n + 255) / 256, 256, 0, st>>>(s->p_actor, s->g_actor, s->m_a, s->v_a, (int)an.n, s->lr_a, 0.9f, 0.999f, 1e-8f, s->d_step);
-  sync_net_weights(s, st);
+  sync_net_weights(s, st, 1);
   // --- critic: a_now ~ pi_student(obs) (no grad); targets = expert Q(ref_obs, a_now)
   if (b2q_mlp_forward(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_SAMPLE, 0, eps, s->cur_a, s->cur_logp, nullptr, st)) return -2;
   if (b2q_mlp_forward(expert_critic, ref_obs, ref_obs_dim, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->qn, nullptr, nullptr, st)) return -2;
@@ -534,7 +561,7 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   k_critic_dq<<<dim3(NB, 2), TB, 0, st>>>(s->q, s->qn, B, s->dq, s->losses + 0, B);
   if (critic_backward(s, st)) return -2;
   k_adam<<<((int)(2 * cn.n) + 255) / 256, 256, 0, st>>>(s->p_critic, s->g_critic, s->m_c, s->v_c, (int)(2 * cn.n), s->lr_c, 0.9f, 0.999f, 1e-8f, s->d_step);
-  sync_net_weights(s, st);
+  sync_net_weights(s, st, 2);
   s->launches += 12;
   if (losses_out) cudaMemcpyAsync(losses_out, s->losses, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st);
   cudaError_t e = cudaGetLastError();
