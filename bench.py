@@ -42,6 +42,23 @@ class ClockSampler(threading.Thread):
         self.gpu, self.rows, self._halt = gpu, [], threading.Event()
 
     def run(self):
+        # NVML directly (5 ms period: the timed region is only ~0.1 s long); nvidia-smi subprocess as the fallback
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            bits = ((0x8, 2), (0x40, 3), (0x20, 4), (0x4, 5))     # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+            while not self._halt.is_set():
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                row = [str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(mx), "", "", "", ""]
+                for bit, col in bits:
+                    row[col] = "Active" if (r & bit) else "Not Active"
+                self.rows.append(row)
+                self._halt.wait(0.005)
+            return
+        except Exception:
+            pass
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self._halt.is_set():
             try:
