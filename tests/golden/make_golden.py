@@ -102,6 +102,15 @@ def main():
     for k, v in md.items():
         out["dynloss_" + k] = v
     out["dynloss_value"] = np.array(env["loss_func"](drpy, motor, md, "exp"))
+    # --- BC student observation noise (BCtrain.py:53-59), ast-extracted (the module imports rlschool); global NumPy RNG seeded
+    src = open(ns.REF + "/BCtrain.py").read()
+    env = {"np": np, "copy": __import__("copy").copy}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == "obs2noise":
+            exec(compile(ast.Module([node], []), "BCtrain.py", "exec"), env)
+    obs49 = rng.normal(0, 1, (8, 49))
+    np.random.seed(7)
+    out["noise_obs_in"], out["noise_obs_out"] = obs49, np.array([env["obs2noise"](o) for o in obs49])
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     # reference's own golden artefacts (data)
     shutil.copy(ns.REF + "/gait_action_list_ETG_exp.npy", os.path.join(HERE, "gait_action_list_ETG_exp.npy"))

@@ -126,3 +126,25 @@ def test_train_loop_runs_and_reward_improves():
     early = np.mean([r["mean_step_reward"] for r in log[:2]])
     late = np.mean([r["mean_step_reward"] for r in log[-3:]])
     assert np.isfinite(late) and late > early + 0.5, (early, late)
+
+
+def test_bc_loop_clones_expert():
+    """f-3 end to end (paddlerobotics_b200/bc.py ~ ETGRL/BCtrain.py:86-146): a 46-dim noisy-observation student acting in the
+    batched env is cloned from a 49-dim expert; the BC actor loss (negative log-likelihood of the expert action) must fall."""
+    import torch
+    from paddlerobotics_b200 import bc
+    from paddlerobotics_b200.agent import MujocoAgent
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    from paddlerobotics_b200.etg import ETG_layer, Opt_with_points
+    layer = ETG_layer(0.5, 0.026, 20, 0.04, np.array([-np.pi / 2, 0]), 0.2, 0.5)
+    w, b, _ = Opt_with_points(ETG=layer, ETG_T=0.5, Footheight=0.03, Steplength=0.02)
+    env = VecQuadrupedalEnv(512, auto_reset=True, max_episode_steps=100)
+    expert, student = MujocoAgent(49, 12, seed=1), MujocoAgent(46, 12, seed=2)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    o = torch.randn(64, 49, device="cuda", generator=g)
+    n1 = bc.obs2noise_batch(o, g)
+    assert torch.equal(n1[:, :7], o[:, :7]) and torch.equal(n1[:, 37:], o[:, 37:]) and not torch.equal(n1[:, 7:37], o[:, 7:37])
+    losses = bc.run_bc(env, student, expert, w, b, iters=60, batch=512, train_every=1)
+    a = np.array([l[1] for l in losses])
+    assert len(a) >= 50 and np.isfinite(a).all() and a[-10:].mean() < a[:10].mean() - 0.05, (a[:10].mean(), a[-10:].mean())
+    env.close()
