@@ -80,6 +80,8 @@ typedef struct B2QConfig {
   int32_t hf_nx, hf_ny;
   double hf_x0, hf_y0, hf_cell;
   const double* hf_host;     /* HOST pointer, [hf_ny][hf_nx], copied at create */
+  int32_t clip_motor_commands; /* A1.ApplyAction -> _ClipMotorCommands (a1.py:428-458; enable_clip_motor_commands, default 0 as a1.py:229) */
+  double max_angle_change;   /* MAX_MOTOR_ANGLE_CHANGE_PER_STEP = 0.2 rad per substep (a1.py:62) */
 } B2QConfig;
 
 typedef struct B2QEnv* B2QHandle;

@@ -94,6 +94,7 @@ void orc_default_config(OrcConfig* c) {
   memset(c, 0, sizeof *c);
   c->sim_dt = 0.002; c->action_repeat = 13; c->solver_iters = 23; c->erp = 0.2; c->warmstart = 0.85; c->contact_margin = 0.02;
   c->action_interp = 0; c->torque_limit = 0; c->settle_steps = 500; c->action_filter = 0; c->filter_highcut = 4.0; c->etg_enabled = 1;
+  c->clip_motor_commands = 0; c->max_angle_change = 0.2;
   c->etg_T = 0.5; c->etg_T2 = 0.5; c->etg_sigma_sq = 0.04; c->etg_amp = 0.2; c->etg_phase[0] = -M_PI / 2; c->etg_phase[1] = 0; /* train.py:296-297 */
   c->w_torso = 1.5; c->w_feet = 0.3; c->w_up = 0.6; c->w_tau = 0.07; c->w_stand = 0; c->w_badfoot = 0.1; c->w_footcontact = 0.1; c->w_done = 1; /* train.py:478-484 */
   c->reward_p = 5; c->vel_d = 0.5; c->foot_radius = 0.02; c->terrain_type = 0;
@@ -522,8 +523,12 @@ void orc_substep(const OrcConfig* c, OrcEnv* e, const double target[12]) {
   build_model(e->param, &D->mdl);
   dyn_kinematics(e, D);
   /* ApplyAction: PD on the *current* observation (pd_latency = 0, minitaur.py:100,1195-1199) */
-  double tau[12];
-  orc_motor_torque(e->param, e->param + 12, target, e->q, e->qd, c->torque_limit, tau);
+  double tau[12], cmd[12];
+  for (int j = 0; j < 12; j++) {   /* A1._ClipMotorCommands, a1.py:440-458: np.clip(cmd, q - max_change, q + max_change) on the current angles */
+    cmd[j] = target[j];
+    if (c->clip_motor_commands) cmd[j] = fmin(fmax(cmd[j], e->q[j] - c->max_angle_change), e->q[j] + c->max_angle_change);
+  }
+  orc_motor_torque(e->param, e->param + 12, cmd, e->q, e->qd, c->torque_limit, tau);
   memcpy(e->last_tau, tau, sizeof tau);
   double qdd[12], a0[6];
   dyn_aba(e, D, tau, qdd, a0);

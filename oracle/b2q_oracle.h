@@ -55,6 +55,8 @@ typedef struct {
   double foot_radius;       /* 0.02 */
   int terrain_type;         /* 0 plane, 1 height field */
   int hf_nx, hf_ny; double hf_x0, hf_y0, hf_cell; const double* hf; /* row-major [ny][nx] */
+  int clip_motor_commands;  /* A1.ApplyAction -> _ClipMotorCommands (a1.py:428-458; enable_clip_motor_commands, default False a1.py:229) */
+  double max_angle_change;  /* MAX_MOTOR_ANGLE_CHANGE_PER_STEP = 0.2, a1.py:62 */
 } OrcConfig;
 
 typedef struct {

@@ -34,6 +34,7 @@ class Config(C.Structure):
         ("reward_p", C.c_double), ("vel_d", C.c_double), ("foot_radius", C.c_double),
         ("terrain_type", C.c_int), ("hf_nx", C.c_int), ("hf_ny", C.c_int),
         ("hf_x0", C.c_double), ("hf_y0", C.c_double), ("hf_cell", C.c_double), ("hf", C.POINTER(C.c_double)),
+        ("clip_motor_commands", C.c_int), ("max_angle_change", C.c_double),
     ]
 
 

@@ -22,4 +22,5 @@ class B2QConfig(C.Structure):
         ("foot_radius", C.c_double), ("ring_depth", C.c_int32), ("auto_reset", C.c_int32), ("terrain_type", C.c_int32),
         ("hf_nx", C.c_int32), ("hf_ny", C.c_int32), ("hf_x0", C.c_double), ("hf_y0", C.c_double), ("hf_cell", C.c_double),
         ("hf_host", C.POINTER(C.c_double)),
+        ("clip_motor_commands", C.c_int32), ("max_angle_change", C.c_double),
     ]

@@ -13,6 +13,7 @@ inline Cfg<T> make_cfg(const B2QConfig& c, const T* hf_dev) {
   k.dt = (T)c.sim_dt; k.R = c.action_repeat; k.iters = c.solver_iters; k.erp = (T)c.erp; k.warm = (T)c.warmstart; k.margin = (T)c.contact_margin;
   k.interp = c.action_interp; k.tau_limit = (T)c.torque_limit; k.settle_steps = c.settle_steps;
   k.filter = c.action_filter; k.etg = c.etg_enabled; k.max_steps = c.max_episode_steps;
+  k.clip_cmd = c.clip_motor_commands; k.max_dq = (T)c.max_angle_change;
   {  // scipy.signal.butter(2, highcut / (fs/2)) in closed form (bilinear transform), fs = 1 / control period
     const double PI = 3.14159265358979323846, fs = 1.0 / (c.sim_dt * c.action_repeat);
     const double K = std::tan(PI * c.filter_highcut / fs), n = 1.0 / (1.0 + std::sqrt(2.0) * K + K * K);
@@ -33,7 +34,7 @@ inline void default_config(B2QConfig* c) {
   c->action_interp = 0; c->torque_limit = 0; c->settle_steps = 500; c->action_filter = 0; c->filter_highcut = 4.0; c->etg_enabled = 1;
   c->etg_T = 0.5; c->etg_T2 = 0.5; c->etg_sigma_sq = 0.04; c->etg_amp = 0.2; c->etg_phase0 = -3.14159265358979323846 / 2; c->etg_phase1 = 0;
   c->w_torso = 1.5; c->w_feet = 0.3; c->w_up = 0.6; c->w_tau = 0.07; c->w_stand = 0; c->w_badfoot = 0.1; c->w_footcontact = 0.1; c->w_done = 1;
-  c->reward_p = 5; c->vel_d = 0.5; c->foot_radius = 0.02; c->ring_depth = 1; c->auto_reset = 0; c->terrain_type = 0;
+  c->reward_p = 5; c->vel_d = 0.5; c->foot_radius = 0.02; c->ring_depth = 1; c->auto_reset = 0; c->terrain_type = 0; c->clip_motor_commands = 0; c->max_angle_change = 0.2;
 }
 
 inline const char* validate_config(const B2QConfig& c) {
@@ -43,6 +44,7 @@ inline const char* validate_config(const B2QConfig& c) {
   if (c.solver_iters < 1 || c.solver_iters > 1000) return "solver_iters out of range";
   if (!(c.sim_dt > 0)) return "sim_dt must be > 0";
   if (c.action_filter && !(c.filter_highcut > 0)) return "filter_highcut must be > 0";
+  if (c.clip_motor_commands && !(c.max_angle_change > 0)) return "max_angle_change must be > 0";
   if (c.ring_depth < 1 || c.ring_depth > 16) return "ring_depth out of range [1,16]";
   if (c.terrain_type == 1 && (c.hf_nx < 2 || c.hf_ny < 2 || !c.hf_host || !(c.hf_cell > 0))) return "height field needs hf_nx,hf_ny>=2, hf_cell>0 and hf_host";
   if (c.terrain_type != 0 && c.terrain_type != 1) return "terrain_type must be 0 or 1";

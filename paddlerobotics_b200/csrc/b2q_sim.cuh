@@ -60,6 +60,7 @@ struct Cfg {
   T etg_T, etg_T2, etg_sigma_sq, etg_amp, etg_ph0, etg_ph1;
   T w_torso, w_feet, w_up, w_tau, w_stand, w_badfoot, w_footcontact, w_done, reward_p, vel_d;
   int terrain, hf_nx, hf_ny; T hf_x0, hf_y0, hf_cell, hf_icell, idt; const T* hf;
+  int clip_cmd; T max_dq;   // A1._ClipMotorCommands (a1.py:440-458)
 };
 template <typename T>
 struct Buffers {
@@ -190,7 +191,9 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
   T tau[3];
 #pragma unroll
   for (int j = 0; j < 3; j++) {
-    T t = T(-1) * (pr.kp[j] * (s.q[j] - target[j])) - pr.kd[j] * (s.qd[j] - T(0));
+    T cmd = target[j];
+    if (cf.clip_cmd) cmd = m_min(m_max(cmd, s.q[j] - cf.max_dq), s.q[j] + cf.max_dq);   // a1.py:452-457 (off by default)
+    T t = T(-1) * (pr.kp[j] * (s.q[j] - cmd)) - pr.kd[j] * (s.qd[j] - T(0));
     if (cf.tau_limit > T(0)) t = m_min(m_max(t, -cf.tau_limit), cf.tau_limit);
     tau[j] = t; tau_out[j] = t;
   }

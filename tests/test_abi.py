@@ -42,6 +42,7 @@ def test_config_struct_mirror_matches_header_defaults():
     assert (c.w_torso, c.w_feet, c.w_up, c.w_tau, c.w_badfoot, c.w_footcontact, c.reward_p, c.vel_d) == (1.5, 0.3, 0.6, 0.07, 0.1, 0.1, 5.0, 0.5)  # train.py:461-487
     assert c.etg_T == 0.5 and c.etg_sigma_sq == 0.04 and c.etg_amp == 0.2 and c.ring_depth == 1
     assert c.action_filter == 0 and c.filter_highcut == 4.0          # train.py:502, action_filter.py:44
+    assert c.clip_motor_commands == 0 and c.max_angle_change == 0.2  # a1.py:229,62
 
 
 def test_create_fails_loudly_without_gpu_or_with_bad_config():

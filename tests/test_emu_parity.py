@@ -13,7 +13,7 @@ from oracle import oracle as O  # noqa: E402
 
 
 def _pair(precision, w, b, n=1, **kw):
-    ocfg = O.default_config(**{k: v for k, v in kw.items() if k in ("action_interp", "torque_limit", "solver_iters", "action_repeat", "action_filter", "max_episode_steps")})
+    ocfg = O.default_config(**{k: v for k, v in kw.items() if k in ("action_interp", "torque_limit", "solver_iters", "action_repeat", "action_filter", "max_episode_steps", "clip_motor_commands", "max_angle_change")})
     e = emu.EmuEnv(n, precision, **kw)
     o = O.OracleEnv(ocfg)
     return e, o, e.reset(w, b), o.reset(w, b)
@@ -81,6 +81,16 @@ def test_f64_options_interp_torque_limit_latency(etg_stable):
         ob, rw, dn, inf = o.step(a); ob2, rw2, dn2, inf2 = e.step(a)
         assert np.abs(inf2[0] - inf).max() < 1e-8
     e.close()
+    # A1._ClipMotorCommands (a1.py:428-458): target clipped to the current angle +-max_angle_change every substep; a large
+    # residual makes the clip bind, and the clipped run must differ from the unclipped one
+    e, o, _, _ = _pair(1, w, b, clip_motor_commands=1, max_angle_change=0.05)
+    e0, _, _, _ = _pair(1, w, b)
+    for k in range(12):
+        a = rng.uniform(-0.6, 0.6, 12)
+        ob, rw, dn, inf = o.step(a); ob2, rw2, dn2, inf2 = e.step(a); ob0 = e0.step(a)[0]
+        assert np.abs(ob2[0] - ob).max() < 1e-8 and np.abs(inf2[0] - inf).max() < 1e-8, k
+    assert np.abs(ob2[0] - ob0[0]).max() > 1e-3
+    e.close(); e0.close()
     # per-env episode truncation (per-env form of donef=(steps>max_step), train.py:147)
     e, o, _, _ = _pair(1, w, b, max_episode_steps=7)
     for k in range(9):

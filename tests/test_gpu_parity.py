@@ -135,9 +135,10 @@ def test_randomised_dynamics_latency_terrain_f64(torch_cuda, etg_stable):
     rows = np.array(rows)
     xs = -1.6 + 0.04 * np.arange(128)
     hf = 0.02 * np.sin(6 * xs)[None, :] * np.ones((128, 1)) + 0.01 * np.cos(5 * xs)[:, None]
-    env = VecQuadrupedalEnv(4, precision="f64", ring_depth=4, heightfield=(hf, -1.6, -1.6, 0.04), action_interp=1, action_filter=1)
+    env = VecQuadrupedalEnv(4, precision="f64", ring_depth=4, heightfield=(hf, -1.6, -1.6, 0.04), action_interp=1, action_filter=1,
+                            clip_motor_commands=1, max_angle_change=0.15)
     env.set_dynamics(rows); env.reset(w, b)
-    cfg = O.default_config(action_interp=1, action_filter=1); O.set_heightfield(cfg, hf, -1.6, -1.6, 0.04)
+    cfg = O.default_config(action_interp=1, action_filter=1, clip_motor_commands=1, max_angle_change=0.15); O.set_heightfield(cfg, hf, -1.6, -1.6, 0.04)
     os_ = [O.OracleEnv(cfg, rows[i]) for i in range(4)]
     for o in os_:
         o.reset(w, b)
