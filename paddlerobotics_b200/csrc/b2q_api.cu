@@ -26,6 +26,8 @@ struct WarpComm {
   }
   template <typename T>
   __device__ __forceinline__ T bcast(T v, int f) const { return __shfl_sync(0xffffffffu, v, f, 4); }
+  template <typename T> __device__ __forceinline__ T xor1(T v) const { return __shfl_xor_sync(0xffffffffu, v, 1); }   // partner lanes of the
+  template <typename T> __device__ __forceinline__ T xor2(T v) const { return __shfl_xor_sync(0xffffffffu, v, 2); }   // 4-lane butterfly
 };
 
 template <typename T>

@@ -267,34 +267,54 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
     D[2][2] = (M11 * M22 - M21 * M21) * id;
   }
   T bj[3] = {tau[0] - hj[0], tau[1] - hj[1], tau[2] - hj[2]};
+  // F_k D_k (6x3) and the leg's Schur contribution C_k - (F D) F^T as PAIRS of adjacent components with the packed FP32 ops
+  // (the body is instruction-fetch bound): FP[i][p] = (F_i[2p], F_i[2p+1]), FDP[j][p] likewise.
+  P2<T> FP[3][3], FDP[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { FP[i][0] = p2mk(Fc[i].a.x, Fc[i].a.y); FP[i][1] = p2mk(Fc[i].a.z, Fc[i].l.x); FP[i][2] = p2mk(Fc[i].l.y, Fc[i].l.z); }
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+#pragma unroll
+    for (int p = 0; p < 3; p++) FDP[j][p] = p2fma(FP[2][p], p2s(D[2][j]), p2fma(FP[1][p], p2s(D[1][j]), p2mul(FP[0][p], p2s(D[0][j]))));
+  }
+#define FDA(k, i) (((i) & 1) ? FDP[k][(i) >> 1].y : FDP[k][(i) >> 1].x)
   V6<T> FD[3];
 #pragma unroll
-  for (int j = 0; j < 3; j++) FD[j] = Fc[0] * D[0][j] + Fc[1] * D[1][j] + Fc[2] * D[2][j];
+  for (int j = 0; j < 3; j++) { FD[j].a = mk<T>(FDA(j, 0), FDA(j, 1), FDA(j, 2)); FD[j].l = mk<T>(FDA(j, 3), FDA(j, 4), FDA(j, 5)); }
 
-  // --- leg contribution to the base Schur complement and rhs; reduce over the 4 legs
+  // --- leg contribution to the base Schur complement and rhs; reduce over the 4 legs (4-lane butterflies on pairs)
   T S[21], r6[6];
   {
-    T Fa[3][6], FDa[3][6];
-#pragma unroll
-    for (int j = 0; j < 3; j++) { v6_to_arr(Fc[j], Fa[j]); v6_to_arr(FD[j], FDa[j]); }
-    // composite C1 as 6x6: [[I1c, hx],[hx^T, m 1]], hx = skew(h1c)
-    T C[21];
-    C[tri(0, 0)] = I1c.xx; C[tri(1, 0)] = I1c.xy; C[tri(1, 1)] = I1c.yy; C[tri(2, 0)] = I1c.xz; C[tri(2, 1)] = I1c.yz; C[tri(2, 2)] = I1c.zz;
-    // lower-left block rows 3..5 (lin), cols 0..2 (ang) = hx^T = -skew(h): [[0,hz,-hy],[-hz,0,hx],[hy,-hx,0]]
-    C[tri(3, 0)] = 0; C[tri(3, 1)] = h1c.z; C[tri(3, 2)] = -h1c.y;
-    C[tri(4, 0)] = -h1c.z; C[tri(4, 1)] = 0; C[tri(4, 2)] = h1c.x;
-    C[tri(5, 0)] = h1c.y; C[tri(5, 1)] = -h1c.x; C[tri(5, 2)] = 0;
-    C[tri(3, 3)] = m1c; C[tri(4, 3)] = 0; C[tri(4, 4)] = m1c; C[tri(5, 3)] = 0; C[tri(5, 4)] = 0; C[tri(5, 5)] = m1c;
-    T NOa[6] = {NO.x, NO.y, NO.z, F1.x, F1.y, F1.z};
+    // composite C1 as 6x6: [[I1c, hx],[hx^T, m 1]], hx = skew(h1c); lower-left block = hx^T = [[0,hz,-hy],[-hz,0,hx],[hy,-hx,0]]
+    const T Z = T(0);
+    const T Cf[6][6] = {{I1c.xx, I1c.xy, I1c.xz, Z, -h1c.z, h1c.y},
+                        {I1c.xy, I1c.yy, I1c.yz, h1c.z, Z, -h1c.x},
+                        {I1c.xz, I1c.yz, I1c.zz, -h1c.y, h1c.x, Z},
+                        {Z, h1c.z, -h1c.y, m1c, Z, Z},
+                        {-h1c.z, Z, h1c.x, Z, m1c, Z},
+                        {h1c.y, -h1c.x, Z, Z, Z, m1c}};
 #pragma unroll
     for (int i = 0; i < 6; i++) {
 #pragma unroll
-      for (int j = 0; j <= i; j++) {
-        T v = C[tri(i, j)] - (FDa[0][i] * Fa[0][j] + FDa[1][i] * Fa[1][j] + FDa[2][i] * Fa[2][j]);
-        S[tri(i, j)] = cm.sum4(v);
+      for (int p = 0; 2 * p <= i; p++) {   // columns (2p, 2p+1) of row i; for even i the last pair's second half is the mirror entry (unused)
+        P2<T> v = p2mk(Cf[i][2 * p], Cf[i][2 * p + 1]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) v = p2fma(FP[k][p], p2s(-FDA(k, i)), v);
+        v = p2add(v, p2mk(cm.xor1(v.x), cm.xor1(v.y)));
+        v = p2add(v, p2mk(cm.xor2(v.x), cm.xor2(v.y)));
+        S[tri(i, 2 * p)] = v.x;
+        if (2 * p + 1 <= i) S[tri(i, 2 * p + 1)] = v.y;
       }
-      T rv = -NOa[i] - (FDa[0][i] * bj[0] + FDa[1][i] * bj[1] + FDa[2][i] * bj[2]);
-      r6[i] = cm.sum4(rv);
+    }
+    const T NOa[6] = {NO.x, NO.y, NO.z, F1.x, F1.y, F1.z};
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+      P2<T> v = p2mk(-NOa[2 * p], -NOa[2 * p + 1]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) v = p2fma(FDP[k][p], p2s(-bj[k]), v);
+      v = p2add(v, p2mk(cm.xor1(v.x), cm.xor1(v.y)));
+      v = p2add(v, p2mk(cm.xor2(v.x), cm.xor2(v.y)));
+      r6[2 * p] = v.x; r6[2 * p + 1] = v.y;
     }
   }
   {
@@ -339,8 +359,14 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
       Jk[e][0] = dot(eB[e], r1); Jk[e][1] = dot(eB[e], r2); Jk[e][2] = dot(eB[e], r3);
       V6<T> Jb; Jb.a = cross(xc, eB[e]); Jb.l = eB[e];
       u[e] = dot(Jb.a, wBs) + dot(Jb.l, vBs) + Jk[e][0] * qds[0] + Jk[e][1] * qds[1] + Jk[e][2] * qds[2];
-      V6<T> G = Jb - (FD[0] * Jk[e][0] + FD[1] * Jk[e][1] + FD[2] * Jk[e][2]);
-      v6_to_arr(G, Y[e]);
+      const T Jba[6] = {Jb.a.x, Jb.a.y, Jb.a.z, Jb.l.x, Jb.l.y, Jb.l.z};
+#pragma unroll
+      for (int p = 0; p < 3; p++) {
+        P2<T> g = p2mk(Jba[2 * p], Jba[2 * p + 1]);
+#pragma unroll
+        for (int j = 0; j < 3; j++) g = p2fma(FDP[j][p], p2s(-Jk[e][j]), g);
+        Y[e][2 * p] = g.x; Y[e][2 * p + 1] = g.y;
+      }
       fwd6(S, Li, Y[e]);
     }
 #pragma unroll
@@ -352,6 +378,7 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
       for (int e2 = 0; e2 < 3; e2++) Wl[e2][e] = Jk[e2][0] * dj[0] + Jk[e2][1] * dj[1] + Jk[e2][2] * dj[2];
     }
   }
+#undef FDA
   // --- gather every foot's rows on every lane (4-lane broadcasts), then the whole 12x12 contact problem is solved
   //     REDUNDANTLY in registers by all four lanes: the Gauss-Seidel sweep below has no shuffle on its dependent chain.
   //     Row index r = 3*foot + e (e: 0 normal, 1,2 friction).
