@@ -226,15 +226,15 @@ def main():
         except Exception:
             pass
         # secondary (the bound that actually applies): warp-instruction issue slots.  Instructions per launch are the
-        # ncu count of the committed capture (profiles/step_kernel_r01d_ncu_full.csv); duration and SM clock are this run's.
+        # ncu count of the committed capture (profiles/step_kernel_r01e_ncu_full.csv); duration and SM clock are this run's.
         issue = None
         try:
-            prof = dict(l.split(",")[0::2] for l in open(os.path.join(ROOT, "profiles", "step_kernel_r01d_ncu_full.csv")).read().splitlines()[2:] if l.count(",") == 2)
+            prof = dict(l.split(",")[0::2] for l in open(os.path.join(ROOT, "profiles", "step_kernel_r01e_ncu_full.csv")).read().splitlines()[2:] if l.count(",") == 2)
             inst = float(prof["smsp__inst_executed.sum"]) * n / 4096.0
             mhz = (clocks or {}).get("sm_mhz") or 1965.0
             slots = ms_per_step * 1e-3 * mhz * 1e6 * 148 * 4
             issue = {"warp_instructions_per_launch": inst, "issue_slot_frac": inst / slots, "fma_pipe_pct_ncu": float(prof["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]),
-                     "warps_per_sm_ncu": float(prof["sm__warps_active.avg.per_cycle_active"]), "source": "profiles/step_kernel_r01d_ncu_full.csv"}
+                     "warps_per_sm_ncu": float(prof["sm__warps_active.avg.per_cycle_active"]), "source": "profiles/step_kernel_r01e_ncu_full.csv"}
         except Exception:
             pass
         cpu = None
