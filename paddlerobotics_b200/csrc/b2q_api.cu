@@ -253,8 +253,12 @@ struct EnvT : EnvBase {
     T* obs_dev = nullptr; T* rew_dev = nullptr; uint8_t* done_dev = nullptr;
     if (host_io >= 2) { obs_dev = (T*)mapped(obs); rew_dev = (T*)mapped(rew); done_dev = (uint8_t*)mapped(done); }
     const bool direct = obs_dev && rew_dev && done_dev;
-    int rc = direct ? step(act_dev, donef, obs_dev, rew_dev, done_dev, st_info, s) : step(act_dev, donef, st_obs, st_rew, st_done, st_info, s);
+    // info rows are produced in 3-float pieces (not staged): zero-copy only for small batches (the N=1 reference-style env),
+    // where a handful of small PCIe writes beats a D2H copy launch; larger batches stage on the device + one D2H
+    T* info_dev = (direct && info && N * INFO_DIM * sizeof(T) <= 16384) ? (T*)mapped(info) : nullptr;
+    int rc = direct ? step(act_dev, donef, obs_dev, rew_dev, done_dev, info_dev ? info_dev : st_info, s) : step(act_dev, donef, st_obs, st_rew, st_done, st_info, s);
     if (rc) return rc;
+    if (info_dev) info = nullptr;
     const size_t b_obs = N * OBS_DIM * sizeof(T), b_rew = N * sizeof(T);
     if (direct) {
     } else if ((uint8_t*)rew == (uint8_t*)obs + b_obs && done == (uint8_t*)rew + b_rew) {

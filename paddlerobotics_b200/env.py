@@ -65,7 +65,7 @@ class VecQuadrupedalEnv:
         self.control_dt = c.sim_dt * c.action_repeat
         self.observation_dim, self.action_dim = OBS_DIM, ACT_DIM
         # host API staging (pinned) — allocated lazily
-        self._h_act = self._h_obs = self._h_rew = self._h_done = self._d_act = None
+        self._h_act = self._h_obs = self._h_rew = self._h_done = self._d_act = self._h_info = None
 
     # ------------------------------------------------------------------ device API
     def _stream(self):
@@ -123,15 +123,21 @@ class VecQuadrupedalEnv:
             self._h_done = self._h_out[n * (OBS_DIM + 1) * es:]
             self._np_act, self._np_obs, self._np_rew, self._np_done = self._h_act.numpy(), self._h_obs.numpy(), self._h_rew.numpy(), self._h_done.numpy()
 
-    def step_host(self, action_np, donef=False):
-        """The reference-facing call with HOST buffers (numpy in / numpy out), one C call: pinned H2D of the actions, the
-        step kernel, D2H of obs/reward/done, stream sync (b2q_step_host)."""
+    def step_host(self, action_np, donef=False, info=False):
+        """The reference-facing call with HOST buffers (numpy in / numpy out), one C call and one stream sync: the step kernel
+        reads the actions from and stores obs / reward / done to pinned host memory (b2q_step_host).  info=True also returns
+        the [N,56] info rows.  The returned arrays are views of the pinned buffers (overwritten by the next call)."""
         self._host_bufs()
         np.copyto(self._np_act, np.asarray(action_np).reshape(self.num_envs, ACT_DIM), casting="same_kind")
+        if info and self._h_info is None:
+            self._h_info = torch.empty(self.num_envs, INFO_DIM, dtype=self.dtype).pin_memory()
+            self._np_info = self._h_info.numpy()
         rc = self.lib.b2q_step_host(self.h, self._h_act.data_ptr(), int(bool(donef)), self._h_obs.data_ptr(), self._h_rew.data_ptr(),
-                                    self._h_done.data_ptr(), None, self._stream())
+                                    self._h_done.data_ptr(), self._h_info.data_ptr() if info else None, self._stream())
         if rc != 0:
             _check(self.lib, self.h, rc, "b2q_step_host")
+        if info:
+            return self._np_obs, self._np_rew, self._np_done, self._np_info
         return self._np_obs, self._np_rew, self._np_done
 
     def h2d_bytes_per_step(self):
@@ -210,8 +216,9 @@ class QuadrupedalEnv:
         return obs[0].double().cpu().numpy(), info
 
     def step(self, action, donef=False, **kw):
-        obs, rew, done, info = self.vec.step(np.asarray(action, dtype=np.float64).reshape(1, ACT_DIM), donef)
-        return obs[0].double().cpu().numpy(), float(rew[0]), bool(done[0]), info_dict(info[0].double().cpu().numpy())
+        # one C call + one stream sync: actions in, obs / reward / done / info out through pinned host buffers
+        obs, rew, done, info = self.vec.step_host(np.asarray(action).reshape(1, ACT_DIM), donef, info=True)
+        return obs[0].astype(np.float64), float(rew[0]), bool(done[0]), info_dict(info[0])
 
 
 ETG_H_CONST = ETG_H
