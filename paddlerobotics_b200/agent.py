@@ -149,13 +149,30 @@ class MujocoAgent:
         return out[0, :, 0], out[1, :, 0]
 
     # ---- reference call shapes (numpy, batch 1): mujoco_agent.py:29-41
+    def _single(self, obs, mode, seed):
+        """One observation through the fused MLP with pinned host buffers as kernel arguments (the kernel reads the 49 floats
+        from and writes the 12 actions to host memory over PCIe): one launch + one stream sync, no copy launches."""
+        if getattr(self, "_h1", None) is None:
+            A = self.act_dim
+            self._h1 = (torch.empty(1, self.obs_dim).pin_memory(), torch.empty(1, 1, A).pin_memory(), torch.empty(1, 1).pin_memory())
+            self._h1np = (self._h1[0].numpy(), self._h1[1].numpy())
+        hin, hout, hlogp = self._h1
+        self._h1np[0][0, :] = np.asarray(obs, dtype=np.float32).reshape(-1)
+        a = self.actor
+        st = torch.cuda.current_stream(a.device)
+        rc = a.lib.b2q_mlp_forward(a.h, hin.data_ptr(), self.obs_dim, None, 1, mode, C.c_uint64(seed), None, hout.data_ptr(),
+                                   hlogp.data_ptr() if mode == SAMPLE else None, None, C.c_void_p(st.cuda_stream))
+        if rc != 0:
+            raise RuntimeError("b2q_mlp_forward: %s" % a.lib.b2q_mlp_last_error(a.h).decode())
+        st.synchronize()
+        return self._h1np[1][0, 0].copy()
+
     def predict(self, obs):
-        o = torch.as_tensor(np.asarray(obs, dtype=np.float32).reshape(1, -1), device=self.device)
-        return self.predict_batch(o)[0].cpu().numpy().flatten()
+        return self._single(obs, PREDICT, 0)
 
     def sample(self, obs):
-        o = torch.as_tensor(np.asarray(obs, dtype=np.float32).reshape(1, -1), device=self.device)
-        return self.sample_batch(o)[0][0].cpu().numpy().flatten()
+        self._sample_calls += 1
+        return self._single(obs, SAMPLE, self._sample_calls)
 
 
 ACTOR_KEYS = ("actor_model.l1", "actor_model.l2")

@@ -21,3 +21,10 @@ t0 = time.perf_counter()
 for _ in range(1000): old_step(a)
 dt = (time.perf_counter() - t0) / 1000
 print(json.dumps({"what": "same through device tensors + 4 D2H reads (previous wrapper)", "us_per_step": dt * 1e6, "steps_per_s": 1 / dt}))
+from paddlerobotics_b200.agent import MujocoAgent
+agent = MujocoAgent(49, 12, seed=0)
+for _ in range(50): agent.sample(obs)
+t0 = time.perf_counter()
+for _ in range(1000): act = agent.sample(obs)
+dt = (time.perf_counter() - t0) / 1000
+print(json.dumps({"what": "agent.sample(obs) numpy [49] -> numpy [12] (fused tcgen05 MLP on pinned buffers)", "us_per_call": dt * 1e6}))

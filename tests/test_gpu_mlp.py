@@ -130,3 +130,21 @@ def test_policy_in_the_rollout_loop(etg_default):
         obs, r, d, info = env.step(a)
     assert torch.isfinite(obs).all() and torch.isfinite(r).all()
     env.close()
+
+
+def test_single_observation_calls_match_batch():
+    """MujocoAgent.predict / sample (mujoco_agent.py:29-41, numpy [obs] -> numpy [act]) run the kernel on pinned host buffers;
+    they must equal row 0 of the batched device call bit for bit (same seed for sample)."""
+    import torch
+    from paddlerobotics_b200.agent import MujocoAgent
+    agent = MujocoAgent(49, 12, seed=3)
+    rng = np.random.default_rng(0)
+    for k in range(3):
+        o = rng.normal(0, 1, 49).astype(np.float32)
+        ot = torch.as_tensor(o[None], device="cuda")
+        a1 = agent.predict(o)
+        assert a1.shape == (12,) and np.array_equal(a1, agent.predict_batch(ot)[0].cpu().numpy())
+        calls = agent._sample_calls
+        a2 = agent.sample(o)
+        ref = agent.sample_batch(ot, seed=calls + 1)[0][0].cpu().numpy()
+        assert np.array_equal(a2, ref) and not np.array_equal(a1, a2)
