@@ -111,6 +111,24 @@ def main():
     obs49 = rng.normal(0, 1, (8, 49))
     np.random.seed(7)
     out["noise_obs_in"], out["noise_obs_out"] = obs49, np.array([env["obs2noise"](o) for o in obs49])
+    # --- observation history stack (deployment/envs/EnvWrapper.py:195-241), class ast-extracted, driven by a fake env
+    src = open(ns.REF + "/deployment/envs/EnvWrapper.py").read()
+    env = {"np": np, "copy": __import__("copy").copy}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.ClassDef) and node.name == "ObservationWrapper":
+            exec(compile(ast.Module([node], []), "EnvWrapper.py", "exec"), env)
+    seq = rng.normal(0, 1, (12, 7))                       # reset obs + 11 step obs of a 7-dim sensor
+
+    class _Fake:
+        def __init__(self): self.k = 0
+        def get_obs_dim(self): return 7
+        def get_observation(self): self.k += 1; return seq[self.k].copy(), {}
+        def reset(self, **kw): self.k = 0; return seq[0].copy(), {}
+    out["hist_seq"] = seq
+    for mode, T, I in (("stack", 3, 1), ("stack", 2, 2), ("GRU", 3, 1)):
+        wr = env["ObservationWrapper"](_Fake(), None, {"RNN": {"time_steps": T, "time_interval": I, "mode": mode}})
+        rows = [np.asarray(wr.reset()[0])] + [np.asarray(wr.get_observation()[0]) for _ in range(11)]
+        out["hist_%s_%d_%d" % (mode, T, I)] = np.array(rows)
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     # reference's own golden artefacts (data)
     shutil.copy(ns.REF + "/gait_action_list_ETG_exp.npy", os.path.join(HERE, "gait_action_list_ETG_exp.npy"))
