@@ -282,16 +282,22 @@ struct EnvT : EnvBase {
     return nullptr;
   }
   int get_state(void* out, cudaStream_t s) override {
+    if (!out) { err = "b2q_get_state: null pointer"; return B2Q_EINVAL; }
+    CK(cudaSetDevice(cfg.device));
     b2q_get_state_kernel<T><<<(B.N + 127) / 128, 128, 0, s>>>(B.state, (T*)out, B.N); launches++;
     CK(cudaGetLastError());
     return B2Q_OK;
   }
   int set_state(const void* in, cudaStream_t s) override {
+    if (!in) { err = "b2q_set_state: null pointer"; return B2Q_EINVAL; }
+    CK(cudaSetDevice(cfg.device));
     b2q_set_state_kernel<T><<<(B.N + 127) / 128, 128, 0, s>>>(B.state, (const T*)in, B.N); launches++;
     CK(cudaGetLastError());
     return B2Q_OK;
   }
   int get_step_count(int32_t* out, cudaStream_t s) override {
+    if (!out) { err = "b2q_get_step_count: null pointer"; return B2Q_EINVAL; }
+    CK(cudaSetDevice(cfg.device));
     CK(cudaMemcpyAsync(out, B.step_count, sizeof(int) * B.N, cudaMemcpyDeviceToDevice, s));
     return B2Q_OK;
   }
