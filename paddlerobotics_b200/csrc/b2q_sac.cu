@@ -298,6 +298,8 @@ struct B2QSac {
   bf16 *xc_rm = nullptr, *xc_t = nullptr, *hc1_rm = nullptr, *hc1_t = nullptr, *hc2_rm = nullptr, *hc2_t = nullptr;
   bf16 *xa_rm = nullptr, *xa_t = nullptr, *ha1_rm = nullptr, *ha1_t = nullptr, *ha2_rm = nullptr, *ha2_t = nullptr;
   bf16 *dh_rm = nullptr, *dh_t = nullptr, *dy_bf = nullptr;
+  bf16 *dh_rm2 = nullptr, *dh_t2 = nullptr; float *G2 = nullptr, *da_c2 = nullptr;   // second scratch set: the twin critics' backward chains run on two streams
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float *G = nullptr, *tq = nullptr, *q = nullptr, *qn = nullptr, *dq = nullptr, *next_a = nullptr, *next_logp = nullptr, *cur_a = nullptr, *cur_logp = nullptr, *raw_a = nullptr,
         *da_c = nullptr, *dy = nullptr, *losses = nullptr;
   std::vector<void*> allocs;
@@ -317,6 +319,12 @@ template <typename T> bool dalloc(B2QSac* s, T** p, size_t count) {
   return true;
 }
 
+// Fork / join of an internal side stream off the caller's stream (plain events: also legal inside a stream capture, where
+// they become graph edges).  The twin critics' chains are independent and each kernel is latency-bound on a few SMs, so
+// running them side by side nearly halves that part of a learn step.
+void fork(B2QSac* s, cudaStream_t st) { cudaEventRecord(s->ev_fork, st); cudaStreamWaitEvent(s->side, s->ev_fork, 0); }
+void join(B2QSac* s, cudaStream_t st) { cudaEventRecord(s->ev_join, s->side); cudaStreamWaitEvent(st, s->ev_join, 0); }
+
 int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int ldb, float* C, int ldc, int M, int N, int K, bool splitk) {
   GemmArgs g; g.A = A; g.lda = lda; g.B = Bm; g.ldb = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
   g.BN = ((N + 15) / 16) * 16;
@@ -333,41 +341,49 @@ int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-// forward images + bf16 backward copies after a parameter change; `which`: bit 0 actor, bit 1 critics, bit 2 target critics
+// forward images + bf16 backward copies after a parameter change; `which`: bit 0 actor, bit 1 critics, bit 2 target critics.
+// Net 0 / the actor are repacked on the caller's stream, net 1 on the side stream (small independent kernels).
 void sync_net_weights(B2QSac* s, cudaStream_t st, int which = 7) {
   const Net& a = s->an; const Net& c = s->cn;
+  fork(s, st);
   if (which & 1) {
     b2q_mlp_set_weights(s->mlp_actor, 0, s->p_actor + a.oW1, s->p_actor + a.ob1, s->p_actor + a.oW2, s->p_actor + a.ob2, s->p_actor + a.oW3, s->p_actor + a.ob3, st);
     k_make_bwd_weights<<<(H * H + 255) / 256, 256, 0, st>>>(s->p_actor + a.oW1, a.in_dim, 0, 0, s->p_actor + a.oW2, s->p_actor + a.oW3, a.od, s->W2T[0], s->W3T[0], s->W1A[0]);
     s->launches += 2;
   }
   for (int i = 0; i < 2; i++) {
+    cudaStream_t sx = i ? s->side : st;
     float* p = s->p_critic + (size_t)i * c.n; float* t = s->p_target + (size_t)i * c.n;
     if (which & 2) {
-      b2q_mlp_set_weights(s->mlp_critic, i, p + c.oW1, p + c.ob1, p + c.oW2, p + c.ob2, p + c.oW3, p + c.ob3, st);
-      k_make_bwd_weights<<<(H * H + 255) / 256, 256, 0, st>>>(p + c.oW1, c.in_dim, s->D, s->A, p + c.oW2, p + c.oW3, c.od, s->W2T[1 + i], s->W3T[1 + i], s->W1A[1 + i]);
+      b2q_mlp_set_weights(s->mlp_critic, i, p + c.oW1, p + c.ob1, p + c.oW2, p + c.ob2, p + c.oW3, p + c.ob3, sx);
+      k_make_bwd_weights<<<(H * H + 255) / 256, 256, 0, sx>>>(p + c.oW1, c.in_dim, s->D, s->A, p + c.oW2, p + c.oW3, c.od, s->W2T[1 + i], s->W3T[1 + i], s->W1A[1 + i]);
       s->launches += 2;
     }
-    if (which & 4) { b2q_mlp_set_weights(s->mlp_target, i, t + c.oW1, t + c.ob1, t + c.oW2, t + c.ob2, t + c.oW3, t + c.ob3, st); s->launches++; }
+    if (which & 4) { b2q_mlp_set_weights(s->mlp_target, i, t + c.oW1, t + c.ob1, t + c.oW2, t + c.ob2, t + c.oW3, t + c.ob3, s->side); s->launches++; }
   }
+  join(s, st);
 }
 
 }  // namespace
 
 namespace {
 // weight gradients of both critics from dq [2][B] and the activation dumps of the last critic forward
-int critic_backward(B2QSac* s, cudaStream_t st) {
+int critic_backward(B2QSac* s, cudaStream_t st0) {
   const int B = s->B; const Net& cn = s->cn;
+  fork(s, st0);
   for (int i = 0; i < 2; i++) {
+    cudaStream_t st = i ? s->side : st0;
+    bf16 *dh_rm = i ? s->dh_rm2 : s->dh_rm, *dh_t = i ? s->dh_t2 : s->dh_t; float* G = i ? s->G2 : s->G;
     float* g = s->g_critic + (size_t)i * cn.n; const float* p = s->p_critic + (size_t)i * cn.n;
     const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h1t = s->hc1_t + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
-    k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dq + (size_t)i * B, 1, p + cn.oW3, h2, s->dh_rm, s->dh_t, g + cn.oW3, g + cn.ob3, g + cn.ob2, B);   // dh2, dW3, db3, db2
-    if (gemm(s, st, s->dh_t, B, h1t, B, g + cn.oW2, H, H, H, B, true)) return -2;
-    if (gemm(s, st, s->dh_rm, H, s->W2T[1 + i], H, s->G, H, B, H, H, false)) return -2;
-    k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(s->G, h1, s->dh_rm, s->dh_t, g + cn.ob1, B);                                                      // dh1, db1
-    if (gemm(s, st, s->dh_t, B, s->xc_t, B, g + cn.oW1, cn.in_dim, H, cn.in_dim, B, true)) return -2;
+    k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dq + (size_t)i * B, 1, p + cn.oW3, h2, dh_rm, dh_t, g + cn.oW3, g + cn.ob3, g + cn.ob2, B);   // dh2, dW3, db3, db2
+    if (gemm(s, st, dh_t, B, h1t, B, g + cn.oW2, H, H, H, B, true)) return -2;
+    if (gemm(s, st, dh_rm, H, s->W2T[1 + i], H, G, H, B, H, H, false)) return -2;
+    k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(G, h1, dh_rm, dh_t, g + cn.ob1, B);                                                      // dh1, db1
+    if (gemm(s, st, dh_t, B, s->xc_t, B, g + cn.oW1, cn.in_dim, H, cn.in_dim, B, true)) return -2;
     s->launches += 5;
   }
+  join(s, st0);
   return 0;
 }
 // actor weight gradients from dy [B][2A] and the activation dumps of the last actor forward
@@ -405,7 +421,10 @@ int b2q_sac_create(int device, int obs_dim, int act_dim, int batch, float gamma,
        dalloc(s, &s->ha2_rm, Bz * H) && dalloc(s, &s->ha2_t, Bz * H) && dalloc(s, &s->dh_rm, Bz * H) && dalloc(s, &s->dh_t, Bz * H) && dalloc(s, &s->dy_bf, Bz * 64) &&
        dalloc(s, &s->G, Bz * H) && dalloc(s, &s->tq, Bz) && dalloc(s, &s->q, 2 * Bz) && dalloc(s, &s->qn, 2 * Bz) && dalloc(s, &s->dq, 2 * Bz) && dalloc(s, &s->next_a, Bz * 12) &&
        dalloc(s, &s->next_logp, Bz) && dalloc(s, &s->cur_a, Bz * 12) && dalloc(s, &s->cur_logp, Bz) && dalloc(s, &s->raw_a, Bz * 24) && dalloc(s, &s->da_c, Bz * 16) &&
-       dalloc(s, &s->dy, Bz * 24) && dalloc(s, &s->losses, 4) && dalloc(s, &s->d_step, 1);
+       dalloc(s, &s->dy, Bz * 24) && dalloc(s, &s->losses, 4) && dalloc(s, &s->d_step, 1) &&
+       dalloc(s, &s->dh_rm2, Bz * H) && dalloc(s, &s->dh_t2, Bz * H) && dalloc(s, &s->G2, Bz * H) && dalloc(s, &s->da_c2, Bz * 16);
+  ok = ok && cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+       cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && b2q_mlp_create(device, obs_dim, 2 * act_dim, 1, &s->mlp_actor) == 0 && b2q_mlp_create(device, obs_dim + act_dim, 1, 2, &s->mlp_critic) == 0 &&
        b2q_mlp_create(device, obs_dim + act_dim, 1, 2, &s->mlp_target) == 0;
   ok = ok && cudaFuncSetAttribute(b2q_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM) == cudaSuccess;
@@ -418,6 +437,9 @@ int b2q_sac_destroy(B2QSacHandle s) {
   if (!s) return -1;
   cudaSetDevice(s->device);
   for (void* p : s->allocs) cudaFree(p);
+  if (s->side) cudaStreamDestroy(s->side);
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+  if (s->ev_join) cudaEventDestroy(s->ev_join);
   if (s->mlp_actor) b2q_mlp_destroy(s->mlp_actor);
   if (s->mlp_critic) b2q_mlp_destroy(s->mlp_critic);
   if (s->mlp_target) b2q_mlp_destroy(s->mlp_target);
@@ -468,12 +490,14 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     cudaMemsetAsync(s->losses, 0, 4 * sizeof(float), st);
     cudaMemsetAsync(s->g_critic, 0, 2 * cn.n * sizeof(float), st);
     // target: next action ~ pi(next_obs), twin target Q (sac.py:85-91)
-    if (b2q_mlp_forward(s->mlp_actor, next_obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2 + 1, eps_next, s->next_a, s->next_logp, nullptr, st)) return -2;
-    if (b2q_mlp_forward(s->mlp_target, next_obs, D, s->next_a, B, B2Q_MLP_RAW, 0, nullptr, s->qn, nullptr, nullptr, st)) return -2;
-    k_target_q<<<NB, TB, 0, st>>>(rew, term, s->qn, s->qn + B, s->next_logp, s->gamma, s->alpha, s->tq, B);
-    // current Q with activation dumps
+    fork(s, st);
+    if (b2q_mlp_forward(s->mlp_actor, next_obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2 + 1, eps_next, s->next_a, s->next_logp, nullptr, s->side)) return -2;
+    if (b2q_mlp_forward(s->mlp_target, next_obs, D, s->next_a, B, B2Q_MLP_RAW, 0, nullptr, s->qn, nullptr, nullptr, s->side)) return -2;
+    k_target_q<<<NB, TB, 0, s->side>>>(rew, term, s->qn, s->qn + B, s->next_logp, s->gamma, s->alpha, s->tq, B);
+    // current Q with activation dumps (independent of the target chain: main stream)
     B2QMlpSaves sv = {s->xc_rm, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
     if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, act, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, st)) return -2;
+    join(s, st);
     k_critic_dq<<<dim3(NB, 2), TB, 0, st>>>(s->q, s->tq, 0, s->dq, s->losses + 0, B);
     s->launches += 5;
     if (critic_backward(s, st)) return -2;
@@ -494,7 +518,6 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
   } else if (phase == 2) {
     if (!obs) return -1;
     cudaMemsetAsync(s->g_actor, 0, an.n * sizeof(float), st);
-    cudaMemsetAsync(s->da_c, 0, (size_t)B * 16 * sizeof(float), st);
     // a ~ pi(obs) with dumps; Q(obs, a) with dumps (sac.py:102-106)
     B2QMlpSaves sa = {s->xa_rm, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
     if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2, eps_cur, s->cur_a, s->cur_logp, s->raw_a, &sa, st)) return -2;
@@ -503,16 +526,21 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     k_minq_dq<<<NB, TB, 0, st>>>(s->q, s->dq, B);
     s->launches += 3;
     // d(-min q)/da through both critics (no critic weight gradients: only the actor optimiser steps here)
+    fork(s, st);
     for (int i = 0; i < 2; i++) {
+      cudaStream_t sx = i ? s->side : st;
+      bf16 *dh_rm = i ? s->dh_rm2 : s->dh_rm, *dh_t = i ? s->dh_t2 : s->dh_t; float *G = i ? s->G2 : s->G, *da = i ? s->da_c2 : s->da_c;
       const float* p = s->p_critic + (size_t)i * cn.n;
       const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
-      k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dq + (size_t)i * B, 1, p + cn.oW3, h2, s->dh_rm, s->dh_t, s->G /*scratch dW3*/, nullptr, nullptr, B);
-      if (gemm(s, st, s->dh_rm, H, s->W2T[1 + i], H, s->G, H, B, H, H, false)) return -2;
-      k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(s->G, h1, s->dh_rm, s->dh_t, nullptr, B);
-      if (gemm(s, st, s->dh_rm, H, s->W1A[1 + i], H, s->G, 16, B, 16, H, false)) return -2;                    // da_i [B][16]
-      k_add_f32<<<(B * 16 + 255) / 256, 256, 0, st>>>(s->da_c, s->G, B * 16);
-      s->launches += 3;
+      k_head_bwd<<<(B + 31) / 32, H, 0, sx>>>(s->dq + (size_t)i * B, 1, p + cn.oW3, h2, dh_rm, dh_t, G /*scratch dW3*/, nullptr, nullptr, B);
+      if (gemm(s, sx, dh_rm, H, s->W2T[1 + i], H, G, H, B, H, H, false)) return -2;
+      k_relu_mask<<<(B + 31) / 32, H, 0, sx>>>(G, h1, dh_rm, dh_t, nullptr, B);
+      if (gemm(s, sx, dh_rm, H, s->W1A[1 + i], H, da, 16, B, 16, H, false)) return -2;                    // da_i [B][16]
+      s->launches += 2;
     }
+    join(s, st);
+    k_add_f32<<<(B * 16 + 255) / 256, 256, 0, st>>>(s->da_c, s->da_c2, B * 16);                              // da = da_1 + da_2
+    s->launches++;
     if (!eps_cur) return -1;   // the explicit-noise path is required for the backward pass
     k_actor_dy<<<NB, TB, 0, st>>>(s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->alpha, s->dy, s->losses + 1, B, A);
     if (actor_backward(s, st)) return -2;
