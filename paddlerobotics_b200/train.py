@@ -61,7 +61,7 @@ def main(argv=None):
                                     act_bound=args.act_bound) if args.ES else None
     obs = env.reset(w, b).clone()
     total, it, last_es, t0 = 0, 0, 0, time.perf_counter()
-    ret_acc = torch.zeros(n, device=env.device); ep_rets = []
+    ret_acc = torch.zeros(n, device=env.device); ep_rets = []; last_log = (0, 0.0)
     log = []
     while total < args.max_steps:
         if rpm.size() < args.warmup_steps:
@@ -82,7 +82,8 @@ def main(argv=None):
         if it % args.log_every == 0:
             torch.cuda.synchronize()
             el = time.perf_counter() - t0
-            rec = {"env_steps": total, "iters": it, "env_steps_per_s": total / el, "mean_step_reward": float(rew.mean()), "done_frac": float(done.float().mean()),
+            rate_int = (total - last_log[0]) / max(el - last_log[1], 1e-9); last_log = (total, el)
+            rec = {"env_steps": total, "iters": it, "env_steps_per_s": total / el, "interval_env_steps_per_s": rate_int, "mean_step_reward": float(rew.mean()), "done_frac": float(done.float().mean()),
                    "episode_return": ep_rets[-1] if ep_rets else None,
                    "critic_loss": float(losses[0]) if rpm.size() >= args.warmup_steps else None, "actor_loss": float(losses[1]) if rpm.size() >= args.warmup_steps else None}
             log.append(rec); print(json.dumps(rec), flush=True)
