@@ -42,6 +42,7 @@ def main(argv=None):
     p.add_argument("--sigma_decay", type=float, default=0.99)
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--log_every", type=int, default=50)
+    p.add_argument("--overlap", type=int, default=1, help="run the SAC update on a second stream beside the env step")
     p.add_argument("--torso", type=float, default=1.5); p.add_argument("--feet", type=float, default=0.3); p.add_argument("--up", type=float, default=0.6)
     p.add_argument("--tau", type=float, default=0.07); p.add_argument("--badfoot", type=float, default=0.1); p.add_argument("--footcontact", type=float, default=0.1)
     args = p.parse_args(argv)
@@ -61,6 +62,7 @@ def main(argv=None):
                                     act_bound=args.act_bound) if args.ES else None
     obs = env.reset(w, b).clone()
     total, it, last_es, t0 = 0, 0, 0, time.perf_counter()
+    s_learn = torch.cuda.Stream(device=env.device)
     ret_acc = torch.zeros(n, device=env.device); ep_rets = []; last_log = (0, 0.0)
     log = []
     while total < args.max_steps:
@@ -68,8 +70,21 @@ def main(argv=None):
             act = torch.rand(n, 12, device=env.device) * 2 - 1                         # train.py:141-142
         else:
             act = learner.actor.forward(obs, mode=1, seed=it + 1)[0][0]               # agent.sample(obs)
+        learning = rpm.size() >= args.warmup_steps
+        if learning and args.overlap:
+            # the learner step (latency-bound small kernels) runs on its own stream NEXT TO the env step (one warp per scheduler):
+            # it samples transitions up to t-1 and its new weights are first used by the policy forward of step t+1, exactly as
+            # in the sequential order, except that transition t itself joins the replay one update later
+            batch_t = rpm.sample_batch(args.batch)
+            s_learn.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_learn):
+                for x in batch_t:
+                    x.record_stream(s_learn)
+                losses = learner.learn(*batch_t, graph=True, pull=False)
         nobs, rew, done, info = env.step(act * args.act_bound)
         rpm.append(obs, act, rew, nobs, 1.0 - done.float())                            # terminal = 1 - done, train.py:148-149,159
+        if learning and args.overlap:
+            torch.cuda.current_stream().wait_stream(s_learn)
         ret_acc += rew
         fin = done.bool()
         if it % args.log_every == 0 and bool(fin.any()):
@@ -77,7 +92,7 @@ def main(argv=None):
         ret_acc = torch.where(fin, torch.zeros_like(ret_acc), ret_acc)
         obs.copy_(nobs)
         total += n; it += 1
-        if rpm.size() >= args.warmup_steps:
+        if rpm.size() >= args.warmup_steps and not (learning and args.overlap):
             losses = learner.learn(*rpm.sample_batch(args.batch), graph=True, pull=False)   # one update per control step, train.py:163-169
         if it % args.log_every == 0:
             torch.cuda.synchronize()
