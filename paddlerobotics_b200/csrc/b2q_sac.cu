@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128) b2q_gemm_kernel(GemmArgs g) {
   if ((sbase & 1023u) != 0) __trap();
   const uint32_t bar_free0 = sbase + 2 * G_STAGE, bar_done = bar_free0 + 16;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 2 * G_STAGE + 32);
-  const int row0 = blockIdx.x * 128;
+  const int row0 = blockIdx.x * 128, n0 = blockIdx.y * g.BN;   // output tile: 128 rows x BN columns
   const int nk_total = (g.K + 63) / 64;
   const int kc0 = blockIdx.z * g.chunks_per_split, kc1 = min(nk_total, kc0 + g.chunks_per_split), nk = kc1 - kc0;
   const uint32_t tm_cols = g.BN <= 32 ? 32u : (g.BN <= 64 ? 64u : (g.BN <= 128 ? 128u : 256u));
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) b2q_gemm_kernel(GemmArgs g) {
   const uint32_t tmem = *tmem_slot;
   if (nk > 0) {
     load_panel(sbase, g.A, g.lda, row0, g.M, 128, kc0 * 64, g.K, tid);
-    load_panel(sbase + G_STAGE_A, g.B, g.ldb, 0, g.N, g.BN, kc0 * 64, g.K, tid);
+    load_panel(sbase + G_STAGE_A, g.B, g.ldb, n0, g.N, g.BN, kc0 * 64, g.K, tid);
     asm volatile("cp.async.commit_group;" ::: "memory");
     const uint32_t idesc = umma_idesc(128, g.BN);
     for (int kc = 0; kc < nk; kc++) {
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(128) b2q_gemm_kernel(GemmArgs g) {
         const int s1 = (kc + 1) & 1;
         if (kc + 1 >= 2) mbar_wait(bar_free0 + 8 * s1, (uint32_t)(((kc + 1) / 2 - 1) & 1));
         load_panel(sbase + s1 * G_STAGE, g.A, g.lda, row0, g.M, 128, (kc0 + kc + 1) * 64, g.K, tid);
-        load_panel(sbase + s1 * G_STAGE + G_STAGE_A, g.B, g.ldb, 0, g.N, g.BN, (kc0 + kc + 1) * 64, g.K, tid);
+        load_panel(sbase + s1 * G_STAGE + G_STAGE_A, g.B, g.ldb, n0, g.N, g.BN, (kc0 + kc + 1) * 64, g.K, tid);
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 1;" ::: "memory");
       } else {
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(128) b2q_gemm_kernel(GemmArgs g) {
       if (row < g.M) {
 #pragma unroll
         for (int j = 0; j < 32; j++) {
-          int col = cc * 32 + j;
+          int col = n0 + cc * 32 + j;
           if (col < g.N) {
             float* c = g.C + (size_t)row * g.ldc + col;
             if (g.atomic) atomicAdd(c, __uint_as_float(r[j])); else *c = __uint_as_float(r[j]);
@@ -328,6 +328,9 @@ void join(B2QSac* s, cudaStream_t st) { cudaEventRecord(s->ev_join, s->side); cu
 int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int ldb, float* C, int ldc, int M, int N, int K, bool splitk) {
   GemmArgs g; g.A = A; g.lda = lda; g.B = Bm; g.ldb = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
   g.BN = ((N + 15) / 16) * 16;
+  static const int bn_max = [] { const char* e = std::getenv("B2Q_GEMM_BN"); int v = e ? std::atoi(e) : 64; return (v == 64 || v == 128 || v == 256) ? v : 64; }();   // output-tile width (measured: 64 < 128 < 256 in learn time)
+  if (g.BN > bn_max) g.BN = bn_max;                      // N tiled (grid.y): more CTAs, smaller B panel per k-chunk
+  const int ntiles = (N + g.BN - 1) / g.BN;
   int nk = (K + 63) / 64, splits = 1;
   static const int split_div = [] { const char* e = std::getenv("B2Q_GEMM_SPLIT_DIV"); int v = e ? std::atoi(e) : 8; return v < 1 ? 1 : v; }();   // K chunks (of 64) per split-K CTA
   if (splitk) { splits = nk / split_div; if (splits < 1) splits = 1; if (splits > 64) splits = 64; }
@@ -335,7 +338,7 @@ int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int
   splits = (nk + g.chunks_per_split - 1) / g.chunks_per_split;
   g.atomic = splits > 1 ? 1 : 0;
   if (g.atomic) cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st);
-  dim3 grid((M + 127) / 128, 1, splits);
+  dim3 grid((M + 127) / 128, ntiles, splits);
   b2q_gemm_kernel<<<grid, 128, G_SMEM, st>>>(g);
   s->launches++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
