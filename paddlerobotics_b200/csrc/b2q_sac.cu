@@ -300,6 +300,8 @@ struct B2QSac {
   bf16 *dh_rm = nullptr, *dh_t = nullptr, *dy_bf = nullptr;
   bf16 *dh_rm2 = nullptr, *dh_t2 = nullptr; float *G2 = nullptr, *da_c2 = nullptr;   // second scratch set: the twin critics' backward chains run on two streams
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t aux[2] = {nullptr, nullptr}; cudaEvent_t ev_aux[4] = {nullptr, nullptr, nullptr, nullptr};   // per-chain helper streams: dW2 GEMM beside the dh1 -> dW1 chain
+  bf16 *dh1_rm[2] = {nullptr, nullptr}, *dh1_t[2] = {nullptr, nullptr};                                      // layer-1 gradients (separate from dh2 so both GEMM branches can run)
   float *G = nullptr, *tq = nullptr, *q = nullptr, *qn = nullptr, *dq = nullptr, *next_a = nullptr, *next_logp = nullptr, *cur_a = nullptr, *cur_logp = nullptr, *raw_a = nullptr,
         *da_c = nullptr, *dy = nullptr, *losses = nullptr;
   std::vector<void*> allocs;
@@ -371,6 +373,23 @@ void sync_net_weights(B2QSac* s, cudaStream_t st, int which = 7) {
 
 namespace {
 // weight gradients of both critics from dq [2][B] and the activation dumps of the last critic forward
+// one MLP's weight-gradient chain after its head backward: dW2 (split-K GEMM over the batch) runs on the helper stream `ax`
+// beside  dh1 = (dh2 W2) . relu'  ->  dW1  on `st`
+int hidden_backward(B2QSac* s, cudaStream_t st, int slot, const bf16* dh2_rm, const bf16* dh2_t, float* G, const bf16* h1_rm, const bf16* h1_t, const bf16* x_t,
+                    const bf16* W2T, float* gW2, float* gb1, float* gW1, int in_dim) {
+  const int B = s->B;
+  cudaStream_t ax = s->aux[slot];
+  cudaEventRecord(s->ev_aux[2 * slot], st); cudaStreamWaitEvent(ax, s->ev_aux[2 * slot], 0);
+  if (gemm(s, ax, dh2_t, B, h1_t, B, gW2, H, H, H, B, true)) return -2;
+  cudaEventRecord(s->ev_aux[2 * slot + 1], ax);
+  if (gemm(s, st, dh2_rm, H, W2T, H, G, H, B, H, H, false)) return -2;
+  k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(G, h1_rm, s->dh1_rm[slot], s->dh1_t[slot], gb1, B);                                                      // dh1, db1
+  if (gemm(s, st, s->dh1_t[slot], B, x_t, B, gW1, in_dim, H, in_dim, B, true)) return -2;
+  cudaStreamWaitEvent(st, s->ev_aux[2 * slot + 1], 0);
+  s->launches += 4;
+  return 0;
+}
+// weight gradients of both critics from dq [2][B] and the activation dumps of the last critic forward
 int critic_backward(B2QSac* s, cudaStream_t st0) {
   const int B = s->B; const Net& cn = s->cn;
   fork(s, st0);
@@ -380,11 +399,8 @@ int critic_backward(B2QSac* s, cudaStream_t st0) {
     float* g = s->g_critic + (size_t)i * cn.n; const float* p = s->p_critic + (size_t)i * cn.n;
     const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h1t = s->hc1_t + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
     k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dq + (size_t)i * B, 1, p + cn.oW3, h2, dh_rm, dh_t, g + cn.oW3, g + cn.ob3, g + cn.ob2, B);   // dh2, dW3, db3, db2
-    if (gemm(s, st, dh_t, B, h1t, B, g + cn.oW2, H, H, H, B, true)) return -2;
-    if (gemm(s, st, dh_rm, H, s->W2T[1 + i], H, G, H, B, H, H, false)) return -2;
-    k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(G, h1, dh_rm, dh_t, g + cn.ob1, B);                                                      // dh1, db1
-    if (gemm(s, st, dh_t, B, s->xc_t, B, g + cn.oW1, cn.in_dim, H, cn.in_dim, B, true)) return -2;
-    s->launches += 5;
+    s->launches++;
+    if (hidden_backward(s, st, i, dh_rm, dh_t, G, h1, h1t, s->xc_t, s->W2T[1 + i], g + cn.oW2, g + cn.ob1, g + cn.oW1, cn.in_dim)) return -2;
   }
   join(s, st0);
   return 0;
@@ -394,12 +410,8 @@ int actor_backward(B2QSac* s, cudaStream_t st) {
   const int B = s->B, A = s->A; const Net& an = s->an;
   float* g = s->g_actor;
   k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dy, 2 * A, s->p_actor + an.oW3, s->ha2_rm, s->dh_rm, s->dh_t, g + an.oW3, g + an.ob3, g + an.ob2, B);
-  if (gemm(s, st, s->dh_t, B, s->ha1_t, B, g + an.oW2, H, H, H, B, true)) return -2;
-  if (gemm(s, st, s->dh_rm, H, s->W2T[0], H, s->G, H, B, H, H, false)) return -2;
-  k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(s->G, s->ha1_rm, s->dh_rm, s->dh_t, g + an.ob1, B);
-  if (gemm(s, st, s->dh_t, B, s->xa_t, B, g + an.oW1, an.in_dim, H, an.in_dim, B, true)) return -2;
-  s->launches += 5;
-  return 0;
+  s->launches++;
+  return hidden_backward(s, st, 0, s->dh_rm, s->dh_t, s->G, s->ha1_rm, s->ha1_t, s->xa_t, s->W2T[0], g + an.oW2, g + an.ob1, g + an.oW1, an.in_dim);
 }
 }  // namespace
 
@@ -425,7 +437,10 @@ int b2q_sac_create(int device, int obs_dim, int act_dim, int batch, float gamma,
        dalloc(s, &s->G, Bz * H) && dalloc(s, &s->tq, Bz) && dalloc(s, &s->q, 2 * Bz) && dalloc(s, &s->qn, 2 * Bz) && dalloc(s, &s->dq, 2 * Bz) && dalloc(s, &s->next_a, Bz * 12) &&
        dalloc(s, &s->next_logp, Bz) && dalloc(s, &s->cur_a, Bz * 12) && dalloc(s, &s->cur_logp, Bz) && dalloc(s, &s->raw_a, Bz * 24) && dalloc(s, &s->da_c, Bz * 16) &&
        dalloc(s, &s->dy, Bz * 24) && dalloc(s, &s->losses, 4) && dalloc(s, &s->d_step, 1) &&
-       dalloc(s, &s->dh_rm2, Bz * H) && dalloc(s, &s->dh_t2, Bz * H) && dalloc(s, &s->G2, Bz * H) && dalloc(s, &s->da_c2, Bz * 16);
+       dalloc(s, &s->dh_rm2, Bz * H) && dalloc(s, &s->dh_t2, Bz * H) && dalloc(s, &s->G2, Bz * H) && dalloc(s, &s->da_c2, Bz * 16) &&
+       dalloc(s, &s->dh1_rm[0], Bz * H) && dalloc(s, &s->dh1_t[0], Bz * H) && dalloc(s, &s->dh1_rm[1], Bz * H) && dalloc(s, &s->dh1_t[1], Bz * H);
+  for (int i = 0; i < 2 && ok; i++) ok = cudaStreamCreateWithFlags(&s->aux[i], cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreateWithFlags(&s->ev_aux[i], cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
        cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && b2q_mlp_create(device, obs_dim, 2 * act_dim, 1, &s->mlp_actor) == 0 && b2q_mlp_create(device, obs_dim + act_dim, 1, 2, &s->mlp_critic) == 0 &&
@@ -441,6 +456,8 @@ int b2q_sac_destroy(B2QSacHandle s) {
   cudaSetDevice(s->device);
   for (void* p : s->allocs) cudaFree(p);
   if (s->side) cudaStreamDestroy(s->side);
+  for (int i = 0; i < 2; i++) if (s->aux[i]) cudaStreamDestroy(s->aux[i]);
+  for (int i = 0; i < 4; i++) if (s->ev_aux[i]) cudaEventDestroy(s->ev_aux[i]);
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
   if (s->ev_join) cudaEventDestroy(s->ev_join);
   if (s->mlp_actor) b2q_mlp_destroy(s->mlp_actor);
