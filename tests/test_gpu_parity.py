@@ -65,7 +65,7 @@ def test_f32_free_running_1000_steps_drift(torch_cuda, etg_stable):
         mism += int(not np.array_equal(_np(ob)[0][3:7], oo[3:7]))
         assert not do
     print("f32 1000-step drift: q %.3g rad, base pos %.3g m, reward %.3g, contact-flag mismatches %d/1000" % (worst_q, worst_p, worst_r, mism))
-    assert worst_q < 5e-4      # measured 2.0e-4 rad on B200 (1.1e-4 relative to the 1.8 rad knee angle), see DESIGN.md §6
+    assert worst_q < 5e-4      # measured 1.7e-4 rad on B200 (9e-5 relative to the 1.8 rad knee angle), see DESIGN.md §6
     assert worst_r < 1e-2
     assert worst_p < 2e-3
     assert mism <= 10
