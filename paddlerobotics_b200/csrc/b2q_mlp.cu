@@ -1,6 +1,6 @@
 // b2q_mlp.cu — K3: fused 3-layer MLP forward (in<=64 -> 256 -> 256 -> out<=32) on tcgen05 tensor cores.
 //
-// One CTA (128 threads) per 128-row tile of the batch:
+// One CTA (256 threads: two warps per TMEM lane quarter, each taking half of the columns in the epilogues) per 128-row tile of the batch:
 //   * weights live in HBM as ready-made shared-memory images (bf16, K-major, 128-byte swizzle, 64-column panels) and are
 //     brought in by bulk async copies (cp.async.bulk -> UBLKCP) that complete on mbarriers;
 //   * the input tile is converted f32 -> bf16 by the CTA's threads straight into the swizzled A-operand layout;
@@ -52,10 +52,12 @@ struct FwdArgs {
   B2QMlpSaves sv; int save;
 };
 
-__global__ void __launch_bounds__(128, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
+constexpr int NTHR = 256;
+__global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, net = blockIdx.y;
-  const int row0 = blockIdx.x * TILE_M, row = row0 + tid;
+  const int trow = tid & (TILE_M - 1), chalf = tid >> 7;   // tile row owned in the epilogues; column half (0: cols 0..127, 1: 128..255)
+  const int row0 = blockIdx.x * TILE_M, row = row0 + trow;
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0) __trap();   // SWIZZLE_128B operands need a 1024-byte aligned base
   const uint32_t sA = sbase + OFF_A, sW2 = sbase + OFF_W2, sW13 = sbase + OFF_W13;
@@ -84,11 +86,11 @@ __global__ void __launch_bounds__(128, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
     const int in2_dim = a.in_dim - a.in1_dim;
     // 64 elements per thread in batches of 16 independent loads (all loads of a batch are in flight before the first use)
 #pragma unroll 1
-    for (int j0 = 0; j0 < 64; j0 += 16) {
+    for (int j0 = 0; j0 < 64 * TILE_M / NTHR; j0 += 16) {
       float v[16];
 #pragma unroll
       for (int j = 0; j < 16; j++) {
-        const int idx = tid + 128 * (j0 + j), r = idx >> 6, k = idx & 63, gr = row0 + r;
+        const int idx = tid + NTHR * (j0 + j), r = idx >> 6, k = idx & 63, gr = row0 + r;
         float x = 0.f;
         if (gr < a.M) {
           if (k < a.in1_dim) x = __ldg(a.in1 + (size_t)gr * a.in1_dim + k);
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(128, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
       }
 #pragma unroll
       for (int j = 0; j < 16; j++) {
-        const int idx = tid + 128 * (j0 + j), r = idx >> 6, k = idx & 63, gr = row0 + r;
+        const int idx = tid + NTHR * (j0 + j), r = idx >> 6, k = idx & 63, gr = row0 + r;
         __nv_bfloat16 vb = __float2bfloat16(v[j]);
         *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + sw128_offset(r, k, TILE_M)) = vb;
         if (a.save && net == 0 && gr < a.M) { a.sv.x_rm[(size_t)gr * 64 + k] = vb; a.sv.x_t[(size_t)k * a.M + gr] = vb; }
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(128, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // a warp may touch TMEM lanes 32*(warp%4)..+31
 
   // ---- layer 1: [128 x 64] x [256 x 64]^T -> TMEM cols 0..255
   if (tid == 0) {
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(128, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
   }
   auto epilogue_hidden = [&](uint32_t col_base, const float* b, __nv_bfloat16* d_rm, __nv_bfloat16* d_t) {
 #pragma unroll 1
-    for (int cc = 0; cc < 8; cc++) {
+    for (int cc = 4 * chalf; cc < 4 * chalf + 4; cc++) {
       uint32_t r[32];
       __syncwarp();
       tmem_ld32(lane_addr + col_base + cc * 32, r);
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(128, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
           __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
           pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
-        *reinterpret_cast<uint4*>(smem + OFF_A + sw128_offset(tid, cc * 32 + j0, TILE_M)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(smem + OFF_A + sw128_offset(trow, cc * 32 + j0, TILE_M)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         if (d_rm && row < a.M) {
           const int col = cc * 32 + j0;
           *reinterpret_cast<uint4*>(d_rm + ((size_t)net * a.M + row) * HID + col) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(128, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
   __syncwarp();
   mbar_wait(bar_mma, 0);
   tc_fence_after();
-  {
+  if (chalf == 0) {
     uint32_t r[32];
     __syncwarp();
     tmem_ld32(lane_addr, r);
@@ -304,7 +306,7 @@ int b2q_mlp_forward_ex(B2QMlpHandle h, const float* in1, int in1_dim, const floa
   FwdArgs a{in1, in2, in1_dim, h->in_dim, h->out_dim, M, mode, seed, eps, out, logp, raw, h->img, IMG_BYTES, B2QMlpSaves{}, 0};
   if (saves) { a.sv = *saves; a.save = 1; }
   dim3 grid((M + TILE_M - 1) / TILE_M, h->nets);
-  b2q_mlp_fwd_kernel<<<grid, 128, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  b2q_mlp_fwd_kernel<<<grid, NTHR, SMEM_BYTES, (cudaStream_t)stream>>>(a);
   h->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return -2; }
