@@ -138,75 +138,140 @@ __global__ void k_critic_dq(const float* q /*[2][B]*/, const float* tq /*[B] or 
   for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
   if ((threadIdx.x & 31) == 0) atomicAdd(loss, l);
 }
-// Both kernels below process a tile of 32 batch rows x 256 hidden columns per block (thread = column): the row-major
-// gradient is stored directly (coalesced), the [width x batch] copy goes through a shared-memory transpose so that it is
-// written as 64-byte row segments, and the bias gradient (column sums) is accumulated on the fly (one atomic per column
-// per block) -- no separate reduction launches.
-//
-// dh2[b,:] = dy[b,:] . W3 (out_dim x 256), masked by relu(h2) > 0; dW3 += dy^T h2; db3 += sum_b dy; db2 += sum_b dh2
-__global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ dy /*[B][od]*/, int od, const float* __restrict__ W3 /*[od][256]*/,
-                                                  const bf16* __restrict__ h2 /*[B][256]*/, bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t,
-                                                  float* dW3 /*[od][256]*/, float* db3 /*[od] or null*/, float* db2 /*[256] or null*/, int B) {
-  __shared__ bf16 tile[32][H + 2];
-  __shared__ float sdy[32][24];
-  const int col = threadIdx.x, b0 = blockIdx.x * 32, nr = min(32, B - b0);
-  for (int i = threadIdx.x; i < nr * od; i += blockDim.x) sdy[i / od][i % od] = dy[(size_t)b0 * od + i];
-  __syncthreads();
-  float w[24], acc[24], colsum = 0.f;
-  for (int o = 0; o < od; o++) { w[o] = W3[o * H + col]; acc[o] = 0.f; }
-  // rows in groups of 8 with the activation loads issued together (a serial row loop is bound by the load latency)
-  for (int r8 = 0; r8 < nr; r8 += 8) {
-    float hv[8];
+// Vectorised tile kernels (32 batch rows x 256 hidden columns per block, 256 threads): a warp handles one row at a time,
+// each lane 8 consecutive columns (16-byte bf16 / 2 x 16-byte f32 accesses, fully coalesced); column sums are reduced over
+// the block's 8 warps in shared memory (one atomic per column per block); the [width x batch] copy goes through the
+// shared-memory tile as 64-byte row segments.
+__device__ __forceinline__ void tile_finish(bf16 (*tile)[H + 8], float (*csum)[H], const float* cs /*8 column sums of this thread*/, int chunk, int warp,
+                                            bf16* __restrict__ dh_t, float* db, int B, int b0, int nr) {
 #pragma unroll
-    for (int u = 0; u < 8; u++) hv[u] = (r8 + u < nr) ? __bfloat162float(h2[(size_t)(b0 + r8 + u) * H + col]) : 0.f;
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const int r = r8 + u;
-      if (r < nr) {
-        float g = 0.f;
-        for (int o = 0; o < od; o++) { float d = sdy[r][o]; g += d * w[o]; acc[o] += d * hv[u]; }
-        g = hv[u] > 0.f ? g : 0.f;
-        bf16 gb = __float2bfloat16(g);
-        colsum += __bfloat162float(gb);
-        dh_rm[(size_t)(b0 + r) * H + col] = gb;
-        tile[r][col] = gb;
-      }
-    }
-  }
-  for (int o = 0; o < od; o++) atomicAdd(dW3 + o * H + col, acc[o]);
-  if (db2) atomicAdd(db2 + col, colsum);
-  if (db3 && col < od) { float sd = 0.f; for (int r = 0; r < nr; r++) sd += sdy[r][col]; atomicAdd(db3 + col, sd); }
+  for (int j = 0; j < 8; j++) csum[warp][chunk * 8 + j] = cs[j];
   __syncthreads();
-  for (int i = threadIdx.x; i < H * 32; i += blockDim.x) { int c = i >> 5, r = i & 31; if (r < nr) dh_t[(size_t)c * B + b0 + r] = tile[r][c]; }
+  if (db) { float t = 0.f; for (int w = 0; w < 8; w++) t += csum[w][threadIdx.x]; atomicAdd(db + threadIdx.x, t); }
+  for (int i = threadIdx.x; i < H * 32; i += 256) { int c = i >> 5, r = i & 31; if (r < nr) dh_t[(size_t)c * B + b0 + r] = tile[r][c]; }
 }
 // dh = G (f32 [B][256]) masked by h>0 -> bf16 row-major + transposed; db += column sums
 __global__ void __launch_bounds__(256) k_relu_mask(const float* __restrict__ G, const bf16* __restrict__ h, bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t,
                                                    float* db /*[256] or null*/, int B) {
-  __shared__ bf16 tile[32][H + 2];
-  const int col = threadIdx.x, b0 = blockIdx.x * 32, nr = min(32, B - b0);
-  float colsum = 0.f;
-  for (int r8 = 0; r8 < nr; r8 += 8) {
-    float hv[8], gv[8];
+  __shared__ __align__(16) bf16 tile[32][H + 8];
+  __shared__ float csum[8][H];
+  const int chunk = threadIdx.x & 31, warp = threadIdx.x >> 5, b0 = blockIdx.x * 32, nr = min(32, B - b0);
+  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint4 hv[4]; float4 g0[4], g1[4];
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const bool ok = r8 + u < nr;
-      hv[u] = ok ? __bfloat162float(h[(size_t)(b0 + r8 + u) * H + col]) : 0.f;
-      gv[u] = ok ? G[(size_t)(b0 + r8 + u) * H + col] : 0.f;
-    }
+  for (int k = 0; k < 4; k++) {      // all loads of the thread's four rows in flight before the first use
+    const int r = warp + 8 * k; const size_t off = (size_t)(b0 + r) * H + chunk * 8;
+    if (r < nr) { hv[k] = *reinterpret_cast<const uint4*>(h + off); g0[k] = *reinterpret_cast<const float4*>(G + off); g1[k] = *reinterpret_cast<const float4*>(G + off + 4); }
+  }
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const int r = r8 + u;
-      if (r < nr) {
-        bf16 vb = __float2bfloat16(hv[u] > 0.f ? gv[u] : 0.f);
-        colsum += __bfloat162float(vb);
-        dh_rm[(size_t)(b0 + r) * H + col] = vb;
-        tile[r][col] = vb;
-      }
+  for (int k = 0; k < 4; k++) {
+    const int r = warp + 8 * k;
+    if (r < nr) {
+      const bf16* hb = reinterpret_cast<const bf16*>(&hv[k]);
+      const float gv[8] = {g0[k].x, g0[k].y, g0[k].z, g0[k].w, g1[k].x, g1[k].y, g1[k].z, g1[k].w};
+      __align__(16) bf16 o[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) { o[j] = __float2bfloat16(__bfloat162float(hb[j]) > 0.f ? gv[j] : 0.f); cs[j] += __bfloat162float(o[j]); }
+      *reinterpret_cast<uint4*>(dh_rm + (size_t)(b0 + r) * H + chunk * 8) = *reinterpret_cast<const uint4*>(o);
+      *reinterpret_cast<uint4*>(&tile[r][chunk * 8]) = *reinterpret_cast<const uint4*>(o);
     }
   }
-  if (db) atomicAdd(db + col, colsum);
+  tile_finish(tile, csum, cs, chunk, warp, dh_t, db, B, b0, nr);
+}
+// critic head backward (out_dim = 1), same tiling: dh2[b,:] = dq[b] W3 masked by h2 > 0; dW3 += sum_b dq[b] h2[b,:]; db3 += sum_b dq; db2 += sum_b dh2
+__global__ void __launch_bounds__(256) k_head_bwd1(const float* __restrict__ dq /*[B]*/, const float* __restrict__ W3 /*[256]*/, const bf16* __restrict__ h2,
+                                                   bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t, float* dW3 /*[256]*/, float* db3 /*[1] or null*/, float* db2 /*[256] or null*/, int B) {
+  __shared__ __align__(16) bf16 tile[32][H + 8];
+  __shared__ float csum[8][H];
+  const int chunk = threadIdx.x & 31, warp = threadIdx.x >> 5, b0 = blockIdx.x * 32, nr = min(32, B - b0);
+  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, w[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) w[j] = W3[chunk * 8 + j];   // scalar loads: the second critic's parameter block starts at an odd float offset
+  uint4 hv[4]; float d[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int r = warp + 8 * k;
+    if (r < nr) { hv[k] = *reinterpret_cast<const uint4*>(h2 + (size_t)(b0 + r) * H + chunk * 8); d[k] = dq[b0 + r]; } else d[k] = 0.f;
+  }
+  float sdq = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int r = warp + 8 * k;
+    if (r < nr) {
+      const bf16* hb = reinterpret_cast<const bf16*>(&hv[k]);
+      __align__(16) bf16 o[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float hf = __bfloat162float(hb[j]);
+        acc[j] += d[k] * hf;
+        o[j] = __float2bfloat16(hf > 0.f ? d[k] * w[j] : 0.f);
+        cs[j] += __bfloat162float(o[j]);
+      }
+      *reinterpret_cast<uint4*>(dh_rm + (size_t)(b0 + r) * H + chunk * 8) = *reinterpret_cast<const uint4*>(o);
+      *reinterpret_cast<uint4*>(&tile[r][chunk * 8]) = *reinterpret_cast<const uint4*>(o);
+      sdq += d[k];
+    }
+  }
+  // dW3: reduce the per-thread partial sums over the 8 warps through csum, then the db2 column sums the same way
+#pragma unroll
+  for (int j = 0; j < 8; j++) csum[warp][chunk * 8 + j] = acc[j];
   __syncthreads();
-  for (int i = threadIdx.x; i < H * 32; i += blockDim.x) { int c = i >> 5, r = i & 31; if (r < nr) dh_t[(size_t)c * B + b0 + r] = tile[r][c]; }
+  { float t = 0.f; for (int ww = 0; ww < 8; ww++) t += csum[ww][threadIdx.x]; atomicAdd(dW3 + threadIdx.x, t); }
+  if (db3 && chunk == 0) atomicAdd(db3, sdq);        // every lane of a warp holds the same rows: one lane per warp adds its four dq
+  __syncthreads();
+  tile_finish(tile, csum, cs, chunk, warp, dh_t, db2, B, b0, nr);
+}
+// general head backward (actor: out_dim = 2A <= 24), same tiling: dh2[b,:] = dy[b,:] . W3 masked by h2 > 0; dW3 += dy^T h2 (one output
+// row at a time: per-thread partials over its four batch rows, reduced over the 8 warps in shared memory); db3, db2
+__global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ dy /*[B][od]*/, int od, const float* __restrict__ W3 /*[od][256]*/,
+                                                  const bf16* __restrict__ h2 /*[B][256]*/, bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t,
+                                                  float* dW3 /*[od][256]*/, float* db3 /*[od] or null*/, float* db2 /*[256] or null*/, int B) {
+  __shared__ __align__(16) bf16 tile[32][H + 8];
+  __shared__ float csum[8][H];
+  __shared__ float sdy[32][24];
+  const int chunk = threadIdx.x & 31, warp = threadIdx.x >> 5, b0 = blockIdx.x * 32, nr = min(32, B - b0);
+  for (int i = threadIdx.x; i < 32 * od; i += 256) { int r = i / od, o = i % od; sdy[r][o] = r < nr ? dy[(size_t)(b0 + r) * od + o] : 0.f; }
+  float hf[4][8], g[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int r = warp + 8 * k;
+    uint4 hv = make_uint4(0, 0, 0, 0);
+    if (r < nr) hv = *reinterpret_cast<const uint4*>(h2 + (size_t)(b0 + r) * H + chunk * 8);
+    const bf16* hb = reinterpret_cast<const bf16*>(&hv);
+#pragma unroll
+    for (int j = 0; j < 8; j++) { hf[k][j] = __bfloat162float(hb[j]); g[k][j] = 0.f; }
+  }
+  __syncthreads();
+  for (int o = 0; o < od; o++) {
+    float w8[8], acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { w8[j] = W3[o * H + chunk * 8 + j]; acc[j] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float d = sdy[warp + 8 * k][o];
+#pragma unroll
+      for (int j = 0; j < 8; j++) { g[k][j] += d * w8[j]; acc[j] += d * hf[k][j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) csum[warp][chunk * 8 + j] = acc[j];
+    __syncthreads();
+    { float t = 0.f; for (int ww = 0; ww < 8; ww++) t += csum[ww][threadIdx.x]; atomicAdd(dW3 + o * H + threadIdx.x, t); }
+    __syncthreads();
+  }
+  if (db3 && threadIdx.x < od) { float sd = 0.f; for (int r = 0; r < nr; r++) sd += sdy[r][threadIdx.x]; atomicAdd(db3 + threadIdx.x, sd); }
+  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int r = warp + 8 * k;
+    if (r < nr) {
+      __align__(16) bf16 o8[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) { o8[j] = __float2bfloat16(hf[k][j] > 0.f ? g[k][j] : 0.f); cs[j] += __bfloat162float(o8[j]); }
+      *reinterpret_cast<uint4*>(dh_rm + (size_t)(b0 + r) * H + chunk * 8) = *reinterpret_cast<const uint4*>(o8);
+      *reinterpret_cast<uint4*>(&tile[r][chunk * 8]) = *reinterpret_cast<const uint4*>(o8);
+    }
+  }
+  tile_finish(tile, csum, cs, chunk, warp, dh_t, db2, B, b0, nr);
 }
 // actor head: from raw y=[mean|raw_ls], eps, da_c (critic gradient wrt action, already includes -1/B routing) build dy and the loss
 __global__ void k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const float* act /*[B][A] tanh(x)*/, const float* logp, const float* q /*[2][B]*/,
@@ -398,7 +463,7 @@ int critic_backward(B2QSac* s, cudaStream_t st0) {
     bf16 *dh_rm = i ? s->dh_rm2 : s->dh_rm, *dh_t = i ? s->dh_t2 : s->dh_t; float* G = i ? s->G2 : s->G;
     float* g = s->g_critic + (size_t)i * cn.n; const float* p = s->p_critic + (size_t)i * cn.n;
     const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h1t = s->hc1_t + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
-    k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dq + (size_t)i * B, 1, p + cn.oW3, h2, dh_rm, dh_t, g + cn.oW3, g + cn.ob3, g + cn.ob2, B);   // dh2, dW3, db3, db2
+    k_head_bwd1<<<(B + 31) / 32, H, 0, st>>>(s->dq + (size_t)i * B, p + cn.oW3, h2, dh_rm, dh_t, g + cn.oW3, g + cn.ob3, g + cn.ob2, B);   // dh2, dW3, db3, db2
     s->launches++;
     if (hidden_backward(s, st, i, dh_rm, dh_t, G, h1, h1t, s->xc_t, s->W2T[1 + i], g + cn.oW2, g + cn.ob1, g + cn.oW1, cn.in_dim)) return -2;
   }
@@ -552,7 +617,7 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
       bf16 *dh_rm = i ? s->dh_rm2 : s->dh_rm, *dh_t = i ? s->dh_t2 : s->dh_t; float *G = i ? s->G2 : s->G, *da = i ? s->da_c2 : s->da_c;
       const float* p = s->p_critic + (size_t)i * cn.n;
       const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
-      k_head_bwd<<<(B + 31) / 32, H, 0, sx>>>(s->dq + (size_t)i * B, 1, p + cn.oW3, h2, dh_rm, dh_t, G /*scratch dW3*/, nullptr, nullptr, B);
+      k_head_bwd1<<<(B + 31) / 32, H, 0, sx>>>(s->dq + (size_t)i * B, p + cn.oW3, h2, dh_rm, dh_t, G /*scratch dW3*/, nullptr, nullptr, B);
       if (gemm(s, sx, dh_rm, H, s->W2T[1 + i], H, G, H, B, H, H, false)) return -2;
       k_relu_mask<<<(B + 31) / 32, H, 0, sx>>>(G, h1, dh_rm, dh_t, nullptr, B);
       if (gemm(s, sx, dh_rm, H, s->W1A[1 + i], H, da, 16, B, 16, H, false)) return -2;                    // da_i [B][16]
