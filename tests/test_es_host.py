@@ -67,3 +67,26 @@ def test_population_gather_world2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_bc_replay_and_batched_noise_on_cpu_tensors():
+    """Host logic of bc.py on CPU tensors: ring wrap-around keeps (student, expert) rows paired; obs2noise_batch touches only
+    the rpy / drpy / q / qd slices with the sigmas of BCtrain.py:55-58 (already divided by the sensor normalisers)."""
+    import torch
+    from paddlerobotics_b200 import bc
+    m = bc.BCReplayMemory(10, 46, 49, device="cpu")
+    for k in range(4):                                   # 4 x 4 rows into a ring of 10
+        ref = torch.full((4, 49), float(k)) + torch.arange(4).reshape(4, 1) * 0.1
+        m.append(ref[:, 3:].clone(), ref)
+    assert m.size() == 10
+    o, r = m.sample_batch_by_index(torch.arange(10))
+    assert torch.equal(o, r[:, 3:])                      # pairs stay aligned after the wrap
+    assert set(float(x) for x in r[:, 0].round().unique()) == {1.0, 2.0, 3.0}   # oldest batch (k=0) overwritten except by wrap rows
+    g = torch.Generator().manual_seed(0)
+    x = torch.zeros(20000, 49)
+    n = bc.obs2noise_batch(x, g)
+    assert torch.equal(n[:, :7], x[:, :7]) and torch.equal(n[:, 37:], x[:, 37:])
+    for lo, hi, sig in bc.NOISE:
+        assert abs(float(n[:, lo:hi].std()) - sig) < 0.03 * sig and abs(float(n[:, lo:hi].mean())) < 0.02 * sig
+    a = bc.cal_agent_obs(x, sensor_noise=False)
+    assert a.shape == (20000, 46)
