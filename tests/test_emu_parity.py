@@ -189,3 +189,26 @@ def test_f32_teacher_forced_step_error(etg_stable):
         assert np.abs(se[25:37] - so[25:37]).max() < 1e-4 * max(1.0, np.abs(so[25:37]).max()) + 2e-3
         assert np.abs(se[:7] - so[:7]).max() < 1e-4
     e.close()
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_f64_random_dynamics_terrain_latency(etg_stable, seed):
+    """Randomised per-env dynamics rows (param2dynamic_dict, train.py:112-126: masses, inertias, gains, friction, gravity, latency),
+    a random smooth height field and a control latency of several substeps: the device code in CPU emulation still equals the
+    oracle to rounding over 25 free-running steps."""
+    from paddlerobotics_b200.etg import param2dynamic_dict, dynamic_dict_to_row
+    w, b = etg_stable
+    rng = np.random.default_rng(seed)
+    d = param2dynamic_dict(rng.uniform(-0.4, 0.4, 48)); d["control_latency"] = float(rng.uniform(1.0, 20.0)); d["footfriction"] = float(rng.uniform(0.5, 1.2))
+    row = dynamic_dict_to_row(d)
+    xs = -1.6 + 0.05 * np.arange(64)
+    hf = 0.015 * np.sin(rng.uniform(3, 7) * xs)[None, :] * np.ones((64, 1)) + 0.01 * np.cos(rng.uniform(3, 7) * xs)[:, None]
+    e = emu.EmuEnv(1, 1, ring_depth=3, heightfield=(hf, -1.6, -1.6, 0.05), action_interp=int(seed % 2))
+    e.set_dynamics(row[None, :]); e.reset(w, b)
+    cfg = O.default_config(action_interp=int(seed % 2)); O.set_heightfield(cfg, hf, -1.6, -1.6, 0.05)
+    o = O.OracleEnv(cfg, row); o.reset(w, b)
+    for k in range(25):
+        a = rng.uniform(-0.2, 0.2, 12)
+        ob, rw, dn, inf = o.step(a); ob2, rw2, dn2, inf2 = e.step(a)
+        assert np.abs(ob2[0] - ob).max() < 1e-7 and abs(rw2[0] - rw) < 1e-7 and bool(dn2[0]) == dn, (seed, k)
+    e.close()
