@@ -39,7 +39,7 @@ extern "C" {
 #define B2Q_ENOMEM (-3)
 
 #define B2Q_ACT_DIM 12
-#define B2Q_OBS_DIM 49   /* dis3 | contact4 | rpy3 drpy3 | q12 qd12 | ETG12  (EnvWrapper.py:60-109 order) */
+#define B2Q_OBS_DIM 49   /* full layout: dis3 | contact4 | rpy3 drpy3 | q12 qd12 | ETG12  (EnvWrapper.py:60-109 order); b2q_obs_dim(h) <= 49 */
 #define B2Q_INFO_DIM 56
 #define B2Q_STATE_DIM 37 /* pos3 quat4(xyzw) vlin3 vang3 (world) q12 qd12 */
 #define B2Q_DYN_DIM 48   /* kp12 kd12 mu latency_s g3 basemass baseinertia3 legmass3 leginertia12 */
@@ -82,6 +82,25 @@ typedef struct B2QConfig {
   const double* hf_host;     /* HOST pointer, [hf_ny][hf_nx], copied at create */
   int32_t clip_motor_commands; /* A1.ApplyAction -> _ClipMotorCommands (a1.py:428-458; enable_clip_motor_commands, default 0 as a1.py:229) */
   double max_angle_change;   /* MAX_MOTOR_ANGLE_CHANGE_PER_STEP = 0.2 rad per substep (a1.py:62) */
+  /* ---- round 2 additions (all default to the round-1 behaviour) ---- */
+  /* observation layout = sensor_mode of the reference (train.py:259-277; SimpleEnv.get_observation, deployment/envs/EnvWrapper.py:60-109):
+   * blocks in sorted-key order  BaseDisplacement(3) | FootContactSensor(4) | IMU(6 or 3) | MotorAngle(12) / MotorAngleAcc(24) | ETG(12) */
+  int32_t sensor_dis;        /* 1 */
+  int32_t sensor_contact;    /* 1 */
+  int32_t sensor_imu;        /* 1 = rpy+drpy (6), 2 = drpy only (3), 0 = off */
+  int32_t sensor_motor;      /* 1 = angles+velocities (24), 2 = angles only (12), 0 = off */
+  int32_t sensor_etg;        /* 1 */
+  int32_t obs_normal;        /* 1 = normalised as EnvWrapper.py:66-106 (`normal`, train.py:306); 0 = raw sensor units */
+  double noise_stdev[5];     /* Minitaur._AddSensorNoise stdevs: motor angle, motor velocity, motor torque, base rpy, base rpy rate
+                              * (minitaur.py:59,635,762,785,805,880,1206-1211); all 0 = off */
+  uint64_t noise_seed;       /* counter-based RNG key (Philox4x32-10 over (seed, env, step)) */
+  int32_t stuck_termination; /* 1: done when the base position std over the last 10 control steps <= 2e-4 after step 10 (rlschool [EXT]) */
+  int32_t body_collisions;   /* 1: `badfoot` counts non-toe leg links / trunk corners touching the terrain (not only low knees) */
+  int32_t motor_mode;        /* 0 POSITION (laikago_motor.py:139-145), 1 TORQUE (laikago_motor.py:131-134: the action IS the torque) */
+  int32_t joint_limits;      /* 1: URDF joint limits (a1.py:186-223) as unilateral rows of the contact solve (one slot per leg) */
+  int32_t external_force;    /* 1: per-env base push set with b2q_set_external_force (random_param['random_force'], train.py:254) */
+  double base_damping[4];    /* Bullet btMultiBody base damping: linear k1,k2, angular k1,k2 (force = m v (k1 + k2 |v|)); 0 = off */
+  double etg_foot_y_inset;   /* ETG nominal footholds pulled towards the body midline by this much (make_env(step_y=), train.py:463; balancebeam) */
 } B2QConfig;
 
 typedef struct B2QEnv* B2QHandle;
@@ -101,7 +120,11 @@ int b2q_elem_size(B2QHandle h);            /* 4 or 8 */
 int b2q_set_dynamics(B2QHandle h, const uint8_t* env_mask, const void* dyn, void* stream);
 /* env_mask [N] u8 or NULL (= all). etg_w [N,3,20], etg_b [N,3] or NULL (keep). obs_out [N,49] or NULL. */
 int b2q_reset(B2QHandle h, const uint8_t* env_mask, const void* etg_w, const void* etg_b, void* obs_out, void* stream);
-/* action [N,12] (already scaled by act_bound, joint-space residual). obs [N,49], reward [N], done [N] u8, info [N,56]. */
+/* b2q_reset plus a per-env initial x offset of the base [N] (env.reset(x_noise=...), train.py:131,505); x_offset may be NULL. */
+int b2q_reset_ex(B2QHandle h, const uint8_t* env_mask, const void* etg_w, const void* etg_b, const void* x_offset, void* obs_out, void* stream);
+/* world-frame force [N,3] applied at the base COM during every following control step (NULL = clear); needs cfg.external_force. */
+int b2q_set_external_force(B2QHandle h, const void* force, void* stream);
+/* action [N,12] (already scaled by act_bound, joint-space residual). obs [N,obs_dim], reward [N], done [N] u8, info [N,56]. */
 int b2q_step(B2QHandle h, const void* action, int donef, void* obs, void* reward, uint8_t* done, void* info, void* stream);
 /* The same step with HOST buffers (the reference-facing call: numpy in / numpy out), synchronous: on return obs / reward /
  * done (and info if non-NULL) hold this step's results.  With page-locked host memory (b2q_host_alloc, cudaHostAlloc,

@@ -98,6 +98,25 @@ void orc_default_config(OrcConfig* c) {
   c->etg_T = 0.5; c->etg_T2 = 0.5; c->etg_sigma_sq = 0.04; c->etg_amp = 0.2; c->etg_phase[0] = -M_PI / 2; c->etg_phase[1] = 0; /* train.py:296-297 */
   c->w_torso = 1.5; c->w_feet = 0.3; c->w_up = 0.6; c->w_tau = 0.07; c->w_stand = 0; c->w_badfoot = 0.1; c->w_footcontact = 0.1; c->w_done = 1; /* train.py:478-484 */
   c->reward_p = 5; c->vel_d = 0.5; c->foot_radius = 0.02; c->terrain_type = 0;
+  c->sensor_dis = 1; c->sensor_contact = 1; c->sensor_imu = 1; c->sensor_motor = 1; c->sensor_etg = 1; c->obs_normal = 1; /* train.py:494-500 */
+}
+int orc_obs_dim(const OrcConfig* c) {
+  return (c->sensor_dis ? 3 : 0) + (c->sensor_contact ? 4 : 0) + (c->sensor_imu == 1 ? 6 : c->sensor_imu == 2 ? 3 : 0) +
+         (c->sensor_motor == 1 ? 24 : c->sensor_motor == 2 ? 12 : 0) + (c->sensor_etg ? 12 : 0);
+}
+/* counter-based Gaussian shared with the device code (integer part bit-identical): Philox4x32-10, Box-Muller */
+void orc_normal4(unsigned long long seed, unsigned c0, unsigned c1, unsigned c2, double n[4]) {
+  unsigned c3 = 0, k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+  for (int i = 0; i < 10; i++) {
+    unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+    unsigned h0 = (unsigned)(p0 >> 32), l0 = (unsigned)p0, h1 = (unsigned)(p1 >> 32), l1 = (unsigned)p1;
+    unsigned n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const double sc = 1.0 / 16777216.0;
+  double u0 = ((double)(c0 >> 8) + 0.5) * sc, u1 = ((double)(c1 >> 8) + 0.5) * sc, u2 = ((double)(c2 >> 8) + 0.5) * sc, u3 = ((double)(c3 >> 8) + 0.5) * sc;
+  double ra = sqrt(-2.0 * log(u0)), rb = sqrt(-2.0 * log(u2));
+  n[0] = ra * cos(2 * M_PI * u1); n[1] = ra * sin(2 * M_PI * u1); n[2] = rb * cos(2 * M_PI * u3); n[3] = rb * sin(2 * M_PI * u3);
 }
 void orc_default_param(double* p) {
   for (int i = 0; i < 12; i++) { p[i] = 100.0; p[12 + i] = (i % 3 == 0) ? 1.0 : 2.0; } /* a1.py:75-80 */
@@ -159,7 +178,7 @@ void orc_etg_act(const OrcConfig* c, const double w[3][ORC_ETG_H], const double 
     double ang[3];
     for (int tries = 0; tries < 200; tries++) { /* act_clip: shrink delta until IK is finite [EXT] */
       double f[3];
-      for (int a = 0; a < 3; a++) f[a] = BASE_FOOT[leg][a] + d[a] - ((a < 2 ? HIP_XY[leg][a] : 0.0) + COM_OFFSET[a]);
+      for (int a = 0; a < 3; a++) f[a] = BASE_FOOT[leg][a] - (a == 1 ? (BASE_FOOT[leg][1] > 0 ? c->etg_foot_y_inset : -c->etg_foot_y_inset) : 0.0) + d[a] - ((a < 2 ? HIP_XY[leg][a] : 0.0) + COM_OFFSET[a]);
       orc_ik_leg(f, (leg % 2) ? 1 : -1, ang);
       if (!(isnan(ang[0]) || isnan(ang[1]) || isnan(ang[2]))) break;
       for (int a = 0; a < 3; a++) d[a] *= 0.95;
@@ -316,6 +335,7 @@ typedef struct {
   double v[13][6], c[12][6], IA[13][36], pA[13][6], U[12][6], d[12], u[12], a[13][6];
   double R0[9];                  /* base->world */
   double Rw[12][9], pw[12][3];   /* link->world rotation, link origin in world */
+  double damp[4], fext_b[3];     /* base damping coefficients, external push in base coordinates */
 } Dyn;
 
 static void dyn_kinematics(const OrcEnv* e, Dyn* D) {
@@ -331,6 +351,7 @@ static void dyn_kinematics(const OrcEnv* e, Dyn* D) {
     D->pw[i][0] = pp[0] + t[0]; D->pw[i][1] = pp[1] + t[1]; D->pw[i][2] = pp[2] + t[2];
     m3m(Rp, Rl, D->Rw[i]);
   }
+  memset(D->damp, 0, sizeof D->damp); memset(D->fext_b, 0, sizeof D->fext_b);
 }
 
 static void dyn_aba(const OrcEnv* e, Dyn* D, const double tau[12], double qdd[12], double a0[6]) {
@@ -339,7 +360,15 @@ static void dyn_aba(const OrcEnv* e, Dyn* D, const double tau[12], double qdd[12
   m3tv(D->R0, e->vang, w); m3tv(D->R0, e->vlin, vl);
   for (int k = 0; k < 3; k++) { D->v[0][k] = w[k]; D->v[0][3 + k] = vl[k]; }
   memcpy(D->IA[0], D->mdl.I0, sizeof D->IA[0]);
-  { double Iv[6]; m6v(D->mdl.I0, D->v[0], Iv); crf(D->v[0], Iv, D->pA[0]); }
+  { double Iv[6]; m6v(D->mdl.I0, D->v[0], Iv); crf(D->v[0], Iv, D->pA[0]);
+    /* Bullet base damping (force = m v (k1 + k2|v|), torque = I w (k1 + k2|w|)) and the external push, both as bias forces of the base */
+    double lv = sqrt(v3dot(D->v[0] + 3, D->v[0] + 3)), lw = sqrt(v3dot(D->v[0], D->v[0]));
+    for (int k = 0; k < 3; k++) {
+      D->pA[0][k] += Iv[k] * (D->damp[2] + D->damp[3] * lw);
+      D->pA[0][3 + k] += Iv[3 + k] * (D->damp[0] + D->damp[1] * lv);
+      D->pA[0][3 + k] -= D->fext_b[k];
+    }
+  }
   for (int i = 0; i < 12; i++) {
     int pb = (i % 3 == 0) ? 0 : i; /* body index of parent: base=0, link j -> body j+1 */
     double vj[6] = {0, 0, 0, 0, 0, 0}; vj[D->mdl.axis[i]] = e->qd[i];
@@ -529,7 +558,13 @@ void orc_substep(const OrcConfig* c, OrcEnv* e, const double target[12]) {
     if (c->clip_motor_commands) cmd[j] = fmin(fmax(cmd[j], e->q[j] - c->max_angle_change), e->q[j] + c->max_angle_change);
   }
   orc_motor_torque(e->param, e->param + 12, cmd, e->q, e->qd, c->torque_limit, tau);
+  if (c->motor_mode == 1) for (int j = 0; j < 12; j++) { /* MotorControlMode.TORQUE: the command is the torque, laikago_motor.py:131-134 */
+    double t = target[j]; if (c->torque_limit > 0) { if (t > c->torque_limit) t = c->torque_limit; if (t < -c->torque_limit) t = -c->torque_limit; }
+    tau[j] = t;
+  }
   memcpy(e->last_tau, tau, sizeof tau);
+  memcpy(D->damp, c->base_damping, sizeof D->damp);
+  if (c->external_force) m3tv(D->R0, e->ext_force, D->fext_b);
   double qdd[12], a0[6];
   dyn_aba(e, D, tau, qdd, a0);
   /* unconstrained velocities, world-frame base velocity as Bullet stores it */
@@ -632,17 +667,38 @@ void orc_env_init(const OrcConfig* c, OrcEnv* e, const double* p) {
   (void)c;
 }
 
-static void pack_obs(const OrcConfig* c, const OrcEnv* e, const double start_pos[3], double* obs, double* ctrl_out) {
+static void pack_obs(const OrcConfig* c, const OrcEnv* e, const double start_pos[3], double* obs_out, double* ctrl_out, int noisy) {
+  double obs[ORC_OBS_DIM];
   double ctrl[ORC_HIST_W]; delayed_obs(c, e, e->param[25], ctrl);
+  double nrpy[3] = {0, 0, 0}, ndrpy[3] = {0, 0, 0};
+  int noise_on = 0; for (int i = 0; i < 5; i++) if (c->noise_stdev[i] > 0) noise_on = 1;
+  if (noisy && noise_on) { /* Minitaur._AddSensorNoise (minitaur.py:1206-1211) on the motor angle / velocity / torque and IMU getters */
+    double n4[4];
+    for (int leg = 0; leg < 4; leg++) for (int qty = 0; qty < 3; qty++) {
+      orc_normal4(c->noise_seed, (unsigned)e->env_id, (unsigned)e->step_count, (unsigned)(16 * leg + qty), n4);
+      for (int j = 0; j < 3; j++) ctrl[12 * qty + 3 * leg + j] += c->noise_stdev[qty] * n4[j];
+    }
+    orc_normal4(c->noise_seed, (unsigned)e->env_id, (unsigned)e->step_count, 64u, n4); for (int k = 0; k < 3; k++) nrpy[k] = c->noise_stdev[3] * n4[k];
+    orc_normal4(c->noise_seed, (unsigned)e->env_id, (unsigned)e->step_count, 65u, n4); for (int k = 0; k < 3; k++) ndrpy[k] = c->noise_stdev[4] * n4[k];
+  }
   double dtc = c->sim_dt * c->action_repeat;
   for (int k = 0; k < 3; k++) obs[k] = (e->pos[k] - start_pos[k]) / dtc;
   for (int k = 0; k < 4; k++) obs[3 + k] = e->contact[k] ? 1.0 : 0.0;
   double rpy[3]; orc_quat_to_rpy(e->quat, rpy);
   double R[9], wb[3]; quat_to_mat(e->quat, R); m3tv(R, e->vang, wb);
-  for (int k = 0; k < 3; k++) { obs[7 + k] = (rpy[k] - e->rpy0[k]) / 0.1; obs[10 + k] = wb[k] / 0.5; }     /* EnvWrapper.py:79-88 */
+  for (int k = 0; k < 3; k++) { obs[7 + k] = (rpy[k] + nrpy[k] - e->rpy0[k]) / 0.1; obs[10 + k] = (wb[k] + ndrpy[k]) / 0.5; }     /* EnvWrapper.py:79-88 */
   for (int j = 0; j < 12; j++) { obs[13 + j] = (map_pi(ctrl[j]) - POSE_ORI[j]) / 0.1; obs[25 + j] = ctrl[12 + j] / 1.0; } /* :64-70 */
   for (int j = 0; j < 12; j++) obs[37 + j] = (e->etg_act[j] - ETG_MEAN[j]) / ETG_STD[j];                     /* :103-106 */
   if (ctrl_out) memcpy(ctrl_out, ctrl, sizeof ctrl);
+  /* sensor_mode selection in sorted-key order (BaseDisplacement, FootContactSensor, IMU, MotorAngle[Acc]) then ETG; normal=0 -> raw units */
+  int n = 0; const int nr = c->obs_normal;
+  if (c->sensor_dis) for (int i = 0; i < 3; i++) obs_out[n++] = obs[i];
+  if (c->sensor_contact) for (int i = 0; i < 4; i++) obs_out[n++] = obs[3 + i];
+  if (c->sensor_imu == 1) for (int i = 0; i < 3; i++) obs_out[n++] = nr ? obs[7 + i] : obs[7 + i] * 0.1;
+  if (c->sensor_imu) for (int i = 0; i < 3; i++) obs_out[n++] = nr ? obs[10 + i] : obs[10 + i] * 0.5;
+  if (c->sensor_motor) for (int i = 0; i < 12; i++) obs_out[n++] = nr ? obs[13 + i] : obs[13 + i] * 0.1 + POSE_ORI[i];
+  if (c->sensor_motor == 1) for (int i = 0; i < 12; i++) obs_out[n++] = obs[25 + i];
+  if (c->sensor_etg) for (int i = 0; i < 12; i++) obs_out[n++] = nr ? obs[37 + i] : obs[37 + i] * ETG_STD[i] + ETG_MEAN[i];
 }
 
 void orc_env_settle(const OrcConfig* c, OrcEnv* e) {
@@ -661,12 +717,14 @@ void orc_env_settle(const OrcConfig* c, OrcEnv* e) {
   true_obs(e, e->snap_obs); memcpy(e->snap_lam, e->lam_warm, sizeof e->snap_lam);
 }
 
-void orc_env_reset(const OrcConfig* c, OrcEnv* e, const double* w, const double* b, double* obs) {
+void orc_env_reset(const OrcConfig* c, OrcEnv* e, const double* w, const double* b, double* obs) { orc_env_reset_ex(c, e, w, b, 0.0, obs); }
+void orc_env_reset_ex(const OrcConfig* c, OrcEnv* e, const double* w, const double* b, double x_offset, double* obs) {
   /* K2 semantics: masked copy of the pre-settled snapshot; history filled with the settled observation */
   memcpy(e->pos, e->snap, 3 * sizeof(double)); memcpy(e->quat, e->snap + 3, 4 * sizeof(double));
   memcpy(e->vlin, e->snap + 7, 3 * sizeof(double)); memcpy(e->vang, e->snap + 10, 3 * sizeof(double));
   memcpy(e->q, e->snap + 13, 12 * sizeof(double)); memcpy(e->qd, e->snap + 25, 12 * sizeof(double));
-  memcpy(e->lam_warm, e->snap_lam, sizeof e->snap_lam);
+  e->pos[0] += x_offset;   /* env.reset(x_noise=...): the episode starts displaced along x (train.py:131,505) */
+  memcpy(e->lam_warm, e->snap_lam, sizeof e->snap_lam); memset(e->lam_lim, 0, sizeof e->lam_lim);
   memcpy(e->last_tau, e->snap_obs + 24, 12 * sizeof(double));
   for (int k = 0; k < ORC_HIST; k++) memcpy(e->hist[k], e->snap_obs, sizeof e->snap_obs);
   e->hist_len = 100; e->hist_head = 0;
@@ -677,7 +735,7 @@ void orc_env_reset(const OrcConfig* c, OrcEnv* e, const double* w, const double*
   if (b) memcpy(e->etg_b, b, sizeof e->etg_b);
   orc_quat_to_rpy(e->quat, e->rpy0);
   orc_etg_act(c, e->etg_w, e->etg_b, 0.0, e->etg_act, NULL);
-  if (obs) pack_obs(c, e, e->pos, obs, NULL);
+  if (obs) pack_obs(c, e, e->pos, obs, NULL, 0);
 }
 
 static double c_prec(double v, double t, double m) { double w = (v - t) * atanh(sqrt(0.95)) / m; return tanh(w * w); }
@@ -687,6 +745,7 @@ void orc_env_step(const OrcConfig* c, OrcEnv* e, const double action[12], int do
   const int R = c->action_repeat; const double dtc = c->sim_dt * R;
   double target[12], start_pos[3], feet0[4][3], feet1[4][3];
   for (int j = 0; j < 12; j++) target[j] = POSE_ORI[j] + e->etg_act[j] + action[j]; /* deployment/test.py:95-99 */
+  if (c->motor_mode == 1) memcpy(target, action, sizeof target);                     /* TORQUE mode: the action is the torque */
   if (c->action_filter) { /* Minitaur.Step: action = _FilterAction(action), minitaur.py:250-251 */
     double fb[3], fa[3]; orc_butter2(c->filter_highcut, 1.0 / dtc, fb, fa);
     for (int j = 0; j < 12; j++) orc_filter_step(fb, fa, target[j], &e->fx1[j], &e->fx2[j], &e->fy1[j], &e->fy2[j], &target[j]);
@@ -703,7 +762,7 @@ void orc_env_step(const OrcConfig* c, OrcEnv* e, const double action[12], int do
   e->step_count++;
   orc_etg_act(c, e->etg_w, e->etg_b, e->step_count * dtc, e->etg_act, NULL);
   double ctrl[ORC_HIST_W];
-  pack_obs(c, e, start_pos, obs, ctrl);
+  pack_obs(c, e, start_pos, obs, ctrl, 1);
   /* reward (this repo's definition; rlschool RewardShaping absent) */
   orc_foot_world(e, feet1);
   double velx = (e->pos[0] - start_pos[0]) / dtc;
@@ -720,7 +779,19 @@ void orc_env_step(const OrcConfig* c, OrcEnv* e, const double action[12], int do
     Dyn Dstack; Dyn* D = &Dstack; build_model(e->param, &D->mdl); dyn_kinematics(e, D);
     for (int k = 0; k < 4; k++) {
       double nrm[3]; double h = terrain_height(c, D->pw[3 * k + 2][0], D->pw[3 * k + 2][1], nrm);
-      if (D->pw[3 * k + 2][2] - h < 0.03) bad++;
+      if (!c->body_collisions) { if (D->pw[3 * k + 2][2] - h < 0.03) bad++; }
+      else { /* knee sphere r 0.02, hip joint cylinder r 0.046, two trunk-box corners per leg quadrant (a1 URDF shapes [EXT]) */
+        if (D->pw[3 * k + 2][2] - h < 0.02) bad++;
+        double hh = terrain_height(c, D->pw[3 * k + 1][0], D->pw[3 * k + 1][1], nrm);
+        if (D->pw[3 * k + 1][2] - hh < 0.046) bad++;
+        double cx = (k < 2) ? 0.1335 : -0.1335, cy = (k & 1) ? 0.097 : -0.097;
+        for (int zz = 0; zz < 2; zz++) {
+          double cb[3] = {cx + COM_OFFSET[0], cy + COM_OFFSET[1], (zz ? 0.057 : -0.057) + COM_OFFSET[2]}, cw[3];
+          m3v(Rm, cb, cw);
+          double ch = terrain_height(c, e->pos[0] + cw[0], e->pos[1] + cw[1], nrm);
+          if (e->pos[2] + cw[2] - ch < 0) bad++;
+        }
+      }
       if (!e->contact[k]) nofoot++;
       double fb_w[3] = {feet1[k][0] - e->pos[0], feet1[k][1] - e->pos[1], feet1[k][2] - e->pos[2]}, fb[3];
       m3tv(Rm, fb_w, fb); meanz += fb[2] / 4.0; if (fb[2] > 0) above = 1;
@@ -733,7 +804,17 @@ void orc_env_step(const OrcConfig* c, OrcEnv* e, const double action[12], int do
   double r_torso = c->w_torso * torso, r_feet = c->w_feet * feet, r_up = c->w_up * up, r_tau = -c->w_tau * energy;
   double r_bad = -c->w_badfoot * bad, r_fc = -c->w_footcontact * (nofoot > 2 ? nofoot - 2 : 0), r_done = fall ? -c->w_done : 0.0;
   *reward = c->reward_p * (r_torso + r_feet + r_up + r_tau + r_bad + r_fc + r_done);
-  *done = fall || donef || (c->max_episode_steps > 0 && e->step_count >= c->max_episode_steps);
+  int stuck = 0;
+  if (c->stuck_termination) {
+    memcpy(e->pos_hist[(e->step_count - 1) % 10], e->pos, 3 * sizeof(double));
+    if (e->step_count > 10) {
+      double m[3] = {0, 0, 0}, v = 0;
+      for (int h = 0; h < 10; h++) for (int k = 0; k < 3; k++) m[k] += (e->pos_hist[h][k] - e->pos[k]) / 10.0;
+      for (int h = 0; h < 10; h++) for (int k = 0; k < 3; k++) { double d = e->pos_hist[h][k] - e->pos[k] - m[k]; v += d * d / 10.0; }
+      stuck = v <= 2e-4 * 2e-4;
+    }
+  }
+  *done = fall || donef || (c->max_episode_steps > 0 && e->step_count >= c->max_episode_steps) || stuck;
   if (info) {
     memset(info, 0, sizeof(double) * ORC_INFO_DIM);
     info[0] = velx; info[1] = r_torso; info[2] = r_feet; info[3] = r_up; info[4] = r_tau; info[5] = 0; info[6] = r_bad; info[7] = r_fc; info[8] = r_done;

@@ -57,6 +57,17 @@ typedef struct {
   int hf_nx, hf_ny; double hf_x0, hf_y0, hf_cell; const double* hf; /* row-major [ny][nx] */
   int clip_motor_commands;  /* A1.ApplyAction -> _ClipMotorCommands (a1.py:428-458; enable_clip_motor_commands, default False a1.py:229) */
   double max_angle_change;  /* MAX_MOTOR_ANGLE_CHANGE_PER_STEP = 0.2, a1.py:62 */
+  /* sensor_mode / normal of SimpleEnv.get_observation (deployment/envs/EnvWrapper.py:60-109; train.py:259-277,306) */
+  int sensor_dis, sensor_contact, sensor_imu /*1: rpy+drpy, 2: drpy*/, sensor_motor /*1: q+qd, 2: q*/, sensor_etg, obs_normal;
+  double noise_stdev[5];    /* Minitaur._AddSensorNoise: motor angle, velocity, torque, rpy, rpy rate (minitaur.py:59,1206-1211) */
+  unsigned long long noise_seed;
+  int stuck_termination;    /* rlschool [EXT]: base position spread over the last 10 control steps <= 2e-4 after step 10 */
+  int body_collisions;      /* badfoot counts non-toe link / trunk-corner ground contacts */
+  int motor_mode;           /* 0 POSITION, 1 TORQUE (laikago_motor.py:131-134) */
+  int joint_limits;         /* URDF joint limits a1.py:186-223 as unilateral solver rows (one slot per leg) */
+  int external_force;       /* base push (random_param['random_force'], train.py:254) */
+  double base_damping[4];   /* Bullet btMultiBody base damping lin k1,k2 ang k1,k2 [EXT] */
+  double etg_foot_y_inset;  /* make_env(step_y=): nominal footholds pulled towards the midline */
 } OrcConfig;
 
 typedef struct {
@@ -75,6 +86,10 @@ typedef struct {
   double fx1[12], fx2[12], fy1[12], fy2[12]; /* action-filter history (order 2) */
   /* snapshot for reset */
   double snap[37]; double snap_obs[ORC_HIST_W]; double snap_lam[4];
+  double pos_hist[10][3];      /* stuck termination */
+  double ext_force[3];         /* world-frame push at the base COM */
+  double lam_lim[4];           /* warm start of the per-leg joint-limit row */
+  int env_id;                  /* index of this env in its batch: the sensor-noise counter */
 } OrcEnv;
 
 void orc_default_config(OrcConfig* c);
@@ -98,6 +113,9 @@ void orc_foot_world(const OrcEnv* e, double feet[4][3]);
 void orc_env_init(const OrcConfig* c, OrcEnv* e, const double* param48);
 void orc_env_settle(const OrcConfig* c, OrcEnv* e);     /* reset pose + settle + snapshot */
 void orc_env_reset(const OrcConfig* c, OrcEnv* e, const double* etg_w /*3x20 or NULL*/, const double* etg_b, double* obs);
+void orc_env_reset_ex(const OrcConfig* c, OrcEnv* e, const double* etg_w, const double* etg_b, double x_offset, double* obs);
+int orc_obs_dim(const OrcConfig* c);
+void orc_normal4(unsigned long long seed, unsigned c0, unsigned c1, unsigned c2, double n[4]);   /* Philox4x32-10 + Box-Muller */
 void orc_substep(const OrcConfig* c, OrcEnv* e, const double target[12]);
 void orc_env_step(const OrcConfig* c, OrcEnv* e, const double action[12], int donef,
                   double* obs, double* reward, int* done, double* info);

@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "_ref", "libb2q_oracle.so")
+_SO = os.path.join(_HERE, "_build", "libb2q_oracle.so")
 
 NJ, HIST, OBS_DIM, INFO_DIM, NPARAM, ETG_H, HIST_W = 12, 128, 49, 56, 48, 20, 43
 
@@ -35,6 +35,10 @@ class Config(C.Structure):
         ("terrain_type", C.c_int), ("hf_nx", C.c_int), ("hf_ny", C.c_int),
         ("hf_x0", C.c_double), ("hf_y0", C.c_double), ("hf_cell", C.c_double), ("hf", C.POINTER(C.c_double)),
         ("clip_motor_commands", C.c_int), ("max_angle_change", C.c_double),
+        ("sensor_dis", C.c_int), ("sensor_contact", C.c_int), ("sensor_imu", C.c_int), ("sensor_motor", C.c_int), ("sensor_etg", C.c_int), ("obs_normal", C.c_int),
+        ("noise_stdev", C.c_double * 5), ("noise_seed", C.c_ulonglong),
+        ("stuck_termination", C.c_int), ("body_collisions", C.c_int), ("motor_mode", C.c_int), ("joint_limits", C.c_int), ("external_force", C.c_int),
+        ("base_damping", C.c_double * 4), ("etg_foot_y_inset", C.c_double),
     ]
 
 
@@ -50,6 +54,7 @@ class Env(C.Structure):
         ("contact", C.c_int * 4), ("last_tau", C.c_double * 12),
         ("fx1", C.c_double * 12), ("fx2", C.c_double * 12), ("fy1", C.c_double * 12), ("fy2", C.c_double * 12),
         ("snap", C.c_double * 37), ("snap_obs", C.c_double * HIST_W), ("snap_lam", C.c_double * 4),
+        ("pos_hist", (C.c_double * 3) * 10), ("ext_force", C.c_double * 3), ("lam_lim", C.c_double * 4), ("env_id", C.c_int),
     ]
 
 
@@ -79,6 +84,10 @@ def default_config(**kw):
     for k, v in kw.items():
         if k == "etg_phase":
             c.etg_phase[0], c.etg_phase[1] = v
+        elif k in ("noise_stdev", "base_damping"):
+            arr = getattr(c, k)
+            for i, x in enumerate(v):
+                arr[i] = float(x)
         else:
             setattr(c, k, v)
     return c
@@ -185,19 +194,26 @@ class OracleEnv:
         if settle:
             lib().orc_env_settle(C.byref(self.cfg), C.byref(self.e))
 
-    def reset(self, etg_w=None, etg_b=None):
-        obs = np.zeros(OBS_DIM)
+    def obs_dim(self):
+        return int(lib().orc_obs_dim(C.byref(self.cfg)))
+
+    def set_force(self, f=None):
+        for k in range(3):
+            self.e.ext_force[k] = 0.0 if f is None else float(f[k])
+
+    def reset(self, etg_w=None, etg_b=None, x_offset=0.0):
+        obs = np.zeros(self.obs_dim())
         wp = bp = None
         if etg_w is not None:
             w, wp = _d(np.asarray(etg_w).reshape(3, ETG_H))
         if etg_b is not None:
             b, bp = _d(np.asarray(etg_b).reshape(3))
-        lib().orc_env_reset(C.byref(self.cfg), C.byref(self.e), wp, bp, obs.ctypes.data_as(C.POINTER(C.c_double)))
+        lib().orc_env_reset_ex(C.byref(self.cfg), C.byref(self.e), wp, bp, C.c_double(float(x_offset)), obs.ctypes.data_as(C.POINTER(C.c_double)))
         return obs
 
     def step(self, action, donef=False):
         a, ap = _d(action)
-        obs = np.zeros(OBS_DIM)
+        obs = np.zeros(self.obs_dim())
         info = np.zeros(INFO_DIM)
         rew = C.c_double()
         done = C.c_int()
@@ -260,6 +276,8 @@ class OracleBatch:
             else:
                 o = OracleEnv(self.cfg, params[i])
                 C.memmove(C.byref(self.envs[i]), C.byref(o.e), C.sizeof(Env))
+        for i in range(n):
+            self.envs[i].env_id = i
         self.obs = np.zeros((n, OBS_DIM))
         dp = C.POINTER(C.c_double)
         for i in range(n):

@@ -23,4 +23,8 @@ class B2QConfig(C.Structure):
         ("hf_nx", C.c_int32), ("hf_ny", C.c_int32), ("hf_x0", C.c_double), ("hf_y0", C.c_double), ("hf_cell", C.c_double),
         ("hf_host", C.POINTER(C.c_double)),
         ("clip_motor_commands", C.c_int32), ("max_angle_change", C.c_double),
+        ("sensor_dis", C.c_int32), ("sensor_contact", C.c_int32), ("sensor_imu", C.c_int32), ("sensor_motor", C.c_int32), ("sensor_etg", C.c_int32),
+        ("obs_normal", C.c_int32), ("noise_stdev", C.c_double * 5), ("noise_seed", C.c_uint64),
+        ("stuck_termination", C.c_int32), ("body_collisions", C.c_int32), ("motor_mode", C.c_int32), ("joint_limits", C.c_int32),
+        ("external_force", C.c_int32), ("base_damping", C.c_double * 4), ("etg_foot_y_inset", C.c_double),
     ]

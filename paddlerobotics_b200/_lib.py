@@ -22,6 +22,8 @@ SYMBOLS = {
     "b2q_elem_size": (_i, [_vp]),
     "b2q_set_dynamics": (_i, [_vp, _u8p, _vp, _vp]),
     "b2q_reset": (_i, [_vp, _u8p, _vp, _vp, _vp, _vp]),
+    "b2q_reset_ex": (_i, [_vp, _u8p, _vp, _vp, _vp, _vp, _vp]),
+    "b2q_set_external_force": (_i, [_vp, _vp, _vp]),
     "b2q_step": (_i, [_vp, _vp, _i, _vp, _vp, _u8p, _vp, _vp]),
     "b2q_step_host": (_i, [_vp, _vp, _i, _vp, _vp, _u8p, _vp, _vp]),
     "b2q_host_alloc": (_vp, [C.c_size_t]),

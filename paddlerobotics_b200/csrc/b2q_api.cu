@@ -42,7 +42,16 @@ __device__ __forceinline__ const Model<T>& stage_model(const Model<T>* g, unsign
   return *s;
 }
 
+// the CTA's staged 49-wide rows -> the caller's [N][obs_dim] array (sensor_mode selection applied), coalesced
 template <typename T>
+__device__ __forceinline__ void emit_obs_block(const Model<T>& md, const T* stage, T* __restrict__ obs, int env0, int rows) {
+  const int od = md.obs_dim;
+  T* dst = obs + (size_t)env0 * od;
+  if (md.obs_identity) { for (int i = threadIdx.x; i < rows * OBS_DIM; i += blockDim.x) dst[i] = stage[i]; return; }
+  for (int i = threadIdx.x; i < rows * od; i += blockDim.x) { int r = i / od, j = i - r * od; dst[i] = obs_out_elem(md, stage + r * OBS_DIM, j); }
+}
+
+template <typename T, int FEAT>
 __global__ void __launch_bounds__(128) b2q_step_kernel(Cfg<T> cf, const Model<T>* __restrict__ gm, Buffers<T> B, const T* __restrict__ action, int donef,
                                                        int auto_reset, T* __restrict__ obs, T* __restrict__ reward, uint8_t* __restrict__ done, T* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -55,18 +64,17 @@ __global__ void __launch_bounds__(128) b2q_step_kernel(Cfg<T> cf, const Model<T>
   int env = gid >> 2;
   const int env0 = (blockIdx.x * blockDim.x) >> 2, per_cta = blockDim.x >> 2;
   bool valid = env < B.N;
-  if (!valid) env = B.N - 1;  // whole warps stay convergent for the shuffles; invalid lanes never store
+  // whole warps stay convergent for the shuffles; invalid lanes (ragged last CTA) redo the CTA's first robot in their own staging
+  // row and never store to global memory
+  const int srow = env0 + (int)(threadIdx.x >> 2);
+  if (!valid) env = B.N - 1;
   WarpComm cm{(int)(threadIdx.x & 3)};
-  const bool staged = env0 + per_cta <= B.N;   // a ragged last CTA (clamped envs) writes its rows directly
-  step_lane<T>(cm, cf, md, B, env, valid, action, donef, auto_reset, staged ? stage : obs, reward, done, info, staged ? env0 : 0);
-  if (staged) {
-    __syncthreads();
-    T* dst = obs + (size_t)env0 * OBS_DIM;
-    for (int i = threadIdx.x; i < per_cta * OBS_DIM; i += blockDim.x) dst[i] = stage[i];
-  }
+  step_lane<T, FEAT>(cm, cf, md, B, env, valid, action, donef, auto_reset, stage + (ptrdiff_t)(srow - env) * OBS_DIM, reward, done, info, env0);
+  __syncthreads();
+  emit_obs_block(md, stage, obs, env0, min(per_cta, B.N - env0));
 }
 
-template <typename T>
+template <typename T, int FEAT>
 __global__ void __launch_bounds__(128) b2q_settle_kernel(Cfg<T> cf, const Model<T>* __restrict__ gm, Buffers<T> B, const uint8_t* __restrict__ mask) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Model<T>& md = stage_model(gm, smem);
@@ -76,27 +84,46 @@ __global__ void __launch_bounds__(128) b2q_settle_kernel(Cfg<T> cf, const Model<
   if (!valid) env = B.N - 1;
   if (mask && !mask[env]) valid = false;
   WarpComm cm{(int)(threadIdx.x & 3)};
-  settle_lane<T>(cm, cf, md, B, env, valid);
+  settle_lane<T, FEAT>(cm, cf, md, B, env, valid);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(128) b2q_reset_kernel(Cfg<T> cf, const Model<T>* __restrict__ gm, Buffers<T> B, const uint8_t* __restrict__ mask, T* __restrict__ obs) {
+__global__ void __launch_bounds__(128) b2q_reset_kernel(Cfg<T> cf, const Model<T>* __restrict__ gm, Buffers<T> B, const uint8_t* __restrict__ mask, const T* __restrict__ xoff,
+                                                        T* __restrict__ obs) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Model<T>& md = stage_model(gm, smem);
+  T* stage = reinterpret_cast<T*>(smem + ((sizeof(Model<T>) + 15) & ~size_t(15)));
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = gid >> 2;
+  const int env0 = (blockIdx.x * blockDim.x) >> 2;
   bool valid = env < B.N;
   if (!valid) env = B.N - 1;
   if (mask && !mask[env]) valid = false;
   WarpComm cm{(int)(threadIdx.x & 3)};
-  reset_lane<T>(cm, cf, md, B, env, valid, obs ? obs + (size_t)env * OBS_DIM : (T*)nullptr);
+  T* srow = stage + (size_t)(threadIdx.x >> 2) * OBS_DIM;
+  reset_lane<T>(cm, cf, md, B, env, valid, obs ? srow : (T*)nullptr, xoff);
+  if (obs) {   // masked-out envs keep their previous observation row
+    __syncwarp();
+    if (valid) { const int od = md.obs_dim; for (int j = threadIdx.x & 3; j < od; j += 4) obs[(size_t)env * od + j] = obs_out_elem(md, srow, j); }
+  }
+  (void)env0;
 }
 
 template <typename T>
-__global__ void b2q_pack_param_kernel(const T* __restrict__ dyn, const T* __restrict__ def48, P4<T>* param, const uint8_t* __restrict__ mask, int N) {
+__global__ void b2q_pack_param_kernel(const T* __restrict__ dyn, const T* __restrict__ def48, P4<T>* param, const uint8_t* __restrict__ mask, int N, T max_latency,
+                                      int* __restrict__ overflow) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= N || (mask && !mask[env])) return;
   pack_param_env<T>(dyn, def48, param, N, env);
+  const T lat = dyn ? dyn[(size_t)env * 48 + 25] : def48[25];
+  if (!(lat <= max_latency)) atomicMax(overflow, 1);   // control latency beyond the observation ring: refuse instead of clamping silently
+}
+template <typename T>
+__global__ void b2q_pack_force_kernel(const T* __restrict__ f, P4<T>* extf, int N) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= N) return;
+  P4<T> p; p.x = f ? f[(size_t)env * 3] : T(0); p.y = f ? f[(size_t)env * 3 + 1] : T(0); p.z = f ? f[(size_t)env * 3 + 2] : T(0); p.w = T(0);
+  extf[env] = p;
 }
 template <typename T>
 __global__ void b2q_pack_etg_kernel(const T* __restrict__ w, const T* __restrict__ b, P4<T>* etg, const uint8_t* __restrict__ mask, int N) {
@@ -124,7 +151,9 @@ struct EnvBase {
   int64_t launches = 0;
   virtual ~EnvBase() {}
   virtual int set_dynamics(const uint8_t* mask, const void* dyn, cudaStream_t s) = 0;
-  virtual int reset(const uint8_t* mask, const void* w, const void* b, void* obs, cudaStream_t s) = 0;
+  virtual int reset(const uint8_t* mask, const void* w, const void* b, const void* xoff, void* obs, cudaStream_t s) = 0;
+  virtual int set_force(const void* f, cudaStream_t s) = 0;
+  int obs_dim = B2Q_OBS_DIM;
   virtual int step(const void* action, int donef, void* obs, void* rew, uint8_t* done, void* info, cudaStream_t s) = 0;
   virtual int step_host(const void* a, int donef, void* obs, void* rew, uint8_t* done, void* info, cudaStream_t s) = 0;
   virtual int get_state(void* out, cudaStream_t s) = 0;
@@ -158,6 +187,7 @@ struct EnvT : EnvBase {
     if (d_def48) cudaFree(d_def48);
     if (d_hf) cudaFree(d_hf);
     if (st_act) cudaFree(st_act);
+    if (h_flag) cudaFreeHost(h_flag);
   }
   int grid_lanes() const { return (B.N * 4 + tpb - 1) / tpb; }
 
@@ -178,25 +208,29 @@ struct EnvT : EnvBase {
       CK(e1);
     }
     kc = make_cfg<T>(c, d_hf);
-    Model<T> hm; build_model_host(hm, c.foot_radius, c.etg_T, c.etg_amp, c.etg_phase0, c.etg_phase1);
+    Model<T> hm; build_model_host(hm, c.foot_radius, c.etg_T, c.etg_amp, c.etg_phase0, c.etg_phase1, c.etg_foot_y_inset);
+    build_obs_map(hm, c); obs_dim = hm.obs_dim;
+    feat = config_feat(c);
+    CK(cudaHostAlloc((void**)&h_flag, sizeof(int), cudaHostAllocDefault));
     CK(cudaMalloc(&d_model, sizeof(Model<T>)));
     CK(cudaMemcpy(d_model, &hm, sizeof(Model<T>), cudaMemcpyHostToDevice));
     double d48[48]; default_dyn_row(d48); T t48[48]; for (int i = 0; i < 48; i++) t48[i] = (T)d48[i];
     CK(cudaMalloc(&d_def48, sizeof(t48)));
     CK(cudaMemcpy(d_def48, t48, sizeof(t48), cudaMemcpyHostToDevice));
     // one pool for the SoA env state: [state NS | snap NS | snap_obs 12 | param NP | etg NE | ring Dm*24] packs x N, + step counters
-    size_t packs = (size_t)(NS + NS + 12 + NP + NE + Dm * 24) * N;
-    size_t bytes = packs * sizeof(P4<T>) + (size_t)N * sizeof(int);
+    size_t packs = (size_t)(NS + NS + 12 + NP + NE + Dm * 24 + STUCK_H + 1) * N;
+    size_t bytes = packs * sizeof(P4<T>) + (size_t)(N + 1) * sizeof(int);
     CK(cudaMalloc(&d_pool, bytes));
     CK(cudaMemset(d_pool, 0, bytes));
     P4<T>* p = (P4<T>*)d_pool;
     B.N = N; B.Dm = Dm;
     B.state = p; p += (size_t)NS * N; B.snap = p; p += (size_t)NS * N; B.snap_obs = p; p += (size_t)12 * N;
     B.param = p; p += (size_t)NP * N; B.etg = p; p += (size_t)NE * N; B.ring = p; p += (size_t)Dm * 24 * N;
-    B.step_count = (int*)p;
+    B.pos_hist = p; p += (size_t)STUCK_H * N; B.extf = p; p += (size_t)N;
+    B.step_count = (int*)p; d_flag = B.step_count + N;
     int rc = set_dynamics(nullptr, nullptr, 0);
     if (rc) return rc;
-    rc = reset(nullptr, nullptr, nullptr, nullptr, 0);
+    rc = reset(nullptr, nullptr, nullptr, nullptr, nullptr, 0);
     if (rc) return rc;
     CK(cudaDeviceSynchronize());
     return B2Q_OK;
@@ -206,25 +240,48 @@ struct EnvT : EnvBase {
   int set_dynamics(const uint8_t* mask, const void* dyn, cudaStream_t s) override {
     CK(cudaSetDevice(cfg.device));
     int N = B.N;
-    b2q_pack_param_kernel<T><<<(N + 127) / 128, 128, 0, s>>>((const T*)dyn, d_def48, const_cast<P4<T>*>(B.param), mask, N);
-    b2q_settle_kernel<T><<<grid_lanes(), tpb, smem_bytes(), s>>>(kc, d_model, B, mask);
-    launches += 2;
+    // latencies the two-sample-per-step observation ring can serve: n_lag <= ring_depth*R - 2 substeps (step_lane)
+    const double max_lat = ((double)B.Dm * cfg.action_repeat - 2) * cfg.sim_dt * (1.0 + 1e-9);
+    CK(cudaMemsetAsync(d_flag, 0, sizeof(int), s));
+    b2q_pack_param_kernel<T><<<(N + 127) / 128, 128, 0, s>>>((const T*)dyn, d_def48, const_cast<P4<T>*>(B.param), mask, N, (T)max_lat, d_flag);
+    CK(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));      // set_dynamics is a rare, heavyweight call (it re-settles 500 substeps): one sync is fine
+    launches += 1;
+    if (*h_flag) {
+      char buf[200];
+      snprintf(buf, sizeof buf, "b2q_set_dynamics: a control_latency exceeds %.4f s, the most ring_depth=%d can serve (need ring_depth >= ceil((latency/sim_dt + 2) / action_repeat))", max_lat, B.Dm);
+      err = buf;
+      return B2Q_EINVAL;
+    }
+    if (feat) b2q_settle_kernel<T, 1><<<grid_lanes(), tpb, smem_bytes(), s>>>(kc, d_model, B, mask);
+    else b2q_settle_kernel<T, 0><<<grid_lanes(), tpb, smem_bytes(), s>>>(kc, d_model, B, mask);
+    launches += 1;
     CK(cudaGetLastError());
     return B2Q_OK;
   }
-  int reset(const uint8_t* mask, const void* w, const void* b, void* obs, cudaStream_t s) override {
+  int reset(const uint8_t* mask, const void* w, const void* b, const void* xoff, void* obs, cudaStream_t s) override {
     CK(cudaSetDevice(cfg.device));
     int N = B.N;
     if (w || b) { b2q_pack_etg_kernel<T><<<(N + 127) / 128, 128, 0, s>>>((const T*)w, (const T*)b, const_cast<P4<T>*>(B.etg), mask, N); launches++; }
-    b2q_reset_kernel<T><<<grid_lanes(), tpb, smem_bytes(), s>>>(kc, d_model, B, mask, (T*)obs);
+    b2q_reset_kernel<T><<<grid_lanes(), tpb, smem_bytes(), s>>>(kc, d_model, B, mask, (const T*)xoff, (T*)obs);
     launches++;
     CK(cudaGetLastError());
     return B2Q_OK;
   }
+  int set_force(const void* f, cudaStream_t s) override {
+    if (!cfg.external_force) { err = "b2q_set_external_force: the handle was created with external_force = 0"; return B2Q_EINVAL; }
+    CK(cudaSetDevice(cfg.device));
+    b2q_pack_force_kernel<T><<<(B.N + 127) / 128, 128, 0, s>>>((const T*)f, const_cast<P4<T>*>(B.extf), B.N);
+    launches++;
+    CK(cudaGetLastError());
+    return B2Q_OK;
+  }
+  int feat = 0; int* d_flag = nullptr; int* h_flag = nullptr;
   int step(const void* action, int donef, void* obs, void* rew, uint8_t* done, void* info, cudaStream_t s) override {
     if (!action || !obs || !rew || !done || !info) { err = "b2q_step: null device pointer"; return B2Q_EINVAL; }
     { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != cfg.device) CK(cudaSetDevice(cfg.device)); }   // handles are per GPU
-    b2q_step_kernel<T><<<grid_lanes(), tpb, smem_bytes(), s>>>(kc, d_model, B, (const T*)action, donef, cfg.auto_reset, (T*)obs, (T*)rew, done, (T*)info);
+    if (feat) b2q_step_kernel<T, 1><<<grid_lanes(), tpb, smem_bytes(), s>>>(kc, d_model, B, (const T*)action, donef, cfg.auto_reset, (T*)obs, (T*)rew, done, (T*)info);
+    else b2q_step_kernel<T, 0><<<grid_lanes(), tpb, smem_bytes(), s>>>(kc, d_model, B, (const T*)action, donef, cfg.auto_reset, (T*)obs, (T*)rew, done, (T*)info);
     launches++;
     CK(cudaGetLastError());
     return B2Q_OK;
@@ -259,7 +316,7 @@ struct EnvT : EnvBase {
     int rc = direct ? step(act_dev, donef, obs_dev, rew_dev, done_dev, info_dev ? info_dev : st_info, s) : step(act_dev, donef, st_obs, st_rew, st_done, st_info, s);
     if (rc) return rc;
     if (info_dev) info = nullptr;
-    const size_t b_obs = N * OBS_DIM * sizeof(T), b_rew = N * sizeof(T);
+    const size_t b_obs = N * (size_t)obs_dim * sizeof(T), b_rew = N * sizeof(T);
     if (direct) {
     } else if ((uint8_t*)rew == (uint8_t*)obs + b_obs && done == (uint8_t*)rew + b_rew) {
       CK(cudaMemcpyAsync(obs, st_obs, b_obs + b_rew + N, cudaMemcpyDeviceToHost, s));      // caller's host buffers are contiguous too
@@ -333,12 +390,16 @@ int b2q_create(const B2QConfig* cfg, B2QHandle* out) {
 int b2q_destroy(B2QHandle h) { if (!h) return B2Q_EINVAL; delete h->impl; delete h; return B2Q_OK; }
 const char* b2q_last_error(B2QHandle h) { return h ? h->impl->err.c_str() : g_create_err.c_str(); }
 int b2q_num_envs(B2QHandle h) { return h ? h->impl->cfg.num_envs : B2Q_EINVAL; }
-int b2q_obs_dim(B2QHandle h) { return h ? B2Q_OBS_DIM : B2Q_EINVAL; }
+int b2q_obs_dim(B2QHandle h) { return h ? h->impl->obs_dim : B2Q_EINVAL; }
 int b2q_act_dim(B2QHandle h) { return h ? B2Q_ACT_DIM : B2Q_EINVAL; }
 int b2q_info_dim(B2QHandle h) { return h ? B2Q_INFO_DIM : B2Q_EINVAL; }
 int b2q_elem_size(B2QHandle h) { return h ? (h->impl->prec ? 8 : 4) : B2Q_EINVAL; }
 int b2q_set_dynamics(B2QHandle h, const uint8_t* m, const void* dyn, void* s) { return h ? h->impl->set_dynamics(m, dyn, (cudaStream_t)s) : B2Q_EINVAL; }
-int b2q_reset(B2QHandle h, const uint8_t* m, const void* w, const void* b, void* obs, void* s) { return h ? h->impl->reset(m, w, b, obs, (cudaStream_t)s) : B2Q_EINVAL; }
+int b2q_reset(B2QHandle h, const uint8_t* m, const void* w, const void* b, void* obs, void* s) { return h ? h->impl->reset(m, w, b, nullptr, obs, (cudaStream_t)s) : B2Q_EINVAL; }
+int b2q_reset_ex(B2QHandle h, const uint8_t* m, const void* w, const void* b, const void* xoff, void* obs, void* s) {
+  return h ? h->impl->reset(m, w, b, xoff, obs, (cudaStream_t)s) : B2Q_EINVAL;
+}
+int b2q_set_external_force(B2QHandle h, const void* f, void* s) { return h ? h->impl->set_force(f, (cudaStream_t)s) : B2Q_EINVAL; }
 int b2q_step(B2QHandle h, const void* a, int donef, void* obs, void* rew, uint8_t* done, void* info, void* s) {
   return h ? h->impl->step(a, donef, obs, rew, done, info, (cudaStream_t)s) : B2Q_EINVAL;
 }

@@ -14,6 +14,10 @@ inline Cfg<T> make_cfg(const B2QConfig& c, const T* hf_dev) {
   k.interp = c.action_interp; k.tau_limit = (T)c.torque_limit; k.settle_steps = c.settle_steps;
   k.filter = c.action_filter; k.etg = c.etg_enabled; k.max_steps = c.max_episode_steps;
   k.clip_cmd = c.clip_motor_commands; k.max_dq = (T)c.max_angle_change;
+  k.noise_on = 0; for (int i = 0; i < 5; i++) { k.noise[i] = (T)c.noise_stdev[i]; if (c.noise_stdev[i] > 0) k.noise_on = 1; }
+  k.noise_seed = c.noise_seed; k.stuck = c.stuck_termination; k.body_coll = c.body_collisions;
+  k.motor_mode = c.motor_mode; k.jlim = c.joint_limits; k.extf = c.external_force;
+  for (int i = 0; i < 4; i++) k.damp[i] = (T)c.base_damping[i];
   {  // scipy.signal.butter(2, highcut / (fs/2)) in closed form (bilinear transform), fs = 1 / control period
     const double PI = 3.14159265358979323846, fs = 1.0 / (c.sim_dt * c.action_repeat);
     const double K = std::tan(PI * c.filter_highcut / fs), n = 1.0 / (1.0 + std::sqrt(2.0) * K + K * K);
@@ -34,7 +38,34 @@ inline void default_config(B2QConfig* c) {
   c->action_interp = 0; c->torque_limit = 0; c->settle_steps = 500; c->action_filter = 0; c->filter_highcut = 4.0; c->etg_enabled = 1;
   c->etg_T = 0.5; c->etg_T2 = 0.5; c->etg_sigma_sq = 0.04; c->etg_amp = 0.2; c->etg_phase0 = -3.14159265358979323846 / 2; c->etg_phase1 = 0;
   c->w_torso = 1.5; c->w_feet = 0.3; c->w_up = 0.6; c->w_tau = 0.07; c->w_stand = 0; c->w_badfoot = 0.1; c->w_footcontact = 0.1; c->w_done = 1;
-  c->reward_p = 5; c->vel_d = 0.5; c->foot_radius = 0.02; c->ring_depth = 1; c->auto_reset = 0; c->terrain_type = 0; c->clip_motor_commands = 0; c->max_angle_change = 0.2;
+  c->reward_p = 5; c->vel_d = 0.5; c->foot_radius = 0.02; c->ring_depth = 4; c->auto_reset = 0; c->terrain_type = 0; c->clip_motor_commands = 0; c->max_angle_change = 0.2;
+  c->sensor_dis = 1; c->sensor_contact = 1; c->sensor_imu = 1; c->sensor_motor = 1; c->sensor_etg = 1; c->obs_normal = 1;   // train.py:494-500 defaults
+}
+
+// which kernel instantiation a config needs: 0 = the lean default body, 1 = the variant with TORQUE mode / joint-limit rows / base push / damping
+inline int config_feat(const B2QConfig& c) {
+  return (c.motor_mode || c.joint_limits || c.external_force || c.base_damping[0] != 0 || c.base_damping[1] != 0 || c.base_damping[2] != 0 || c.base_damping[3] != 0) ? 1 : 0;
+}
+// observation width selected by the sensor flags (SimpleEnv.get_observation, deployment/envs/EnvWrapper.py:60-109)
+inline int config_obs_dim(const B2QConfig& c) {
+  return (c.sensor_dis ? 3 : 0) + (c.sensor_contact ? 4 : 0) + (c.sensor_imu == 1 ? 6 : c.sensor_imu == 2 ? 3 : 0) +
+         (c.sensor_motor == 1 ? 24 : c.sensor_motor == 2 ? 12 : 0) + (c.sensor_etg ? 12 : 0);
+}
+template <typename T>
+inline void build_obs_map(Model<T>& M, const B2QConfig& c) {
+  int n = 0;
+  auto put = [&](int src, double scale, double shift) { M.obs_src[n] = src; M.obs_scale[n] = (T)scale; M.obs_shift[n] = (T)shift; n++; };
+  const bool nrm = c.obs_normal != 0;
+  if (c.sensor_dis) for (int i = 0; i < 3; i++) put(i, 1, 0);                                          // BaseDisplacement
+  if (c.sensor_contact) for (int i = 0; i < 4; i++) put(3 + i, 1, 0);                                  // FootContactSensor
+  if (c.sensor_imu == 1) for (int i = 0; i < 3; i++) put(7 + i, nrm ? 1 : 0.1, 0);                     // IMU: rpy (/0.1) ...
+  if (c.sensor_imu) for (int i = 0; i < 3; i++) put(10 + i, nrm ? 1 : 0.5, 0);                         // ... drpy (/0.5)
+  if (c.sensor_motor) for (int i = 0; i < 12; i++) put(13 + i, nrm ? 1 : 0.1, nrm ? 0 : (double)M.pose_ori[i % 3]);   // MotorAngle
+  if (c.sensor_motor == 1) for (int i = 0; i < 12; i++) put(25 + i, 1, 0);                             // + velocities (MotorAngleAcc)
+  if (c.sensor_etg) for (int i = 0; i < 12; i++) put(37 + i, nrm ? 1 : (double)M.etg_std[i], nrm ? 0 : (double)M.etg_mean[i]);
+  M.obs_dim = n;
+  M.obs_identity = (n == OBS_DIM && nrm) ? 1 : 0;
+  for (; n < OBS_DIM; n++) { M.obs_src[n] = 0; M.obs_scale[n] = 0; M.obs_shift[n] = 0; }
 }
 
 inline const char* validate_config(const B2QConfig& c) {
@@ -48,7 +79,12 @@ inline const char* validate_config(const B2QConfig& c) {
   if (c.ring_depth < 1 || c.ring_depth > 16) return "ring_depth out of range [1,16]";
   if (c.terrain_type == 1 && (c.hf_nx < 2 || c.hf_ny < 2 || !c.hf_host || !(c.hf_cell > 0))) return "height field needs hf_nx,hf_ny>=2, hf_cell>0 and hf_host";
   if (c.terrain_type != 0 && c.terrain_type != 1) return "terrain_type must be 0 or 1";
-  if (c.threads_per_block != 0 && (c.threads_per_block % 32 != 0 || c.threads_per_block > 1024)) return "threads_per_block must be a multiple of 32";
+  if (c.sensor_imu < 0 || c.sensor_imu > 2 || c.sensor_motor < 0 || c.sensor_motor > 2) return "sensor_imu / sensor_motor must be 0, 1 or 2";
+  if (config_obs_dim(c) < 1) return "sensor flags select an empty observation";
+  if (c.motor_mode != 0 && c.motor_mode != 1) return "motor_mode must be 0 (POSITION) or 1 (TORQUE); HYBRID is not provided";
+  for (int i = 0; i < 5; i++) if (!(c.noise_stdev[i] >= 0)) return "noise_stdev must be >= 0";
+  for (int i = 0; i < 4; i++) if (!(c.base_damping[i] >= 0)) return "base_damping must be >= 0";
+  if (c.threads_per_block != 0 && (c.threads_per_block % 32 != 0 || c.threads_per_block > 128)) return "threads_per_block must be a multiple of 32, at most 128 (kernels are __launch_bounds__(128))";
   return nullptr;
 }
 

@@ -52,6 +52,30 @@ B2Q_HD bool m_isfinite(double x) { return (x - x) == 0.0; }
 B2Q_HD bool m_isnan(float x) { return x != x; }
 B2Q_HD bool m_isnan(double x) { return x != x; }
 
+B2Q_HD float m_log(float x) { return logf(x); }
+B2Q_HD double m_log(double x) { return log(x); }
+
+// counter-based Gaussian for sensor noise: Philox4x32-10 keyed by the 64-bit seed, counter (c0,c1,c2,0) -> 4 x u32 -> two Box-Muller
+// pairs.  Integer part identical on host and device; the transform is evaluated in T.
+B2Q_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
+B2Q_HD void philox4(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t out[4]) {
+  uint32_t c3 = 0, k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int i = 0; i < 10; i++) {
+    uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0, h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+template <typename T> B2Q_HD void philox_normal4(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, T n[4]) {
+  uint32_t r[4]; philox4(seed, c0, c1, c2, r);
+  const T two_pi = T(6.283185307179586476925286766559), sc = T(1.0 / 16777216.0);
+  T u0 = (T(r[0] >> 8) + T(0.5)) * sc, u1 = (T(r[1] >> 8) + T(0.5)) * sc, u2 = (T(r[2] >> 8) + T(0.5)) * sc, u3 = (T(r[3] >> 8) + T(0.5)) * sc;
+  T ra = m_sqrt(T(-2) * m_log(u0)), rb = m_sqrt(T(-2) * m_log(u2));
+  n[0] = ra * m_cos(two_pi * u1); n[1] = ra * m_sin(two_pi * u1); n[2] = rb * m_cos(two_pi * u3); n[3] = rb * m_sin(two_pi * u3);
+}
+
 // reciprocal: one MUFU.RCP + one Newton step on the GPU (<= 1 ulp, no slow path / branch); exact division elsewhere
 #if defined(__CUDA_ARCH__)
 B2Q_HD float m_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return fmaf(r, fmaf(-x, r, 1.0f), r); }

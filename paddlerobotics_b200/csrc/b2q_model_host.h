@@ -14,7 +14,7 @@ struct A1Nominal {
 };
 
 template <typename T>
-inline void build_model_host(Model<T>& M, double foot_radius, double etg_T, double etg_amp, double ph0, double ph1) {
+inline void build_model_host(Model<T>& M, double foot_radius, double etg_T, double etg_amp, double ph0, double ph1, double foot_y_inset = 0.0) {
   const double COM_OFF[3] = {-0.012731, -0.002186, -0.000515};
   const double HIP_XY[4][2] = {{0.183, -0.047}, {0.183, 0.047}, {-0.183, -0.047}, {-0.183, 0.047}};
   const double BASE_FOOT[4][3] = {{0.18, -0.15, -0.23}, {0.18, 0.148, -0.23}, {-0.18, -0.14, -0.23}, {-0.18, 0.135, -0.23}};
@@ -37,6 +37,11 @@ inline void build_model_host(Model<T>& M, double foot_radius, double etg_T, doub
   for (int i = 0; i < 6; i++) M.I0[i] = (T)TRUNK_I[i];
   M.foot_r = (T)foot_radius; M.l_up = (T)A1Nominal::l_up; M.l_low = (T)A1Nominal::l_low;
   M.pose_ori[0] = (T)0.0; M.pose_ori[1] = (T)0.9; M.pose_ori[2] = (T)-1.8;
+  M.qlo[0] = (T)-0.802851455917; M.qhi[0] = (T)0.802851455917;      // a1.py:186-223 (same bounds on the four legs)
+  M.qlo[1] = (T)-1.0471975512; M.qhi[1] = (T)4.18879020479;
+  M.qlo[2] = (T)-2.69653369433; M.qhi[2] = (T)-0.916297857297;
+  M.obs_dim = OBS_DIM; M.obs_identity = 1;
+  for (int j = 0; j < OBS_DIM; j++) { M.obs_src[j] = j; M.obs_scale[j] = (T)1; M.obs_shift[j] = (T)0; }
   for (int j = 0; j < 12; j++) { M.etg_mean[j] = (T)ETG_MEAN[j]; M.etg_std[j] = (T)ETG_STD[j]; M.etg_istd[j] = (T)(1.0 / ETG_STD[j]); }
   for (int h = 0; h < ETG_H; h++) {  // RBF centres: forward(h*T/(H-0.9)), SURVEY App. A
     double t = h * etg_T / (ETG_H - 0.9), om = 2 * PI / etg_T;
@@ -48,7 +53,7 @@ inline void build_model_host(Model<T>& M, double foot_radius, double etg_T, doub
     double mirror = (leg % 2) ? 1.0 : -1.0, fh = (leg < 2) ? 1.0 : -1.0;
     L.p1[0] = (T)(HIP_XY[leg][0] + COM_OFF[0]); L.p1[1] = (T)(HIP_XY[leg][1] + COM_OFF[1]); L.p1[2] = (T)COM_OFF[2];
     L.lhip = (T)(A1Nominal::l_hip * mirror);
-    for (int a = 0; a < 3; a++) M.base_foot[leg][a] = (T)BASE_FOOT[leg][a];
+    for (int a = 0; a < 3; a++) M.base_foot[leg][a] = (T)(BASE_FOOT[leg][a] - (a == 1 ? (BASE_FOOT[leg][1] > 0 ? foot_y_inset : -foot_y_inset) : 0.0));
     // hip
     L.m[0] = (T)HIP_M;
     L.com[0][0] = (T)(HIP_C[0] * fh); L.com[0][1] = (T)(HIP_C[1] * mirror); L.com[0][2] = (T)HIP_C[2];

@@ -52,6 +52,11 @@ struct Model {
   T base_foot[4][3];
   T etg_mean[12], etg_std[12], etg_istd[12];
   T pose_ori[3];
+  T qlo[3], qhi[3];                 // URDF joint limits (a1.py:186-223): hip, upper, lower
+  // observation layout selected by sensor_mode / normal (EnvWrapper.py:60-109): out[j] = full49[obs_src[j]] * obs_scale[j] + obs_shift[j]
+  int obs_dim, obs_identity;
+  int obs_src[OBS_DIM];
+  T obs_scale[OBS_DIM], obs_shift[OBS_DIM];
 };
 template <typename T>
 struct Cfg {
@@ -61,7 +66,11 @@ struct Cfg {
   T w_torso, w_feet, w_up, w_tau, w_stand, w_badfoot, w_footcontact, w_done, reward_p, vel_d;
   int terrain, hf_nx, hf_ny; T hf_x0, hf_y0, hf_cell, hf_icell, idt; const T* hf;
   int clip_cmd; T max_dq;   // A1._ClipMotorCommands (a1.py:440-458)
+  int noise_on; T noise[5]; unsigned long long noise_seed;   // Minitaur._AddSensorNoise (minitaur.py:1206-1211)
+  int stuck, body_coll;     // stuck termination, non-toe collision count for `badfoot`
+  int motor_mode, jlim, extf; T damp[4];   // FEAT variant only: TORQUE mode, joint-limit rows, base push, Bullet base damping
 };
+constexpr int STUCK_H = 10;   // control steps of base-position history for the stuck termination
 template <typename T>
 struct Buffers {
   int N, Dm;
@@ -72,6 +81,8 @@ struct Buffers {
   const P4<T>* etg;      // [NE][N]
   P4<T>* ring;           // [Dm][2][12][N]
   int* step_count;       // [N]
+  P4<T>* pos_hist;       // [STUCK_H][N] base positions of the last control steps (stuck termination)
+  const P4<T>* extf;     // [N] world-frame push on the base (external_force)
 };
 template <typename T>
 struct LaneParam {
@@ -178,9 +189,12 @@ B2Q_HD void etg_act_leg(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, co
 
 // ---------------------------------------------------------------------------------------------------------------
 // one physics substep for this lane's leg (+ redundant base)
-template <typename T, class Comm>
+// FEAT = 0: the lean default body (POSITION mode, toe contacts only).  FEAT = 1 adds, behind runtime flags, TORQUE mode, the base
+// push, Bullet's base damping and the joint-limit rows; it is a separate instantiation so that the default body stays as
+// small as it is (the body is instruction-fetch bound).
+template <typename T, int FEAT, class Comm>
 B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const LaneParam<T>& pr, LaneState<T>& s,
-                    const T* target, T* tau_out) {
+                    const T* target, T* tau_out, V3<T> fext = V3<T>{0, 0, 0}) {
   const int k = cm.leg();
   const LegModel<T>& lm = md.leg[k];
   const T dt = cf.dt, idt = cf.idt;
@@ -194,6 +208,7 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
     T cmd = target[j];
     if (cf.clip_cmd) cmd = m_min(m_max(cmd, s.q[j] - cf.max_dq), s.q[j] + cf.max_dq);   // a1.py:452-457 (off by default)
     T t = T(-1) * (pr.kp[j] * (s.q[j] - cmd)) - pr.kd[j] * (s.qd[j] - T(0));
+    if (FEAT && cf.motor_mode == 1) t = target[j];   // MotorControlMode.TORQUE: the command is the torque (laikago_motor.py:131-134)
     if (cf.tau_limit > T(0)) t = m_min(m_max(t, -cf.tau_limit), cf.tau_limit);
     tau[j] = t; tau_out[j] = t;
   }
@@ -325,6 +340,13 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
     S[tri(0, 0)] += I0.xx; S[tri(1, 0)] += I0.xy; S[tri(1, 1)] += I0.yy; S[tri(2, 0)] += I0.xz; S[tri(2, 1)] += I0.yz; S[tri(2, 2)] += I0.zz;
     S[tri(3, 3)] += m0; S[tri(4, 4)] += m0; S[tri(5, 5)] += m0;
     V3<T> n0 = cross(wB, mul(I0, wB)), f0 = pdd0 * m0;
+    if (FEAT) {
+      // Bullet btMultiBody base damping (force = m v (k1 + k2 |v|), torque = I w (k1 + k2 |w|)) and the external push (world frame, at the COM)
+      T lv = m_sqrt(dot(vB, vB)), lw = m_sqrt(dot(wB, wB));
+      f0 = f0 + vB * (m0 * (cf.damp[0] + cf.damp[1] * lv));
+      n0 = n0 + mul(I0, wB) * (cf.damp[2] + cf.damp[3] * lw);
+      if (cf.extf) f0 = f0 - rotT(R, fext);
+    }
     r6[0] -= n0.x; r6[1] -= n0.y; r6[2] -= n0.z; r6[3] -= f0.x; r6[4] -= f0.y; r6[5] -= f0.z;
   }
   T Li[6];
@@ -607,7 +629,7 @@ template <typename T> B2Q_HD T c_prec(T v, T t, T m) { T w = (v - t) * T(2.17827
 // observation row (EnvWrapper.py:60-109 layout; sorted sensor keys, then normalised ETG)
 template <typename T, class Comm>
 B2Q_HD void write_obs(const Comm& cm, const Model<T>& md, T* obs, bool valid, const LaneState<T>& s, V3<T> start_pos, T dtc, V3<T> rpy0,
-                      const T* dq, const T* dqd, const T* etg_act) {
+                      const T* dq, const T* dqd, const T* etg_act, const T* nz = nullptr /* additive noise on rpy(3), drpy(3) */) {
   if (!valid) return;
   const int k = cm.leg();
   if (k == 0) {
@@ -616,6 +638,7 @@ B2Q_HD void write_obs(const Comm& cm, const Model<T>& md, T* obs, bool valid, co
     V3<T> rpy = quat_to_rpy(s.qx, s.qy, s.qz, s.qw);
     R3<T> R = quat_to_R(s.qx, s.qy, s.qz, s.qw);
     V3<T> wb = rotT(R, s.vang);
+    if (nz) { rpy.x += nz[0]; rpy.y += nz[1]; rpy.z += nz[2]; wb.x += nz[3]; wb.y += nz[4]; wb.z += nz[5]; }
     obs[7] = (rpy.x - rpy0.x) * T(10); obs[8] = (rpy.y - rpy0.y) * T(10); obs[9] = (rpy.z - rpy0.z) * T(10);   // /0.1, EnvWrapper.py:87
     obs[10] = wb.x * T(2); obs[11] = wb.y * T(2); obs[12] = wb.z * T(2);                                            // /0.5, EnvWrapper.py:88
   }
@@ -628,10 +651,16 @@ B2Q_HD void write_obs(const Comm& cm, const Model<T>& md, T* obs, bool valid, co
   }
 }
 
+// one output row from a full 49-wide staged row (sensor_mode selection / de-normalisation), element j
+template <typename T> B2Q_HD T obs_out_elem(const Model<T>& md, const T* full49, int j) {
+  return md.obs_identity ? full49[j] : full49[md.obs_src[j]] * md.obs_scale[j] + md.obs_shift[j];
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // reset = masked copy of the settled snapshot (K2); history ring filled with the settled observation
 template <typename T, class Comm>
-B2Q_HD void reset_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const Buffers<T>& B, int env, bool valid, T* obs /*row or null*/) {
+B2Q_HD void reset_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const Buffers<T>& B, int env, bool valid, T* obs /*49-wide row or null*/,
+                       const T* xoff = nullptr /* [N] initial base x offsets (reset(x_noise=)) or null */) {
   const int k = cm.leg(), N = B.N;
   LaneState<T> s; T la[3], ea[3]; int hl; V3<T> rpy0;
   load_state(cm, B.snap, N, env, s, la, ea, hl, rpy0);
@@ -641,6 +670,7 @@ B2Q_HD void reset_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, con
     sq[0] = a.x; sq[1] = a.y; sq[2] = a.z; stau[0] = a.w; sqd[0] = b.x; sqd[1] = b.y; sqd[2] = b.z; stau[1] = b.w; stau[2] = c.x;
   }
   s.contact = s.lam_n > T(0);
+  if (xoff) s.pos.x += xoff[env];
   rpy0 = quat_to_rpy(s.qx, s.qy, s.qz, s.qw);
   etg_act_leg(cm, cf, md, B.etg, N, env, T(0), ea);
   la[0] = la[1] = la[2] = T(0);
@@ -654,7 +684,7 @@ B2Q_HD void reset_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, con
 }
 
 // settle: reset pose, hold INIT_MOTOR_ANGLES for settle_steps substeps (a1.py:289-304), then snapshot
-template <typename T, class Comm>
+template <typename T, int FEAT, class Comm>
 B2Q_HD void settle_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const Buffers<T>& B, int env, bool valid) {
   const int k = cm.leg(), N = B.N;
   LaneParam<T> pr; load_param(cm, B, env, pr);
@@ -664,8 +694,9 @@ B2Q_HD void settle_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, co
 #pragma unroll
   for (int j = 0; j < 3; j++) { s.q[j] = md.pose_ori[j]; s.qd[j] = 0; tgt[j] = md.pose_ori[j]; }
   s.lam_n = 0; s.contact = 0;
+  Cfg<T> cs = cf; cs.motor_mode = 0;   // the reset pose is held by the POSITION controller whatever the policy's motor mode (a1.py:289-304)
 #pragma unroll 1
-  for (int i = 0; i < cf.settle_steps; i++) substep(cm, cf, md, pr, s, tgt, tau);
+  for (int i = 0; i < cf.settle_steps; i++) substep<T, FEAT>(cm, cs, md, pr, s, tgt, tau);
   if (valid) {
     T z3[3] = {0, 0, 0};
     store_state(cm, B.snap, N, env, s, z3, z3, 0, mk<T>(0, 0, 0));
@@ -677,7 +708,7 @@ B2Q_HD void settle_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, co
 
 // ---------------------------------------------------------------------------------------------------------------
 // one control step (= R physics substeps) for this lane: env.step() of the reference
-template <typename T, class Comm>
+template <typename T, int FEAT, class Comm>
 B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const Buffers<T>& B, int env, bool valid,
                       const T* action, int donef, int auto_reset, T* obs, T* reward, uint8_t* done, T* info, int obs_env0 = 0) {
   // `obs` is the row block starting at env `obs_env0`: the whole [N][OBS_DIM] array (obs_env0 = 0) or a CTA-local staging block
@@ -690,6 +721,14 @@ B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, cons
   T target[3];
 #pragma unroll
   for (int j = 0; j < 3; j++) target[j] = md.pose_ori[j] + etg_act[j] + action[(size_t)env * 12 + 3 * k + j];  // deployment/test.py:95-99
+  V3<T> fext = mk<T>(0, 0, 0);
+  if (FEAT) {
+    if (cf.motor_mode == 1) {   // TORQUE mode: the (already scaled) action is the motor torque, no ETG / pose offset
+#pragma unroll
+      for (int j = 0; j < 3; j++) target[j] = action[(size_t)env * 12 + 3 * k + j];
+    }
+    if (cf.extf) { P4<T> f = B.extf[env]; fext = mk<T>(f.x, f.y, f.z); }
+  }
   if (cf.filter) {  // Minitaur.Step: action = _FilterAction(action) (minitaur.py:250-251); y = b.x_hist - a.y_hist (action_filter.py:111-120)
     P4<T> x1 = ldp(B.state, 21 + 4 * k, N, env), x2 = ldp(B.state, 22 + 4 * k, N, env), y1 = ldp(B.state, 23 + 4 * k, N, env), y2 = ldp(B.state, 24 + 4 * k, N, env);
     T ax1[3] = {x1.x, x1.y, x1.z}, ax2[3] = {x2.x, x2.y, x2.z}, ay1[3] = {y1.x, y1.y, y1.z}, ay2[3] = {y2.x, y2.y, y2.z}, yy[3];
@@ -728,7 +767,7 @@ B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, cons
 #pragma unroll
       for (int j = 0; j < 3; j++) proc[j] = target[j];
     }
-    substep(cm, cf, md, pr, s, proc, tau);
+    substep<T, FEAT>(cm, cf, md, pr, s, proc, tau, fext);
     if (valid && i == ia) ring_write(B, slot, 0, k, env, s.q, s.qd, tau);
     if (valid && i == ib) ring_write(B, slot, 1, k, env, s.q, s.qd, tau);
   }
@@ -749,9 +788,28 @@ B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, cons
     }
   }
   step += 1;
+  T nz6[6] = {0, 0, 0, 0, 0, 0};
+  if (cf.noise_on) {   // Minitaur._AddSensorNoise on GetMotorAngles / Velocities / Torques / rpy / rpy rate (minitaur.py:635,762,785,805,880)
+    T n4[4];
+    philox_normal4<T>(cf.noise_seed, (uint32_t)env, (uint32_t)step, (uint32_t)(16 * k + 0), n4);
+#pragma unroll
+    for (int j = 0; j < 3; j++) dq[j] += cf.noise[0] * n4[j];
+    philox_normal4<T>(cf.noise_seed, (uint32_t)env, (uint32_t)step, (uint32_t)(16 * k + 1), n4);
+#pragma unroll
+    for (int j = 0; j < 3; j++) dqd[j] += cf.noise[1] * n4[j];
+    philox_normal4<T>(cf.noise_seed, (uint32_t)env, (uint32_t)step, (uint32_t)(16 * k + 2), n4);
+#pragma unroll
+    for (int j = 0; j < 3; j++) dtau[j] += cf.noise[2] * n4[j];
+    if (k == 0) {
+      philox_normal4<T>(cf.noise_seed, (uint32_t)env, (uint32_t)step, 64u, n4);
+      nz6[0] = cf.noise[3] * n4[0]; nz6[1] = cf.noise[3] * n4[1]; nz6[2] = cf.noise[3] * n4[2];
+      philox_normal4<T>(cf.noise_seed, (uint32_t)env, (uint32_t)step, 65u, n4);
+      nz6[3] = cf.noise[4] * n4[0]; nz6[4] = cf.noise[4] * n4[1]; nz6[5] = cf.noise[4] * n4[2];
+    }
+  }
   etg_act_leg(cm, cf, md, B.etg, N, env, T(step) * dtc, etg_act);
   T* orow = obs + (size_t)(env - obs_env0) * OBS_DIM;
-  write_obs(cm, md, orow, valid, s, start_pos, dtc, rpy0, dq, dqd, etg_act);
+  write_obs(cm, md, orow, valid, s, start_pos, dtc, rpy0, dq, dqd, etg_act, cf.noise_on ? nz6 : (const T*)nullptr);
 
   // ---- reward / termination (this repo's definition)
   R3<T> Rb = quat_to_R(s.qx, s.qy, s.qz, s.qw);
@@ -766,7 +824,24 @@ B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, cons
   T pw = cm.sum4(dtau[0] * dqd[0] + dtau[1] * dqd[1] + dtau[2] * dqd[2]);
   T energy = m_abs(pw) * cf.dt * T(R);  // minitaur.py:810-818
   T kh = terrain_height(cf, knee_w.x, knee_w.y, nrm);
-  T bad = cm.sum4((knee_w.z - kh < T(0.03)) ? T(1) : T(0));
+  T badk = (knee_w.z - kh < T(0.03)) ? T(1) : T(0);
+  if (cf.body_coll) {
+    // non-toe links touching the terrain (what Bullet's contact list on leg links / trunk would report; `badfoot` counts them):
+    // knee joint sphere (calf/thigh box end, r 0.02), hip joint (hip cylinder r 0.046, a1 URDF collision shapes [EXT] SURVEY B.3) and
+    // this lane's two corners of the trunk box (0.267 x 0.194 x 0.114)
+    V3<T> hip_w = s.pos + rot(Rb, K.p2);
+    T hh = terrain_height(cf, hip_w.x, hip_w.y, nrm);
+    badk = (knee_w.z - kh < T(0.02)) ? T(1) : T(0);
+    badk += (hip_w.z - hh < T(0.046)) ? T(1) : T(0);
+    const T cx = (k < 2) ? T(0.1335) : T(-0.1335), cy = (k & 1) ? T(0.097) : T(-0.097);
+#pragma unroll
+    for (int zz = 0; zz < 2; zz++) {
+      V3<T> c_w = s.pos + rot(Rb, mk<T>(cx - T(0.012731), cy - T(0.002186), (zz ? T(0.057) : T(-0.057)) - T(0.000515)));
+      T ch = terrain_height(cf, c_w.x, c_w.y, nrm);
+      badk += (c_w.z - ch < T(0)) ? T(1) : T(0);
+    }
+  }
+  T bad = cm.sum4(badk);
   T nofoot = cm.sum4(s.contact ? T(0) : T(1));
   T meanz = cm.sum4(K.toe.z * T(0.25));
   T above = cm.sum4(K.toe.z > T(0) ? T(1) : T(0));
@@ -777,7 +852,27 @@ B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, cons
   T r_torso = cf.w_torso * torso, r_feet = cf.w_feet * feet, r_up = cf.w_up * up, r_tau = -cf.w_tau * energy;
   T r_bad = -cf.w_badfoot * bad, r_fc = -cf.w_footcontact * (nofoot > T(2) ? nofoot - T(2) : T(0)), r_done = fall ? -cf.w_done : T(0);
   T rew = cf.reward_p * (r_torso + r_feet + r_up + r_tau + r_bad + r_fc + r_done);
-  bool dn = fall || donef || (cf.max_steps > 0 && step >= cf.max_steps);
+  T stuckf = T(0);
+  if (cf.stuck) {   // rlschool [EXT]: episode ends when the base has not moved over the last STUCK_H control steps (after step 10)
+    if (k == 0) {
+      if (valid) stp(B.pos_hist, (step - 1) % STUCK_H, N, env, s.pos.x, s.pos.y, s.pos.z, T(0));
+      if (step > STUCK_H) {
+        T mx = 0, my = 0, mz = 0, vx = 0, vy = 0, vz = 0;
+        for (int h = 0; h < STUCK_H; h++) {
+          P4<T> ph = ldp(B.pos_hist, h, N, env);
+          // relative to the current position (variance is translation invariant; avoids the cancellation of E[x^2]-E[x]^2 far from the origin)
+          T dx = ((step - 1) % STUCK_H == h) ? T(0) : ph.x - s.pos.x, dy = ((step - 1) % STUCK_H == h) ? T(0) : ph.y - s.pos.y, dz = ((step - 1) % STUCK_H == h) ? T(0) : ph.z - s.pos.z;
+          mx += dx; my += dy; mz += dz; vx += dx * dx; vy += dy * dy; vz += dz * dz;
+        }
+        const T inv = T(1) / T(STUCK_H);
+        mx *= inv; my *= inv; mz *= inv;
+        T var = (vx * inv - mx * mx) + (vy * inv - my * my) + (vz * inv - mz * mz);
+        stuckf = (var <= T(2e-4) * T(2e-4)) ? T(1) : T(0);
+      }
+    }
+    stuckf = cm.bcast(stuckf, 0);
+  }
+  bool dn = fall || donef || (cf.max_steps > 0 && step >= cf.max_steps) || (stuckf > T(0));
   if (valid) {
     T* irow = info + (size_t)env * INFO_DIM;
     if (k == 0) {

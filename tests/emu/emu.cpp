@@ -62,7 +62,8 @@ struct HostComm {
 template <typename T>
 struct Emu {
   B2QConfig cfg; Cfg<T> kc; Model<T> md; Buffers<T> B;
-  std::vector<P4<T>> state, snap, snap_obs, param, etg, ring; std::vector<int> step_count; std::vector<T> hf;
+  std::vector<P4<T>> state, snap, snap_obs, param, etg, ring, pos_hist, extf; std::vector<int> step_count; std::vector<T> hf; std::vector<T> stage;
+  int feat = 0;
   T def48[48];
   Exchange ex;
   template <class F>
@@ -82,7 +83,9 @@ Emu<T>* create_t(const B2QConfig& c) {
   int N = c.num_envs, Dm = c.ring_depth;
   if (c.terrain_type == 1) { e->hf.resize((size_t)c.hf_nx * c.hf_ny); for (size_t i = 0; i < e->hf.size(); i++) e->hf[i] = (T)c.hf_host[i]; }
   e->kc = make_cfg<T>(c, e->hf.empty() ? nullptr : e->hf.data());
-  build_model_host(e->md, c.foot_radius, c.etg_T, c.etg_amp, c.etg_phase0, c.etg_phase1);
+  build_model_host(e->md, c.foot_radius, c.etg_T, c.etg_amp, c.etg_phase0, c.etg_phase1, c.etg_foot_y_inset);
+  build_obs_map(e->md, c); e->feat = config_feat(c);
+  e->pos_hist.assign((size_t)STUCK_H * N, P4<T>{0, 0, 0, 0}); e->extf.assign((size_t)N, P4<T>{0, 0, 0, 0}); e->stage.assign((size_t)N * OBS_DIM, T(0));
   e->state.assign((size_t)NS * N, P4<T>{0, 0, 0, 0}); e->snap = e->state;
   e->snap_obs.assign((size_t)12 * N, P4<T>{0, 0, 0, 0}); e->param.assign((size_t)NP * N, P4<T>{0, 0, 0, 0});
   e->etg.assign((size_t)NE * N, P4<T>{0, 0, 0, 0}); e->ring.assign((size_t)Dm * 2 * 12 * N, P4<T>{0, 0, 0, 0});
@@ -90,6 +93,7 @@ Emu<T>* create_t(const B2QConfig& c) {
   double d48[48]; default_dyn_row(d48); for (int i = 0; i < 48; i++) e->def48[i] = (T)d48[i];
   e->B.N = N; e->B.Dm = Dm; e->B.state = e->state.data(); e->B.snap = e->snap.data(); e->B.snap_obs = e->snap_obs.data();
   e->B.param = e->param.data(); e->B.etg = e->etg.data(); e->B.ring = e->ring.data(); e->B.step_count = e->step_count.data();
+  e->B.pos_hist = e->pos_hist.data(); e->B.extf = e->extf.data();
   return e;
 }
 
@@ -97,18 +101,36 @@ template <typename T>
 void set_dynamics_t(Emu<T>* e, const uint8_t* mask, const T* dyn) {
   int N = e->B.N;
   for (int i = 0; i < N; i++) if (!mask || mask[i]) pack_param_env<T>(dyn, e->def48, e->param.data(), N, i);
-  e->run4([&](const HostComm<T>& cm) { for (int i = 0; i < N; i++) if (!mask || mask[i]) settle_lane(cm, e->kc, e->md, e->B, i, true); });
+  e->run4([&](const HostComm<T>& cm) {
+    for (int i = 0; i < N; i++) if (!mask || mask[i]) { if (e->feat) settle_lane<T, 1>(cm, e->kc, e->md, e->B, i, true); else settle_lane<T, 0>(cm, e->kc, e->md, e->B, i, true); }
+  });
 }
 template <typename T>
-void reset_t(Emu<T>* e, const uint8_t* mask, const T* w, const T* b, T* obs) {
+void emit_rows(Emu<T>* e, const uint8_t* mask, T* obs) {
+  const int od = e->md.obs_dim;
+  for (int i = 0; i < e->B.N; i++) if (!mask || mask[i]) for (int j = 0; j < od; j++) obs[(size_t)i * od + j] = obs_out_elem(e->md, e->stage.data() + (size_t)i * OBS_DIM, j);
+}
+template <typename T>
+void reset_t(Emu<T>* e, const uint8_t* mask, const T* w, const T* b, const T* xoff, T* obs) {
   int N = e->B.N;
   for (int i = 0; i < N; i++) if (!mask || mask[i]) pack_etg_env<T>(w, b, e->etg.data(), N, i);
-  e->run4([&](const HostComm<T>& cm) { for (int i = 0; i < N; i++) if (!mask || mask[i]) reset_lane(cm, e->kc, e->md, e->B, i, true, obs ? obs + (size_t)i * OBS_DIM : (T*)nullptr); });
+  e->run4([&](const HostComm<T>& cm) { for (int i = 0; i < N; i++) if (!mask || mask[i]) reset_lane(cm, e->kc, e->md, e->B, i, true, e->stage.data() + (size_t)i * OBS_DIM, xoff); });
+  if (obs) emit_rows(e, mask, obs);
 }
 template <typename T>
 void step_t(Emu<T>* e, const T* action, int donef, T* obs, T* rew, uint8_t* done, T* info) {
   int N = e->B.N;
-  e->run4([&](const HostComm<T>& cm) { for (int i = 0; i < N; i++) step_lane(cm, e->kc, e->md, e->B, i, true, action, donef, e->cfg.auto_reset, obs, rew, done, info); });
+  e->run4([&](const HostComm<T>& cm) {
+    for (int i = 0; i < N; i++) {
+      if (e->feat) step_lane<T, 1>(cm, e->kc, e->md, e->B, i, true, action, donef, e->cfg.auto_reset, e->stage.data(), rew, done, info);
+      else step_lane<T, 0>(cm, e->kc, e->md, e->B, i, true, action, donef, e->cfg.auto_reset, e->stage.data(), rew, done, info);
+    }
+  });
+  emit_rows<T>(e, nullptr, obs);
+}
+template <typename T>
+void set_force_t(Emu<T>* e, const T* f) {
+  for (int i = 0; i < e->B.N; i++) e->extf[i] = f ? P4<T>{f[3 * i], f[3 * i + 1], f[3 * i + 2], T(0)} : P4<T>{0, 0, 0, 0};
 }
 
 }  // namespace
@@ -130,11 +152,18 @@ int emu_set_dynamics(void* hv, const uint8_t* mask, const void* dyn) {
   if (h->prec) set_dynamics_t<double>((Emu<double>*)h->p, mask, (const double*)dyn); else set_dynamics_t<float>((Emu<float>*)h->p, mask, (const float*)dyn);
   return 0;
 }
-int emu_reset(void* hv, const uint8_t* mask, const void* w, const void* b, void* obs) {
+int emu_reset(void* hv, const uint8_t* mask, const void* w, const void* b, const void* xoff, void* obs) {
   auto* h = (Handle*)hv;
-  if (h->prec) reset_t<double>((Emu<double>*)h->p, mask, (const double*)w, (const double*)b, (double*)obs); else reset_t<float>((Emu<float>*)h->p, mask, (const float*)w, (const float*)b, (float*)obs);
+  if (h->prec) reset_t<double>((Emu<double>*)h->p, mask, (const double*)w, (const double*)b, (const double*)xoff, (double*)obs);
+  else reset_t<float>((Emu<float>*)h->p, mask, (const float*)w, (const float*)b, (const float*)xoff, (float*)obs);
   return 0;
 }
+int emu_set_force(void* hv, const void* f) {
+  auto* h = (Handle*)hv;
+  if (h->prec) set_force_t<double>((Emu<double>*)h->p, (const double*)f); else set_force_t<float>((Emu<float>*)h->p, (const float*)f);
+  return 0;
+}
+int emu_obs_dim(void* hv) { auto* h = (Handle*)hv; return h->prec ? ((Emu<double>*)h->p)->md.obs_dim : ((Emu<float>*)h->p)->md.obs_dim; }
 int emu_step(void* hv, const void* action, int donef, void* obs, void* rew, uint8_t* done, void* info) {
   auto* h = (Handle*)hv;
   if (h->prec) step_t<double>((Emu<double>*)h->p, (const double*)action, donef, (double*)obs, (double*)rew, done, (double*)info);

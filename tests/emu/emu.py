@@ -40,6 +40,12 @@ class EmuEnv:
                 cfg.hf_ny, cfg.hf_nx = hf.shape
                 cfg.hf_x0, cfg.hf_y0, cfg.hf_cell = x0, y0, cell
                 cfg.hf_host = hf.ctypes.data_as(C.POINTER(C.c_double))
+            elif k == "noise_stdev":
+                for i in range(5):
+                    cfg.noise_stdev[i] = float(v[i])
+            elif k == "base_damping":
+                for i in range(4):
+                    cfg.base_damping[i] = float(v[i])
             else:
                 setattr(cfg, k, v)
         self.cfg = cfg
@@ -55,18 +61,26 @@ class EmuEnv:
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         lib().emu_set_dynamics(self.h, None if m is None else m.ctypes.data_as(C.c_void_p), None if d is None else d.ctypes.data_as(C.c_void_p))
 
-    def reset(self, etg_w=None, etg_b=None, mask=None):
+    def obs_dim(self):
+        return int(lib().emu_obs_dim(self.h))
+
+    def set_force(self, f=None):
+        a = None if f is None else self._a(f, (self.n, 3))
+        lib().emu_set_force(self.h, None if a is None else a.ctypes.data_as(C.c_void_p))
+
+    def reset(self, etg_w=None, etg_b=None, mask=None, x_offset=None):
         w = None if etg_w is None else self._a(np.broadcast_to(np.asarray(etg_w).reshape(-1, 3, 20), (self.n, 3, 20)), (self.n, 3, 20))
         b = None if etg_b is None else self._a(np.broadcast_to(np.asarray(etg_b).reshape(-1, 3), (self.n, 3)), (self.n, 3))
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
-        obs = np.zeros((self.n, OBS_DIM), dtype=self.dtype)
+        obs = np.zeros((self.n, self.obs_dim()), dtype=self.dtype)
+        x = None if x_offset is None else self._a(x_offset, (self.n,))
         p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
-        lib().emu_reset(self.h, p(m), p(w), p(b), p(obs))
+        lib().emu_reset(self.h, p(m), p(w), p(b), p(x), p(obs))
         return obs
 
     def step(self, action, donef=False):
         a = self._a(action, (self.n, 12))
-        obs = np.zeros((self.n, OBS_DIM), dtype=self.dtype)
+        obs = np.zeros((self.n, self.obs_dim()), dtype=self.dtype)
         rew = np.zeros(self.n, dtype=self.dtype)
         done = np.zeros(self.n, dtype=np.uint8)
         info = np.zeros((self.n, INFO_DIM), dtype=self.dtype)
