@@ -23,6 +23,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ENVS_PER_GPU = 4096
+WORKLOAD = "BASELINE configs[1]: 4096 parallel A1 envs per GPU, flat terrain, fixed ETG (Opt_with_points 0.1/0.05) + uniform(-0.3,0.3) residual rollout, auto-reset on fall"
 # algorithmic HBM bytes per env-step of b2q_step_kernel<float>: every per-env array touched once
 ALG_BYTES_IN = 21 * 16 + 15 * 16 + 16 * 16 + 48 + 4 + 2 * 3 * 4 * 16      # state, params, ETG, action, counter, history reads
 ALG_BYTES_OUT = 21 * 16 + 2 * 3 * 4 * 16 + 49 * 4 + 4 + 1 + 56 * 4 + 4      # state, history writes, obs, reward, done, info, counter
@@ -112,8 +113,13 @@ def run_reference(args):
         return
     threads = host_threads()
     w, b = etg_weights()
-    n_envs = max(256, 32 * threads)                           # bounded sample of the 4096-env workload per step
+    rate1, _ = cpu_oracle_rate(64, 6, 1, w, b)
     W, K = max(args.warmup, 1), args.steps
+    budget_s = 150.0                                          # the whole --steps/--warmup run must end within a few minutes on any host
+    est = rate1 * threads * 0.7                               # env-steps/s this host should reach
+    # the SAME workload as the GPU arm (one step = 4096 envs) whenever (W + K) such steps fit the budget; only a host too slow for that
+    # falls back to a bounded sample of the env batch per step (throughput per env is the same: every thread stays saturated)
+    n_envs = ENVS_PER_GPU if (W + K) * ENVS_PER_GPU / est <= budget_s else int(max(8 * threads, budget_s * est / (W + K)))
     from oracle import oracle as O
     batch = O.OracleBatch(n_envs, etg_w=w, etg_b=b)
     rng = np.random.default_rng(1234)
@@ -126,13 +132,145 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "env-steps/sec (A1, 4096 envs)", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "A1 flat-terrain rollout, fixed ETG + uniform(-0.3,0.3) residual, auto-reset", "envs_per_step_sample": n_envs,
-                   "note": "CPU oracle (Bullet-style float64 restatement), NOT pybullet: pybullet/rlschool are absent from the image"},
-        "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": "%d envs x %d control steps per measurement, %d pthreads" % (n_envs, K, threads)},
+        "config": {"workload": WORKLOAD, "envs_per_gpu": n_envs, "substeps_per_step": 13, "solver_iters": 23,
+                   "note": "CPU oracle (Bullet-style float64 restatement), NOT pybullet: pybullet/rlschool are absent from the image; %s" % ("full 4096-env workload per step" if n_envs == ENVS_PER_GPU else "bounded sample of %d envs per step (host too slow for 4096 x %d steps in %.0f s)" % (n_envs, K, budget_s))},
+        "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port", "per_thread": val / threads, "single_thread": rate1,
+                         "sample": "%d envs x %d control steps, %d pthreads (one contiguous env slice per thread)" % (n_envs, K, threads)},
         "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def _max_over_ranks(x, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def run_extras(args, rank, world, local, dev, w, b):
+    """BASELINE configs[2..4] and the strong-scaling form of configs[1]/[4], measured in the same run on the same N ranks:
+    every number is device-timed (CUDA events, max over ranks) except the ES generation, which includes host work and is wall-clocked
+    between synchronised barriers."""
+    import torch
+    import torch.distributed as dist
+    from paddlerobotics_b200.agent import MujocoAgent, SACLearner
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    from paddlerobotics_b200.es import PopulationEvaluator, SimpleGA, solutions_to_etg_device
+    from paddlerobotics_b200.etg import ETG_layer, Opt_with_points, shipped_gait
+    from paddlerobotics_b200.terrain import make_terrain
+    out = {"n_ranks": world}
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+
+    def rollout_rate(env, n_local, K, W=20):
+        g = torch.Generator(device=dev); g.manual_seed(99 + rank)
+        pool = torch.rand(32, n_local, 12, device=dev, generator=g) * 0.6 - 0.3
+        for k in range(W):
+            env.step(pool[k % 32])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for k in range(K):
+            flush.zero_()
+            ev[k][0].record(); env.step(pool[(W + k) % 32]); ev[k][1].record()
+        torch.cuda.synchronize()
+        ms = _max_over_ranks(sum(a.elapsed_time(c) for a, c in ev), dev, world)
+        return ms / K
+
+    # (i) strong scaling of configs[1]: 4096 envs IN TOTAL, 4096/N per rank, flat terrain
+    n_local = ENVS_PER_GPU // world
+    env = VecQuadrupedalEnv(n_local, device=local, auto_reset=True); env.reset(w, b)
+    ms = rollout_rate(env, n_local, 200)
+    out["strong_scaling_flat"] = {"envs_total": ENVS_PER_GPU, "envs_per_rank": n_local, "ms_per_step": ms, "value": ENVS_PER_GPU / (ms * 1e-3), "unit": "env-steps/s",
+                                  "note": "fixed total work; the driver's speed-up is value(N)/value(1)"}
+    env.close()
+    # (iv) configs[4]: stairs height field (make_terrain('stairstair'), train.py:48-50 parameters), 4096 envs in total, strong scaling;
+    # the reference's shipped walking gait drives the robots onto the stairs, starts spread over +-0.3 m (reset(x_noise))
+    ws, bs = shipped_gait()
+    env = VecQuadrupedalEnv(n_local, device=local, auto_reset=True, heightfield=make_terrain("stairstair"), body_collisions=1, max_episode_steps=400)
+    g = torch.Generator(device=dev); g.manual_seed(5 + rank)
+    env.reset(ws, bs, x_offset=torch.rand(n_local, device=dev, generator=g) * 0.6 - 0.1)
+    for k in range(120):                                          # walk to the staircase before timing (4.7 s of simulated time)
+        env.step(torch.zeros(n_local, 12, device=dev))
+    ms = rollout_rate(env, n_local, 200)
+    st = env.get_state()
+    out["strong_scaling_stairs"] = {"envs_total": ENVS_PER_GPU, "envs_per_rank": n_local, "ms_per_step": ms, "value": ENVS_PER_GPU / (ms * 1e-3), "unit": "env-steps/s",
+                                    "terrain": "stairstair height field 0.02 m cells, step 0.08 x 0.30 m x 5 up / 5 down",
+                                    "frac_envs_past_first_step": float((st[:, 0] > 0.8).float().mean()), "mean_base_height": float(st[:, 2].mean())}
+    env.close()
+    # (ii) configs[2]: one ES generation, pop 256 x 16 rollouts x 400 steps, individuals sharded whole over the ranks, ONE all-gather
+    pop, roll, T = 256, 16, 400
+    layer = ETG_layer(0.5, 0.026, 20, 0.04, np.array([-np.pi / 2, 0]), 0.2, 0.5)
+    w0, b0, pts = Opt_with_points(ETG=layer, ETG_T=0.5, Footheight=0.1, Steplength=0.05)
+    np.random.seed(0)                                            # identical populations on every rank (SimpleGA draws from the global RNG, es.py:259-271)
+    ga = SimpleGA(12, sigma_init=0.02, sigma_decay=0.99, sigma_limit=0.005, elite_ratio=0.1, weight_decay=0.005, popsize=pop, param=np.zeros(12))
+    ev = PopulationEvaluator(pop, roll, max_steps=T, rank=rank, world=world, device=local)
+    gens, t_gen, t_gather = 3, [], []
+    for gi in range(gens + 1):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        sol = ga.ask()
+        wsd, bsd = solutions_to_etg_device(sol, pts, w0, b0, device=local)
+        fit, mlen = ev.evaluate(wsd.cpu().numpy(), bsd.cpu().numpy())
+        fit_h = fit.double().cpu().numpy()
+        ga.tell(fit_h)
+        torch.cuda.synchronize()
+        dt = _max_over_ranks(time.perf_counter() - t0, dev, world)
+        if gi > 0:
+            t_gen.append(dt)
+    if world > 1:                                                # the collective alone: [world, 2, pop/world] floats
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        buf = torch.empty(world, 2, pop // world, device=dev)
+        for _ in range(5):
+            dist.all_gather_into_tensor(buf, ev._fl.reshape(1, 2, -1))
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(50):
+            dist.all_gather_into_tensor(buf, ev._fl.reshape(1, 2, -1))
+        e1.record(); torch.cuda.synchronize()
+        t_gather = _max_over_ranks(e0.elapsed_time(e1) / 50 * 1e3, dev, world)
+    chk = torch.tensor(fit_h, device=dev)
+    same = True
+    if world > 1:
+        ref = chk.clone(); dist.broadcast(ref, 0); same = bool(torch.equal(ref, chk))
+    out["es_generation"] = {"popsize": pop, "rollouts": roll, "steps": T, "envs_per_rank": pop * roll // world, "s_per_generation": float(np.mean(t_gen)),
+                            "generations_per_s": 1.0 / float(np.mean(t_gen)), "env_steps_per_s": pop * roll * T / float(np.mean(t_gen)),
+                            "allgather_us": t_gather if world > 1 else None, "allgather_bytes": 2 * pop * 4, "fitness_identical_on_every_rank": same,
+                            "includes": "SimpleGA.ask, on-device Opt_with_points for 256 individuals, reset, 400 control steps + per-step return accumulation, fitness kernel, ONE all-gather of [fitness|length], tell"}
+    ev.env.close()
+    # (iii) configs[3]: SAC learn, global batch 8192 = 8192/N per rank, ONE flat gradient bucket all-reduced (NCCL) between gradient and Adam phases
+    B = 8192 // world
+    ag = MujocoAgent(49, 12, device=local, seed=3)
+    L = SACLearner(ag, B, world=world, sync="flat")
+    d = lambda *sh: torch.randn(*sh, device=dev)
+    o, no, ac, r, t = d(B, 49), d(B, 49), torch.rand(B, 12, device=dev) * 2 - 1, d(B), torch.ones(B, device=dev)
+    e1_, e2_ = d(B, 12), d(B, 12)
+    for _ in range(5):
+        L.learn(o, ac, r, no, t, eps_next=e1_, eps_cur=e2_, pull=False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    it = 30
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(it)]
+    ar = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(it)]
+    for k in range(it):
+        L.allreduce_events = ar[k] if world > 1 else None
+        evs[k][0].record(); L.learn(o, ac, r, no, t, eps_next=e1_, eps_cur=e2_, pull=False); evs[k][1].record()
+    torch.cuda.synchronize()
+    learn_us = _max_over_ranks(sum(a.elapsed_time(c) for a, c in evs) / it * 1e3, dev, world)
+    ar_us = _max_over_ranks(sum(a.elapsed_time(c) for a, c in ar) / it * 1e3, dev, world) if world > 1 else None
+    out["sac_learn"] = {"global_batch": 8192, "batch_per_rank": B, "us_per_learn": learn_us, "allreduce_us": ar_us, "allreduce_floats": L.na + L.nc,
+                        "samples_per_s": 8192 / (learn_us * 1e-6), "sync": "flat: critic + actor gradients against the pre-update parameters, ONE ncclAllReduce(avg) of [actor|critic], then both Adam steps + Polyak",
+                        "launches_per_learn": None}
+    l0 = int(L.lib.b2q_sac_launch_count(L.h)); L.learn(o, ac, r, no, t, eps_next=e1_, eps_cur=e2_, pull=False)
+    out["sac_learn"]["launches_per_learn"] = int(L.lib.b2q_sac_launch_count(L.h)) - l0
+    L.close()
+    return out
 
 
 def main():
@@ -143,6 +281,7 @@ def main():
     ap.add_argument("--impl", type=str, default="b2q")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE configs[2..4] / strong-scaling block")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -195,14 +334,14 @@ def main():
     # end to end through the host-facing API: pinned H2D of the actions + step + D2H of obs/reward/done every step
     host_acts = np.random.default_rng(1234 + rank).uniform(-0.3, 0.3, (16, n, 12)).astype(np.float32)
     for k in range(5):
-        env.step_host(host_acts[k % 16])
+        env.step_host(host_acts[k % 16], info=True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     Ke = min(K, 200)
     t0 = time.perf_counter()
     for k in range(Ke):
-        env.step_host(host_acts[k % 16])
+        env.step_host(host_acts[k % 16], info=True)             # obs, reward, done AND the info rows train.py:150-157 reads every step
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -210,6 +349,13 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * n * Ke / float(te[0])
     clocks = sampler.stop() if rank == 0 else None
+    env.close()
+    extras = None
+    if not args.no_extras:
+        try:
+            extras = run_extras(args, rank, world, local, dev, w, b)
+        except Exception as ex:                                    # the headline line must survive a failing secondary measurement
+            extras = {"error": repr(ex)}
 
     if rank == 0:
         peaks = {}
@@ -229,40 +375,42 @@ def main():
         # ncu count of the committed capture (profiles/step_kernel_r01e_ncu_full.csv); duration and SM clock are this run's.
         issue = None
         try:
-            prof = dict(l.split(",")[0::2] for l in open(os.path.join(ROOT, "profiles", "step_kernel_r01e_ncu_full.csv")).read().splitlines()[2:] if l.count(",") == 2)
+            cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("step_kernel_r0") and f.endswith("_ncu_full.csv"))
+            prof_name = cands[-1]
+            prof = dict(l.split(",")[0::2] for l in open(os.path.join(ROOT, "profiles", prof_name)).read().splitlines()[2:] if l.count(",") == 2)
             inst = float(prof["smsp__inst_executed.sum"]) * n / 4096.0
             mhz = (clocks or {}).get("sm_mhz") or 1965.0
             slots = ms_per_step * 1e-3 * mhz * 1e6 * 148 * 4
             issue = {"warp_instructions_per_launch": inst, "issue_slot_frac": inst / slots, "fma_pipe_pct_ncu": float(prof["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]),
-                     "warps_per_sm_ncu": float(prof["sm__warps_active.avg.per_cycle_active"]), "source": "profiles/step_kernel_r01e_ncu_full.csv"}
+                     "warps_per_sm_ncu": float(prof["sm__warps_active.avg.per_cycle_active"]), "source": "profiles/" + prof_name}
         except Exception:
             pass
         cpu = None
         if not args.no_cpu_baseline:
             threads = host_threads()
             rate1, _ = cpu_oracle_rate(64, 8, 1, w, b)
-            n_c = max(512, 32 * threads)
-            steps_c = int(min(400, max(4, 12.0 * rate1 * threads / n_c)))                # ~12 s of CPU work at the ideal multi-thread rate
+            n_c = n                                                                        # the full 4096-env workload (same config as the GPU arm)
+            steps_c = int(min(400, max(3, 12.0 * rate1 * threads / n_c)))                # ~12 s of CPU work at the ideal multi-thread rate
             rate, secs = cpu_oracle_rate(n_c, steps_c, threads, w, b)
-            cpu = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
+            cpu = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port", "per_thread": rate / threads, "single_thread": rate1,
                    "sample": "%d envs x %d control steps (%.1f s), float64 C oracle on %d pthreads; single-thread rate %.0f env-steps/s; NOT pybullet (absent)" % (n_c, steps_c, secs, threads, rate1)}
         line = {
             "metric": "env-steps/sec (A1, 4096 envs)", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: 4096 parallel A1 envs per GPU, flat terrain, fixed ETG (Opt_with_points 0.1/0.05) + uniform(-0.3,0.3) residual rollout, auto-reset on fall",
+            "config": {"workload": WORKLOAD,
                        "envs_per_gpu": n, "substeps_per_step": 13, "solver_iters": 23, "l2": "flushed between timed steps (256 MiB write outside the event pair)",
                        "timing": "per-step CUDA event pairs on the launching stream, max over ranks", "done_frac_last_step": done_frac},
-            "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": env.h2d_bytes_per_step(), "d2h_bytes_per_step": env.d2h_bytes_per_step(), "steps": Ke,
-                    "transport": "numpy action -> pinned buffer -> step kernel reads it over PCIe and stores obs|reward|done to pinned host memory (b2q_step_host, B2Q_HOST_IO=2), stream sync every step"},
+            "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": env.h2d_bytes_per_step(), "d2h_bytes_per_step": env.d2h_bytes_per_step(info=True), "steps": Ke,
+                    "transport": "numpy action -> pinned buffer -> step kernel reads it over PCIe and stores obs|reward|done to pinned host memory (b2q_step_host, B2Q_HOST_IO=2); info rows [N,56] staged on the device + one D2H; stream sync every step"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "b2q_step_kernel<float>", "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP, "issue": issue,
                          "note": "latency/FP32-issue bound by construction (13 substeps x 23 PGS sweeps per launch on ~2.4 KB of state): HBM fraction is structurally tiny, see DESIGN.md §5"},
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "extras": extras,
         }
         print(json.dumps(line))
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -43,7 +43,10 @@ int b2q_sac_bc_learn(B2QSacHandle h, const float* obs, const float* ref_obs, int
 /* the learner's own forward objects (0 actor, 1 twin critic, 2 target critic): always up to date with the parameters, so a
  * rollout can sample from the policy being trained without copying weights.  Owned by the learner. */
 B2QMlpHandle b2q_sac_mlp(B2QSacHandle h, int which);
-float* b2q_sac_grad_ptr(B2QSacHandle h, int which);   /* device gradient bucket (for ncclAllReduce in place) */
+/* device gradient buckets for an in-place ncclAllReduce: which = 0 actor, 1 twin critic, 2 the ONE flat bucket [actor | critic]
+ * (b2q_sac_param_count(h,0) + b2q_sac_param_count(h,1) floats).  With the flat bucket a data-parallel step is
+ * phase 0, phase 2, all-reduce, phase 1, phase 3 (both gradients against the pre-update parameters, one collective). */
+float* b2q_sac_grad_ptr(B2QSacHandle h, int which);
 float* b2q_sac_loss_ptr(B2QSacHandle h);
 int64_t b2q_sac_launch_count(B2QSacHandle h);
 #ifdef __cplusplus

@@ -710,7 +710,8 @@ void orc_env_settle(const OrcConfig* c, OrcEnv* e) {
   memset(e->lam_warm, 0, sizeof e->lam_warm); memset(e->last_tau, 0, sizeof e->last_tau);
   e->hist_len = 0; e->hist_head = 0; e->has_last = 0; e->step_count = 0;
   double ob[ORC_HIST_W]; true_obs(e, ob); hist_push(e, ob);
-  for (int i = 0; i < c->settle_steps; i++) orc_substep(c, e, POSE_ORI);
+  OrcConfig cs = *c; cs.motor_mode = 0; /* the reset pose is held by the POSITION controller (a1.py:289-304) whatever the policy's motor mode */
+  for (int i = 0; i < c->settle_steps; i++) orc_substep(&cs, e, POSE_ORI);
   memcpy(e->snap, e->pos, 3 * sizeof(double)); memcpy(e->snap + 3, e->quat, 4 * sizeof(double));
   memcpy(e->snap + 7, e->vlin, 3 * sizeof(double)); memcpy(e->snap + 10, e->vang, 3 * sizeof(double));
   memcpy(e->snap + 13, e->q, 12 * sizeof(double)); memcpy(e->snap + 25, e->qd, 12 * sizeof(double));

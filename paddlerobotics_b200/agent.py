@@ -118,6 +118,8 @@ class MujocoAgent:
                 raise ValueError("shape mismatch for %s: %s vs %s" % (k, tuple(sd[k].shape), tuple(self.params[k].shape)))
             self.params[k] = sd[k].to(self.device, torch.float32).contiguous()
         self.sync_weights()
+        for L in getattr(self, "_learners", {}).values():      # learners hold their own device copy of the parameters: refresh it, or the
+            L.push()                                            # next learn() would overwrite the restored weights with the stale copy
 
     def save(self, path):
         torch.save(self.state_dict(), path)
@@ -212,9 +214,13 @@ class SACLearner:
     """SAC.learn on the device (csrc/b2q_sac.cu): same hyper-parameters and update order as ETGRL/alg/sac.py:30-118.
     `world`>1: data-parallel learner, gradient buckets all-reduced (NCCL) between the gradient and optimiser phases."""
 
-    def __init__(self, agent, batch, gamma=0.99, tau=0.005, alpha=0.2, actor_lr=3e-4, critic_lr=3e-4, world=1):
+    def __init__(self, agent, batch, gamma=0.99, tau=0.005, alpha=0.2, actor_lr=3e-4, critic_lr=3e-4, world=1, sync="exact"):
+        """sync (world > 1): "exact" = the reference's update order (critic step, then the actor gradient against the UPDATED critic,
+        sac.py:77-118) which needs two all-reduces; "flat" = both gradients against the pre-update parameters and ONE all-reduce of the
+        single flat bucket [actor | critic].  sync="flat" with world == 1 runs the same phase order on one GPU."""
         self.lib = _lib.load()
-        self.agent, self.batch, self.world = agent, batch, world
+        self.agent, self.batch, self.world, self.sync = agent, batch, world, sync
+        self.allreduce_events = None
         self.h = C.c_void_p()
         rc = self.lib.b2q_sac_create(agent.device.index or 0, agent.obs_dim, agent.act_dim, batch, gamma, tau, alpha, actor_lr, critic_lr, C.byref(self.h))
         if rc != 0:
@@ -282,6 +288,24 @@ class SACLearner:
             for x, sx in zip(ins, self._static):
                 sx.copy_(x)
             self._graph.replay()
+        elif self.sync == "flat":
+            import torch.distributed as dist
+            for ph in (0, 2):
+                rc = self.lib.b2q_sac_phase(self.h, ph, *args, self._stream())
+                if rc != 0:
+                    raise RuntimeError("b2q_sac_phase %d: %d" % (ph, rc))
+            if self.world > 1:
+                g = self._grad_view(2, self.na + self.nc)
+                if self.allreduce_events is not None:
+                    self.allreduce_events[0].record()
+                dist.all_reduce(g, op=dist.ReduceOp.AVG)          # ONE collective: 248 602 floats at obs 49 (NCCL averages in the reduction)
+                if self.allreduce_events is not None:
+                    self.allreduce_events[1].record()
+            for ph in (1, 3):
+                rc = self.lib.b2q_sac_phase(self.h, ph, *args, self._stream())
+                if rc != 0:
+                    raise RuntimeError("b2q_sac_phase %d: %d" % (ph, rc))
+            self.losses.copy_(torch.as_tensor(_CudaBuf(self.lib.b2q_sac_loss_ptr(self.h), 2), device=dev))
         elif self.world == 1:
             rc = self.lib.b2q_sac_learn(self.h, *args, self.losses.data_ptr(), self._stream())
             if rc != 0:
@@ -294,8 +318,7 @@ class SACLearner:
                     raise RuntimeError("b2q_sac_phase %d: %d" % (ph, rc))
                 if ph in (0, 2):   # one flat bucket per optimiser: all-reduce(mean) then the fused Adam kernel consumes it
                     g = self._grad_view(0 if ph == 2 else 1, self.na if ph == 2 else self.nc)
-                    dist.all_reduce(g, op=dist.ReduceOp.SUM)
-                    g.mul_(1.0 / self.world)
+                    dist.all_reduce(g, op=dist.ReduceOp.AVG)
             self.losses.copy_(torch.as_tensor(_CudaBuf(self.lib.b2q_sac_loss_ptr(self.h), 2), device=dev))
         if pull:
             self.pull()
@@ -328,12 +351,25 @@ class _CudaBuf:
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
 
 
+def _get_learner(self, n, actor_lr=3e-4, critic_lr=3e-4):
+    """One SACLearner per (batch, learning rates), shared by learn() and BClearn(); agent.params is the single source of truth — a
+    learner that was not the last one used re-reads it before stepping, so mixing learn / BClearn / restore never forks the weights."""
+    if not hasattr(self, "_learners"):
+        self._learners, self._active = {}, None
+    key = (int(n), float(actor_lr), float(critic_lr))
+    L = self._learners.get(key)
+    if L is None:
+        L = self._learners[key] = SACLearner(self, n, actor_lr=actor_lr, critic_lr=critic_lr)      # pushes agent.params
+    elif self._active is not L:
+        L.push()
+    self._active = L
+    return L
+
+
 def _agent_learn(self, obs, action, reward, next_obs, terminal):
     """MujocoAgent.learn(obs, act, reward, next_obs, terminal) -> (critic_loss, actor_loss), mujoco_agent.py:43-54."""
     n = np.asarray(obs).shape[0] if not isinstance(obs, torch.Tensor) else obs.shape[0]
-    if getattr(self, "_learner", None) is None or self._learner.batch != n:
-        self._learner = SACLearner(self, n)
-    l = self._learner.learn(obs, action, reward, next_obs, terminal)
+    l = _get_learner(self, n).learn(obs, action, reward, next_obs, terminal)
     return float(l[0]), float(l[1])
 
 
@@ -341,10 +377,7 @@ MujocoAgent.learn = _agent_learn
 
 
 def _agent_bclearn(self, obs, ref_obs, ref_agent, actor_lr=3e-4, critic_lr=3e-4):
-    n = obs.shape[0]
-    if getattr(self, "_bc_learner", None) is None or self._bc_learner.batch != n:
-        self._bc_learner = SACLearner(self, n, actor_lr=actor_lr, critic_lr=critic_lr)
-    l = self._bc_learner.bc_learn(obs, ref_obs, ref_agent)
+    l = _get_learner(self, obs.shape[0], actor_lr, critic_lr).bc_learn(obs, ref_obs, ref_agent)
     return float(l[0]), float(l[1])
 
 

@@ -303,6 +303,7 @@ int b2q_mlp_forward_ex(B2QMlpHandle h, const float* in1, int in1_dim, const floa
                        float* logp, float* raw, const B2QMlpSaves* saves, void* stream) {
   if (!h || !in1 || !out || M < 1 || in1_dim < 1 || in1_dim > h->in_dim || (in1_dim < h->in_dim && !in2) || mode < 0 || mode > 2 ||
       (mode != B2Q_MLP_RAW && (h->out_dim & 1))) { if (h) h->err = "b2q_mlp_forward: bad argument"; return -1; }
+  { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) cudaSetDevice(h->device); }   // handles are per GPU
   FwdArgs a{in1, in2, in1_dim, h->in_dim, h->out_dim, M, mode, seed, eps, out, logp, raw, h->img, IMG_BYTES, B2QMlpSaves{}, 0};
   if (saves) { a.sv = *saves; a.save = 1; }
   dim3 grid((M + TILE_M - 1) / TILE_M, h->nets);

@@ -493,8 +493,10 @@ int b2q_sac_create(int device, int obs_dim, int act_dim, int batch, float gamma,
   s->device = device; s->D = obs_dim; s->A = act_dim; s->B = batch; s->gamma = gamma; s->tau = tau; s->alpha = alpha; s->lr_a = actor_lr; s->lr_c = critic_lr;
   s->an.layout(obs_dim, 2 * act_dim); s->cn.layout(obs_dim + act_dim, 1);
   const size_t Bz = batch;
-  bool ok = dalloc(s, &s->p_actor, s->an.n) && dalloc(s, &s->g_actor, s->an.n) && dalloc(s, &s->m_a, s->an.n) && dalloc(s, &s->v_a, s->an.n) &&
-            dalloc(s, &s->p_critic, 2 * s->cn.n) && dalloc(s, &s->p_target, 2 * s->cn.n) && dalloc(s, &s->g_critic, 2 * s->cn.n) && dalloc(s, &s->m_c, 2 * s->cn.n) && dalloc(s, &s->v_c, 2 * s->cn.n);
+  // ONE flat gradient bucket [actor | critic 1 | critic 2] (SURVEY §8e collective 2: a single ncclAllReduce over 248 602 floats at obs 49)
+  bool ok = dalloc(s, &s->p_actor, s->an.n) && dalloc(s, &s->g_actor, s->an.n + 2 * s->cn.n) && dalloc(s, &s->m_a, s->an.n) && dalloc(s, &s->v_a, s->an.n) &&
+            dalloc(s, &s->p_critic, 2 * s->cn.n) && dalloc(s, &s->p_target, 2 * s->cn.n) && dalloc(s, &s->m_c, 2 * s->cn.n) && dalloc(s, &s->v_c, 2 * s->cn.n);
+  if (ok) s->g_critic = s->g_actor + s->an.n;
   for (int i = 0; i < 3 && ok; i++) ok = dalloc(s, &s->W2T[i], (size_t)H * H) && dalloc(s, &s->W3T[i], (size_t)H * 64) && dalloc(s, &s->W1A[i], (size_t)16 * H);
   ok = ok && dalloc(s, &s->xc_rm, Bz * 64) && dalloc(s, &s->xc_t, 64 * Bz) && dalloc(s, &s->hc1_rm, 2 * Bz * H) && dalloc(s, &s->hc1_t, 2 * Bz * H) && dalloc(s, &s->hc2_rm, 2 * Bz * H) &&
        dalloc(s, &s->hc2_t, 2 * Bz * H) && dalloc(s, &s->xa_rm, Bz * 64) && dalloc(s, &s->xa_t, 64 * Bz) && dalloc(s, &s->ha1_rm, Bz * H) && dalloc(s, &s->ha1_t, Bz * H) &&
@@ -566,6 +568,9 @@ int b2q_sac_get_grads(B2QSacHandle s, float* actor, float* critic, void* stream)
 int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act, const float* rew, const float* next_obs, const float* term,
                   const float* eps_next, const float* eps_cur, uint64_t seed, void* stream) {
   if (!s) return -1;
+  if (phase < 0 || phase > 3) return -1;
+  if (phase == 2 && (!obs || !eps_cur)) return -1;   // the explicit-noise path is required for the actor's backward pass: refuse before launching anything
+  cudaSetDevice(s->device);                          // handles are per GPU
   cudaStream_t st = (cudaStream_t)stream;
   const int B = s->B, A = s->A, D = s->D;
   const Net& an = s->an; const Net& cn = s->cn;
@@ -682,7 +687,7 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   return 0;
 }
 B2QMlpHandle b2q_sac_mlp(B2QSacHandle s, int which) { return !s ? nullptr : (which == 0 ? s->mlp_actor : (which == 1 ? s->mlp_critic : s->mlp_target)); }
-float* b2q_sac_grad_ptr(B2QSacHandle s, int which) { return !s ? nullptr : (which == 0 ? s->g_actor : s->g_critic); }
+float* b2q_sac_grad_ptr(B2QSacHandle s, int which) { return !s ? nullptr : (which == 1 ? s->g_critic : s->g_actor); }   // which == 2: the flat bucket (starts at the actor part)
 float* b2q_sac_loss_ptr(B2QSacHandle s) { return s ? s->losses : nullptr; }
 
 

@@ -165,8 +165,8 @@ class PopulationEvaluator:
         self.alive = torch.ones(self.n, dtype=torch.uint8, device=dev)
         self.ret = torch.zeros(self.n, dtype=dt, device=dev)
         self.len = torch.zeros(self.n, dtype=torch.int32, device=dev)
-        self.fitness = torch.zeros(self.pop_local, dtype=dt, device=dev)
-        self.mean_len = torch.zeros(self.pop_local, dtype=dt, device=dev)
+        self._fl = torch.zeros(2, self.pop_local, dtype=dt, device=dev)      # [fitness | mean length] packed: ONE all-gather per generation
+        self.fitness, self.mean_len = self._fl[0], self._fl[1]
         self.policy, self.act_bound = policy, act_bound
         self.zero_act = torch.zeros(self.n, 12, dtype=dt, device=dev)
         self.es_launches = 0
@@ -198,9 +198,10 @@ class PopulationEvaluator:
                                      self.pop_local, self.rollouts, es, stream)
         assert rc == 0
         self.es_launches += 1
-        fit = all_gather_concat(self.fitness, self.world, self.rank)
-        ml = all_gather_concat(self.mean_len, self.world, self.rank)
-        return fit, ml
+        if self.world == 1:
+            return self.fitness, self.mean_len
+        g = all_gather_concat(self._fl.reshape(1, 2, self.pop_local), self.world, self.rank)     # [world, 2, pop_local], one collective
+        return g[:, 0, :].reshape(-1), g[:, 1, :].reshape(-1)
 
 
 class DynamicsEvaluator:

@@ -61,6 +61,41 @@ def foot_position_in_hip_frame_to_joint_angle(foot_position, l_hip_sign=1):
     return np.array([np.arctan2(s1, c1), th, tk])
 
 
+def foot_position_in_hip_frame(angles, l_hip_sign=1):
+    """Closed-form A1 leg FK, same formula as a1.py:113-129 (host copy used to turn a gait table back into ETG weights)."""
+    ab, hip, knee = angles
+    l_up, l_low, l_hip = 0.2, 0.2, 0.08505 * l_hip_sign
+    ld = np.sqrt(l_up ** 2 + l_low ** 2 + 2 * l_up * l_low * np.cos(knee))
+    eff = hip + knee / 2
+    ox, oz = -ld * np.sin(eff), -ld * np.cos(eff)
+    return np.array([ox, np.cos(ab) * l_hip - np.sin(ab) * oz, np.sin(ab) * l_hip + np.cos(ab) * oz])
+
+
+def fit_etg_from_table(table, t0=0.026, T=0.5, dt=0.026, H=20, sigma_sq=0.04, amp=0.2, phase=(-np.pi / 2, 0.0)):
+    """Recover (w [3,20], b [3]) from an info['ETG_act'] table (e.g. the reference's gait_action_list_ETG_exp.npy, whose sample k is
+    t = 0.026 (k + 1); deployment tables start at t0 = 0): joint offsets -> feet through the FK -> least squares on the RBF features."""
+    layer = ETG_layer(T, dt, H, sigma_sq, np.asarray(phase), amp, T)
+    table = np.asarray(table, dtype=np.float64)
+    A, Y = [], []
+    for k in range(table.shape[0]):
+        q = table[k] + POSE_ORI
+        for leg in (0, 1):
+            foot = foot_position_in_hip_frame(q[3 * leg:3 * leg + 3], (-1) ** (leg + 1)) + HIP_OFFSETS[leg]
+            tt = t0 + dt * k + (0.0 if leg == 0 else 0.5 * T)
+            A.append(np.concatenate([layer.update(tt), [1.0]]))
+            Y.append(foot - BASE_FOOT[leg])
+    sol = np.linalg.lstsq(np.array(A), np.array(Y), rcond=None)[0]
+    return np.ascontiguousarray(sol[:H].T), np.ascontiguousarray(sol[H])
+
+
+def shipped_gait():
+    """(w, b) of the walking gait the reference ships as ETGRL/gait_action_list_ETG_exp.npy (fitted once by scripts/make_shipped_gait.py
+    into data/etg_shipped_gait.npz): ~0.48 m/s open loop on flat ground."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "etg_shipped_gait.npz"))
+    return z["w"], z["b"]
+
+
 class ETG_model:
     """forward(): foot-space deltas per leg (FR,RL in phase; FL,RR half a period later); act_clip(): IK to joint
     offsets relative to POSE_ORI with the shrink-until-finite loop."""

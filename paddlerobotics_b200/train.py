@@ -7,6 +7,7 @@ Everything per-step stays on the device: obs -> fused MLP (tcgen05) -> step kern
 """
 import argparse
 import json
+import os
 import time
 
 import numpy as np
@@ -17,6 +18,7 @@ from .env import VecQuadrupedalEnv
 from .es import PopulationEvaluator, SimpleGA, solutions_to_etg_device
 from .etg import ETG_layer, Opt_with_points
 from .replay import ReplayMemory
+from .terrain import make_terrain
 
 GAMMA, TAU, ALPHA, ACTOR_LR, CRITIC_LR = 0.99, 0.005, 0.2, 3e-4, 3e-4     # train.py:43-47
 
@@ -45,21 +47,41 @@ def main(argv=None):
     p.add_argument("--overlap", type=int, default=1, help="run the SAC update on a second stream beside the env step")
     p.add_argument("--torso", type=float, default=1.5); p.add_argument("--feet", type=float, default=0.3); p.add_argument("--up", type=float, default=0.6)
     p.add_argument("--tau", type=float, default=0.07); p.add_argument("--badfoot", type=float, default=0.1); p.add_argument("--footcontact", type=float, default=0.1)
+    p.add_argument("--task_mode", type=str, default="stairstair")      # train.py:462
+    p.add_argument("--step_y", type=float, default=0.05)               # train.py:463
+    p.add_argument("--outdir", type=str, default="", help="where itr_<steps>.pt / .npz are written (train.py:386-390); empty = no checkpoints")
+    p.add_argument("--suffix", type=str, default="exp0")
+    p.add_argument("--eval_every_steps", type=int, default=0, help="checkpoint cadence in env steps; 0 = EVAL_EVERY_STEPS (1e4) per env")
+    p.add_argument("--load", type=str, default="", help="itr_*.pt to restore the agent from (and the .npz next to it for w, b, param)")
     args = p.parse_args(argv)
     torch.manual_seed(args.seed); np.random.seed(args.seed)
     n = args.num_envs
     layer = ETG_layer(args.ETG_T, 0.026, 20, 0.04, np.array([-np.pi / 2, 0]), 0.2, args.ETG_T)
     w0, b0, prior_points = Opt_with_points(ETG=layer, ETG_T=args.ETG_T, Footheight=args.footheight, Steplength=args.steplen)     # train.py:298-299
     w, b = w0, b0
-    env = VecQuadrupedalEnv(n, auto_reset=True, max_episode_steps=args.e_step, w_torso=args.torso, w_feet=args.feet, w_up=args.up, w_tau=args.tau,
-                            w_badfoot=args.badfoot, w_footcontact=args.footcontact)
+    # the reward weights of the command line (train.py:255-261) go to BOTH the training env and the ES evaluator: ES must optimise the
+    # reward SAC is trained on
+    env_cfg = dict(w_torso=args.torso, w_feet=args.feet, w_up=args.up, w_tau=args.tau, w_badfoot=args.badfoot, w_footcontact=args.footcontact,
+                   heightfield=make_terrain(args.task_mode, step_y=args.step_y), stuck_termination=1, body_collisions=1,
+                   etg_foot_y_inset=args.step_y if args.task_mode == "balancebeam" else 0.0)
+    env = VecQuadrupedalEnv(n, auto_reset=True, max_episode_steps=args.e_step, **env_cfg)
     agent = MujocoAgent(49, 12, seed=args.seed)
+    ETG_best_param = np.zeros(12)                                                                                                 # ES_solver.get_best_param(), train.py:348
+    if args.load:
+        agent.restore(args.load)
+        z = np.load(args.load[:-3] + ".npz")                                                                                      # train.py:439-441
+        w, b, ETG_best_param = z["w"], z["b"], z["param"].reshape(-1)
+    outdir = os.path.join(args.outdir, args.suffix) if args.outdir else ""
+    if outdir:
+        os.makedirs(outdir, exist_ok=True)
+    ckpt_every = args.eval_every_steps or int(1e4) * n
+    next_ckpt = ckpt_every
     learner = SACLearner(agent, args.batch, gamma=GAMMA, tau=TAU, alpha=ALPHA, actor_lr=ACTOR_LR, critic_lr=CRITIC_LR)
     rpm = ReplayMemory(args.memory, 49, 12)
     solver = SimpleGA(12, sigma_init=args.sigma, sigma_decay=args.sigma_decay, sigma_limit=0.005, elite_ratio=0.1, weight_decay=0.005,
-                      popsize=args.popsize, param=np.zeros(12))                                                                  # train.py:288-295
+                      popsize=args.popsize, param=ETG_best_param.copy())                                                          # train.py:288-295
     evaluator = PopulationEvaluator(args.popsize, args.es_rollouts, max_steps=args.e_step, policy=lambda o: learner.actor.forward(o)[0][0],
-                                    act_bound=args.act_bound) if args.ES else None
+                                    act_bound=args.act_bound, **env_cfg) if args.ES else None
     obs = env.reset(w, b).clone()
     total, it, last_es, t0 = 0, 0, 0, time.perf_counter()
     s_learn = torch.cuda.Stream(device=env.device)
@@ -102,21 +124,32 @@ def main(argv=None):
                    "episode_return": ep_rets[-1] if ep_rets else None,
                    "critic_loss": float(losses[0]) if rpm.size() >= args.warmup_steps else None, "actor_loss": float(losses[1]) if rpm.size() >= args.warmup_steps else None}
             log.append(rec); print(json.dumps(rec), flush=True)
+        if outdir and total >= next_ckpt:                                               # agent.save + np.savez(w, b, param), train.py:386-390
+            next_ckpt += ckpt_every
+            learner.pull()
+            agent.save(os.path.join(outdir, "itr_%d.pt" % total))
+            np.savez(os.path.join(outdir, "itr_%d.npz" % total), w=w, b=b, param=ETG_best_param)
         if evaluator is not None and total - last_es >= args.es_every_steps and rpm.size() >= args.warmup_steps:
             last_es = total
-            best_fit, best_param = -1e9, None
+            # the incumbent ETG seeds best_reward (train.py:395-396): a sampled individual replaces it only if it is actually better
+            inc_fit, _ = evaluator.evaluate(np.repeat(np.asarray(w)[None], args.popsize, 0), np.repeat(np.asarray(b)[None], args.popsize, 0))
+            inc = inc_fit.double().cpu().numpy()
+            best_fit = float(np.nanmean(inc)) if np.isfinite(inc).any() else -np.inf
+            best_param = ETG_best_param.copy()
             for gen in range(args.es_train_steps):                                     # train.py:397-418
                 sol = solver.ask()
                 ws, bs = solutions_to_etg_device(sol, prior_points, w0, b0, ETG_T=args.ETG_T)
                 fit, mlen = evaluator.evaluate(ws.cpu().numpy(), bs.cpu().numpy())
                 fit_np = fit.double().cpu().numpy()
+                fit_np = np.where(np.isfinite(fit_np), fit_np, -1e9)                    # a diverged rollout must lose, not poison tell()
                 solver.tell(fit_np)
                 if fit_np.max() > best_fit:
-                    best_fit, best_param = float(fit_np.max()), sol[int(fit_np.argmax())]
+                    best_fit, best_param = float(fit_np.max()), np.asarray(sol[int(fit_np.argmax())]).copy()
                 print(json.dumps({"ES_gen": gen, "fitness_max": float(fit_np.max()), "fitness_mean": float(fit_np.mean()), "mean_len": float(mlen.mean())}), flush=True)
-            pts = prior_points + best_param.reshape(-1, 2)                              # train.py:433-437
+            ETG_best_param = best_param
+            pts = prior_points + ETG_best_param.reshape(-1, 2)                          # train.py:433-437
             w, b, _ = Opt_with_points(ETG=layer, ETG_T=args.ETG_T, w0=w0, b0=b0, points=pts)
-            solver.reset(best_param)
+            solver.reset(ETG_best_param)
             obs = env.reset(w, b).clone(); ret_acc.zero_()
     torch.cuda.synchronize()
     learner.pull()

@@ -33,3 +33,28 @@ def etg_stable():
     layer = ETG_layer(0.5, 0.026, 20, 0.04, np.array([-np.pi / 2, 0]), 0.2, 0.5)
     w, b, _ = Opt_with_points(ETG=layer, ETG_T=0.5, Footheight=0.03, Steplength=0.02)
     return w, b
+
+
+def fit_etg_from_table(table, t0):
+    """W,b of the ETG whose info['ETG_act'] table this is (least squares through the pinned FK; sample k is t0 + 0.026 k)."""
+    from oracle import oracle as O
+    from paddlerobotics_b200 import etg as E
+    cfg = O.default_config()
+    ts = t0 + 0.026 * np.arange(table.shape[0])
+    pose = np.array([0, .9, -1.8] * 4)
+    A, Y = [], []
+    for k in range(table.shape[0]):
+        q = table[k] + pose
+        for leg in (0, 1):
+            foot = O.fk_leg(q[3 * leg:3 * leg + 3], (-1) ** (leg + 1)) + E.HIP_OFFSETS[leg]
+            A.append(np.concatenate([O.etg_features(cfg, ts[k] if leg == 0 else ts[k] + 0.25), [1.0]]))
+            Y.append(foot - E.BASE_FOOT[leg])
+    sol = np.linalg.lstsq(np.array(A), np.array(Y), rcond=None)[0]
+    return np.ascontiguousarray(sol[:20].T), np.ascontiguousarray(sol[20])
+
+
+@pytest.fixture(scope="session")
+def etg_shipped():
+    """The gait the reference itself ships (ETGRL/gait_action_list_ETG_exp.npy, 600 samples of info['ETG_act'], sample k = t 0.026(k+1)),
+    fitted back to W,b: it walks forward at ~0.48 m/s open loop in the oracle — the long-horizon parity workload."""
+    return fit_etg_from_table(np.load(os.path.join(GOLDEN, "gait_action_list_ETG_exp.npy")), 0.026)

@@ -1,0 +1,156 @@
+"""Round-2 env features (sensor_mode layouts, sensor noise, stuck termination, non-toe collision count, TORQUE mode, base push /
+damping, x-offset reset, terrain presets): the DEVICE code in CPU emulation (tests/emu) against the float64 oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import emu  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+_OKEYS = {f[0] for f in O.Config._fields_}
+
+
+def _pair(w, b, x_offset=None, heightfield=None, **kw):
+    ocfg = O.default_config(**{k: v for k, v in kw.items() if k in _OKEYS})
+    if heightfield is not None:
+        O.set_heightfield(ocfg, *heightfield)
+        kw = dict(kw, heightfield=heightfield)
+    e = emu.EmuEnv(1, 1, **kw)
+    o = O.OracleEnv(ocfg)
+    oe = e.reset(w, b, x_offset=None if x_offset is None else [x_offset])
+    oo = o.reset(w, b, x_offset=0.0 if x_offset is None else x_offset)
+    assert oe.shape[1] == oo.shape[0] and np.abs(oe[0] - oo).max() < 1e-9
+    return e, o
+
+
+def _run(e, o, acts, tol=1e-8):
+    outs = []
+    for k, a in enumerate(acts):
+        ob, rw, dn, inf = o.step(a); ob2, rw2, dn2, inf2 = e.step(a)
+        assert ob2.shape[1] == ob.shape[0]
+        assert np.abs(ob2[0] - ob).max() < tol and abs(rw2[0] - rw) < tol and bool(dn2[0]) == dn, k
+        assert np.abs(inf2[0] - inf).max() < tol, k
+        outs.append((ob, rw, dn, inf))
+    return outs
+
+
+@pytest.mark.parametrize("sm", [dict(sensor_motor=2), dict(sensor_imu=2, sensor_dis=0), dict(sensor_contact=0, sensor_etg=0, obs_normal=0),
+                                dict(obs_normal=0), dict(sensor_motor=0, sensor_imu=0)])
+def test_sensor_mode_layouts(etg_stable, sm):
+    """sensor_mode / normal of SimpleEnv.get_observation (deployment/envs/EnvWrapper.py:60-109): block selection in sorted-key order
+    and raw-unit output; every variant is a column subset / affine image of the full 49-wide row."""
+    w, b = etg_stable
+    e, o = _pair(w, b, **sm)
+    full_e, full_o = _pair(w, b)
+    rng = np.random.default_rng(1)
+    acts = rng.uniform(-0.2, 0.2, (6, 12))
+    outs = _run(e, o, acts)
+    fouts = _run(full_e, full_o, acts)
+    c = dict(sensor_dis=1, sensor_contact=1, sensor_imu=1, sensor_motor=1, sensor_etg=1, obs_normal=1); c.update(sm)
+    dim = 3 * c["sensor_dis"] + 4 * c["sensor_contact"] + {0: 0, 1: 6, 2: 3}[c["sensor_imu"]] + {0: 0, 1: 24, 2: 12}[c["sensor_motor"]] + 12 * c["sensor_etg"]
+    assert outs[-1][0].shape == (dim,) == (e.obs_dim(),)
+    full = fouts[-1][0]
+    pose = np.array([0, .9, -1.8] * 4)
+    exp = []
+    if c["sensor_dis"]: exp += list(full[0:3])
+    if c["sensor_contact"]: exp += list(full[3:7])
+    if c["sensor_imu"] == 1: exp += list(full[7:10] * (1 if c["obs_normal"] else 0.1))
+    if c["sensor_imu"]: exp += list(full[10:13] * (1 if c["obs_normal"] else 0.5))
+    if c["sensor_motor"]: exp += list(full[13:25] if c["obs_normal"] else full[13:25] * 0.1 + pose)
+    if c["sensor_motor"] == 1: exp += list(full[25:37])
+    if c["sensor_etg"]: exp += list(full[37:49] if c["obs_normal"] else np.array(full_o.e.etg_act[:]))
+    assert np.abs(outs[-1][0] - np.array(exp)).max() < 1e-9
+    e.close(); full_e.close()
+
+
+def test_sensor_noise_matches_oracle_and_has_the_stated_statistics(etg_stable):
+    """Minitaur._AddSensorNoise (minitaur.py:1206-1211): zero-mean Gaussian of the configured stdev on motor angles / velocities /
+    torques / rpy / rpy rate; same counter-based stream in the device code and the oracle."""
+    w, b = etg_stable
+    sd = (0.01, 0.05, 0.1, 0.02, 0.04)
+    e, o = _pair(w, b, noise_stdev=sd, noise_seed=12345)
+    clean_e, clean_o = _pair(w, b)
+    acts = np.zeros((40, 12))
+    noisy = _run(e, o, acts, tol=1e-8)
+    clean = _run(clean_e, clean_o, acts)
+    dq = np.array([(n[0][13:25] - c[0][13:25]) * 0.1 for n, c in zip(noisy, clean)])      # obs = (q - pose)/0.1
+    dqd = np.array([n[0][25:37] - c[0][25:37] for n, c in zip(noisy, clean)])
+    drpy = np.array([(n[0][7:10] - c[0][7:10]) * 0.1 for n, c in zip(noisy, clean)])
+    dw = np.array([(n[0][10:13] - c[0][10:13]) * 0.5 for n, c in zip(noisy, clean)])
+    for d, s in ((dq, sd[0]), (dqd, sd[1]), (drpy, sd[3]), (dw, sd[4])):
+        assert abs(d.std() / s - 1.0) < 0.2 and abs(d.mean()) < 0.25 * s, (d.std(), s)
+    assert np.abs([n[3][10] - c[3][10] for n, c in zip(noisy, clean)]).max() > 0            # energy uses the noisy torque / velocity getters
+    n4 = np.zeros(4); O.lib().orc_normal4(C_ull(7), 1, 2, 3, n4.ctypes.data_as(O.C.POINTER(O.C.c_double)))
+    assert np.all(np.isfinite(n4)) and len(set(np.round(n4, 12))) == 4
+    e.close(); clean_e.close()
+
+
+def C_ull(x):
+    return O.C.c_ulonglong(x)
+
+
+def test_stuck_termination(etg_stable):
+    """rlschool [EXT]: an env whose base has not moved over the last 10 control steps (after step 10) reports done."""
+    w, b = etg_stable
+    e, o = _pair(w, b, stuck_termination=1, etg_enabled=0)
+    outs = _run(e, o, np.zeros((45, 12)))
+    dones = [x[2] for x in outs]
+    assert not any(dones[:10]) and any(dones), dones           # standing (the settle sway dies out below 2e-4 after ~30 steps): stuck => done
+    e2, o2 = _pair(w, b, stuck_termination=1)                  # walking: never stuck
+    assert not any(x[2] for x in _run(e2, o2, np.zeros((14, 12))))
+    e.close(); e2.close()
+
+
+def test_body_collision_count_feeds_badfoot(etg_default):
+    """Non-toe contacts (knee, hip joint, trunk corners) are what `badfoot` counts; a robot that falls over collects them."""
+    w, b = etg_default
+    e, o = _pair(w, b, body_collisions=1)
+    rng = np.random.default_rng(3)
+    outs = _run(e, o, rng.uniform(-0.3, 0.3, (45, 12)))
+    bad = np.array([x[3][6] for x in outs])
+    assert (bad < 0).any() and any(x[2] for x in outs)
+    e.close()
+
+
+def test_torque_mode(etg_stable):
+    """MotorControlMode.TORQUE (laikago_motor.py:131-134, train.py:279,317-318): the scaled action is the motor torque."""
+    w, b = etg_stable
+    e, o = _pair(w, b, motor_mode=1)
+    rng = np.random.default_rng(4)
+    hold = np.array([0.0, 1.0, -6.0] * 4)                      # roughly the standing torques
+    outs = _run(e, o, hold + rng.uniform(-1, 1, (10, 12)))
+    assert np.abs(outs[0][3][24:36] - (hold + 0)).max() < 1.01                     # info real_action = the commanded torque
+    e.close()
+
+
+def test_base_push_and_damping(etg_stable):
+    w, b = etg_stable
+    e, o = _pair(w, b, external_force=1, base_damping=(0.04, 0.02, 0.04, 0.01))
+    e0, o0 = _pair(w, b)
+    f = np.array([0.0, 25.0, 0.0])
+    e.set_force(f[None, :]); o.set_force(f)
+    acts = np.zeros((12, 12))
+    _run(e, o, acts); _run(e0, o0, acts)
+    assert o.get_state()[1] - o0.get_state()[1] > 0.01          # pushed towards +y
+    e.set_force(None); o.set_force(None)
+    _run(e, o, acts[:3])
+    e.close(); e0.close()
+
+
+def test_reference_task_terrains(etg_shipped):
+    """make_env(task=...) presets (train.py:48-50,462): the shipped gait, started just before the first obstacle, steps onto it;
+    device code == oracle on every preset."""
+    from paddlerobotics_b200.terrain import make_terrain
+    w, b = etg_shipped
+    for task in ("stairstair", "slopeslope", "stairslope", "slopestair", "terrain", "balancebeam"):
+        hf = make_terrain(task)
+        inset = 0.05 if task == "balancebeam" else 0.0
+        e, o = _pair(w, b, x_offset=0.55, heightfield=hf, etg_foot_y_inset=inset)
+        outs = _run(e, o, np.zeros((30, 12)), tol=1e-7)
+        assert o.get_state()[0] > 0.75, task
+        if task in ("stairstair", "stairslope", "slopeslope", "slopestair"):
+            assert o.foot_world()[:, 2].max() > 0.05, task      # a foot is up on the obstacle
+        e.close()

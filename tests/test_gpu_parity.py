@@ -18,6 +18,184 @@ def _np(t):
     return t.detach().double().cpu().numpy()
 
 
+def test_config1_teacher_forced_1000_steps(torch_cuda, etg_default):
+    """SURVEY §8d config 1 AS SPECIFIED, protocol (1): default gait Opt_with_points(0.1, 0.05), residual sequence
+    default_rng(0).uniform(-1,1,(1000,12))*0.3, 1000 control steps including the falls and resets it produces; before every step the
+    oracle state is loaded into the f32 engine.  Stated tolerance, no extra slack: <= 1e-4 on q and pose, <= 1e-4 relative on
+    q-dot and reward (relative to max(1, |reference|_inf)); contact flags, done and fall bit-exact."""
+    from oracle import oracle as O
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    w, b = etg_default
+    env = VecQuadrupedalEnv(1, precision="f32")
+    o = O.OracleEnv()
+    env.reset(w, b); o.reset(w, b)
+    acts = np.random.default_rng(0).uniform(-1, 1, (1000, 12)) * 0.3
+    wq = wp = wqd = wr = 0.0
+    resets = 0
+    for k in range(1000):
+        env.set_state(o.get_state()[None, :])
+        ob, rw, dn, inf = env.step(acts[k][None, :].astype(np.float32))
+        oo, ro, do, io = o.step(acts[k])
+        st, so = _np(env.get_state())[0], o.get_state()
+        wq = max(wq, np.abs(st[13:25] - so[13:25]).max()); wp = max(wp, np.abs(st[:7] - so[:7]).max())
+        wqd = max(wqd, np.abs(st[25:37] - so[25:37]).max() / max(1.0, np.abs(so[25:37]).max()))
+        wr = max(wr, abs(float(rw[0]) - ro) / max(1.0, abs(ro)))
+        assert np.array_equal(_np(ob)[0][3:7], oo[3:7]), k
+        assert bool(dn[0]) == do and float(inf[0, 54]) == io[54], k
+        if do:
+            o.reset(); env.reset(); resets += 1
+    print("config-1 teacher-forced, 1000 steps, %d resets: q %.3g  pose %.3g  qd(rel) %.3g  reward(rel) %.3g" % (resets, wq, wp, wqd, wr))
+    assert resets >= 10
+    assert wq <= 1e-4 and wp <= 1e-4 and wqd <= 1e-4 and wr <= 1e-4, (wq, wp, wqd, wr)
+    env.close()
+
+
+def test_free_running_shipped_gait_1000_steps(torch_cuda, etg_shipped):
+    """Protocol (2) on a gait that walks: W,b fitted from the reference's own gait_action_list_ETG_exp.npy (0.48 m/s open loop),
+    1000 free-running control steps (13 000 substeps), product f32 kernel vs f64 oracle.  BASELINE target: joint-state drift
+    <= 1e-4; the base travels ~12.6 m, its drift is asserted relative to that distance."""
+    from oracle import oracle as O
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    w, b = etg_shipped
+    env = VecQuadrupedalEnv(1, precision="f32")
+    o = O.OracleEnv()
+    env.reset(w, b); o.reset(w, b)
+    z = np.zeros((1, 12), np.float32)
+    worst_q = worst_r = worst_p = 0.0
+    mism = 0
+    for k in range(1000):
+        ob, rw, dn, inf = env.step(z)
+        oo, ro, do, io = o.step(z[0])
+        st, so = _np(env.get_state())[0], o.get_state()
+        worst_q = max(worst_q, np.abs(st[13:25] - so[13:25]).max())
+        worst_p = max(worst_p, np.abs(st[:3] - so[:3]).max())
+        worst_r = max(worst_r, abs(float(rw[0]) - ro) / max(1.0, abs(ro)))
+        mism += int(not np.array_equal(_np(ob)[0][3:7], oo[3:7]))
+        assert not do and not bool(dn[0]), k
+    dist = o.get_state()[0]
+    print("f32 free-running 1000 steps on the shipped gait: q drift %.3g rad, base pos %.3g m over %.2f m, reward(rel) %.3g, contact-flag mismatches %d"
+          % (worst_q, worst_p, dist, worst_r, mism))
+    assert 0.3 * 26.0 < dist < 0.6 * 26.0
+    assert worst_q <= 1e-4, worst_q
+    assert worst_p <= 1e-4 * dist, (worst_p, dist)
+    assert worst_r <= 1e-3
+    assert mism <= 5
+    env.close()
+
+
+def test_physics_regression_shipped_gait_f32(torch_cuda, etg_shipped):
+    """Pinned to reference-held data: the gait table the reference ships must WALK in this physics — forward speed in
+    [0.3, 0.6] m/s, no fall in 600 control steps (the table's length), upright, on the product f32 kernel, for a whole batch."""
+    import torch
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    w, b = etg_shipped
+    env = VecQuadrupedalEnv(64, precision="f32")
+    env.reset(w, b)
+    x0 = env.get_state()[:, 0].clone()
+    z = torch.zeros(64, 12, device="cuda")
+    for k in range(600):
+        ob, rw, dn, inf = env.step(z)
+        assert int(dn.sum()) == 0, k
+    st = env.get_state()
+    v = (st[:, 0] - x0) / (600 * 0.026)
+    assert ((v > 0.3) & (v < 0.6)).all(), v
+    assert (st[:, 2] > 0.2).all() and (inf[:, 36:38].abs() < 0.3).all()      # base height, roll / pitch
+    env.close()
+
+
+def test_make_env_reference_default_constructor_on_stairs(torch_cuda, etg_shipped):
+    """The reference's exact constructor line (ETGRL/train.py:305-309) with the DEFAULT flags of its argparse block (:455-505) —
+    task_mode 'stairstair', POSITION mode, all sensors on, dynamic_param from param2dynamic_dict (40 ms control latency) — then 400
+    control steps as run_train_episode does (reset(ETG_w, ETG_b, x_noise), step(action*act_bound, donef)).  And kernel == oracle on
+    that terrain (f64)."""
+    from oracle import oracle as O
+    from paddlerobotics_b200.env import make_env, SENSOR_MODE, Random_Param_Dict, VecQuadrupedalEnv
+    from paddlerobotics_b200.etg import param2dynamic_dict, dynamic_dict_to_row
+    from paddlerobotics_b200.terrain import make_terrain
+
+    class MotorControlMode:       # stand-in for robot_config.MotorControlMode.POSITION (enum value 1)
+        name, value = "POSITION", 1
+    sensor_mode = dict(SENSOR_MODE); sensor_mode["RNN"] = {"time_steps": 5, "time_interval": 1, "mode": "None"}
+    reward_param = dict(torso=1.5, feet=0.3, up=0.6, tau=0.07, stand=0, badfoot=0.1, footcontact=0.1)
+    dynamic_param = param2dynamic_dict(np.zeros(48))
+    env = make_env('Quadrupedal', task="stairstair", motor_control_mode=MotorControlMode, render=False, sensor_mode=sensor_mode,
+                   normal=1, dynamic_param=dynamic_param, reward_param=reward_param,
+                   ETG=1, ETG_T=0.5, reward_p=5, ETG_path="None", random_param=dict(Random_Param_Dict),
+                   ETG_H=20, vel_d=0.5, step_y=0.05, enable_action_filter=0)
+    assert env.observation_space.shape[0] == 49 and env.action_space.shape[0] == 12
+    w, b = etg_shipped
+    obs, info = env.reset(ETG_w=w, ETG_b=b, x_noise=0)
+    rng = np.random.default_rng(0)
+    steps, x = 0, 0.0
+    for k in range(400):
+        obs, r, d, info = env.step(rng.uniform(-1, 1, 12) * 0.05, donef=(k + 1 > 400))
+        assert obs.shape == (49,) and np.isfinite(obs).all() and np.isfinite(r)
+        steps += 1; x += info["velx"] * 0.026
+        if d:
+            obs, _ = env.reset(ETG_w=w, ETG_b=b, x_noise=0)
+    assert steps == 400 and x > 0.8          # it reached and climbed the first steps (stairs start at x = 0.8)
+    env.close()
+    # kernel == oracle on the same terrain and dynamics row (float64)
+    hf = make_terrain("stairstair")
+    row = dynamic_dict_to_row(dynamic_param)
+    cfg = O.default_config(stuck_termination=1, body_collisions=1); O.set_heightfield(cfg, *hf)
+    o = O.OracleEnv(cfg, row); v = VecQuadrupedalEnv(1, precision="f64", heightfield=hf, stuck_termination=1, body_collisions=1)
+    v.set_dynamics(row[None, :])
+    assert np.abs(_np(v.reset(w, b, x_offset=[0.5]))[0] - o.reset(w, b, x_offset=0.5)).max() < 1e-9
+    for k in range(60):
+        a = rng.uniform(-0.05, 0.05, 12)
+        ob, rw, dn, inf = v.step(a[None, :]); oo, ro, do, io = o.step(a)
+        assert np.abs(_np(ob)[0] - oo).max() < 1e-7 and abs(float(rw[0]) - ro) < 1e-7 and bool(dn[0]) == do, k
+    assert o.foot_world()[:, 2].max() > 0.06      # feet are on the stairs
+    v.close()
+
+
+def test_env_features_f64_equal_oracle(torch_cuda, etg_stable):
+    """Round-2 features through the C ABI on the GPU (float64 build) == oracle: reduced sensor layout in raw units, sensor noise,
+    TORQUE mode, base push + damping, x-offset reset."""
+    from oracle import oracle as O
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    w, b = etg_stable
+    rng = np.random.default_rng(2)
+    for kw, torque in ((dict(sensor_motor=2, sensor_imu=2, obs_normal=0, noise_stdev=(0.01, 0.05, 0.1, 0.02, 0.04), noise_seed=99), False),
+                       (dict(motor_mode=1), True),
+                       (dict(external_force=1, base_damping=(0.04, 0.02, 0.04, 0.01), body_collisions=1, stuck_termination=1), False)):
+        n = 3
+        env = VecQuadrupedalEnv(n, precision="f64", **kw)
+        os_ = [O.OracleEnv(O.default_config(**kw)) for _ in range(n)]
+        xo = np.array([0.0, 0.05, -0.03])
+        ob0 = _np(env.reset(w, b, x_offset=xo))
+        for i, o in enumerate(os_):
+            o.e.env_id = i
+            assert np.abs(ob0[i] - o.reset(w, b, x_offset=xo[i])).max() < 1e-9
+        if kw.get("external_force"):
+            f = rng.uniform(-20, 20, (n, 3)); env.set_external_force(f)
+            for i, o in enumerate(os_):
+                o.set_force(f[i])
+        for k in range(20):
+            a = (np.array([0.0, 1.0, -6.0] * 4) + rng.uniform(-1, 1, (n, 12))) if torque else rng.uniform(-0.2, 0.2, (n, 12))
+            ob, rw, dn, inf = env.step(a)
+            for i, o in enumerate(os_):
+                oo, ro, do, io = o.step(a[i])
+                assert _np(ob).shape[1] == oo.shape[0] == env.observation_dim
+                assert np.abs(_np(ob)[i] - oo).max() < 1e-7 and abs(float(rw[i]) - ro) < 1e-7 and bool(dn[i]) == do, (kw, k, i)
+                assert np.abs(_np(inf)[i] - io).max() < 1e-7
+        env.close()
+
+
+def test_latency_beyond_the_ring_is_an_error(torch_cuda):
+    """a control latency the observation ring cannot serve must be refused, not clamped."""
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    from paddlerobotics_b200.etg import dynamic_dict_to_row
+    env = VecQuadrupedalEnv(2, ring_depth=1)
+    with pytest.raises(RuntimeError, match="ring_depth"):
+        env.set_dynamics(np.stack([dynamic_dict_to_row({"control_latency": 40.0})] * 2))
+    env.close()
+    env = VecQuadrupedalEnv(2)                                                   # default ring depth 4 serves up to 100 ms
+    env.set_dynamics(np.stack([dynamic_dict_to_row({"control_latency": 80.0})] * 2))
+    env.close()
+
+
 def test_f64_kernels_equal_oracle(torch_cuda, etg_stable):
     """float64 build of the same kernels == oracle to rounding (two independent formulations)."""
     from oracle import oracle as O
@@ -65,7 +243,9 @@ def test_f32_free_running_1000_steps_drift(torch_cuda, etg_stable):
         mism += int(not np.array_equal(_np(ob)[0][3:7], oo[3:7]))
         assert not do
     print("f32 1000-step drift: q %.3g rad, base pos %.3g m, reward %.3g, contact-flag mismatches %d/1000" % (worst_q, worst_p, worst_r, mism))
-    assert worst_q < 5e-4      # measured 1.7e-4 rad on B200 (9e-5 relative to the 1.8 rad knee angle), see DESIGN.md §6
+    # stable gait + +-0.1 residual noise: the noise makes the free-running comparison chaotic (CPU emulation of the same f32 code gives
+    # 0.8e-4 .. 3.3e-4 depending on FMA contraction); the <=1e-4 target is asserted on the noise-free walking run above
+    assert worst_q < 5e-4
     assert worst_r < 1e-2
     assert worst_p < 2e-3
     assert mism <= 10
@@ -88,8 +268,8 @@ def test_f32_teacher_forced(torch_cuda, etg_default):
         st, so = _np(env.get_state())[0], o.get_state()
         assert np.abs(st[13:25] - so[13:25]).max() < 1e-4
         assert np.abs(st[:7] - so[:7]).max() < 1e-4
-        assert np.abs(st[25:37] - so[25:37]).max() < 1e-4 * max(1.0, np.abs(so[25:37]).max()) + 2e-3
-        assert abs(float(rw[0]) - ro) < 1e-4 * max(1.0, abs(ro)) + 5e-3
+        assert np.abs(st[25:37] - so[25:37]).max() <= 1e-4 * max(1.0, np.abs(so[25:37]).max())
+        assert abs(float(rw[0]) - ro) <= 1e-4 * max(1.0, abs(ro))
         assert np.array_equal(_np(ob)[0][3:7], oo[3:7])
         assert bool(dn[0]) == do
         if do:
@@ -158,7 +338,7 @@ def test_make_env_reference_call_shapes(torch_cuda, etg_default):
     from paddlerobotics_b200.env import make_env
     from paddlerobotics_b200.etg import etg_act_table
     w, b = etg_default
-    env = make_env("Quadrupedal", task="ground", render=False, ETG=1, ETG_T=0.5, reward_p=5, vel_d=0.5)
+    env = make_env("Quadrupedal", task="ground", render=False, ETG=1, ETG_T=0.5, reward_p=5, vel_d=0.5, stuck_termination=0)
     assert env.observation_space.shape[0] == 49 and env.action_space.shape[0] == 12
     obs, info = env.reset(ETG_w=w, ETG_b=b, x_noise=0)
     assert obs.shape == (49,)

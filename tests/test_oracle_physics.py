@@ -85,3 +85,26 @@ def test_slope_heightfield_contact_normal():
     env = O.OracleEnv(cfg)
     s = env.get_state()
     assert np.all(np.isfinite(s)) and 0.15 < s[2] < 0.35
+
+
+def test_shipped_gait_walks_in_this_physics(etg_shipped):
+    """Physics regression pinned to reference-held data: the gait table the reference ships (gait_action_list_ETG_exp.npy, fitted back to
+    W,b) must walk — forward speed in [0.3, 0.6] m/s, no fall in 600 control steps (the table's length) — in the oracle AND in the
+    float32 device code (CPU emulation); the hand-picked gaits of round 1 are not the long-horizon workload any more."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+    import emu
+    w, b = etg_shipped
+    o = O.OracleEnv(); o.reset(w, b)
+    e = emu.EmuEnv(1, 0); e.reset(w, b)
+    worst_q = 0.0
+    for k in range(600):
+        ob, r, d, info = o.step(np.zeros(12))
+        ob2, r2, d2, info2 = e.step(np.zeros(12))
+        assert not d and not d2[0], k
+        worst_q = max(worst_q, np.abs(e.get_state()[0][13:25] - o.get_state()[13:25]).max())
+    v = o.get_state()[0] / (600 * 0.026)
+    assert 0.3 < v < 0.6, v
+    assert o.get_state()[2] > 0.2 and abs(info[36]) < 0.3 and abs(info[37]) < 0.3
+    assert worst_q <= 1e-4, worst_q          # f32 device code, free running on the walking gait (BASELINE: joint-state drift <= 1e-4)
+    e.close()
