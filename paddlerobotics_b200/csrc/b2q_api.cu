@@ -69,9 +69,15 @@ __global__ void __launch_bounds__(128) b2q_step_kernel(Cfg<T> cf, const Model<T>
   const int srow = env0 + (int)(threadIdx.x >> 2);
   if (!valid) env = B.N - 1;
   WarpComm cm{(int)(threadIdx.x & 3)};
-  step_lane<T, FEAT>(cm, cf, md, B, env, valid, action, donef, auto_reset, stage + (ptrdiff_t)(srow - env) * OBS_DIM, reward, done, info, env0);
+  // the info rows (56 floats per env, produced in 3-float pieces) are staged the same way: one coalesced block per CTA, so that `info`
+  // too may be pinned HOST memory (train.py:150-157 reads info every step)
+  T* istage = stage + (size_t)per_cta * OBS_DIM;
+  step_lane<T, FEAT>(cm, cf, md, B, env, valid, action, donef, auto_reset, stage + (ptrdiff_t)(srow - env) * OBS_DIM, reward, done, istage, env0, env0);
   __syncthreads();
-  emit_obs_block(md, stage, obs, env0, min(per_cta, B.N - env0));
+  const int rows = min(per_cta, B.N - env0);
+  emit_obs_block(md, stage, obs, env0, rows);
+  T* idst = info + (size_t)env0 * INFO_DIM;
+  for (int i = threadIdx.x; i < rows * INFO_DIM; i += blockDim.x) idst[i] = istage[i];
 }
 
 template <typename T, int FEAT>
@@ -235,7 +241,7 @@ struct EnvT : EnvBase {
     CK(cudaDeviceSynchronize());
     return B2Q_OK;
   }
-  size_t smem_bytes() const { return ((sizeof(Model<T>) + 15) & ~size_t(15)) + (size_t)(tpb / 4) * OBS_DIM * sizeof(T); }
+  size_t smem_bytes() const { return ((sizeof(Model<T>) + 15) & ~size_t(15)) + (size_t)(tpb / 4) * (OBS_DIM + INFO_DIM) * sizeof(T); }
 
   int set_dynamics(const uint8_t* mask, const void* dyn, cudaStream_t s) override {
     CK(cudaSetDevice(cfg.device));
@@ -310,9 +316,8 @@ struct EnvT : EnvBase {
     T* obs_dev = nullptr; T* rew_dev = nullptr; uint8_t* done_dev = nullptr;
     if (host_io >= 2) { obs_dev = (T*)mapped(obs); rew_dev = (T*)mapped(rew); done_dev = (uint8_t*)mapped(done); }
     const bool direct = obs_dev && rew_dev && done_dev;
-    // info rows are produced in 3-float pieces (not staged): zero-copy only for small batches (the N=1 reference-style env),
-    // where a handful of small PCIe writes beats a D2H copy launch; larger batches stage on the device + one D2H
-    T* info_dev = (direct && info && N * INFO_DIM * sizeof(T) <= 16384) ? (T*)mapped(info) : nullptr;
+    // info rows are staged in shared memory and stored as one coalesced block per CTA like the observations: zero-copy too
+    T* info_dev = (direct && info) ? (T*)mapped(info) : nullptr;
     int rc = direct ? step(act_dev, donef, obs_dev, rew_dev, done_dev, info_dev ? info_dev : st_info, s) : step(act_dev, donef, st_obs, st_rew, st_done, st_info, s);
     if (rc) return rc;
     if (info_dev) info = nullptr;

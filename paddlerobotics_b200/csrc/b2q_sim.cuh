@@ -162,19 +162,19 @@ B2Q_HD void etg_act_leg(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, co
   T x0 = cf.etg_amp * m_sin(cf.etg_ph0 + om * tt), x1 = cf.etg_amp * m_sin(cf.etg_ph1 + om * tt);
   T d[3] = {0, 0, 0};
   const T isig = T(1) / cf.etg_sigma_sq;
-  const T* e = reinterpret_cast<const T*>(etg);  // pack p, env -> e[(p*N+env)*4 + c]
-#pragma unroll 4
+  // the env's 63 weights as 16 independent 128-bit loads (all in flight at once), then the 20 RBF features against them
+  T e[4 * NE];
+#pragma unroll
+  for (int p = 0; p < NE; p++) { P4<T> v = ldp(etg, p, N, env); e[4 * p] = v.x; e[4 * p + 1] = v.y; e[4 * p + 2] = v.z; e[4 * p + 3] = v.w; }
+#pragma unroll
   for (int h = 0; h < ETG_H; h++) {
     T dx = x0 - md.etg_u[h][0], dy = x1 - md.etg_u[h][1];
     T r = m_exp(-(dx * dx + dy * dy) * isig);
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
-      int idx = a * ETG_H + h;
-      d[a] += e[((size_t)(idx >> 2) * N + env) * 4 + (idx & 3)] * r;
-    }
+    for (int a = 0; a < 3; a++) d[a] += e[a * ETG_H + h] * r;
   }
 #pragma unroll
-  for (int a = 0; a < 3; a++) { int idx = 60 + a; d[a] += e[((size_t)(idx >> 2) * N + env) * 4 + (idx & 3)]; }
+  for (int a = 0; a < 3; a++) d[a] += e[60 + a];
   const LegModel<T>& lm = md.leg[k];
   T ang[3];
   for (int tries = 0; tries < 200; tries++) {  // act_clip: shrink until IK is finite
@@ -710,8 +710,8 @@ B2Q_HD void settle_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, co
 // one control step (= R physics substeps) for this lane: env.step() of the reference
 template <typename T, int FEAT, class Comm>
 B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const Buffers<T>& B, int env, bool valid,
-                      const T* action, int donef, int auto_reset, T* obs, T* reward, uint8_t* done, T* info, int obs_env0 = 0) {
-  // `obs` is the row block starting at env `obs_env0`: the whole [N][OBS_DIM] array (obs_env0 = 0) or a CTA-local staging block
+                      const T* action, int donef, int auto_reset, T* obs, T* reward, uint8_t* done, T* info, int obs_env0 = 0, int info_env0 = 0) {
+  // `obs` / `info` are row blocks starting at env `obs_env0` / `info_env0`: whole [N][...] arrays (0) or CTA-local staging blocks
   const int k = cm.leg(), N = B.N, R = cf.R;
   const T dtc = cf.dt * T(R);
   LaneParam<T> pr; load_param(cm, B, env, pr);
@@ -874,7 +874,7 @@ B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, cons
   }
   bool dn = fall || donef || (cf.max_steps > 0 && step >= cf.max_steps) || (stuckf > T(0));
   if (valid) {
-    T* irow = info + (size_t)env * INFO_DIM;
+    T* irow = info + (size_t)(env - info_env0) * INFO_DIM;
     if (k == 0) {
       reward[env] = rew; done[env] = dn ? 1 : 0;
       irow[0] = velx; irow[1] = r_torso; irow[2] = r_feet; irow[3] = r_up; irow[4] = r_tau; irow[5] = 0; irow[6] = r_bad; irow[7] = r_fc; irow[8] = r_done;

