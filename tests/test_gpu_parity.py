@@ -172,13 +172,13 @@ def test_env_features_f64_equal_oracle(torch_cuda, etg_stable):
             f = rng.uniform(-20, 20, (n, 3)); env.set_external_force(f)
             for i, o in enumerate(os_):
                 o.set_force(f[i])
-        for k in range(20):
+        for k in range(8 if torque else 20):     # open-loop torques diverge exponentially: compare before the rounding differences are amplified
             a = (np.array([0.0, 1.0, -6.0] * 4) + rng.uniform(-1, 1, (n, 12))) if torque else rng.uniform(-0.2, 0.2, (n, 12))
             ob, rw, dn, inf = env.step(a)
             for i, o in enumerate(os_):
                 oo, ro, do, io = o.step(a[i])
                 assert _np(ob).shape[1] == oo.shape[0] == env.observation_dim
-                tol = 1e-5 if torque else 1e-7        # open-loop torques: no PD loop damps the rounding differences of the two formulations
+                tol = 1e-6 if torque else 1e-7        # open-loop torques: no PD loop damps the rounding differences of the two formulations
                 assert np.abs(_np(ob)[i] - oo).max() < tol and abs(float(rw[i]) - ro) < tol and bool(dn[i]) == do, (kw, k, i)
                 assert np.abs(_np(inf)[i] - io).max() < tol
         env.close()
