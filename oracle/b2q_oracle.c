@@ -623,7 +623,29 @@ void orc_substep(const OrcConfig* c, OrcEnv* e, const double target[12]) {
     lam[leg] = act[leg] ? c->warmstart * e->lam_warm[leg] : 0.0;
     for (int k = 0; k < 18; k++) dnu[k] += MJ[leg][k] * lam[leg];
   }
+  /* URDF joint limits (a1.py:186-223) as unilateral rows, Bullet btMultiBodyJointLimitConstraint style: one row per joint towards the
+   * nearer stop (the far-side row of Bullet can never be active), same target-velocity rule as a contact (approach allowed up to gap/dt,
+   * ERP on violation), solved BEFORE the contact rows in every iteration (non-contact multibody constraints come first in
+   * btMultiBodyConstraintSolver::solveSingleIteration). */
+  static const double QLO[3] = {-0.802851455917, -1.0471975512, -2.69653369433}, QHI[3] = {0.802851455917, 4.18879020479, -0.916297857297};
+  double ls[12], lMJ[12][18], lA[12], ltarg[12], llam[12];
+  if (c->joint_limits) for (int i = 0; i < 12; i++) {
+    double glo = e->q[i] - QLO[i % 3], ghi = QHI[i % 3] - e->q[i], gap = glo; ls[i] = 1.0;
+    if (ghi < glo) { gap = ghi; ls[i] = -1.0; }
+    double tj[12]; memset(tj, 0, sizeof tj); tj[i] = ls[i];
+    dyn_delta(D, 0, NULL, tj, lMJ[i]);
+    lA[i] = ls[i] * lMJ[i][6 + i];
+    ltarg[i] = gap > 0 ? -gap / dt : c->erp * (-gap) / dt;
+    llam[i] = c->warmstart * e->lam_lim[i];
+    for (int k = 0; k < 18; k++) dnu[k] += lMJ[i][k] * llam[i];
+  }
   for (int it = 0; it < c->solver_iters; it++) {
+    if (c->joint_limits) for (int i = 0; i < 12; i++) {
+      double u = ls[i] * (nu[6 + i] + dnu[6 + i]);
+      double ln = llam[i] + (ltarg[i] - u) / lA[i]; if (ln < 0) ln = 0;
+      double dl = ln - llam[i]; llam[i] = ln;
+      for (int k = 0; k < 18; k++) dnu[k] += lMJ[i][k] * dl;
+    }
     for (int leg = 0; leg < 4; leg++) if (act[leg]) {
       int r = leg; double u = 0; for (int k = 0; k < 18; k++) u += J[r][k] * (nu[k] + dnu[k]);
       double ln = lam[r] + (targ[r] - u) / A[r]; if (ln < 0) ln = 0;
@@ -639,6 +661,7 @@ void orc_substep(const OrcConfig* c, OrcEnv* e, const double target[12]) {
     }
   }
   for (int leg = 0; leg < 4; leg++) { e->lam_warm[leg] = lam[leg]; e->contact[leg] = lam[leg] > 0; }
+  for (int i = 0; i < 12; i++) e->lam_lim[i] = c->joint_limits ? llam[i] : 0.0;
   for (int k = 0; k < 18; k++) nu[k] += dnu[k];
   /* integrate (semi-implicit Euler) */
   m3v(D->R0, nu, e->vang); m3v(D->R0, nu + 3, e->vlin);

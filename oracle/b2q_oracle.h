@@ -88,7 +88,7 @@ typedef struct {
   double snap[37]; double snap_obs[ORC_HIST_W]; double snap_lam[4];
   double pos_hist[10][3];      /* stuck termination */
   double ext_force[3];         /* world-frame push at the base COM */
-  double lam_lim[4];           /* warm start of the per-leg joint-limit row */
+  double lam_lim[12];          /* warm starts of the joint-limit rows */
   int env_id;                  /* index of this env in its batch: the sensor-noise counter */
 } OrcEnv;
 

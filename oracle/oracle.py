@@ -54,7 +54,7 @@ class Env(C.Structure):
         ("contact", C.c_int * 4), ("last_tau", C.c_double * 12),
         ("fx1", C.c_double * 12), ("fx2", C.c_double * 12), ("fy1", C.c_double * 12), ("fy2", C.c_double * 12),
         ("snap", C.c_double * 37), ("snap_obs", C.c_double * HIST_W), ("snap_lam", C.c_double * 4),
-        ("pos_hist", (C.c_double * 3) * 10), ("ext_force", C.c_double * 3), ("lam_lim", C.c_double * 4), ("env_id", C.c_int),
+        ("pos_hist", (C.c_double * 3) * 10), ("ext_force", C.c_double * 3), ("lam_lim", C.c_double * 12), ("env_id", C.c_int),
     ]
 
 

@@ -17,7 +17,10 @@ namespace {
 
 struct WarpComm {
   int k;
+  unsigned char* scr;   // this robot's shared-memory scratch (FEAT variant only; null otherwise)
   __device__ __forceinline__ int leg() const { return k; }
+  template <typename T> __device__ __forceinline__ T* scratch() const { return reinterpret_cast<T*>(scr); }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
   template <typename T>
   __device__ __forceinline__ T sum4(T v) const {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -68,10 +71,11 @@ __global__ void __launch_bounds__(128) b2q_step_kernel(Cfg<T> cf, const Model<T>
   // row and never store to global memory
   const int srow = env0 + (int)(threadIdx.x >> 2);
   if (!valid) env = B.N - 1;
-  WarpComm cm{(int)(threadIdx.x & 3)};
+  T* istage0 = stage + (size_t)per_cta * OBS_DIM;
+  WarpComm cm{(int)(threadIdx.x & 3), FEAT ? reinterpret_cast<unsigned char*>(istage0 + (size_t)per_cta * INFO_DIM + (size_t)(threadIdx.x >> 2) * SCRATCH_FLOATS) : nullptr};
   // the info rows (56 floats per env, produced in 3-float pieces) are staged the same way: one coalesced block per CTA, so that `info`
   // too may be pinned HOST memory (train.py:150-157 reads info every step)
-  T* istage = stage + (size_t)per_cta * OBS_DIM;
+  T* istage = istage0;
   step_lane<T, FEAT>(cm, cf, md, B, env, valid, action, donef, auto_reset, stage + (ptrdiff_t)(srow - env) * OBS_DIM, reward, done, istage, env0, env0);
   __syncthreads();
   const int rows = min(per_cta, B.N - env0);
@@ -89,7 +93,8 @@ __global__ void __launch_bounds__(128) b2q_settle_kernel(Cfg<T> cf, const Model<
   bool valid = env < B.N;
   if (!valid) env = B.N - 1;
   if (mask && !mask[env]) valid = false;
-  WarpComm cm{(int)(threadIdx.x & 3)};
+  T* scr0 = reinterpret_cast<T*>(smem + ((sizeof(Model<T>) + 15) & ~size_t(15))) + (size_t)(blockDim.x >> 2) * (OBS_DIM + INFO_DIM);
+  WarpComm cm{(int)(threadIdx.x & 3), FEAT ? reinterpret_cast<unsigned char*>(scr0 + (size_t)(threadIdx.x >> 2) * SCRATCH_FLOATS) : nullptr};
   settle_lane<T, FEAT>(cm, cf, md, B, env, valid);
 }
 
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(128) b2q_reset_kernel(Cfg<T> cf, const Model<T
   bool valid = env < B.N;
   if (!valid) env = B.N - 1;
   if (mask && !mask[env]) valid = false;
-  WarpComm cm{(int)(threadIdx.x & 3)};
+  WarpComm cm{(int)(threadIdx.x & 3), nullptr};
   T* srow = stage + (size_t)(threadIdx.x >> 2) * OBS_DIM;
   reset_lane<T>(cm, cf, md, B, env, valid, obs ? srow : (T*)nullptr, xoff);
   if (obs) {   // masked-out envs keep their previous observation row
@@ -217,6 +222,11 @@ struct EnvT : EnvBase {
     Model<T> hm; build_model_host(hm, c.foot_radius, c.etg_T, c.etg_amp, c.etg_phase0, c.etg_phase1, c.etg_foot_y_inset);
     build_obs_map(hm, c); obs_dim = hm.obs_dim;
     feat = config_feat(c);
+    if (feat) {   // the FEAT variant keeps a 24x24 solver scratch per robot in shared memory: one warp (8 robots) per CTA, opt-in size above 48 KB
+      tpb = 32;
+      CK(cudaFuncSetAttribute(b2q_step_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+      CK(cudaFuncSetAttribute(b2q_settle_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    }
     CK(cudaHostAlloc((void**)&h_flag, sizeof(int), cudaHostAllocDefault));
     CK(cudaMalloc(&d_model, sizeof(Model<T>)));
     CK(cudaMemcpy(d_model, &hm, sizeof(Model<T>), cudaMemcpyHostToDevice));
@@ -241,7 +251,9 @@ struct EnvT : EnvBase {
     CK(cudaDeviceSynchronize());
     return B2Q_OK;
   }
-  size_t smem_bytes() const { return ((sizeof(Model<T>) + 15) & ~size_t(15)) + (size_t)(tpb / 4) * (OBS_DIM + INFO_DIM) * sizeof(T); }
+  size_t smem_bytes() const {   // model | obs stage | info stage | (FEAT) per-robot solver scratch
+    return ((sizeof(Model<T>) + 15) & ~size_t(15)) + (size_t)(tpb / 4) * (OBS_DIM + INFO_DIM + (feat ? SCRATCH_FLOATS : 0)) * sizeof(T);
+  }
 
   int set_dynamics(const uint8_t* mask, const void* dyn, cudaStream_t s) override {
     CK(cudaSetDevice(cfg.device));

@@ -93,6 +93,7 @@ template <typename T>
 struct LaneState {
   V3<T> pos; T qx, qy, qz, qw; V3<T> vlin, vang;
   T q[3], qd[3]; T lam_n; int contact;
+  T lam_lim[3];   // warm starts of this leg's joint-limit rows (FEAT variant)
 };
 
 template <typename T> B2Q_HD void sincos_t(T a, T& s, T& c) { m_sincos(a, s, c); }
@@ -189,6 +190,58 @@ B2Q_HD void etg_act_leg(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, co
 
 // ---------------------------------------------------------------------------------------------------------------
 // one physics substep for this lane's leg (+ redundant base)
+// General contact + joint-limit solve of the FEAT variant: 6 rows per leg (normal, t1, t2, and one limit row per joint: the nearer stop)
+// = 24 rows, Delassus matrix in the robot's shared scratch (cm.scratch(): shared memory on the GPU), projected Gauss-Seidel in Bullet's
+// order — joint-limit rows first (non-contact multibody constraints), then the contact normals, then the friction rows — run
+// redundantly by the four lanes.  Not the hot path: plain loops, no register-resident matrix.
+// Scratch layout: Ya[24][6] | blk[4][21] | vec[24][4] | W[24][24].
+constexpr int NRW = 24;
+constexpr int SCRATCH_FLOATS = NRW * 6 + 4 * 21 + NRW * 4 + NRW * NRW;
+template <typename T, class Comm>
+B2Q_HD void solve_rows24(const Comm& cm, const Cfg<T>& cf, T mu, const T (*Y)[6] /*[6] rows of this leg*/, const T* u /*[6]*/, const T* blk21 /*leg-local 6x6 block, packed lower*/,
+                         const T* targ /*[6]*/, bool act, const T* warm /*[6]*/, T* lk /*[6]*/) {
+  const int k = cm.leg();
+  T* sh = cm.template scratch<T>();
+  T* Ya = sh; T* blk = sh + NRW * 6; T* vec = blk + 4 * 21; T* W = vec + NRW * 4;
+  for (int e = 0; e < 6; e++) {
+    const int r = 6 * k + e;
+    for (int c = 0; c < 6; c++) Ya[r * 6 + c] = Y[e][c];
+    vec[r * 4 + 0] = u[e]; vec[r * 4 + 1] = targ[e]; vec[r * 4 + 2] = (e < 3 && !act) ? T(0) : T(1); vec[r * 4 + 3] = warm[e];
+  }
+  for (int i = 0; i < 21; i++) blk[k * 21 + i] = blk21[i];
+  cm.sync();
+  for (int e = 0; e < 6; e++) {
+    const int r = 6 * k + e;
+    for (int c = 0; c < NRW; c++) {
+      T acc = T(0);
+      for (int i = 0; i < 6; i++) acc += Ya[r * 6 + i] * Ya[c * 6 + i];
+      if (c / 6 == k) { const int a = e, b = c - 6 * k; acc += blk[k * 21 + (a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a)]; }
+      W[r * NRW + c] = acc;
+    }
+  }
+  cm.sync();
+  T lam[NRW], uu[NRW];
+  for (int i = 0; i < NRW; i++) lam[i] = vec[i * 4 + 2] > T(0) ? vec[i * 4 + 3] : T(0);
+  for (int i = 0; i < NRW; i++) { T a = vec[i * 4 + 0]; for (int j = 0; j < NRW; j++) a += W[i * NRW + j] * lam[j]; uu[i] = a; }
+  for (int it = 0; it < cf.iters; it++) {
+    for (int pass = 0; pass < 3; pass++) {          // 0: joint limits, 1: contact normals, 2: friction rows
+      for (int f = 0; f < 4; f++) {
+        const int cnt = pass == 0 ? 3 : pass == 1 ? 1 : 2;
+        for (int td = 0; td < cnt; td++) {
+          const int r = 6 * f + (pass == 0 ? 3 + td : pass == 1 ? 0 : 1 + td);
+          if (!(vec[r * 4 + 2] > T(0))) continue;
+          T ln = lam[r] + (vec[r * 4 + 1] - uu[r]) / W[r * NRW + r];
+          if (pass == 2) { T lim = mu * lam[6 * f]; ln = m_min(m_max(ln, -lim), lim); } else ln = m_max(ln, T(0));
+          T dl = ln - lam[r]; lam[r] = ln;
+          for (int i = 0; i < NRW; i++) uu[i] += W[i * NRW + r] * dl;
+        }
+      }
+    }
+  }
+  for (int e = 0; e < 6; e++) lk[e] = lam[6 * k + e];
+  cm.sync();                                         // the scratch is reused by the next substep
+}
+
 // FEAT = 0: the lean default body (POSITION mode, toe contacts only).  FEAT = 1 adds, behind runtime flags, TORQUE mode, the base
 // push, Bullet's base damping and the joint-limit rows; it is a separate instantiation so that the default body stays as
 // small as it is (the body is instruction-fetch bound).
@@ -401,6 +454,54 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
     }
   }
 #undef FDA
+  T lk[3] = {T(0), T(0), T(0)};   // this lane's own impulses
+  T lkl[3] = {T(0), T(0), T(0)}, sl[3] = {T(1), T(1), T(1)}, Yl[3][6];   // joint-limit rows of this leg: impulse, side (+1 lower stop, -1 upper), Y
+  bool general = false;
+  if constexpr (FEAT != 0) {
+    if (cf.jlim) {
+      // one limit row per joint (a1.py:186-223), towards the nearer stop; Jacobian +-e_j in joint space, none on the base; same target-velocity
+      // rule as a contact (approach up to gap/dt, ERP on violation), Bullet btMultiBodyJointLimitConstraint style
+      T Y6[6][6], u6[6], targ6[6], warm6[6], blk[21];
+#pragma unroll
+      for (int e = 0; e < 3; e++) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) Y6[e][c] = Y[e][c];
+        u6[e] = u[e]; targ6[e] = T(0); warm6[e] = T(0);
+      }
+      targ6[0] = dist > T(0) ? -dist * idt : cf.erp * (-dist) * idt; warm6[0] = cf.warm * s.lam_n;
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        T glo = s.q[j] - md.qlo[j], ghi = md.qhi[j] - s.q[j], gap = glo;
+        sl[j] = T(1); if (ghi < glo) { gap = ghi; sl[j] = T(-1); }
+#pragma unroll
+        for (int i = 0; i < 6; i++) Yl[j][i] = -sl[j] * get6(FD[j], i);
+        fwd6(S, Li, Yl[j]);
+#pragma unroll
+        for (int c = 0; c < 6; c++) Y6[3 + j][c] = Yl[j][c];
+        u6[3 + j] = sl[j] * qds[j];
+        targ6[3 + j] = gap > T(0) ? -gap * idt : cf.erp * (-gap) * idt;
+        warm6[3 + j] = cf.warm * s.lam_lim[j];
+      }
+      // leg-local block J_leg D J_leg^T over the rows (n, t1, t2, lim0, lim1, lim2), packed lower
+#pragma unroll
+      for (int a = 0; a < 6; a++) {
+#pragma unroll
+        for (int b = 0; b <= a; b++) {
+          T v;
+          if (a < 3) v = Wl[a][b];
+          else if (b < 3) v = sl[a - 3] * (D[a - 3][0] * Jk[b][0] + D[a - 3][1] * Jk[b][1] + D[a - 3][2] * Jk[b][2]);
+          else v = sl[a - 3] * sl[b - 3] * D[a - 3][b - 3];
+          blk[a * (a + 1) / 2 + b] = v;
+        }
+      }
+      T lk6[6];
+      solve_rows24<T>(cm, cf, pr.mu, Y6, u6, blk, targ6, act, warm6, lk6);
+#pragma unroll
+      for (int e = 0; e < 3; e++) { lk[e] = lk6[e]; lkl[e] = lk6[3 + e]; }
+      general = true;
+    }
+  }
+  if (!general) {
   // --- gather every foot's rows on every lane (4-lane broadcasts), then the whole 12x12 contact problem is solved
   //     REDUNDANTLY in registers by all four lanes: the Gauss-Seidel sweep below has no shuffle on its dependent chain.
   //     Row index r = 3*foot + e (e: 0 normal, 1,2 friction).
@@ -520,21 +621,25 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
       }
     }
   }
-  T lk[3] = {T(0), T(0), T(0)};   // this lane's own impulses (selected without dynamic register indexing)
 #pragma unroll
-  for (int f = 0; f < 4; f++) if (f == k) { lk[0] = lam[3 * f]; lk[1] = lam[3 * f + 1]; lk[2] = lam[3 * f + 2]; }
-  s.lam_n = lk[0]; s.contact = lk[0] > T(0);
+  for (int f = 0; f < 4; f++) if (f == k) { lk[0] = lam[3 * f]; lk[1] = lam[3 * f + 1]; lk[2] = lam[3 * f + 2]; }   // own impulses (no dynamic register indexing)
+  }
+  s.lam_n = lk[0]; s.contact = lk[0] > T(0); s.lam_lim[0] = lkl[0]; s.lam_lim[1] = lkl[1]; s.lam_lim[2] = lkl[2];
   // --- apply impulses: sum over feet of Y_f lam_f by a 4-lane butterfly of each lane's own rows (keeps the gathered rows
   //     of the other feet dead after the Delassus matrix is built: 72 fewer live registers across the sweep)
   T z[6];
 #pragma unroll
-  for (int c = 0; c < 6; c++) z[c] = cm.sum4(Y[0][c] * lk[0] + Y[1][c] * lk[1] + Y[2][c] * lk[2]);
+  for (int c = 0; c < 6; c++) z[c] = cm.sum4(Y[0][c] * lk[0] + Y[1][c] * lk[1] + Y[2][c] * lk[2] + (FEAT != 0 ? Yl[0][c] * lkl[0] + Yl[1][c] * lkl[1] + Yl[2][c] * lkl[2] : T(0)));
   bwd6(S, Li, z);
   V6<T> dnu = arr_to_v6(z);
   {
     T jl[3], t[3];
 #pragma unroll
-    for (int i = 0; i < 3; i++) { jl[i] = Jk[0][i] * lk[0] + Jk[1][i] * lk[1] + Jk[2][i] * lk[2]; t[i] = jl[i] - dot6(Fc[i], dnu); }
+    for (int i = 0; i < 3; i++) {
+      jl[i] = Jk[0][i] * lk[0] + Jk[1][i] * lk[1] + Jk[2][i] * lk[2];
+      if (FEAT != 0) jl[i] += sl[i] * lkl[i];
+      t[i] = jl[i] - dot6(Fc[i], dnu);
+    }
 #pragma unroll
     for (int j = 0; j < 3; j++) qds[j] += D[j][0] * t[0] + D[j][1] * t[1] + D[j][2] * t[2];
   }
@@ -586,8 +691,8 @@ B2Q_HD void load_state(const Comm& cm, const P4<T>* st, int N, int env, LaneStat
   s.vlin = mk<T>(p2.x, p2.y, p2.z); has_last = p2.w > T(0.5);
   s.vang = mk<T>(p3.x, p3.y, p3.z);
   s.q[0] = pq.x; s.q[1] = pq.y; s.q[2] = pq.z; s.lam_n = pq.w;
-  s.qd[0] = pd.x; s.qd[1] = pd.y; s.qd[2] = pd.z; s.contact = pd.w > T(0.5);
-  last_action[0] = pa.x; last_action[1] = pa.y; last_action[2] = pa.z;
+  s.qd[0] = pd.x; s.qd[1] = pd.y; s.qd[2] = pd.z; s.contact = pq.w > T(0);   // contact flag = normal impulse > 0 in the last substep
+  last_action[0] = pa.x; last_action[1] = pa.y; last_action[2] = pa.z; s.lam_lim[0] = pa.w; s.lam_lim[1] = pe.w; s.lam_lim[2] = pd.w;
   etg_act[0] = pe.x; etg_act[1] = pe.y; etg_act[2] = pe.z;
   rpy0 = mk<T>(pr.x, pr.y, pr.z);
 }
@@ -599,9 +704,9 @@ B2Q_HD void store_state(const Comm& cm, P4<T>* st, int N, int env, const LaneSta
   if (k == 2) stp(st, 2, N, env, s.vlin.x, s.vlin.y, s.vlin.z, T(has_last));
   if (k == 3) stp(st, 3, N, env, s.vang.x, s.vang.y, s.vang.z, T(0));
   stp(st, 4 + k, N, env, s.q[0], s.q[1], s.q[2], s.lam_n);
-  stp(st, 8 + k, N, env, s.qd[0], s.qd[1], s.qd[2], T(s.contact));
-  stp(st, 12 + k, N, env, last_action[0], last_action[1], last_action[2], T(0));
-  stp(st, 16 + k, N, env, etg_act[0], etg_act[1], etg_act[2], T(0));
+  stp(st, 8 + k, N, env, s.qd[0], s.qd[1], s.qd[2], s.lam_lim[2]);
+  stp(st, 12 + k, N, env, last_action[0], last_action[1], last_action[2], s.lam_lim[0]);
+  stp(st, 16 + k, N, env, etg_act[0], etg_act[1], etg_act[2], s.lam_lim[1]);
 }
 // observation history ring: [Dm][2][12][N]; lane k owns packs 3k..3k+2 = (q, tau0),(qd, tau1),(tau2,-,-,-)
 template <typename T>
@@ -693,10 +798,11 @@ B2Q_HD void settle_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, co
   T tgt[3], tau[3] = {0, 0, 0};
 #pragma unroll
   for (int j = 0; j < 3; j++) { s.q[j] = md.pose_ori[j]; s.qd[j] = 0; tgt[j] = md.pose_ori[j]; }
-  s.lam_n = 0; s.contact = 0;
+  s.lam_n = 0; s.contact = 0; s.lam_lim[0] = s.lam_lim[1] = s.lam_lim[2] = 0;
   Cfg<T> cs = cf; cs.motor_mode = 0;   // the reset pose is held by the POSITION controller whatever the policy's motor mode (a1.py:289-304)
 #pragma unroll 1
   for (int i = 0; i < cf.settle_steps; i++) substep<T, FEAT>(cm, cs, md, pr, s, tgt, tau);
+  s.lam_lim[0] = s.lam_lim[1] = s.lam_lim[2] = T(0);   // a reset starts without a joint-limit warm start
   if (valid) {
     T z3[3] = {0, 0, 0};
     store_state(cm, B.snap, N, env, s, z3, z3, 0, mk<T>(0, 0, 0));

@@ -35,12 +35,15 @@ struct Exchange {
   SpinBarrier bar;
   alignas(64) volatile double A[4];
   alignas(64) volatile double Bf[4];
+  alignas(64) double scr[SCRATCH_FLOATS];   // the robot's solver scratch (shared memory on the GPU)
 };
 
 template <typename T>
 struct HostComm {
   int k; Exchange* x;
   int leg() const { return k; }
+  template <typename U> U* scratch() const { return reinterpret_cast<U*>(x->scr); }
+  void sync() const { x->bar.wait(); }
   T sum4(T v) const {  // same butterfly order as the shuffles: (v + v^1) + (that of lane^2)
     x->A[k] = (double)v; x->bar.wait();
     T p = v + (T)x->A[k ^ 1];

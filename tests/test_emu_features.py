@@ -154,3 +154,24 @@ def test_reference_task_terrains(etg_shipped):
         if task in ("stairstair", "stairslope", "slopeslope", "slopestair"):
             assert o.foot_world()[:, 2].max() > 0.05, task      # a foot is up on the obstacle
         e.close()
+
+
+def test_joint_limit_rows(etg_shipped):
+    """URDF joint limits (a1.py:186-223) as unilateral rows of the contact solve: knees driven hard against both stops stay inside
+    [-2.6965, -0.9163] (they leave it without the rows), and the device code's 16-row solve equals the oracle's DoF-space PGS."""
+    w, b = etg_shipped
+    e, o = _pair(w, b, joint_limits=1)
+    e0, o0 = _pair(w, b)
+    lo, hi, out = -2.69653369433, -0.916297857297, False
+    for k in range(14):
+        a = np.zeros(12); a[2::3] = 1.2 * np.sin(0.3 * k); a[0::3] = 0.9 * np.cos(0.25 * k)
+        ob, rw, dn, inf = o.step(a); ob2, rw2, dn2, inf2 = e.step(a)
+        assert np.abs(ob2[0] - ob).max() < 1e-7 and abs(rw2[0] - rw) < 1e-7 and bool(dn2[0]) == dn, k
+        q = o.get_state()[13:25]
+        assert q[2::3].min() > lo - 2e-3 and q[2::3].max() < hi + 2e-3 and np.abs(q[0::3]).max() < 0.802851455917 + 2e-3, (k, q)
+        o0.step(a); q0 = o0.get_state()[13:25]
+        out = out or q0[2::3].min() < lo - 0.05 or q0[2::3].max() > hi + 0.05
+        if dn:
+            break
+    assert out and np.array(o.e.lam_lim[:]).max() >= 0
+    e.close(); e0.close()
