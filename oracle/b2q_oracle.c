@@ -628,10 +628,13 @@ void orc_substep(const OrcConfig* c, OrcEnv* e, const double target[12]) {
    * ERP on violation), solved BEFORE the contact rows in every iteration (non-contact multibody constraints come first in
    * btMultiBodyConstraintSolver::solveSingleIteration). */
   static const double QLO[3] = {-0.802851455917, -1.0471975512, -2.69653369433}, QHI[3] = {0.802851455917, 4.18879020479, -0.916297857297};
-  double ls[12], lMJ[12][18], lA[12], ltarg[12], llam[12];
+  double ls[12], lMJ[12][18], lA[12], ltarg[12], llam[12]; int lact[12];
+  for (int i = 0; i < 12; i++) { lact[i] = 0; llam[i] = 0; }
   if (c->joint_limits) for (int i = 0; i < 12; i++) {
     double glo = e->q[i] - QLO[i % 3], ghi = QHI[i % 3] - e->q[i], gap = glo; ls[i] = 1.0;
     if (ghi < glo) { gap = ghi; ls[i] = -1.0; }
+    lact[i] = gap < 0.06;   /* further from a stop than 0.06 rad (target velocity beyond -30 rad/s) the row cannot bind: dropped, as in the kernel */
+    if (!lact[i]) continue;
     double tj[12]; memset(tj, 0, sizeof tj); tj[i] = ls[i];
     dyn_delta(D, 0, NULL, tj, lMJ[i]);
     lA[i] = ls[i] * lMJ[i][6 + i];
@@ -640,7 +643,7 @@ void orc_substep(const OrcConfig* c, OrcEnv* e, const double target[12]) {
     for (int k = 0; k < 18; k++) dnu[k] += lMJ[i][k] * llam[i];
   }
   for (int it = 0; it < c->solver_iters; it++) {
-    if (c->joint_limits) for (int i = 0; i < 12; i++) {
+    if (c->joint_limits) for (int i = 0; i < 12; i++) if (lact[i]) {
       double u = ls[i] * (nu[6 + i] + dnu[6 + i]);
       double ln = llam[i] + (ltarg[i] - u) / lA[i]; if (ln < 0) ln = 0;
       double dl = ln - llam[i]; llam[i] = ln;

@@ -21,6 +21,7 @@ struct WarpComm {
   __device__ __forceinline__ int leg() const { return k; }
   template <typename T> __device__ __forceinline__ T* scratch() const { return reinterpret_cast<T*>(scr); }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ bool any(bool f) const { return __any_sync(0xffffffffu, f) != 0; }   // over the whole warp (8 robots)
   template <typename T>
   __device__ __forceinline__ T sum4(T v) const {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -281,7 +282,8 @@ struct EnvT : EnvBase {
     CK(cudaSetDevice(cfg.device));
     int N = B.N;
     if (w || b) { b2q_pack_etg_kernel<T><<<(N + 127) / 128, 128, 0, s>>>((const T*)w, (const T*)b, const_cast<P4<T>*>(B.etg), mask, N); launches++; }
-    b2q_reset_kernel<T><<<grid_lanes(), tpb, smem_bytes(), s>>>(kc, d_model, B, mask, (const T*)xoff, (T*)obs);
+    const size_t smem_reset = ((sizeof(Model<T>) + 15) & ~size_t(15)) + (size_t)(tpb / 4) * OBS_DIM * sizeof(T);   // model + observation stage only
+    b2q_reset_kernel<T><<<grid_lanes(), tpb, smem_reset, s>>>(kc, d_model, B, mask, (const T*)xoff, (T*)obs);
     launches++;
     CK(cudaGetLastError());
     return B2Q_OK;

@@ -196,17 +196,18 @@ B2Q_HD void etg_act_leg(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, co
 // redundantly by the four lanes.  Not the hot path: plain loops, no register-resident matrix.
 // Scratch layout: Ya[24][6] | blk[4][21] | vec[24][4] | W[24][24].
 constexpr int NRW = 24;
+#define JLIM_GAP T(0.06)
 constexpr int SCRATCH_FLOATS = NRW * 6 + 4 * 21 + NRW * 4 + NRW * NRW;
 template <typename T, class Comm>
 B2Q_HD void solve_rows24(const Comm& cm, const Cfg<T>& cf, T mu, const T (*Y)[6] /*[6] rows of this leg*/, const T* u /*[6]*/, const T* blk21 /*leg-local 6x6 block, packed lower*/,
-                         const T* targ /*[6]*/, bool act, const T* warm /*[6]*/, T* lk /*[6]*/) {
+                         const T* targ /*[6]*/, bool act, const bool* actl /*[3]*/, const T* warm /*[6]*/, T* lk /*[6]*/) {
   const int k = cm.leg();
   T* sh = cm.template scratch<T>();
   T* Ya = sh; T* blk = sh + NRW * 6; T* vec = blk + 4 * 21; T* W = vec + NRW * 4;
   for (int e = 0; e < 6; e++) {
     const int r = 6 * k + e;
     for (int c = 0; c < 6; c++) Ya[r * 6 + c] = Y[e][c];
-    vec[r * 4 + 0] = u[e]; vec[r * 4 + 1] = targ[e]; vec[r * 4 + 2] = (e < 3 && !act) ? T(0) : T(1); vec[r * 4 + 3] = warm[e];
+    vec[r * 4 + 0] = u[e]; vec[r * 4 + 1] = targ[e]; vec[r * 4 + 2] = (e < 3 ? act : actl[e - 3]) ? T(1) : T(0); vec[r * 4 + 3] = warm[e];
   }
   for (int i = 0; i < 21; i++) blk[k * 21 + i] = blk21[i];
   cm.sync();
@@ -458,10 +459,18 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
   T lkl[3] = {T(0), T(0), T(0)}, sl[3] = {T(1), T(1), T(1)}, Yl[3][6];   // joint-limit rows of this leg: impulse, side (+1 lower stop, -1 upper), Y
   bool general = false;
   if constexpr (FEAT != 0) {
+    // A limit row can only bind when the joint is within JLIM_GAP of a stop (its target velocity is -gap/dt: 0.06 rad <=> 30 rad/s of
+    // approach); rows further away are dropped — identically in the oracle — and the general solve runs only for warps in which some
+    // robot has such a row (warp-uniform switch: the fast path's shuffles need the whole warp).
+    bool near = false;
     if (cf.jlim) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) near = near || (s.q[j] - md.qlo[j] < JLIM_GAP) || (md.qhi[j] - s.q[j] < JLIM_GAP);
+    }
+    if (cf.jlim && cm.any(near)) {
       // one limit row per joint (a1.py:186-223), towards the nearer stop; Jacobian +-e_j in joint space, none on the base; same target-velocity
       // rule as a contact (approach up to gap/dt, ERP on violation), Bullet btMultiBodyJointLimitConstraint style
-      T Y6[6][6], u6[6], targ6[6], warm6[6], blk[21];
+      T Y6[6][6], u6[6], targ6[6], warm6[6], blk[21]; bool actl[3];
 #pragma unroll
       for (int e = 0; e < 3; e++) {
 #pragma unroll
@@ -481,6 +490,7 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
         u6[3 + j] = sl[j] * qds[j];
         targ6[3 + j] = gap > T(0) ? -gap * idt : cf.erp * (-gap) * idt;
         warm6[3 + j] = cf.warm * s.lam_lim[j];
+        actl[j] = gap < JLIM_GAP;
       }
       // leg-local block J_leg D J_leg^T over the rows (n, t1, t2, lim0, lim1, lim2), packed lower
 #pragma unroll
@@ -495,7 +505,7 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
         }
       }
       T lk6[6];
-      solve_rows24<T>(cm, cf, pr.mu, Y6, u6, blk, targ6, act, warm6, lk6);
+      solve_rows24<T>(cm, cf, pr.mu, Y6, u6, blk, targ6, act, actl, warm6, lk6);
 #pragma unroll
       for (int e = 0; e < 3; e++) { lk[e] = lk6[e]; lkl[e] = lk6[3 + e]; }
       general = true;

@@ -44,6 +44,7 @@ struct HostComm {
   int leg() const { return k; }
   template <typename U> U* scratch() const { return reinterpret_cast<U*>(x->scr); }
   void sync() const { x->bar.wait(); }
+  bool any(bool f) const { return sum4(f ? T(1) : T(0)) > T(0); }
   T sum4(T v) const {  // same butterfly order as the shuffles: (v + v^1) + (that of lane^2)
     x->A[k] = (double)v; x->bar.wait();
     T p = v + (T)x->A[k ^ 1];
