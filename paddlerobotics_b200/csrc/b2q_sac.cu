@@ -7,8 +7,11 @@
 // f32 atomics), data gradients contract over the hidden width.  Activations are therefore kept in two bf16 layouts
 // ([batch x width] and [width x batch]) written by the forward kernel's epilogue, and each weight matrix has a transposed
 // bf16 copy refreshed by the optimiser kernel.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdlib>
+#include <map>
+#include <tuple>
 #include <cuda_bf16.h>
 #include <cstdint>
 #include <cstring>
@@ -27,43 +30,45 @@ namespace {
 constexpr int H = 256;
 
 // ---------------------------------------------------------------------------------------------------------------------
-// generic tensor-core GEMM  C[M x N] (+)= A[M x K] . B[N x K]^T   (bf16 K-major operands, f32 result), N <= 256
+// generic tensor-core GEMM  C[M x N] (+)= A[M x K] . B[N x K]^T   (bf16 K-major operands, f32 result), N tiled by BN <= 64
+//
+// Blackwell-native feed: both operands arrive through TMA tensor maps (cp.async.bulk.tensor.2d, SWIZZLE_128B boxes of 64 K-elements:
+// exactly the K-major shared-memory image the tcgen05 descriptors address; out-of-range rows / K are zero-filled by the TMA unit), a
+// 4-stage full/empty mbarrier ring, warp-specialised roles — warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, all four warps =
+// epilogue — and an epilogue that goes TMEM -> registers -> shared memory -> fully coalesced stores (or coalesced f32 reductions for
+// the split-K weight gradients).
 struct GemmArgs {
-  const bf16* A; int lda; const bf16* B; int ldb; float* C; int ldc;
+  float* C; int ldc;
   int M, N, K, BN, chunks_per_split, atomic;
 };
-constexpr uint32_t G_STAGE_A = 128 * 128, G_STAGE_B = 256 * 128, G_STAGE = G_STAGE_A + G_STAGE_B;
-constexpr uint32_t G_SMEM = 2 * G_STAGE + 64;
+constexpr int G_NSTAGE = 4;
+constexpr uint32_t G_STAGE_A = 128 * 128, G_STAGE_B = 64 * 128, G_STAGE = G_STAGE_A + G_STAGE_B;   // bytes: 128 x 64 bf16 and BN(<=64) x 64 bf16
+constexpr uint32_t G_SMEM = G_NSTAGE * G_STAGE + 128 + 1024;                                       // + barriers + alignment slack
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-  uint32_t sz = valid ? 16u : 0u;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void load_panel(uint32_t dst, const bf16* src, int ld, int row0, int rows_valid, int rows_tile, int k0, int K, int tid) {
-  for (int i = tid; i < rows_tile * 8; i += 128) {
-    int r = i >> 3, c = i & 7, k = k0 + c * 8;
-    bool ok = (row0 + r < rows_valid) && (k < K);
-    const bf16* p = ok ? src + (size_t)(row0 + r) * ld + k : src;
-    cp_async16(dst + r * 128 + ((c ^ (r & 7)) << 4), p, ok);
-  }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(128) b2q_gemm_kernel(GemmArgs g) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t sbase = smem_u32(smem);
-  if ((sbase & 1023u) != 0) __trap();
-  const uint32_t bar_free0 = sbase + 2 * G_STAGE, bar_done = bar_free0 + 16;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 2 * G_STAGE + 32);
+__global__ void __launch_bounds__(128) b2q_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;                 // SWIZZLE_128B operand tiles want 1024-byte alignment
+  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar_full = sbase + G_NSTAGE * G_STAGE, bar_empty = bar_full + 8 * G_NSTAGE, bar_done = bar_empty + 8 * G_NSTAGE;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + G_NSTAGE * G_STAGE + 8 * (2 * G_NSTAGE + 1) + 8);
   const int row0 = blockIdx.x * 128, n0 = blockIdx.y * g.BN;   // output tile: 128 rows x BN columns
   const int nk_total = (g.K + 63) / 64;
   const int kc0 = blockIdx.z * g.chunks_per_split, kc1 = min(nk_total, kc0 + g.chunks_per_split), nk = kc1 - kc0;
-  const uint32_t tm_cols = g.BN <= 32 ? 32u : (g.BN <= 64 ? 64u : (g.BN <= 128 ? 128u : 256u));
+  const uint32_t tm_cols = g.BN <= 32 ? 32u : 64u;
   if (tid == 0) {
-    mbar_init(bar_free0, 1); mbar_init(bar_free0 + 8, 1); mbar_init(bar_done, 1);
+    for (int i = 0; i < G_NSTAGE; i++) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    mbar_init(bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
-  if (warp == 1) {
+  if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(const_cast<const uint32_t*>(tmem_slot))), "r"(tm_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -72,56 +77,59 @@ __global__ void __launch_bounds__(128) b2q_gemm_kernel(GemmArgs g) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (nk > 0) {
-    load_panel(sbase, g.A, g.lda, row0, g.M, 128, kc0 * 64, g.K, tid);
-    load_panel(sbase + G_STAGE_A, g.B, g.ldb, n0, g.N, g.BN, kc0 * 64, g.K, tid);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    const uint32_t idesc = umma_idesc(128, g.BN);
-    for (int kc = 0; kc < nk; kc++) {
-      if (kc + 1 < nk) {
-        const int s1 = (kc + 1) & 1;
-        if (kc + 1 >= 2) mbar_wait(bar_free0 + 8 * s1, (uint32_t)(((kc + 1) / 2 - 1) & 1));
-        load_panel(sbase + s1 * G_STAGE, g.A, g.lda, row0, g.M, 128, (kc0 + kc + 1) * 64, g.K, tid);
-        load_panel(sbase + s1 * G_STAGE + G_STAGE_A, g.B, g.ldb, n0, g.N, g.BN, (kc0 + kc + 1) * 64, g.K, tid);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-      } else {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (warp == 0) {
+      if (lane == 0) {   // ---- TMA producer
+        const uint32_t bytes = G_STAGE_A + (uint32_t)g.BN * 128u;
+        for (int kc = 0; kc < nk; kc++) {
+          const int st = kc % G_NSTAGE;
+          if (kc >= G_NSTAGE) mbar_wait(bar_empty + 8 * st, (uint32_t)((kc / G_NSTAGE - 1) & 1));
+          mbar_expect_tx(bar_full + 8 * st, bytes);
+          tma_load_2d(sbase + st * G_STAGE, &tmA, (kc0 + kc) * 64, row0, bar_full + 8 * st);
+          tma_load_2d(sbase + st * G_STAGE + G_STAGE_A, &tmB, (kc0 + kc) * 64, n0, bar_full + 8 * st);
+        }
       }
-      fence_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        const uint32_t sa = sbase + (kc & 1) * G_STAGE, sb = sa + G_STAGE_A;
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {   // ---- MMA issuer
+        const uint32_t idesc = umma_idesc(128, g.BN);
+        for (int kc = 0; kc < nk; kc++) {
+          const int st = kc % G_NSTAGE;
+          mbar_wait(bar_full + 8 * st, (uint32_t)((kc / G_NSTAGE) & 1));
+          tc_fence_after();
+          const uint32_t sa = sbase + st * G_STAGE, sb = sa + G_STAGE_A;
 #pragma unroll
-        for (int ks = 0; ks < 4; ks++) umma_f16(tmem, umma_desc(sa + ks * 32), umma_desc(sb + ks * 32), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-        umma_commit(bar_free0 + 8 * (kc & 1));
-        if (kc == nk - 1) umma_commit(bar_done);
+          for (int ks = 0; ks < 4; ks++) umma_f16(tmem, umma_desc(sa + ks * 32), umma_desc(sb + ks * 32), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(bar_empty + 8 * st);          // frees the stage when these MMAs have read it
+        }
+        umma_commit(bar_done);
       }
       __syncwarp();
     }
+    // ---- epilogue (all four warps): TMEM lane = tile row; stage the tile in shared memory, then coalesced stores / reductions
     mbar_wait(bar_done, 0);
     tc_fence_after();
+    float* stile = reinterpret_cast<float*>(smem);                      // [128][BN + 1] floats: the operand ring is drained by now
+    const int ldt = g.BN + 1;
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-    const int row = row0 + tid;
     for (int cc = 0; cc < (g.BN + 31) / 32; cc++) {
       uint32_t r[32];
       __syncwarp();
       tmem_ld32(lane_addr + cc * 32, r);
-      if (row < g.M) {
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          int col = n0 + cc * 32 + j;
-          if (col < g.N) {
-            float* c = g.C + (size_t)row * g.ldc + col;
-            if (g.atomic) atomicAdd(c, __uint_as_float(r[j])); else *c = __uint_as_float(r[j]);
-          }
-        }
-      }
+      for (int j = 0; j < 32; j++) if (cc * 32 + j < g.BN) stile[tid * ldt + cc * 32 + j] = __uint_as_float(r[j]);
+    }
+    __syncthreads();
+    const int ncol = min(g.BN, g.N - n0), nrow = min(128, g.M - row0);
+    for (int i = tid; i < nrow * ncol; i += 128) {
+      const int r_ = i / ncol, c_ = i - r_ * ncol;
+      float* c = g.C + (size_t)(row0 + r_) * g.ldc + n0 + c_;
+      const float v = stile[r_ * ldt + c_];
+      if (g.atomic) atomicAdd(c, v); else *c = v;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tm_cols) : "memory");
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tm_cols) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -138,140 +146,168 @@ __global__ void k_critic_dq(const float* q /*[2][B]*/, const float* tq /*[B] or 
   for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
   if ((threadIdx.x & 31) == 0) atomicAdd(loss, l);
 }
-// Vectorised tile kernels (32 batch rows x 256 hidden columns per block, 256 threads): a warp handles one row at a time,
-// each lane 8 consecutive columns (16-byte bf16 / 2 x 16-byte f32 accesses, fully coalesced); column sums are reduced over
-// the block's 8 warps in shared memory (one atomic per column per block); the [width x batch] copy goes through the
-// shared-memory tile as 64-byte row segments.
-__device__ __forceinline__ void tile_finish(bf16 (*tile)[H + 8], float (*csum)[H], const float* cs /*8 column sums of this thread*/, int chunk, int warp,
-                                            bf16* __restrict__ dh_t, float* db, int B, int b0, int nr) {
+// Vectorised tile kernels: a block walks SUBT sub-tiles of 32 batch rows x 256 hidden columns (256 threads: a warp handles one row at a
+// time, each lane 8 consecutive columns — 16-byte bf16 / 2 x 16-byte f32 accesses, fully coalesced).  Column sums and the head's weight
+// gradient are accumulated in registers / shared memory over the block's SUBT x 32 rows and flushed with ONE atomic per column per block
+// (64 blocks at batch 8192: a quarter of the atomics and of the per-address contention of one block per 32 rows); the [width x batch]
+// copy goes through the shared-memory tile as 64-byte row segments.
+constexpr int SUBT = 4;
+__device__ __forceinline__ void tile_transpose_out(bf16 (*tile)[H + 8], bf16* __restrict__ dh_t, int B, int b0, int nr) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * 32; i += 256) { int c = i >> 5, r = i & 31; if (r < nr) dh_t[(size_t)c * B + b0 + r] = tile[r][c]; }
+  __syncthreads();
+}
+__device__ __forceinline__ void colsum_flush(float (*csum)[H], const float* cs /*8 column sums of this thread*/, int chunk, int warp, float* db) {
 #pragma unroll
   for (int j = 0; j < 8; j++) csum[warp][chunk * 8 + j] = cs[j];
   __syncthreads();
   if (db) { float t = 0.f; for (int w = 0; w < 8; w++) t += csum[w][threadIdx.x]; atomicAdd(db + threadIdx.x, t); }
-  for (int i = threadIdx.x; i < H * 32; i += 256) { int c = i >> 5, r = i & 31; if (r < nr) dh_t[(size_t)c * B + b0 + r] = tile[r][c]; }
+  __syncthreads();
 }
 // dh = G (f32 [B][256]) masked by h>0 -> bf16 row-major + transposed; db += column sums
 __global__ void __launch_bounds__(256) k_relu_mask(const float* __restrict__ G, const bf16* __restrict__ h, bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t,
                                                    float* db /*[256] or null*/, int B) {
   __shared__ __align__(16) bf16 tile[32][H + 8];
   __shared__ float csum[8][H];
-  const int chunk = threadIdx.x & 31, warp = threadIdx.x >> 5, b0 = blockIdx.x * 32, nr = min(32, B - b0);
+  const int chunk = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  uint4 hv[4]; float4 g0[4], g1[4];
+  for (int sub = 0; sub < SUBT; sub++) {
+    const int b0 = (blockIdx.x * SUBT + sub) * 32, nr = min(32, B - b0);
+    if (nr <= 0) break;
+    uint4 hv[4]; float4 g0[4], g1[4];
 #pragma unroll
-  for (int k = 0; k < 4; k++) {      // all loads of the thread's four rows in flight before the first use
-    const int r = warp + 8 * k; const size_t off = (size_t)(b0 + r) * H + chunk * 8;
-    if (r < nr) { hv[k] = *reinterpret_cast<const uint4*>(h + off); g0[k] = *reinterpret_cast<const float4*>(G + off); g1[k] = *reinterpret_cast<const float4*>(G + off + 4); }
-  }
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int r = warp + 8 * k;
-    if (r < nr) {
-      const bf16* hb = reinterpret_cast<const bf16*>(&hv[k]);
-      const float gv[8] = {g0[k].x, g0[k].y, g0[k].z, g0[k].w, g1[k].x, g1[k].y, g1[k].z, g1[k].w};
-      __align__(16) bf16 o[8];
-#pragma unroll
-      for (int j = 0; j < 8; j++) { o[j] = __float2bfloat16(__bfloat162float(hb[j]) > 0.f ? gv[j] : 0.f); cs[j] += __bfloat162float(o[j]); }
-      *reinterpret_cast<uint4*>(dh_rm + (size_t)(b0 + r) * H + chunk * 8) = *reinterpret_cast<const uint4*>(o);
-      *reinterpret_cast<uint4*>(&tile[r][chunk * 8]) = *reinterpret_cast<const uint4*>(o);
+    for (int k = 0; k < 4; k++) {      // all loads of the thread's four rows in flight before the first use
+      const int r = warp + 8 * k; const size_t off = (size_t)(b0 + r) * H + chunk * 8;
+      if (r < nr) { hv[k] = *reinterpret_cast<const uint4*>(h + off); g0[k] = *reinterpret_cast<const float4*>(G + off); g1[k] = *reinterpret_cast<const float4*>(G + off + 4); }
     }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int r = warp + 8 * k;
+      if (r < nr) {
+        const bf16* hb = reinterpret_cast<const bf16*>(&hv[k]);
+        const float gv[8] = {g0[k].x, g0[k].y, g0[k].z, g0[k].w, g1[k].x, g1[k].y, g1[k].z, g1[k].w};
+        __align__(16) bf16 o[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { o[j] = __float2bfloat16(__bfloat162float(hb[j]) > 0.f ? gv[j] : 0.f); cs[j] += __bfloat162float(o[j]); }
+        *reinterpret_cast<uint4*>(dh_rm + (size_t)(b0 + r) * H + chunk * 8) = *reinterpret_cast<const uint4*>(o);
+        *reinterpret_cast<uint4*>(&tile[r][chunk * 8]) = *reinterpret_cast<const uint4*>(o);
+      }
+    }
+    tile_transpose_out(tile, dh_t, B, b0, nr);
   }
-  tile_finish(tile, csum, cs, chunk, warp, dh_t, db, B, b0, nr);
+  colsum_flush(csum, cs, chunk, warp, db);
 }
 // critic head backward (out_dim = 1), same tiling: dh2[b,:] = dq[b] W3 masked by h2 > 0; dW3 += sum_b dq[b] h2[b,:]; db3 += sum_b dq; db2 += sum_b dh2
 __global__ void __launch_bounds__(256) k_head_bwd1(const float* __restrict__ dq /*[B]*/, const float* __restrict__ W3 /*[256]*/, const bf16* __restrict__ h2,
                                                    bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t, float* dW3 /*[256]*/, float* db3 /*[1] or null*/, float* db2 /*[256] or null*/, int B) {
   __shared__ __align__(16) bf16 tile[32][H + 8];
   __shared__ float csum[8][H];
-  const int chunk = threadIdx.x & 31, warp = threadIdx.x >> 5, b0 = blockIdx.x * 32, nr = min(32, B - b0);
+  const int chunk = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, w[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) w[j] = W3[chunk * 8 + j];   // scalar loads: the second critic's parameter block starts at an odd float offset
-  uint4 hv[4]; float d[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int r = warp + 8 * k;
-    if (r < nr) { hv[k] = *reinterpret_cast<const uint4*>(h2 + (size_t)(b0 + r) * H + chunk * 8); d[k] = dq[b0 + r]; } else d[k] = 0.f;
-  }
   float sdq = 0.f;
+  for (int sub = 0; sub < SUBT; sub++) {
+    const int b0 = (blockIdx.x * SUBT + sub) * 32, nr = min(32, B - b0);
+    if (nr <= 0) break;
+    uint4 hv[4]; float d[4];
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int r = warp + 8 * k;
-    if (r < nr) {
-      const bf16* hb = reinterpret_cast<const bf16*>(&hv[k]);
-      __align__(16) bf16 o[8];
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const float hf = __bfloat162float(hb[j]);
-        acc[j] += d[k] * hf;
-        o[j] = __float2bfloat16(hf > 0.f ? d[k] * w[j] : 0.f);
-        cs[j] += __bfloat162float(o[j]);
-      }
-      *reinterpret_cast<uint4*>(dh_rm + (size_t)(b0 + r) * H + chunk * 8) = *reinterpret_cast<const uint4*>(o);
-      *reinterpret_cast<uint4*>(&tile[r][chunk * 8]) = *reinterpret_cast<const uint4*>(o);
-      sdq += d[k];
+    for (int k = 0; k < 4; k++) {
+      const int r = warp + 8 * k;
+      if (r < nr) { hv[k] = *reinterpret_cast<const uint4*>(h2 + (size_t)(b0 + r) * H + chunk * 8); d[k] = dq[b0 + r]; } else d[k] = 0.f;
     }
-  }
-  // dW3: reduce the per-thread partial sums over the 8 warps through csum, then the db2 column sums the same way
 #pragma unroll
-  for (int j = 0; j < 8; j++) csum[warp][chunk * 8 + j] = acc[j];
-  __syncthreads();
-  { float t = 0.f; for (int ww = 0; ww < 8; ww++) t += csum[ww][threadIdx.x]; atomicAdd(dW3 + threadIdx.x, t); }
-  if (db3 && chunk == 0) atomicAdd(db3, sdq);        // every lane of a warp holds the same rows: one lane per warp adds its four dq
-  __syncthreads();
-  tile_finish(tile, csum, cs, chunk, warp, dh_t, db2, B, b0, nr);
+    for (int k = 0; k < 4; k++) {
+      const int r = warp + 8 * k;
+      if (r < nr) {
+        const bf16* hb = reinterpret_cast<const bf16*>(&hv[k]);
+        __align__(16) bf16 o[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float hf = __bfloat162float(hb[j]);
+          acc[j] += d[k] * hf;
+          o[j] = __float2bfloat16(hf > 0.f ? d[k] * w[j] : 0.f);
+          cs[j] += __bfloat162float(o[j]);
+        }
+        *reinterpret_cast<uint4*>(dh_rm + (size_t)(b0 + r) * H + chunk * 8) = *reinterpret_cast<const uint4*>(o);
+        *reinterpret_cast<uint4*>(&tile[r][chunk * 8]) = *reinterpret_cast<const uint4*>(o);
+        sdq += d[k];
+      }
+    }
+    tile_transpose_out(tile, dh_t, B, b0, nr);
+  }
+  colsum_flush(csum, acc, chunk, warp, dW3);                 // dW3: per-thread partials reduced over the 8 warps, one atomic per column
+  if (db3 && chunk == 0) atomicAdd(db3, sdq);               // every lane of a warp holds the same rows: one lane per warp adds its dq sum
+  colsum_flush(csum, cs, chunk, warp, db2);
 }
 // general head backward (actor: out_dim = 2A <= 24), same tiling: dh2[b,:] = dy[b,:] . W3 masked by h2 > 0; dW3 += dy^T h2 (one output
-// row at a time: per-thread partials over its four batch rows, reduced over the 8 warps in shared memory); db3, db2
+// row at a time: per-thread partials over its four batch rows, reduced over the 8 warps into a shared [od][256] accumulator that is
+// flushed once per block); db3, db2
 __global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ dy /*[B][od]*/, int od, const float* __restrict__ W3 /*[od][256]*/,
                                                   const bf16* __restrict__ h2 /*[B][256]*/, bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t,
                                                   float* dW3 /*[od][256]*/, float* db3 /*[od] or null*/, float* db2 /*[256] or null*/, int B) {
-  __shared__ __align__(16) bf16 tile[32][H + 8];
-  __shared__ float csum[8][H];
+  // the cross-warp reduction buffer aliases the transpose tile (never live at the same time: every use is fenced by __syncthreads),
+  // which keeps the static shared memory under 48 KB next to the [od][256] weight-gradient accumulator
+  __shared__ __align__(16) unsigned char raw_tile[32 * (H + 8) * sizeof(bf16)];
+  bf16 (*tile)[H + 8] = reinterpret_cast<bf16 (*)[H + 8]>(raw_tile);
+  float (*csum)[H] = reinterpret_cast<float (*)[H]>(raw_tile);
   __shared__ float sdy[32][24];
-  const int chunk = threadIdx.x & 31, warp = threadIdx.x >> 5, b0 = blockIdx.x * 32, nr = min(32, B - b0);
-  for (int i = threadIdx.x; i < 32 * od; i += 256) { int r = i / od, o = i % od; sdy[r][o] = r < nr ? dy[(size_t)(b0 + r) * od + o] : 0.f; }
-  float hf[4][8], g[4][8];
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int r = warp + 8 * k;
-    uint4 hv = make_uint4(0, 0, 0, 0);
-    if (r < nr) hv = *reinterpret_cast<const uint4*>(h2 + (size_t)(b0 + r) * H + chunk * 8);
-    const bf16* hb = reinterpret_cast<const bf16*>(&hv);
-#pragma unroll
-    for (int j = 0; j < 8; j++) { hf[k][j] = __bfloat162float(hb[j]); g[k][j] = 0.f; }
-  }
-  __syncthreads();
-  for (int o = 0; o < od; o++) {
-    float w8[8], acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) { w8[j] = W3[o * H + chunk * 8 + j]; acc[j] = 0.f; }
+  __shared__ float accW[24][H];
+  __shared__ float accb[24];
+  const int chunk = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 24 * H; i += 256) (&accW[0][0])[i] = 0.f;
+  if (threadIdx.x < 24) accb[threadIdx.x] = 0.f;
+  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int sub = 0; sub < SUBT; sub++) {
+    const int b0 = (blockIdx.x * SUBT + sub) * 32, nr = min(32, B - b0);
+    if (nr <= 0) break;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * od; i += 256) { int r = i / od, o = i % od; sdy[r][o] = r < nr ? dy[(size_t)(b0 + r) * od + o] : 0.f; }
+    float hf[4][8], g[4][8];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      const float d = sdy[warp + 8 * k][o];
+      const int r = warp + 8 * k;
+      uint4 hv = make_uint4(0, 0, 0, 0);
+      if (r < nr) hv = *reinterpret_cast<const uint4*>(h2 + (size_t)(b0 + r) * H + chunk * 8);
+      const bf16* hb = reinterpret_cast<const bf16*>(&hv);
 #pragma unroll
-      for (int j = 0; j < 8; j++) { g[k][j] += d * w8[j]; acc[j] += d * hf[k][j]; }
+      for (int j = 0; j < 8; j++) { hf[k][j] = __bfloat162float(hb[j]); g[k][j] = 0.f; }
     }
-#pragma unroll
-    for (int j = 0; j < 8; j++) csum[warp][chunk * 8 + j] = acc[j];
     __syncthreads();
-    { float t = 0.f; for (int ww = 0; ww < 8; ww++) t += csum[ww][threadIdx.x]; atomicAdd(dW3 + o * H + threadIdx.x, t); }
-    __syncthreads();
-  }
-  if (db3 && threadIdx.x < od) { float sd = 0.f; for (int r = 0; r < nr; r++) sd += sdy[r][threadIdx.x]; atomicAdd(db3 + threadIdx.x, sd); }
-  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int o = 0; o < od; o++) {
+      float w8[8], acc[8];
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int r = warp + 8 * k;
-    if (r < nr) {
-      __align__(16) bf16 o8[8];
+      for (int j = 0; j < 8; j++) { w8[j] = W3[o * H + chunk * 8 + j]; acc[j] = 0.f; }
 #pragma unroll
-      for (int j = 0; j < 8; j++) { o8[j] = __float2bfloat16(hf[k][j] > 0.f ? g[k][j] : 0.f); cs[j] += __bfloat162float(o8[j]); }
-      *reinterpret_cast<uint4*>(dh_rm + (size_t)(b0 + r) * H + chunk * 8) = *reinterpret_cast<const uint4*>(o8);
-      *reinterpret_cast<uint4*>(&tile[r][chunk * 8]) = *reinterpret_cast<const uint4*>(o8);
+      for (int k = 0; k < 4; k++) {
+        const float d = sdy[warp + 8 * k][o];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { g[k][j] += d * w8[j]; acc[j] += d * hf[k][j]; }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) csum[warp][chunk * 8 + j] = acc[j];
+      __syncthreads();
+      { float t = 0.f; for (int ww = 0; ww < 8; ww++) t += csum[ww][threadIdx.x]; accW[o][threadIdx.x] += t; }
+      __syncthreads();
     }
+    if (threadIdx.x < od) { float sd = 0.f; for (int r = 0; r < nr; r++) sd += sdy[r][threadIdx.x]; accb[threadIdx.x] += sd; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int r = warp + 8 * k;
+      if (r < nr) {
+        __align__(16) bf16 o8[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { o8[j] = __float2bfloat16(hf[k][j] > 0.f ? g[k][j] : 0.f); cs[j] += __bfloat162float(o8[j]); }
+        *reinterpret_cast<uint4*>(dh_rm + (size_t)(b0 + r) * H + chunk * 8) = *reinterpret_cast<const uint4*>(o8);
+        *reinterpret_cast<uint4*>(&tile[r][chunk * 8]) = *reinterpret_cast<const uint4*>(o8);
+      }
+    }
+    tile_transpose_out(tile, dh_t, B, b0, nr);
   }
-  tile_finish(tile, csum, cs, chunk, warp, dh_t, db2, B, b0, nr);
+  __syncthreads();
+  for (int o = 0; o < od; o++) atomicAdd(dW3 + o * H + threadIdx.x, accW[o][threadIdx.x]);
+  if (db3 && threadIdx.x < od) atomicAdd(db3 + threadIdx.x, accb[threadIdx.x]);
+  colsum_flush(csum, cs, chunk, warp, db2);
 }
 // actor head: from raw y=[mean|raw_ls], eps, da_c (critic gradient wrt action, already includes -1/B routing) build dy and the loss
 __global__ void k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const float* act /*[B][A] tanh(x)*/, const float* logp, const float* q /*[2][B]*/,
@@ -370,6 +406,7 @@ struct B2QSac {
   float *G = nullptr, *tq = nullptr, *q = nullptr, *qn = nullptr, *dq = nullptr, *next_a = nullptr, *next_logp = nullptr, *cur_a = nullptr, *cur_logp = nullptr, *raw_a = nullptr,
         *da_c = nullptr, *dy = nullptr, *losses = nullptr;
   std::vector<void*> allocs;
+  void* tmap_cache = nullptr;   // TmapCache*: TMA tensor maps of the GEMM operands
   int* d_step = nullptr;
   int64_t launches = 0;
   std::string err;
@@ -392,11 +429,33 @@ template <typename T> bool dalloc(B2QSac* s, T** p, size_t count) {
 void fork(B2QSac* s, cudaStream_t st) { cudaEventRecord(s->ev_fork, st); cudaStreamWaitEvent(s->side, s->ev_fork, 0); }
 void join(B2QSac* s, cudaStream_t st) { cudaEventRecord(s->ev_join, s->side); cudaStreamWaitEvent(st, s->ev_join, 0); }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// 2-D bf16 tensor map of a row-major [rows][cols] matrix with leading dimension ld: box = 64 K-elements (128 bytes, the swizzle span) x box_rows
+bool make_tmap(CUtensorMap* tm, const bf16* base, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows}, strides[1] = {(cuuint64_t)ld * sizeof(bf16)};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows}, estr[2] = {1u, 1u};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+struct TmapCache { std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> m; };
+TmapCache& tmaps(B2QSac* s) { if (!s->tmap_cache) s->tmap_cache = new TmapCache(); return *static_cast<TmapCache*>(s->tmap_cache); }
+
 int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int ldb, float* C, int ldc, int M, int N, int K, bool splitk) {
-  GemmArgs g; g.A = A; g.lda = lda; g.B = Bm; g.ldb = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  GemmArgs g; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
   g.BN = ((N + 15) / 16) * 16;
-  static const int bn_max = [] { const char* e = std::getenv("B2Q_GEMM_BN"); int v = e ? std::atoi(e) : 64; return (v == 64 || v == 128 || v == 256) ? v : 64; }();   // output-tile width (measured: 64 < 128 < 256 in learn time)
-  if (g.BN > bn_max) g.BN = bn_max;                      // N tiled (grid.y): more CTAs, smaller B panel per k-chunk
+  if (g.BN > 64) g.BN = 64;                              // N tiled by 64 (grid.y): more CTAs on these latency-bound shapes, 8 KB B panel per k-chunk
   const int ntiles = (N + g.BN - 1) / g.BN;
   int nk = (K + 63) / 64, splits = 1;
   static const int split_div = [] { const char* e = std::getenv("B2Q_GEMM_SPLIT_DIV"); int v = e ? std::atoi(e) : 8; return v < 1 ? 1 : v; }();   // K chunks (of 64) per split-K CTA
@@ -404,9 +463,24 @@ int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int
   g.chunks_per_split = (nk + splits - 1) / splits;
   splits = (nk + g.chunks_per_split - 1) / g.chunks_per_split;
   g.atomic = splits > 1 ? 1 : 0;
+  // tensor maps are cached per (pointer, shape): the learner's buffers are fixed, so each map is encoded once
+  auto get = [&](const bf16* p, int rows, int ld, int box_rows) -> const CUtensorMap* {
+    auto key = std::make_tuple((const void*)p, rows, K, ld, box_rows);
+    auto& mp = tmaps(s).m;
+    auto it = mp.find(key);
+    if (it == mp.end()) {
+      CUtensorMap tm;
+      if (!make_tmap(&tm, p, rows, K, ld, box_rows)) return nullptr;
+      it = mp.emplace(key, tm).first;
+    }
+    return &it->second;
+  };
+  const CUtensorMap* ta = get(A, M, lda, 128);
+  const CUtensorMap* tb = get(Bm, N, ldb, g.BN);
+  if (!ta || !tb) { s->err = "cuTensorMapEncodeTiled failed"; return -2; }
   if (g.atomic) cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st);
   dim3 grid((M + 127) / 128, ntiles, splits);
-  b2q_gemm_kernel<<<grid, 128, G_SMEM, st>>>(g);
+  b2q_gemm_kernel<<<grid, 128, G_SMEM, st>>>(*ta, *tb, g);
   s->launches++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
@@ -448,7 +522,7 @@ int hidden_backward(B2QSac* s, cudaStream_t st, int slot, const bf16* dh2_rm, co
   if (gemm(s, ax, dh2_t, B, h1_t, B, gW2, H, H, H, B, true)) return -2;
   cudaEventRecord(s->ev_aux[2 * slot + 1], ax);
   if (gemm(s, st, dh2_rm, H, W2T, H, G, H, B, H, H, false)) return -2;
-  k_relu_mask<<<(B + 31) / 32, H, 0, st>>>(G, h1_rm, s->dh1_rm[slot], s->dh1_t[slot], gb1, B);                                                      // dh1, db1
+  k_relu_mask<<<(B + 32 * SUBT - 1) / (32 * SUBT), H, 0, st>>>(G, h1_rm, s->dh1_rm[slot], s->dh1_t[slot], gb1, B);                                                      // dh1, db1
   if (gemm(s, st, s->dh1_t[slot], B, x_t, B, gW1, in_dim, H, in_dim, B, true)) return -2;
   cudaStreamWaitEvent(st, s->ev_aux[2 * slot + 1], 0);
   s->launches += 4;
@@ -463,7 +537,7 @@ int critic_backward(B2QSac* s, cudaStream_t st0) {
     bf16 *dh_rm = i ? s->dh_rm2 : s->dh_rm, *dh_t = i ? s->dh_t2 : s->dh_t; float* G = i ? s->G2 : s->G;
     float* g = s->g_critic + (size_t)i * cn.n; const float* p = s->p_critic + (size_t)i * cn.n;
     const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h1t = s->hc1_t + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
-    k_head_bwd1<<<(B + 31) / 32, H, 0, st>>>(s->dq + (size_t)i * B, p + cn.oW3, h2, dh_rm, dh_t, g + cn.oW3, g + cn.ob3, g + cn.ob2, B);   // dh2, dW3, db3, db2
+    k_head_bwd1<<<(B + 32 * SUBT - 1) / (32 * SUBT), H, 0, st>>>(s->dq + (size_t)i * B, p + cn.oW3, h2, dh_rm, dh_t, g + cn.oW3, g + cn.ob3, g + cn.ob2, B);   // dh2, dW3, db3, db2
     s->launches++;
     if (hidden_backward(s, st, i, dh_rm, dh_t, G, h1, h1t, s->xc_t, s->W2T[1 + i], g + cn.oW2, g + cn.ob1, g + cn.oW1, cn.in_dim)) return -2;
   }
@@ -474,7 +548,7 @@ int critic_backward(B2QSac* s, cudaStream_t st0) {
 int actor_backward(B2QSac* s, cudaStream_t st) {
   const int B = s->B, A = s->A; const Net& an = s->an;
   float* g = s->g_actor;
-  k_head_bwd<<<(B + 31) / 32, H, 0, st>>>(s->dy, 2 * A, s->p_actor + an.oW3, s->ha2_rm, s->dh_rm, s->dh_t, g + an.oW3, g + an.ob3, g + an.ob2, B);
+  k_head_bwd<<<(B + 32 * SUBT - 1) / (32 * SUBT), H, 0, st>>>(s->dy, 2 * A, s->p_actor + an.oW3, s->ha2_rm, s->dh_rm, s->dh_t, g + an.oW3, g + an.ob3, g + an.ob2, B);
   s->launches++;
   return hidden_backward(s, st, 0, s->dh_rm, s->dh_t, s->G, s->ha1_rm, s->ha1_t, s->xa_t, s->W2T[0], g + an.oW2, g + an.ob1, g + an.oW1, an.in_dim);
 }
@@ -530,6 +604,7 @@ int b2q_sac_destroy(B2QSacHandle s) {
   if (s->mlp_actor) b2q_mlp_destroy(s->mlp_actor);
   if (s->mlp_critic) b2q_mlp_destroy(s->mlp_critic);
   if (s->mlp_target) b2q_mlp_destroy(s->mlp_target);
+  delete static_cast<TmapCache*>(s->tmap_cache);
   delete s;
   return 0;
 }
@@ -622,9 +697,9 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
       bf16 *dh_rm = i ? s->dh_rm2 : s->dh_rm, *dh_t = i ? s->dh_t2 : s->dh_t; float *G = i ? s->G2 : s->G, *da = i ? s->da_c2 : s->da_c;
       const float* p = s->p_critic + (size_t)i * cn.n;
       const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
-      k_head_bwd1<<<(B + 31) / 32, H, 0, sx>>>(s->dq + (size_t)i * B, p + cn.oW3, h2, dh_rm, dh_t, G /*scratch dW3*/, nullptr, nullptr, B);
+      k_head_bwd1<<<(B + 32 * SUBT - 1) / (32 * SUBT), H, 0, sx>>>(s->dq + (size_t)i * B, p + cn.oW3, h2, dh_rm, dh_t, G /*scratch dW3*/, nullptr, nullptr, B);
       if (gemm(s, sx, dh_rm, H, s->W2T[1 + i], H, G, H, B, H, H, false)) return -2;
-      k_relu_mask<<<(B + 31) / 32, H, 0, sx>>>(G, h1, dh_rm, dh_t, nullptr, B);
+      k_relu_mask<<<(B + 32 * SUBT - 1) / (32 * SUBT), H, 0, sx>>>(G, h1, dh_rm, dh_t, nullptr, B);
       if (gemm(s, sx, dh_rm, H, s->W1A[1 + i], H, da, 16, B, 16, H, false)) return -2;                    // da_i [B][16]
       s->launches += 2;
     }
