@@ -149,9 +149,9 @@ __global__ void k_critic_dq(const float* q /*[2][B]*/, const float* tq /*[B] or 
 // Vectorised tile kernels: a block walks SUBT sub-tiles of 32 batch rows x 256 hidden columns (256 threads: a warp handles one row at a
 // time, each lane 8 consecutive columns — 16-byte bf16 / 2 x 16-byte f32 accesses, fully coalesced).  Column sums and the head's weight
 // gradient are accumulated in registers / shared memory over the block's SUBT x 32 rows and flushed with ONE atomic per column per block
-// (64 blocks at batch 8192: a quarter of the atomics and of the per-address contention of one block per 32 rows); the [width x batch]
+// (128 blocks at batch 8192: half the atomics and per-address contention of one block per 32 rows, and still one block per SM); the [width x batch]
 // copy goes through the shared-memory tile as 64-byte row segments.
-constexpr int SUBT = 4;
+constexpr int SUBT = 2;
 __device__ __forceinline__ void tile_transpose_out(bf16 (*tile)[H + 8], bf16* __restrict__ dh_t, int B, int b0, int nr) {
   __syncthreads();
   for (int i = threadIdx.x; i < H * 32; i += 256) { int c = i >> 5, r = i & 31; if (r < nr) dh_t[(size_t)c * B + b0 + r] = tile[r][c]; }
@@ -240,28 +240,27 @@ __global__ void __launch_bounds__(256) k_head_bwd1(const float* __restrict__ dq 
   if (db3 && chunk == 0) atomicAdd(db3, sdq);               // every lane of a warp holds the same rows: one lane per warp adds its dq sum
   colsum_flush(csum, cs, chunk, warp, db2);
 }
-// general head backward (actor: out_dim = 2A <= 24), same tiling: dh2[b,:] = dy[b,:] . W3 masked by h2 > 0; dW3 += dy^T h2 (one output
-// row at a time: per-thread partials over its four batch rows, reduced over the 8 warps into a shared [od][256] accumulator that is
-// flushed once per block); db3, db2
+// general head backward (actor: out_dim = 2A <= 24), same tiling, two mappings per 32-row sub-tile and no per-output barriers:
+//   rows -> warps:    dh2[b,:] = dy[b,:] . W3 masked by h2 > 0 (each warp four rows), written row-major + staged for the transposed copy
+//   outputs -> warps: dW3[o,:] += sum_b dy[b,o] h2[b,:] with warp w owning outputs o = w, w+8, w+16 over ALL rows of the sub-tile (h2 tile
+//                     in shared memory), so the partial sums stay in registers until one atomic flush per block
 __global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ dy /*[B][od]*/, int od, const float* __restrict__ W3 /*[od][256]*/,
                                                   const bf16* __restrict__ h2 /*[B][256]*/, bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t,
                                                   float* dW3 /*[od][256]*/, float* db3 /*[od] or null*/, float* db2 /*[256] or null*/, int B) {
-  // the cross-warp reduction buffer aliases the transpose tile (never live at the same time: every use is fenced by __syncthreads),
-  // which keeps the static shared memory under 48 KB next to the [od][256] weight-gradient accumulator
   __shared__ __align__(16) unsigned char raw_tile[32 * (H + 8) * sizeof(bf16)];
   bf16 (*tile)[H + 8] = reinterpret_cast<bf16 (*)[H + 8]>(raw_tile);
-  float (*csum)[H] = reinterpret_cast<float (*)[H]>(raw_tile);
+  float (*csum)[H] = reinterpret_cast<float (*)[H]>(raw_tile);          // aliases the tile: only used after the last transpose-out
+  __shared__ __align__(16) bf16 h2s[32][H + 8];
   __shared__ float sdy[32][24];
-  __shared__ float accW[24][H];
-  __shared__ float accb[24];
   const int chunk = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 24 * H; i += 256) (&accW[0][0])[i] = 0.f;
-  if (threadIdx.x < 24) accb[threadIdx.x] = 0.f;
-  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, accw[3][8], accb = 0.f;
+#pragma unroll
+  for (int oi = 0; oi < 3; oi++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) accw[oi][j] = 0.f;
   for (int sub = 0; sub < SUBT; sub++) {
     const int b0 = (blockIdx.x * SUBT + sub) * 32, nr = min(32, B - b0);
     if (nr <= 0) break;
-    __syncthreads();
     for (int i = threadIdx.x; i < 32 * od; i += 256) { int r = i / od, o = i % od; sdy[r][o] = r < nr ? dy[(size_t)(b0 + r) * od + o] : 0.f; }
     float hf[4][8], g[4][8];
 #pragma unroll
@@ -269,28 +268,23 @@ __global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ dy /
       const int r = warp + 8 * k;
       uint4 hv = make_uint4(0, 0, 0, 0);
       if (r < nr) hv = *reinterpret_cast<const uint4*>(h2 + (size_t)(b0 + r) * H + chunk * 8);
+      *reinterpret_cast<uint4*>(&h2s[r][chunk * 8]) = hv;
       const bf16* hb = reinterpret_cast<const bf16*>(&hv);
 #pragma unroll
       for (int j = 0; j < 8; j++) { hf[k][j] = __bfloat162float(hb[j]); g[k][j] = 0.f; }
     }
     __syncthreads();
-    for (int o = 0; o < od; o++) {
-      float w8[8], acc[8];
+    for (int o = 0; o < od; o++) {          // rows -> warps
+      float w8[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) { w8[j] = W3[o * H + chunk * 8 + j]; acc[j] = 0.f; }
+      for (int j = 0; j < 8; j++) w8[j] = W3[o * H + chunk * 8 + j];
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const float d = sdy[warp + 8 * k][o];
 #pragma unroll
-        for (int j = 0; j < 8; j++) { g[k][j] += d * w8[j]; acc[j] += d * hf[k][j]; }
+        for (int j = 0; j < 8; j++) g[k][j] += d * w8[j];
       }
-#pragma unroll
-      for (int j = 0; j < 8; j++) csum[warp][chunk * 8 + j] = acc[j];
-      __syncthreads();
-      { float t = 0.f; for (int ww = 0; ww < 8; ww++) t += csum[ww][threadIdx.x]; accW[o][threadIdx.x] += t; }
-      __syncthreads();
     }
-    if (threadIdx.x < od) { float sd = 0.f; for (int r = 0; r < nr; r++) sd += sdy[r][threadIdx.x]; accb[threadIdx.x] += sd; }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int r = warp + 8 * k;
@@ -302,11 +296,32 @@ __global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ dy /
         *reinterpret_cast<uint4*>(&tile[r][chunk * 8]) = *reinterpret_cast<const uint4*>(o8);
       }
     }
+#pragma unroll
+    for (int oi = 0; oi < 3; oi++) {        // outputs -> warps
+      const int o = warp + 8 * oi;
+      if (o < od) {
+        for (int r = 0; r < nr; r++) {
+          const float d = sdy[r][o];
+          const uint4 hv = *reinterpret_cast<const uint4*>(&h2s[r][chunk * 8]);
+          const bf16* hb = reinterpret_cast<const bf16*>(&hv);
+#pragma unroll
+          for (int j = 0; j < 8; j++) accw[oi][j] += d * __bfloat162float(hb[j]);
+        }
+      }
+    }
+    if (threadIdx.x < od) for (int r = 0; r < nr; r++) accb += sdy[r][threadIdx.x];
     tile_transpose_out(tile, dh_t, B, b0, nr);
   }
+#pragma unroll
+  for (int oi = 0; oi < 3; oi++) {
+    const int o = warp + 8 * oi;
+    if (o < od) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) atomicAdd(dW3 + o * H + chunk * 8 + j, accw[oi][j]);
+    }
+  }
+  if (db3 && threadIdx.x < od) atomicAdd(db3 + threadIdx.x, accb);
   __syncthreads();
-  for (int o = 0; o < od; o++) atomicAdd(dW3 + o * H + threadIdx.x, accW[o][threadIdx.x]);
-  if (db3 && threadIdx.x < od) atomicAdd(db3 + threadIdx.x, accb[threadIdx.x]);
   colsum_flush(csum, cs, chunk, warp, db2);
 }
 // actor head: from raw y=[mean|raw_ls], eps, da_c (critic gradient wrt action, already includes -1/B routing) build dy and the loss
