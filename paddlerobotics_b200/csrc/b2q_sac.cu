@@ -198,7 +198,23 @@ __global__ void __launch_bounds__(256) k_relu_mask(const float* __restrict__ G, 
   colsum_flush(csum, cs, chunk, warp, db);
 }
 // critic head backward (out_dim = 1), same tiling: dh2[b,:] = dq[b] W3 masked by h2 > 0; dW3 += sum_b dq[b] h2[b,:]; db3 += sum_b dq; db2 += sum_b dh2
-__global__ void __launch_bounds__(256) k_head_bwd1(const float* __restrict__ dq /*[B]*/, const float* __restrict__ W3 /*[256]*/, const bf16* __restrict__ h2,
+// How a row's dq is obtained: from an array, or computed in place so that the tiny dq kernels drop out of the dependency chain
+//   DQ_CRITIC: dq = 2 (q - tq)/B with tq = r + gamma * term * (min(q1', q2') - alpha * logp')  (sac.py:85-95; loss += (q - tq)^2 / B)
+//   DQ_MINQ:   d(-min(q1, q2))/dq_i / B for the actor loss (torch.min picks the first on ties; sac.py:104-106)
+enum { DQ_ARRAY = 0, DQ_CRITIC = 1, DQ_MINQ = 2 };
+struct DqSrc { int mode, net; const float *q /*[2][B]*/, *rew, *term, *qn /*[2][B]*/, *logpn; float gamma, alpha; float* loss; };
+__device__ __forceinline__ float dq_of_row(const DqSrc& d, const float* dq, int b, int B, float& loss_acc) {
+  if (d.mode == DQ_ARRAY) return dq[b];
+  if (d.mode == DQ_CRITIC) {
+    const float tq = d.rew[b] + d.gamma * d.term[b] * (fminf(d.qn[b], d.qn[B + b]) - d.alpha * d.logpn[b]);
+    const float e = d.q[d.net * B + b] - tq;
+    loss_acc += e * e / (float)B;
+    return 2.f * e / (float)B;
+  }
+  const bool first = d.q[b] <= d.q[B + b];
+  return ((d.net == 0) == first) ? -1.f / (float)B : 0.f;
+}
+__global__ void __launch_bounds__(256) k_head_bwd1(const float* __restrict__ dq /*[B]*/, DqSrc src, const float* __restrict__ W3 /*[256]*/, const bf16* __restrict__ h2,
                                                    bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t, float* dW3 /*[256]*/, float* db3 /*[1] or null*/, float* db2 /*[256] or null*/, int B) {
   __shared__ __align__(16) bf16 tile[32][H + 8];
   __shared__ float csum[8][H];
@@ -206,7 +222,7 @@ __global__ void __launch_bounds__(256) k_head_bwd1(const float* __restrict__ dq 
   float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, w[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) w[j] = W3[chunk * 8 + j];   // scalar loads: the second critic's parameter block starts at an odd float offset
-  float sdq = 0.f;
+  float sdq = 0.f, sloss = 0.f;
   for (int sub = 0; sub < SUBT; sub++) {
     const int b0 = (blockIdx.x * SUBT + sub) * 32, nr = min(32, B - b0);
     if (nr <= 0) break;
@@ -214,7 +230,7 @@ __global__ void __launch_bounds__(256) k_head_bwd1(const float* __restrict__ dq 
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int r = warp + 8 * k;
-      if (r < nr) { hv[k] = *reinterpret_cast<const uint4*>(h2 + (size_t)(b0 + r) * H + chunk * 8); d[k] = dq[b0 + r]; } else d[k] = 0.f;
+      if (r < nr) { hv[k] = *reinterpret_cast<const uint4*>(h2 + (size_t)(b0 + r) * H + chunk * 8); d[k] = dq_of_row(src, dq, b0 + r, B, sloss); } else d[k] = 0.f;
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -238,6 +254,7 @@ __global__ void __launch_bounds__(256) k_head_bwd1(const float* __restrict__ dq 
   }
   colsum_flush(csum, acc, chunk, warp, dW3);                 // dW3: per-thread partials reduced over the 8 warps, one atomic per column
   if (db3 && chunk == 0) atomicAdd(db3, sdq);               // every lane of a warp holds the same rows: one lane per warp adds its dq sum
+  if (src.mode == DQ_CRITIC && chunk == 0) atomicAdd(src.loss, sloss);   // ... and its share of the critic loss
   colsum_flush(csum, cs, chunk, warp, db2);
 }
 // general head backward (actor: out_dim = 2A <= 24), same tiling, two mappings per 32-row sub-tile and no per-output barriers:
@@ -326,7 +343,7 @@ __global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ dy /
 }
 // actor head: from raw y=[mean|raw_ls], eps, da_c (critic gradient wrt action, already includes -1/B routing) build dy and the loss
 __global__ void k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const float* act /*[B][A] tanh(x)*/, const float* logp, const float* q /*[2][B]*/,
-                           const float* da_c /*[B][16] (cols 0..A-1)*/, float alpha, float* dy /*[B][2A]*/, float* loss, int B, int A) {
+                           const float* da_c /*[B][16] (cols 0..A-1)*/, const float* da_c2 /*second critic's part or null*/, float alpha, float* dy /*[B][2A]*/, float* loss, int B, int A) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   float l = 0.f;
   if (b < B) {
@@ -334,7 +351,7 @@ __global__ void k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const
     for (int j = 0; j < A; j++) {
       float a = act[(size_t)b * A + j], rl = raw[(size_t)b * 2 * A + A + j];
       float ls = fminf(fmaxf(rl, -20.f), 2.f), sd = expf(ls), e = eps[(size_t)b * A + j];
-      float ga = da_c[(size_t)b * 16 + j] + (alpha / (float)B) * (2.f * a / ((1.f - a * a) + 1e-6f));
+      float ga = da_c[(size_t)b * 16 + j] + (da_c2 ? da_c2[(size_t)b * 16 + j] : 0.f) + (alpha / (float)B) * (2.f * a / ((1.f - a * a) + 1e-6f));
       float gx = ga * (1.f - a * a);
       float gls = gx * sd * e - alpha / (float)B;
       dy[(size_t)b * 2 * A + j] = gx;
@@ -370,18 +387,21 @@ __global__ void k_add_f32(float* dst, const float* src, int n) { int i = blockId
 // Adam (torch.optim.Adam defaults: betas 0.9/0.999, eps 1e-8, no weight decay), sac.py:55-58
 __global__ void k_step_inc(int* step) { *step += 1; }
 // the step counter lives on the device so that the whole learn() can be replayed from a CUDA graph
+// `step` holds the number of COMPLETED optimiser steps; both Adam kernels of a learn use step + 1 and the last kernel of the learn
+// (k_polyak / k_step_inc) advances it — no separate increment kernel in front of the Adam on the dependency chain
 __global__ void k_adam(float* p, const float* g, float* m, float* v, int n, float lr, float b1, float b2, float eps, const int* step) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    const float t = (float)(*step), bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+    const float t = (float)(*step + 1), bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
     float gi = g[i], mi = b1 * m[i] + (1.f - b1) * gi, vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi; v[i] = vi;
     p[i] -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
   }
 }
-__global__ void k_polyak(float* tgt, const float* src, int n, float tau) {   // sync_target, sac.py:112-118: target = tau*param + (1-tau)*target
+__global__ void k_polyak(float* tgt, const float* src, int n, float tau, int* step) {   // sync_target, sac.py:112-118: target = tau*param + (1-tau)*target
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) tgt[i] = tau * src[i] + (1.f - tau) * tgt[i];
+  if (i == 0 && step) *step += 1;
 }
 // bf16 helper copies of one net's weights for the backward GEMMs: W2T [256][256], W3T64 [256][64] (k = output index, zero padded),
 // W1A [16][256] (rows = action columns of W1, for d/da)
@@ -505,21 +525,25 @@ int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int
 void sync_net_weights(B2QSac* s, cudaStream_t st, int which = 7) {
   const Net& a = s->an; const Net& c = s->cn;
   fork(s, st);
+  // the forward-image pack and the bf16 backward copies of a net are independent: the copies run on a helper stream beside the pack
+  // (one stage of the dependency chain instead of two)
+  cudaEventRecord(s->ev_aux[0], st); cudaStreamWaitEvent(s->aux[0], s->ev_aux[0], 0);
   if (which & 1) {
+    k_make_bwd_weights<<<(H * H + 255) / 256, 256, 0, s->aux[0]>>>(s->p_actor + a.oW1, a.in_dim, 0, 0, s->p_actor + a.oW2, s->p_actor + a.oW3, a.od, s->W2T[0], s->W3T[0], s->W1A[0]);
     b2q_mlp_set_weights(s->mlp_actor, 0, s->p_actor + a.oW1, s->p_actor + a.ob1, s->p_actor + a.oW2, s->p_actor + a.ob2, s->p_actor + a.oW3, s->p_actor + a.ob3, st);
-    k_make_bwd_weights<<<(H * H + 255) / 256, 256, 0, st>>>(s->p_actor + a.oW1, a.in_dim, 0, 0, s->p_actor + a.oW2, s->p_actor + a.oW3, a.od, s->W2T[0], s->W3T[0], s->W1A[0]);
     s->launches += 2;
   }
   for (int i = 0; i < 2; i++) {
     cudaStream_t sx = i ? s->side : st;
     float* p = s->p_critic + (size_t)i * c.n; float* t = s->p_target + (size_t)i * c.n;
     if (which & 2) {
+      k_make_bwd_weights<<<(H * H + 255) / 256, 256, 0, s->aux[0]>>>(p + c.oW1, c.in_dim, s->D, s->A, p + c.oW2, p + c.oW3, c.od, s->W2T[1 + i], s->W3T[1 + i], s->W1A[1 + i]);
       b2q_mlp_set_weights(s->mlp_critic, i, p + c.oW1, p + c.ob1, p + c.oW2, p + c.ob2, p + c.oW3, p + c.ob3, sx);
-      k_make_bwd_weights<<<(H * H + 255) / 256, 256, 0, sx>>>(p + c.oW1, c.in_dim, s->D, s->A, p + c.oW2, p + c.oW3, c.od, s->W2T[1 + i], s->W3T[1 + i], s->W1A[1 + i]);
       s->launches += 2;
     }
     if (which & 4) { b2q_mlp_set_weights(s->mlp_target, i, t + c.oW1, t + c.ob1, t + c.oW2, t + c.ob2, t + c.oW3, t + c.ob3, s->side); s->launches++; }
   }
+  cudaEventRecord(s->ev_aux[1], s->aux[0]); cudaStreamWaitEvent(st, s->ev_aux[1], 0);
   join(s, st);
 }
 
@@ -544,7 +568,7 @@ int hidden_backward(B2QSac* s, cudaStream_t st, int slot, const bf16* dh2_rm, co
   return 0;
 }
 // weight gradients of both critics from dq [2][B] and the activation dumps of the last critic forward
-int critic_backward(B2QSac* s, cudaStream_t st0) {
+int critic_backward(B2QSac* s, cudaStream_t st0, DqSrc src = DqSrc{DQ_ARRAY, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr}) {
   const int B = s->B; const Net& cn = s->cn;
   fork(s, st0);
   for (int i = 0; i < 2; i++) {
@@ -552,7 +576,8 @@ int critic_backward(B2QSac* s, cudaStream_t st0) {
     bf16 *dh_rm = i ? s->dh_rm2 : s->dh_rm, *dh_t = i ? s->dh_t2 : s->dh_t; float* G = i ? s->G2 : s->G;
     float* g = s->g_critic + (size_t)i * cn.n; const float* p = s->p_critic + (size_t)i * cn.n;
     const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h1t = s->hc1_t + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
-    k_head_bwd1<<<(B + 32 * SUBT - 1) / (32 * SUBT), H, 0, st>>>(s->dq + (size_t)i * B, p + cn.oW3, h2, dh_rm, dh_t, g + cn.oW3, g + cn.ob3, g + cn.ob2, B);   // dh2, dW3, db3, db2
+    src.net = i;
+    k_head_bwd1<<<(B + 32 * SUBT - 1) / (32 * SUBT), H, 0, st>>>(s->dq + (size_t)i * B, src, p + cn.oW3, h2, dh_rm, dh_t, g + cn.oW3, g + cn.ob3, g + cn.ob2, B);   // (dq,) dh2, dW3, db3, db2
     s->launches++;
     if (hidden_backward(s, st, i, dh_rm, dh_t, G, h1, h1t, s->xc_t, s->W2T[1 + i], g + cn.oW2, g + cn.ob1, g + cn.oW1, cn.in_dim)) return -2;
   }
@@ -673,24 +698,22 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     fork(s, st);
     if (b2q_mlp_forward(s->mlp_actor, next_obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2 + 1, eps_next, s->next_a, s->next_logp, nullptr, s->side)) return -2;
     if (b2q_mlp_forward(s->mlp_target, next_obs, D, s->next_a, B, B2Q_MLP_RAW, 0, nullptr, s->qn, nullptr, nullptr, s->side)) return -2;
-    k_target_q<<<NB, TB, 0, s->side>>>(rew, term, s->qn, s->qn + B, s->next_logp, s->gamma, s->alpha, s->tq, B);
     // current Q with activation dumps (independent of the target chain: main stream)
     B2QMlpSaves sv = {s->xc_rm, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
     if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, act, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, st)) return -2;
     join(s, st);
-    k_critic_dq<<<dim3(NB, 2), TB, 0, st>>>(s->q, s->tq, 0, s->dq, s->losses + 0, B);
-    s->launches += 5;
-    if (critic_backward(s, st)) return -2;
+    s->launches += 3;
+    DqSrc src{DQ_CRITIC, 0, s->q, rew, term, s->qn, s->next_logp, s->gamma, s->alpha, s->losses + 0};   // target Q and dq are computed inside the head backward
+    if (critic_backward(s, st, src)) return -2;
   } else if (phase == 1 || phase == 3) {
     const float b1 = 0.9f, b2 = 0.999f;
     if (phase == 1) {
       int n = (int)(2 * cn.n);
-      k_step_inc<<<1, 1, 0, st>>>(s->d_step);
       k_adam<<<(n + 255) / 256, 256, 0, st>>>(s->p_critic, s->g_critic, s->m_c, s->v_c, n, s->lr_c, b1, b2, 1e-8f, s->d_step);
     } else {
       int n = (int)an.n, nc = (int)(2 * cn.n);
       k_adam<<<(n + 255) / 256, 256, 0, st>>>(s->p_actor, s->g_actor, s->m_a, s->v_a, n, s->lr_a, b1, b2, 1e-8f, s->d_step);
-      k_polyak<<<(nc + 255) / 256, 256, 0, st>>>(s->p_target, s->p_critic, nc, s->tau);
+      k_polyak<<<(nc + 255) / 256, 256, 0, st>>>(s->p_target, s->p_critic, nc, s->tau, s->d_step);
       s->launches++;
     }
     s->launches++;
@@ -703,8 +726,7 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2, eps_cur, s->cur_a, s->cur_logp, s->raw_a, &sa, st)) return -2;
     B2QMlpSaves sv = {s->xc_rm, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
     if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, st)) return -2;
-    k_minq_dq<<<NB, TB, 0, st>>>(s->q, s->dq, B);
-    s->launches += 3;
+    s->launches += 2;
     // d(-min q)/da through both critics (no critic weight gradients: only the actor optimiser steps here)
     fork(s, st);
     for (int i = 0; i < 2; i++) {
@@ -712,17 +734,16 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
       bf16 *dh_rm = i ? s->dh_rm2 : s->dh_rm, *dh_t = i ? s->dh_t2 : s->dh_t; float *G = i ? s->G2 : s->G, *da = i ? s->da_c2 : s->da_c;
       const float* p = s->p_critic + (size_t)i * cn.n;
       const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
-      k_head_bwd1<<<(B + 32 * SUBT - 1) / (32 * SUBT), H, 0, sx>>>(s->dq + (size_t)i * B, p + cn.oW3, h2, dh_rm, dh_t, G /*scratch dW3*/, nullptr, nullptr, B);
+      DqSrc src{DQ_MINQ, i, s->q, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr};
+      k_head_bwd1<<<(B + 32 * SUBT - 1) / (32 * SUBT), H, 0, sx>>>(nullptr, src, p + cn.oW3, h2, dh_rm, dh_t, G /*scratch dW3*/, nullptr, nullptr, B);
       if (gemm(s, sx, dh_rm, H, s->W2T[1 + i], H, G, H, B, H, H, false)) return -2;
       k_relu_mask<<<(B + 32 * SUBT - 1) / (32 * SUBT), H, 0, sx>>>(G, h1, dh_rm, dh_t, nullptr, B);
       if (gemm(s, sx, dh_rm, H, s->W1A[1 + i], H, da, 16, B, 16, H, false)) return -2;                    // da_i [B][16]
       s->launches += 2;
     }
     join(s, st);
-    k_add_f32<<<(B * 16 + 255) / 256, 256, 0, st>>>(s->da_c, s->da_c2, B * 16);                              // da = da_1 + da_2
-    s->launches++;
     if (!eps_cur) return -1;   // the explicit-noise path is required for the backward pass
-    k_actor_dy<<<NB, TB, 0, st>>>(s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->alpha, s->dy, s->losses + 1, B, A);
+    k_actor_dy<<<NB, TB, 0, st>>>(s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->da_c2 /* da = da_1 + da_2 */, s->alpha, s->dy, s->losses + 1, B, A);
     if (actor_backward(s, st)) return -2;
   } else {
     return -1;
@@ -758,7 +779,6 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_RAW, 0, nullptr, s->raw_a, nullptr, nullptr, &sa, st)) return -2;
   k_bc_dy<<<NB, TB, 0, st>>>(s->raw_a, s->next_a, s->dy, s->losses + 1, B, A);
   if (actor_backward(s, st)) return -2;
-  k_step_inc<<<1, 1, 0, st>>>(s->d_step);
   k_adam<<<((int)an.n + 255) / 256, 256, 0, st>>>(s->p_actor, s->g_actor, s->m_a, s->v_a, (int)an.n, s->lr_a, 0.9f, 0.999f, 1e-8f, s->d_step);
   sync_net_weights(s, st, 1);
   // --- critic: a_now ~ pi_student(obs) (no grad); targets = expert Q(ref_obs, a_now)
@@ -769,6 +789,7 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   k_critic_dq<<<dim3(NB, 2), TB, 0, st>>>(s->q, s->qn, B, s->dq, s->losses + 0, B);
   if (critic_backward(s, st)) return -2;
   k_adam<<<((int)(2 * cn.n) + 255) / 256, 256, 0, st>>>(s->p_critic, s->g_critic, s->m_c, s->v_c, (int)(2 * cn.n), s->lr_c, 0.9f, 0.999f, 1e-8f, s->d_step);
+  k_step_inc<<<1, 1, 0, st>>>(s->d_step);        // both Adam kernels used step + 1; the step completes here
   sync_net_weights(s, st, 2);
   s->launches += 12;
   if (losses_out) cudaMemcpyAsync(losses_out, s->losses, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st);
