@@ -292,9 +292,9 @@ __global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ dy /
     }
     __syncthreads();
     for (int o = 0; o < od; o++) {          // rows -> warps
-      float w8[8];
-#pragma unroll
-      for (int j = 0; j < 8; j++) w8[j] = W3[o * H + chunk * 8 + j];
+      // 2 x 128-bit loads: the actor's W3 block starts at a multiple of four floats (256 * in_dim + 256 + 65536 + 256) of a 256-byte aligned base
+      const float4 wa = *reinterpret_cast<const float4*>(W3 + o * H + chunk * 8), wb = *reinterpret_cast<const float4*>(W3 + o * H + chunk * 8 + 4);
+      const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const float d = sdy[warp + 8 * k][o];
