@@ -16,11 +16,22 @@ w, b, _ = Opt_with_points(ETG=layer, ETG_T=0.5, Footheight=0.1, Steplength=0.05)
 rng = np.random.default_rng(0)
 hf = (rng.random((32, 32)) * 0.03).astype(np.float64)
 for kw in (dict(num_envs=13), dict(num_envs=16, precision="f64"), dict(num_envs=24, auto_reset=True, action_filter=1, max_episode_steps=3),
-           dict(num_envs=8, heightfield=(hf, -1.0, -1.0, 0.1)), dict(num_envs=40, threads_per_block=128)):
+           dict(num_envs=8, heightfield=(hf, -1.0, -1.0, 0.1)), dict(num_envs=40, threads_per_block=128),
+           # round-2 paths: reduced sensor layout + noise + stuck / body-collision epilogue; the FEAT variant (joint-limit rows in shared
+           # memory, TORQUE mode, base push, damping) in f32 and f64
+           dict(num_envs=13, sensor_motor=2, sensor_imu=2, obs_normal=0, noise_stdev=(0.01, 0.05, 0.1, 0.02, 0.04), stuck_termination=1, body_collisions=1, auto_reset=True),
+           dict(num_envs=11, joint_limits=1, external_force=1, base_damping=(0.04, 0.02, 0.04, 0.01)), dict(num_envs=9, joint_limits=1, precision="f64"),
+           dict(num_envs=8, motor_mode=1)):
     env = VecQuadrupedalEnv(**kw)
     n = env.num_envs
     env.reset(w, b)
     a = (rng.random((n, 12)) * 0.6 - 0.3)
+    if kw.get("joint_limits"):
+        a[:, 2::3] = 1.2; a[:, 0::3] = 0.9                       # into the stops: the shared-memory 24-row solve runs
+    if kw.get("external_force"):
+        env.set_external_force(rng.uniform(-10, 10, (n, 3)))
+    if kw.get("noise_stdev"):
+        env.reset(w, b, x_offset=rng.uniform(-0.1, 0.1, n))
     for _ in range(4):
         env.step(torch.as_tensor(a, device="cuda", dtype=env.dtype))
     env.step_host(a.astype(np.float32 if env.dtype == torch.float32 else np.float64))
@@ -38,6 +49,8 @@ for _ in range(3):
     rpm.append(torch.randn(512, 49, device="cuda"), torch.rand(512, 12, device="cuda") * 2 - 1, torch.randn(512, device="cuda"), torch.randn(512, 49, device="cuda"), torch.ones(512, device="cuda"))
 for _ in range(2):
     learner.learn(*rpm.sample_batch(256), graph=False)
+flat = SACLearner(agent, 256, sync="flat")
+flat.learn(*rpm.sample_batch(256), graph=False)
 ev = PopulationEvaluator(4, 2, max_steps=5)
 ev.evaluate(np.repeat(w[None], 4, 0), np.repeat(b[None], 4, 0))
 torch.cuda.synchronize()
