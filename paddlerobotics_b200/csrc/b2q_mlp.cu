@@ -53,7 +53,7 @@ struct FwdArgs {
 };
 
 constexpr int NTHR = 256;
-__global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
+__global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_sync();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, net = blockIdx.y;
   const int trow = tid & (TILE_M - 1), chalf = tid >> 7;   // tile row owned in the epilogues; column half (0: cols 0..127, 1: 128..255)
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) {
 
 // f32 nn.Linear weights -> bf16 swizzled operand images (+ f32 biases) in the per-net image
 __global__ void b2q_mlp_pack_kernel(uint8_t* img, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
-                                    int in_dim, int out_dim) {
+                                    int in_dim, int out_dim) { pdl_sync();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < HID * 64) {  // W1 [256 x 64 padded]
     int n = i >> 6, k = i & 63;
@@ -292,7 +292,7 @@ int64_t b2q_mlp_launch_count(B2QMlpHandle h) { return h ? h->launches : 0; }
 
 int b2q_mlp_set_weights(B2QMlpHandle h, int net, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3, void* stream) {
   if (!h || net < 0 || net >= h->nets || !w1 || !b1 || !w2 || !b2 || !w3 || !b3) { if (h) h->err = "b2q_mlp_set_weights: bad argument"; return -1; }
-  b2q_mlp_pack_kernel<<<(HID * HID + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->img + (size_t)net * IMG_BYTES, w1, b1, w2, b2, w3, b3, h->in_dim, h->out_dim);
+  pdl_launch(b2q_mlp_pack_kernel, dim3((HID * HID + 255) / 256), dim3(256), 0, (cudaStream_t)stream, h->img + (size_t)net * IMG_BYTES, w1, b1, w2, b2, w3, b3, h->in_dim, h->out_dim);
   h->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return -2; }
@@ -307,7 +307,7 @@ int b2q_mlp_forward_ex(B2QMlpHandle h, const float* in1, int in1_dim, const floa
   FwdArgs a{in1, in2, in1_dim, h->in_dim, h->out_dim, M, mode, seed, eps, out, logp, raw, h->img, IMG_BYTES, B2QMlpSaves{}, 0};
   if (saves) { a.sv = *saves; a.save = 1; }
   dim3 grid((M + TILE_M - 1) / TILE_M, h->nets);
-  b2q_mlp_fwd_kernel<<<grid, NTHR, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  pdl_launch(b2q_mlp_fwd_kernel, dim3(grid), dim3(NTHR), SMEM_BYTES, (cudaStream_t)stream, a);
   h->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return -2; }

@@ -50,7 +50,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
                ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(128) b2q_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+__global__ void __launch_bounds__(128) b2q_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) { pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;                 // SWIZZLE_128B operand tiles want 1024-byte alignment
@@ -134,12 +134,12 @@ __global__ void __launch_bounds__(128) b2q_gemm_kernel(const __grid_constant__ C
 
 // ---------------------------------------------------------------------------------------------------------------------
 // elementwise / reduction kernels
-__global__ void k_target_q(const float* rew, const float* term, const float* q1n, const float* q2n, const float* logpn, float gamma, float alpha, float* tq, int B) {
+__global__ void k_target_q(const float* rew, const float* term, const float* q1n, const float* q2n, const float* logpn, float gamma, float alpha, float* tq, int B) { pdl_sync();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) tq[b] = rew[b] + gamma * term[b] * (fminf(q1n[b], q2n[b]) - alpha * logpn[b]);   // sac.py:88-91
 }
 // critic head backward for both nets: dq = 2 (q - tq)/B; loss += (q-tq)^2/B; db3 += dq   (mse_loss mean reduction, sac.py:94-95)
-__global__ void k_critic_dq(const float* q /*[2][B]*/, const float* tq /*[B] or [2][B]*/, int tq_stride, float* dq /*[2][B]*/, float* loss, int B) {
+__global__ void k_critic_dq(const float* q /*[2][B]*/, const float* tq /*[B] or [2][B]*/, int tq_stride, float* dq /*[2][B]*/, float* loss, int B) { pdl_sync();
   int b = blockIdx.x * blockDim.x + threadIdx.x, net = blockIdx.y;
   float l = 0.f;
   if (b < B) { float e = q[net * B + b] - tq[net * tq_stride + b]; dq[net * B + b] = 2.f * e / (float)B; l = e * e / (float)B; }
@@ -166,7 +166,7 @@ __device__ __forceinline__ void colsum_flush(float (*csum)[H], const float* cs /
 }
 // dh = G (f32 [B][256]) masked by h>0 -> bf16 row-major + transposed; db += column sums
 __global__ void __launch_bounds__(256) k_relu_mask(const float* __restrict__ G, const bf16* __restrict__ h, bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t,
-                                                   float* db /*[256] or null*/, int B) {
+                                                   float* db /*[256] or null*/, int B) { pdl_sync();
   __shared__ __align__(16) bf16 tile[32][H + 8];
   __shared__ float csum[8][H];
   const int chunk = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -215,7 +215,7 @@ __device__ __forceinline__ float dq_of_row(const DqSrc& d, const float* dq, int 
   return ((d.net == 0) == first) ? -1.f / (float)B : 0.f;
 }
 __global__ void __launch_bounds__(256) k_head_bwd1(const float* __restrict__ dq /*[B]*/, DqSrc src, const float* __restrict__ W3 /*[256]*/, const bf16* __restrict__ h2,
-                                                   bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t, float* dW3 /*[256]*/, float* db3 /*[1] or null*/, float* db2 /*[256] or null*/, int B) {
+                                                   bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t, float* dW3 /*[256]*/, float* db3 /*[1] or null*/, float* db2 /*[256] or null*/, int B) { pdl_sync();
   __shared__ __align__(16) bf16 tile[32][H + 8];
   __shared__ float csum[8][H];
   const int chunk = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256) k_head_bwd1(const float* __restrict__ dq 
 //                     in shared memory), so the partial sums stay in registers until one atomic flush per block
 __global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ dy /*[B][od]*/, int od, const float* __restrict__ W3 /*[od][256]*/,
                                                   const bf16* __restrict__ h2 /*[B][256]*/, bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t,
-                                                  float* dW3 /*[od][256]*/, float* db3 /*[od] or null*/, float* db2 /*[256] or null*/, int B) {
+                                                  float* dW3 /*[od][256]*/, float* db3 /*[od] or null*/, float* db2 /*[256] or null*/, int B) { pdl_sync();
   __shared__ __align__(16) unsigned char raw_tile[32 * (H + 8) * sizeof(bf16)];
   bf16 (*tile)[H + 8] = reinterpret_cast<bf16 (*)[H + 8]>(raw_tile);
   float (*csum)[H] = reinterpret_cast<float (*)[H]>(raw_tile);          // aliases the tile: only used after the last transpose-out
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ dy /
 }
 // actor head: from raw y=[mean|raw_ls], eps, da_c (critic gradient wrt action, already includes -1/B routing) build dy and the loss
 __global__ void k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const float* act /*[B][A] tanh(x)*/, const float* logp, const float* q /*[2][B]*/,
-                           const float* da_c /*[B][16] (cols 0..A-1)*/, const float* da_c2 /*second critic's part or null*/, float alpha, float* dy /*[B][2A]*/, float* loss, int B, int A) {
+                           const float* da_c /*[B][16] (cols 0..A-1)*/, const float* da_c2 /*second critic's part or null*/, float alpha, float* dy /*[B][2A]*/, float* loss, int B, int A) { pdl_sync();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   float l = 0.f;
   if (b < B) {
@@ -362,7 +362,7 @@ __global__ void k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const
   if ((threadIdx.x & 31) == 0) atomicAdd(loss, l);
 }
 // behaviour cloning head (alg/BC.py:53-59): loss = -mean_{b,j} log N(ref | mean, exp(ls)); dy = dloss/d[mean | raw_ls]
-__global__ void k_bc_dy(const float* raw /*[B][2A]*/, const float* ref /*[B][A]*/, float* dy, float* loss, int B, int A) {
+__global__ void k_bc_dy(const float* raw /*[B][2A]*/, const float* ref /*[B][A]*/, float* dy, float* loss, int B, int A) { pdl_sync();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   float l = 0.f;
   const float inv = 1.f / (float)(B * A);
@@ -379,17 +379,17 @@ __global__ void k_bc_dy(const float* raw /*[B][2A]*/, const float* ref /*[B][A]*
   if ((threadIdx.x & 31) == 0) atomicAdd(loss, l);
 }
 // dq routing for the actor loss: d(-min(q1,q2))/dq_i /B
-__global__ void k_minq_dq(const float* q /*[2][B]*/, float* dq /*[2][B]*/, int B) {
+__global__ void k_minq_dq(const float* q /*[2][B]*/, float* dq /*[2][B]*/, int B) { pdl_sync();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) { bool first = q[b] <= q[B + b]; dq[b] = first ? -1.f / (float)B : 0.f; dq[B + b] = first ? 0.f : -1.f / (float)B; }   // torch.min picks the first on ties
 }
-__global__ void k_add_f32(float* dst, const float* src, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) dst[i] += src[i]; }
+__global__ void k_add_f32(float* dst, const float* src, int n) { pdl_sync(); int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) dst[i] += src[i]; }
 // Adam (torch.optim.Adam defaults: betas 0.9/0.999, eps 1e-8, no weight decay), sac.py:55-58
-__global__ void k_step_inc(int* step) { *step += 1; }
+__global__ void k_step_inc(int* step) { pdl_sync(); *step += 1; }
 // the step counter lives on the device so that the whole learn() can be replayed from a CUDA graph
 // `step` holds the number of COMPLETED optimiser steps; both Adam kernels of a learn use step + 1 and the last kernel of the learn
 // (k_polyak / k_step_inc) advances it — no separate increment kernel in front of the Adam on the dependency chain
-__global__ void k_adam(float* p, const float* g, float* m, float* v, int n, float lr, float b1, float b2, float eps, const int* step) {
+__global__ void k_adam(float* p, const float* g, float* m, float* v, int n, float lr, float b1, float b2, float eps, const int* step) { pdl_sync();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     const float t = (float)(*step + 1), bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
@@ -398,14 +398,14 @@ __global__ void k_adam(float* p, const float* g, float* m, float* v, int n, floa
     p[i] -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
   }
 }
-__global__ void k_polyak(float* tgt, const float* src, int n, float tau, int* step) {   // sync_target, sac.py:112-118: target = tau*param + (1-tau)*target
+__global__ void k_polyak(float* tgt, const float* src, int n, float tau, int* step) { pdl_sync();   // sync_target, sac.py:112-118: target = tau*param + (1-tau)*target
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) tgt[i] = tau * src[i] + (1.f - tau) * tgt[i];
   if (i == 0 && step) *step += 1;
 }
 // bf16 helper copies of one net's weights for the backward GEMMs: W2T [256][256], W3T64 [256][64] (k = output index, zero padded),
 // W1A [16][256] (rows = action columns of W1, for d/da)
-__global__ void k_make_bwd_weights(const float* W1, int in_dim, int a_off, int a_dim, const float* W2, const float* W3, int od, bf16* W2T, bf16* W3T, bf16* W1A) {
+__global__ void k_make_bwd_weights(const float* W1, int in_dim, int a_off, int a_dim, const float* W2, const float* W3, int od, bf16* W2T, bf16* W3T, bf16* W1A) { pdl_sync();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < H * H) { int n = i / H, k = i % H; W2T[i] = __float2bfloat16(W2[(size_t)k * H + n]); }
   if (i < H * 64) { int n = i / 64, k = i % 64; W3T[i] = __float2bfloat16(k < od ? W3[(size_t)k * H + n] : 0.f); }
@@ -515,7 +515,7 @@ int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int
   if (!ta || !tb) { s->err = "cuTensorMapEncodeTiled failed"; return -2; }
   if (g.atomic) cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st);
   dim3 grid((M + 127) / 128, ntiles, splits);
-  b2q_gemm_kernel<<<grid, 128, G_SMEM, st>>>(*ta, *tb, g);
+  pdl_launch(b2q_gemm_kernel, dim3(grid), dim3(128), G_SMEM, st, *ta, *tb, g);
   s->launches++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
@@ -529,7 +529,7 @@ void sync_net_weights(B2QSac* s, cudaStream_t st, int which = 7) {
   // (one stage of the dependency chain instead of two)
   cudaEventRecord(s->ev_aux[0], st); cudaStreamWaitEvent(s->aux[0], s->ev_aux[0], 0);
   if (which & 1) {
-    k_make_bwd_weights<<<(H * H + 255) / 256, 256, 0, s->aux[0]>>>(s->p_actor + a.oW1, a.in_dim, 0, 0, s->p_actor + a.oW2, s->p_actor + a.oW3, a.od, s->W2T[0], s->W3T[0], s->W1A[0]);
+    pdl_launch(k_make_bwd_weights, dim3((H * H + 255) / 256), dim3(256), 0, s->aux[0], s->p_actor + a.oW1, a.in_dim, 0, 0, s->p_actor + a.oW2, s->p_actor + a.oW3, a.od, s->W2T[0], s->W3T[0], s->W1A[0]);
     b2q_mlp_set_weights(s->mlp_actor, 0, s->p_actor + a.oW1, s->p_actor + a.ob1, s->p_actor + a.oW2, s->p_actor + a.ob2, s->p_actor + a.oW3, s->p_actor + a.ob3, st);
     s->launches += 2;
   }
@@ -537,7 +537,7 @@ void sync_net_weights(B2QSac* s, cudaStream_t st, int which = 7) {
     cudaStream_t sx = i ? s->side : st;
     float* p = s->p_critic + (size_t)i * c.n; float* t = s->p_target + (size_t)i * c.n;
     if (which & 2) {
-      k_make_bwd_weights<<<(H * H + 255) / 256, 256, 0, s->aux[0]>>>(p + c.oW1, c.in_dim, s->D, s->A, p + c.oW2, p + c.oW3, c.od, s->W2T[1 + i], s->W3T[1 + i], s->W1A[1 + i]);
+      pdl_launch(k_make_bwd_weights, dim3((H * H + 255) / 256), dim3(256), 0, s->aux[0], p + c.oW1, c.in_dim, s->D, s->A, p + c.oW2, p + c.oW3, c.od, s->W2T[1 + i], s->W3T[1 + i], s->W1A[1 + i]);
       b2q_mlp_set_weights(s->mlp_critic, i, p + c.oW1, p + c.ob1, p + c.oW2, p + c.ob2, p + c.oW3, p + c.ob3, sx);
       s->launches += 2;
     }
@@ -561,7 +561,7 @@ int hidden_backward(B2QSac* s, cudaStream_t st, int slot, const bf16* dh2_rm, co
   if (gemm(s, ax, dh2_t, B, h1_t, B, gW2, H, H, H, B, true)) return -2;
   cudaEventRecord(s->ev_aux[2 * slot + 1], ax);
   if (gemm(s, st, dh2_rm, H, W2T, H, G, H, B, H, H, false)) return -2;
-  k_relu_mask<<<(B + 32 * SUBT - 1) / (32 * SUBT), H, 0, st>>>(G, h1_rm, s->dh1_rm[slot], s->dh1_t[slot], gb1, B);                                                      // dh1, db1
+  pdl_launch(k_relu_mask, dim3((B + 32 * SUBT - 1) / (32 * SUBT)), dim3(H), 0, st, G, h1_rm, s->dh1_rm[slot], s->dh1_t[slot], gb1, B);                                                      // dh1, db1
   if (gemm(s, st, s->dh1_t[slot], B, x_t, B, gW1, in_dim, H, in_dim, B, true)) return -2;
   cudaStreamWaitEvent(st, s->ev_aux[2 * slot + 1], 0);
   s->launches += 4;
@@ -577,7 +577,7 @@ int critic_backward(B2QSac* s, cudaStream_t st0, DqSrc src = DqSrc{DQ_ARRAY, 0, 
     float* g = s->g_critic + (size_t)i * cn.n; const float* p = s->p_critic + (size_t)i * cn.n;
     const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h1t = s->hc1_t + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
     src.net = i;
-    k_head_bwd1<<<(B + 32 * SUBT - 1) / (32 * SUBT), H, 0, st>>>(s->dq + (size_t)i * B, src, p + cn.oW3, h2, dh_rm, dh_t, g + cn.oW3, g + cn.ob3, g + cn.ob2, B);   // (dq,) dh2, dW3, db3, db2
+    pdl_launch(k_head_bwd1, dim3((B + 32 * SUBT - 1) / (32 * SUBT)), dim3(H), 0, st, s->dq + (size_t)i * B, src, p + cn.oW3, h2, dh_rm, dh_t, g + cn.oW3, g + cn.ob3, g + cn.ob2, B);   // (dq,) dh2, dW3, db3, db2
     s->launches++;
     if (hidden_backward(s, st, i, dh_rm, dh_t, G, h1, h1t, s->xc_t, s->W2T[1 + i], g + cn.oW2, g + cn.ob1, g + cn.oW1, cn.in_dim)) return -2;
   }
@@ -588,7 +588,7 @@ int critic_backward(B2QSac* s, cudaStream_t st0, DqSrc src = DqSrc{DQ_ARRAY, 0, 
 int actor_backward(B2QSac* s, cudaStream_t st) {
   const int B = s->B, A = s->A; const Net& an = s->an;
   float* g = s->g_actor;
-  k_head_bwd<<<(B + 32 * SUBT - 1) / (32 * SUBT), H, 0, st>>>(s->dy, 2 * A, s->p_actor + an.oW3, s->ha2_rm, s->dh_rm, s->dh_t, g + an.oW3, g + an.ob3, g + an.ob2, B);
+  pdl_launch(k_head_bwd, dim3((B + 32 * SUBT - 1) / (32 * SUBT)), dim3(H), 0, st, s->dy, 2 * A, s->p_actor + an.oW3, s->ha2_rm, s->dh_rm, s->dh_t, g + an.oW3, g + an.ob3, g + an.ob2, B);
   s->launches++;
   return hidden_backward(s, st, 0, s->dh_rm, s->dh_t, s->G, s->ha1_rm, s->ha1_t, s->xa_t, s->W2T[0], g + an.oW2, g + an.ob1, g + an.oW1, an.in_dim);
 }
@@ -709,11 +709,11 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     const float b1 = 0.9f, b2 = 0.999f;
     if (phase == 1) {
       int n = (int)(2 * cn.n);
-      k_adam<<<(n + 255) / 256, 256, 0, st>>>(s->p_critic, s->g_critic, s->m_c, s->v_c, n, s->lr_c, b1, b2, 1e-8f, s->d_step);
+      pdl_launch(k_adam, dim3((n + 255) / 256), dim3(256), 0, st, s->p_critic, s->g_critic, s->m_c, s->v_c, n, s->lr_c, b1, b2, 1e-8f, s->d_step);
     } else {
       int n = (int)an.n, nc = (int)(2 * cn.n);
-      k_adam<<<(n + 255) / 256, 256, 0, st>>>(s->p_actor, s->g_actor, s->m_a, s->v_a, n, s->lr_a, b1, b2, 1e-8f, s->d_step);
-      k_polyak<<<(nc + 255) / 256, 256, 0, st>>>(s->p_target, s->p_critic, nc, s->tau, s->d_step);
+      pdl_launch(k_adam, dim3((n + 255) / 256), dim3(256), 0, st, s->p_actor, s->g_actor, s->m_a, s->v_a, n, s->lr_a, b1, b2, 1e-8f, s->d_step);
+      pdl_launch(k_polyak, dim3((nc + 255) / 256), dim3(256), 0, st, s->p_target, s->p_critic, nc, s->tau, s->d_step);
       s->launches++;
     }
     s->launches++;
@@ -735,15 +735,15 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
       const float* p = s->p_critic + (size_t)i * cn.n;
       const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
       DqSrc src{DQ_MINQ, i, s->q, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr};
-      k_head_bwd1<<<(B + 32 * SUBT - 1) / (32 * SUBT), H, 0, sx>>>(nullptr, src, p + cn.oW3, h2, dh_rm, dh_t, G /*scratch dW3*/, nullptr, nullptr, B);
+      pdl_launch(k_head_bwd1, dim3((B + 32 * SUBT - 1) / (32 * SUBT)), dim3(H), 0, sx, nullptr, src, p + cn.oW3, h2, dh_rm, dh_t, G /*scratch dW3*/, nullptr, nullptr, B);
       if (gemm(s, sx, dh_rm, H, s->W2T[1 + i], H, G, H, B, H, H, false)) return -2;
-      k_relu_mask<<<(B + 32 * SUBT - 1) / (32 * SUBT), H, 0, sx>>>(G, h1, dh_rm, dh_t, nullptr, B);
+      pdl_launch(k_relu_mask, dim3((B + 32 * SUBT - 1) / (32 * SUBT)), dim3(H), 0, sx, G, h1, dh_rm, dh_t, nullptr, B);
       if (gemm(s, sx, dh_rm, H, s->W1A[1 + i], H, da, 16, B, 16, H, false)) return -2;                    // da_i [B][16]
       s->launches += 2;
     }
     join(s, st);
     if (!eps_cur) return -1;   // the explicit-noise path is required for the backward pass
-    k_actor_dy<<<NB, TB, 0, st>>>(s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->da_c2 /* da = da_1 + da_2 */, s->alpha, s->dy, s->losses + 1, B, A);
+    pdl_launch(k_actor_dy, dim3(NB), dim3(TB), 0, st, s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->da_c2 /* da = da_1 + da_2 */, s->alpha, s->dy, s->losses + 1, B, A);
     if (actor_backward(s, st)) return -2;
   } else {
     return -1;
@@ -777,19 +777,19 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   if (b2q_mlp_forward(expert_actor, ref_obs, ref_obs_dim, nullptr, B, B2Q_MLP_PREDICT, 0, nullptr, s->next_a /*ref action*/, nullptr, nullptr, st)) return -2;
   B2QMlpSaves sa = {s->xa_rm, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
   if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_RAW, 0, nullptr, s->raw_a, nullptr, nullptr, &sa, st)) return -2;
-  k_bc_dy<<<NB, TB, 0, st>>>(s->raw_a, s->next_a, s->dy, s->losses + 1, B, A);
+  pdl_launch(k_bc_dy, dim3(NB), dim3(TB), 0, st, s->raw_a, s->next_a, s->dy, s->losses + 1, B, A);
   if (actor_backward(s, st)) return -2;
-  k_adam<<<((int)an.n + 255) / 256, 256, 0, st>>>(s->p_actor, s->g_actor, s->m_a, s->v_a, (int)an.n, s->lr_a, 0.9f, 0.999f, 1e-8f, s->d_step);
+  pdl_launch(k_adam, dim3(((int)an.n + 255) / 256), dim3(256), 0, st, s->p_actor, s->g_actor, s->m_a, s->v_a, (int)an.n, s->lr_a, 0.9f, 0.999f, 1e-8f, s->d_step);
   sync_net_weights(s, st, 1);
   // --- critic: a_now ~ pi_student(obs) (no grad); targets = expert Q(ref_obs, a_now)
   if (b2q_mlp_forward(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_SAMPLE, 0, eps, s->cur_a, s->cur_logp, nullptr, st)) return -2;
   if (b2q_mlp_forward(expert_critic, ref_obs, ref_obs_dim, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->qn, nullptr, nullptr, st)) return -2;
   B2QMlpSaves sv = {s->xc_rm, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
   if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, st)) return -2;
-  k_critic_dq<<<dim3(NB, 2), TB, 0, st>>>(s->q, s->qn, B, s->dq, s->losses + 0, B);
+  pdl_launch(k_critic_dq, dim3(dim3(NB, 2)), dim3(TB), 0, st, s->q, s->qn, B, s->dq, s->losses + 0, B);
   if (critic_backward(s, st)) return -2;
-  k_adam<<<((int)(2 * cn.n) + 255) / 256, 256, 0, st>>>(s->p_critic, s->g_critic, s->m_c, s->v_c, (int)(2 * cn.n), s->lr_c, 0.9f, 0.999f, 1e-8f, s->d_step);
-  k_step_inc<<<1, 1, 0, st>>>(s->d_step);        // both Adam kernels used step + 1; the step completes here
+  pdl_launch(k_adam, dim3(((int)(2 * cn.n) + 255) / 256), dim3(256), 0, st, s->p_critic, s->g_critic, s->m_c, s->v_c, (int)(2 * cn.n), s->lr_c, 0.9f, 0.999f, 1e-8f, s->d_step);
+  pdl_launch(k_step_inc, dim3(1), dim3(1), 0, st, s->d_step);        // both Adam kernels used step + 1; the step completes here
   sync_net_weights(s, st, 2);
   s->launches += 12;
   if (losses_out) cudaMemcpyAsync(losses_out, s->losses, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st);

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cstdint>
+#include <utility>
 
 namespace b2q_tc {
 
@@ -67,5 +68,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may start while its
+// predecessor in the stream is still running; `griddepcontrol.wait` blocks until every prerequisite grid has COMPLETED and flushed its
+// memory, so a kernel that begins with pdl_sync() keeps plain stream-order semantics and only its launch latency / CTA scheduling is
+// hidden behind the predecessor (these learner kernels are small and latency-bound).  launch_dependents goes first so that the next
+// kernel in the chain can be made resident as early as possible.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 }  // namespace b2q_tc
