@@ -101,6 +101,7 @@ typedef struct B2QConfig {
   int32_t external_force;    /* 1: per-env base push set with b2q_set_external_force (random_param['random_force'], train.py:254) */
   double base_damping[4];    /* Bullet btMultiBody base damping: linear k1,k2, angular k1,k2 (force = m v (k1 + k2 |v|)); 0 = off */
   double etg_foot_y_inset;   /* ETG nominal footholds pulled towards the body midline by this much (make_env(step_y=), train.py:463; balancebeam) */
+  int32_t knee_contacts;     /* 1: the knee spheres (calf-joint origin, r 0.02) collide with the terrain: 3 more solver rows per leg (non-toe link contact response) */
 } B2QConfig;
 
 typedef struct B2QEnv* B2QHandle;

@@ -617,6 +617,42 @@ void orc_substep(const OrcConfig* c, OrcEnv* e, const double target[12]) {
     }
     targ[leg] = dist[leg] > 0 ? -dist[leg] / dt : c->erp * (-dist[leg]) / dt;
   }
+  /* knee spheres (calf-joint origin, radius 0.02) against the terrain: rows [kn0..kn3 | (kt1,kt2) x 4], built like the toe rows; no warm start */
+  int kact[4] = {0, 0, 0, 0}; double kJ[12][18], kMJ[12][18], kA[12], klam[12], ktarg[12];
+  memset(kJ, 0, sizeof kJ); memset(klam, 0, sizeof klam); memset(ktarg, 0, sizeof ktarg);
+  if (c->knee_contacts) for (int leg = 0; leg < 4; leg++) {
+    const double kr = 0.02; int ic = 3 * leg + 2; double n[3];
+    double h = terrain_height(c, D->pw[ic][0], D->pw[ic][1], n);
+    double kd = D->pw[ic][2] - h - kr;
+    kact[leg] = kd < c->contact_margin;
+    if (!kact[leg]) continue;
+    double t1[3] = {1 - n[0] * n[0], -n[0] * n[1], -n[0] * n[2]}, nn = sqrt(v3dot(t1, t1)), t2[3];
+    for (int k = 0; k < 3; k++) t1[k] /= nn;
+    v3cross(n, t1, t2);
+    double x[3] = {D->pw[ic][0] - kr * n[0], D->pw[ic][1] - kr * n[1], D->pw[ic][2] - kr * n[2]};
+    const double* dirs[3] = {n, t1, t2};
+    for (int dd = 0; dd < 3; dd++) {
+      int row = dd == 0 ? leg : 4 + 2 * leg + (dd - 1);
+      const double* ew = dirs[dd];
+      double xb_w[3] = {x[0] - e->pos[0], x[1] - e->pos[1], x[2] - e->pos[2]}, xb[3], eb[3], xe[3];
+      m3tv(D->R0, xb_w, xb); m3tv(D->R0, ew, eb); v3cross(xb, eb, xe);
+      for (int k = 0; k < 3; k++) { kJ[row][k] = xe[k]; kJ[row][3 + k] = eb[k]; }
+      for (int l = 0; l < 3; l++) {
+        int i = 3 * leg + l; double aw[3], ax[3] = {0, 0, 0}, rr[3], cr[3];
+        ax[D->mdl.axis[i]] = 1; m3v(D->Rw[i], ax, aw);
+        for (int k = 0; k < 3; k++) rr[k] = x[k] - D->pw[i][k];
+        v3cross(aw, rr, cr);
+        kJ[row][6 + i] = v3dot(ew, cr);
+      }
+      double xl_w[3] = {x[0] - D->pw[ic][0], x[1] - D->pw[ic][1], x[2] - D->pw[ic][2]}, xl[3], el[3], f[6];
+      m3tv(D->Rw[ic], xl_w, xl); m3tv(D->Rw[ic], ew, el); v3cross(xl, el, f);
+      f[3] = el[0]; f[4] = el[1]; f[5] = el[2];
+      dyn_delta(D, ic + 1, f, NULL, kMJ[row]);
+      double ss = 0; for (int k = 0; k < 18; k++) ss += kJ[row][k] * kMJ[row][k];
+      kA[row] = ss;
+    }
+    ktarg[leg] = kd > 0 ? -kd / dt : c->erp * (-kd) / dt;
+  }
   double dnu[18]; memset(dnu, 0, sizeof dnu);
   for (int r = 0; r < 12; r++) lam[r] = 0;
   for (int leg = 0; leg < 4; leg++) {
@@ -655,12 +691,25 @@ void orc_substep(const OrcConfig* c, OrcEnv* e, const double target[12]) {
       double dl = ln - lam[r]; lam[r] = ln;
       for (int k = 0; k < 18; k++) dnu[k] += MJ[r][k] * dl;
     }
+    for (int leg = 0; leg < 4; leg++) if (kact[leg]) {          /* knee normals after the toe normals */
+      int r = leg; double u = 0; for (int k = 0; k < 18; k++) u += kJ[r][k] * (nu[k] + dnu[k]);
+      double ln = klam[r] + (ktarg[r] - u) / kA[r]; if (ln < 0) ln = 0;
+      double dl = ln - klam[r]; klam[r] = ln;
+      for (int k = 0; k < 18; k++) dnu[k] += kMJ[r][k] * dl;
+    }
     for (int leg = 0; leg < 4; leg++) if (act[leg]) for (int tdir = 0; tdir < 2; tdir++) {
       int r = 4 + 2 * leg + tdir; double u = 0; for (int k = 0; k < 18; k++) u += J[r][k] * (nu[k] + dnu[k]);
       double lim = mu * lam[leg], ln = lam[r] + (targ[r] - u) / A[r];
       if (ln > lim) ln = lim; if (ln < -lim) ln = -lim;
       double dl = ln - lam[r]; lam[r] = ln;
       for (int k = 0; k < 18; k++) dnu[k] += MJ[r][k] * dl;
+    }
+    for (int leg = 0; leg < 4; leg++) if (kact[leg]) for (int tdir = 0; tdir < 2; tdir++) {   /* knee friction after the toe friction */
+      int r = 4 + 2 * leg + tdir; double u = 0; for (int k = 0; k < 18; k++) u += kJ[r][k] * (nu[k] + dnu[k]);
+      double lim = mu * klam[leg], ln = klam[r] + (0.0 - u) / kA[r];
+      if (ln > lim) ln = lim; if (ln < -lim) ln = -lim;
+      double dl = ln - klam[r]; klam[r] = ln;
+      for (int k = 0; k < 18; k++) dnu[k] += kMJ[r][k] * dl;
     }
   }
   for (int leg = 0; leg < 4; leg++) { e->lam_warm[leg] = lam[leg]; e->contact[leg] = lam[leg] > 0; }

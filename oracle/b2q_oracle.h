@@ -68,6 +68,7 @@ typedef struct {
   int external_force;       /* base push (random_param['random_force'], train.py:254) */
   double base_damping[4];   /* Bullet btMultiBody base damping lin k1,k2 ang k1,k2 [EXT] */
   double etg_foot_y_inset;  /* make_env(step_y=): nominal footholds pulled towards the midline */
+  int knee_contacts;        /* knee spheres (calf-joint origin, r 0.02) collide with the terrain */
 } OrcConfig;
 
 typedef struct {

@@ -38,7 +38,7 @@ class Config(C.Structure):
         ("sensor_dis", C.c_int), ("sensor_contact", C.c_int), ("sensor_imu", C.c_int), ("sensor_motor", C.c_int), ("sensor_etg", C.c_int), ("obs_normal", C.c_int),
         ("noise_stdev", C.c_double * 5), ("noise_seed", C.c_ulonglong),
         ("stuck_termination", C.c_int), ("body_collisions", C.c_int), ("motor_mode", C.c_int), ("joint_limits", C.c_int), ("external_force", C.c_int),
-        ("base_damping", C.c_double * 4), ("etg_foot_y_inset", C.c_double),
+        ("base_damping", C.c_double * 4), ("etg_foot_y_inset", C.c_double), ("knee_contacts", C.c_int),
     ]
 
 

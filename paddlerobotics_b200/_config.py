@@ -26,5 +26,5 @@ class B2QConfig(C.Structure):
         ("sensor_dis", C.c_int32), ("sensor_contact", C.c_int32), ("sensor_imu", C.c_int32), ("sensor_motor", C.c_int32), ("sensor_etg", C.c_int32),
         ("obs_normal", C.c_int32), ("noise_stdev", C.c_double * 5), ("noise_seed", C.c_uint64),
         ("stuck_termination", C.c_int32), ("body_collisions", C.c_int32), ("motor_mode", C.c_int32), ("joint_limits", C.c_int32),
-        ("external_force", C.c_int32), ("base_damping", C.c_double * 4), ("etg_foot_y_inset", C.c_double),
+        ("external_force", C.c_int32), ("base_damping", C.c_double * 4), ("etg_foot_y_inset", C.c_double), ("knee_contacts", C.c_int32),
     ]

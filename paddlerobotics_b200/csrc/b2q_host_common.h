@@ -16,7 +16,7 @@ inline Cfg<T> make_cfg(const B2QConfig& c, const T* hf_dev) {
   k.clip_cmd = c.clip_motor_commands; k.max_dq = (T)c.max_angle_change;
   k.noise_on = 0; for (int i = 0; i < 5; i++) { k.noise[i] = (T)c.noise_stdev[i]; if (c.noise_stdev[i] > 0) k.noise_on = 1; }
   k.noise_seed = c.noise_seed; k.stuck = c.stuck_termination; k.body_coll = c.body_collisions;
-  k.motor_mode = c.motor_mode; k.jlim = c.joint_limits; k.extf = c.external_force;
+  k.motor_mode = c.motor_mode; k.jlim = c.joint_limits; k.extf = c.external_force; k.knee = c.knee_contacts;
   for (int i = 0; i < 4; i++) k.damp[i] = (T)c.base_damping[i];
   {  // scipy.signal.butter(2, highcut / (fs/2)) in closed form (bilinear transform), fs = 1 / control period
     const double PI = 3.14159265358979323846, fs = 1.0 / (c.sim_dt * c.action_repeat);
@@ -44,7 +44,7 @@ inline void default_config(B2QConfig* c) {
 
 // which kernel instantiation a config needs: 0 = the lean default body, 1 = the variant with TORQUE mode / joint-limit rows / base push / damping
 inline int config_feat(const B2QConfig& c) {
-  return (c.motor_mode || c.joint_limits || c.external_force || c.base_damping[0] != 0 || c.base_damping[1] != 0 || c.base_damping[2] != 0 || c.base_damping[3] != 0) ? 1 : 0;
+  return (c.motor_mode || c.joint_limits || c.external_force || c.knee_contacts || c.base_damping[0] != 0 || c.base_damping[1] != 0 || c.base_damping[2] != 0 || c.base_damping[3] != 0) ? 1 : 0;
 }
 // observation width selected by the sensor flags (SimpleEnv.get_observation, deployment/envs/EnvWrapper.py:60-109)
 inline int config_obs_dim(const B2QConfig& c) {

@@ -40,6 +40,7 @@ inline void build_model_host(Model<T>& M, double foot_radius, double etg_T, doub
   M.qlo[0] = (T)-0.802851455917; M.qhi[0] = (T)0.802851455917;      // a1.py:186-223 (same bounds on the four legs)
   M.qlo[1] = (T)-1.0471975512; M.qhi[1] = (T)4.18879020479;
   M.qlo[2] = (T)-2.69653369433; M.qhi[2] = (T)-0.916297857297;
+  M.knee_r = (T)0.02;
   M.obs_dim = OBS_DIM; M.obs_identity = 1;
   for (int j = 0; j < OBS_DIM; j++) { M.obs_src[j] = j; M.obs_scale[j] = (T)1; M.obs_shift[j] = (T)0; }
   for (int j = 0; j < 12; j++) { M.etg_mean[j] = (T)ETG_MEAN[j]; M.etg_std[j] = (T)ETG_STD[j]; M.etg_istd[j] = (T)(1.0 / ETG_STD[j]); }

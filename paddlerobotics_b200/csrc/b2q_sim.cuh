@@ -53,6 +53,7 @@ struct Model {
   T etg_mean[12], etg_std[12], etg_istd[12];
   T pose_ori[3];
   T qlo[3], qhi[3];                 // URDF joint limits (a1.py:186-223): hip, upper, lower
+  T knee_r;                         // radius of the knee collision sphere at the calf joint (calf / thigh box ends, a1 URDF [EXT])
   // observation layout selected by sensor_mode / normal (EnvWrapper.py:60-109): out[j] = full49[obs_src[j]] * obs_scale[j] + obs_shift[j]
   int obs_dim, obs_identity;
   int obs_src[OBS_DIM];
@@ -68,7 +69,7 @@ struct Cfg {
   int clip_cmd; T max_dq;   // A1._ClipMotorCommands (a1.py:440-458)
   int noise_on; T noise[5]; unsigned long long noise_seed;   // Minitaur._AddSensorNoise (minitaur.py:1206-1211)
   int stuck, body_coll;     // stuck termination, non-toe collision count for `badfoot`
-  int motor_mode, jlim, extf; T damp[4];   // FEAT variant only: TORQUE mode, joint-limit rows, base push, Bullet base damping
+  int motor_mode, jlim, extf, knee; T damp[4];   // FEAT variant only: TORQUE mode, joint-limit rows, base push, knee contact rows, Bullet base damping
 };
 constexpr int STUCK_H = 10;   // control steps of base-position history for the stuck termination
 template <typename T>
@@ -190,33 +191,34 @@ B2Q_HD void etg_act_leg(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, co
 
 // ---------------------------------------------------------------------------------------------------------------
 // one physics substep for this lane's leg (+ redundant base)
-// General contact + joint-limit solve of the FEAT variant: 6 rows per leg (normal, t1, t2, and one limit row per joint: the nearer stop)
-// = 24 rows, Delassus matrix in the robot's shared scratch (cm.scratch(): shared memory on the GPU), projected Gauss-Seidel in Bullet's
-// order — joint-limit rows first (non-contact multibody constraints), then the contact normals, then the friction rows — run
-// redundantly by the four lanes.  Not the hot path: plain loops, no register-resident matrix.
-// Scratch layout: Ya[24][6] | blk[4][21] | vec[24][4] | W[24][24].
-constexpr int NRW = 24;
+// General solve of the FEAT variant: 9 rows per leg — toe contact (normal, t1, t2), knee contact (normal, t1, t2: the sphere at the calf
+// joint, the first non-toe link a stumbling robot puts down) and one limit row per joint (towards the nearer stop) — = 36 rows, Delassus
+// matrix in the robot's shared scratch (cm.scratch(): shared memory on the GPU), projected Gauss-Seidel in Bullet's order: joint-limit
+// rows first (non-contact multibody constraints), then the contact normals (toes, knees), then the friction rows — run redundantly by
+// the four lanes.  Not the hot path: plain loops, no register-resident matrix.
+// Scratch layout: Ya[36][6] | blk[4][45] | vec[36][4] | W[36][36].
+constexpr int RPL = 9, NRW = 4 * RPL;
+constexpr int SCRATCH_FLOATS = NRW * 6 + 4 * 45 + NRW * 4 + NRW * NRW;
 #define JLIM_GAP T(0.06)
-constexpr int SCRATCH_FLOATS = NRW * 6 + 4 * 21 + NRW * 4 + NRW * NRW;
 template <typename T, class Comm>
-B2Q_HD void solve_rows24(const Comm& cm, const Cfg<T>& cf, T mu, const T (*Y)[6] /*[6] rows of this leg*/, const T* u /*[6]*/, const T* blk21 /*leg-local 6x6 block, packed lower*/,
-                         const T* targ /*[6]*/, bool act, const bool* actl /*[3]*/, const T* warm /*[6]*/, T* lk /*[6]*/) {
+B2Q_HD void solve_rows36(const Comm& cm, const Cfg<T>& cf, T mu, const T (*Y)[6] /*[9] rows of this leg*/, const T* u /*[9]*/, const T* blk45 /*leg-local 9x9 block, packed lower*/,
+                         const T* targ /*[9]*/, const bool* act /*[9]*/, const T* warm /*[9]*/, T* lk /*[9]*/) {
   const int k = cm.leg();
   T* sh = cm.template scratch<T>();
-  T* Ya = sh; T* blk = sh + NRW * 6; T* vec = blk + 4 * 21; T* W = vec + NRW * 4;
-  for (int e = 0; e < 6; e++) {
-    const int r = 6 * k + e;
+  T* Ya = sh; T* blk = sh + NRW * 6; T* vec = blk + 4 * 45; T* W = vec + NRW * 4;
+  for (int e = 0; e < RPL; e++) {
+    const int r = RPL * k + e;
     for (int c = 0; c < 6; c++) Ya[r * 6 + c] = Y[e][c];
-    vec[r * 4 + 0] = u[e]; vec[r * 4 + 1] = targ[e]; vec[r * 4 + 2] = (e < 3 ? act : actl[e - 3]) ? T(1) : T(0); vec[r * 4 + 3] = warm[e];
+    vec[r * 4 + 0] = u[e]; vec[r * 4 + 1] = targ[e]; vec[r * 4 + 2] = act[e] ? T(1) : T(0); vec[r * 4 + 3] = warm[e];
   }
-  for (int i = 0; i < 21; i++) blk[k * 21 + i] = blk21[i];
+  for (int i = 0; i < 45; i++) blk[k * 45 + i] = blk45[i];
   cm.sync();
-  for (int e = 0; e < 6; e++) {
-    const int r = 6 * k + e;
+  for (int e = 0; e < RPL; e++) {
+    const int r = RPL * k + e;
     for (int c = 0; c < NRW; c++) {
       T acc = T(0);
       for (int i = 0; i < 6; i++) acc += Ya[r * 6 + i] * Ya[c * 6 + i];
-      if (c / 6 == k) { const int a = e, b = c - 6 * k; acc += blk[k * 21 + (a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a)]; }
+      if (c / RPL == k) { const int a = e, b = c - RPL * k; acc += blk[k * 45 + (a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a)]; }
       W[r * NRW + c] = acc;
     }
   }
@@ -224,22 +226,24 @@ B2Q_HD void solve_rows24(const Comm& cm, const Cfg<T>& cf, T mu, const T (*Y)[6]
   T lam[NRW], uu[NRW];
   for (int i = 0; i < NRW; i++) lam[i] = vec[i * 4 + 2] > T(0) ? vec[i * 4 + 3] : T(0);
   for (int i = 0; i < NRW; i++) { T a = vec[i * 4 + 0]; for (int j = 0; j < NRW; j++) a += W[i * NRW + j] * lam[j]; uu[i] = a; }
+  // row sequence of one iteration: (row-in-leg, parent normal row or -1) per group, each group visited for legs 0..3
+  const int grp_row[9] = {6, 7, 8, 0, 3, 1, 2, 4, 5}, grp_par[9] = {-1, -1, -1, -1, -1, 0, 0, 3, 3};
   for (int it = 0; it < cf.iters; it++) {
-    for (int pass = 0; pass < 3; pass++) {          // 0: joint limits, 1: contact normals, 2: friction rows
+    for (int seg = 0; seg < 5; seg++) {             // limits | toe normals | knee normals | toe friction | knee friction
+      const int g0 = seg == 0 ? 0 : seg == 1 ? 3 : seg == 2 ? 4 : seg == 3 ? 5 : 7, g1 = seg == 0 ? 3 : seg == 1 ? 4 : seg == 2 ? 5 : seg == 3 ? 7 : 9;
       for (int f = 0; f < 4; f++) {
-        const int cnt = pass == 0 ? 3 : pass == 1 ? 1 : 2;
-        for (int td = 0; td < cnt; td++) {
-          const int r = 6 * f + (pass == 0 ? 3 + td : pass == 1 ? 0 : 1 + td);
+        for (int g = g0; g < g1; g++) {
+          const int r = RPL * f + grp_row[g];
           if (!(vec[r * 4 + 2] > T(0))) continue;
           T ln = lam[r] + (vec[r * 4 + 1] - uu[r]) / W[r * NRW + r];
-          if (pass == 2) { T lim = mu * lam[6 * f]; ln = m_min(m_max(ln, -lim), lim); } else ln = m_max(ln, T(0));
+          if (grp_par[g] >= 0) { T lim = mu * lam[RPL * f + grp_par[g]]; ln = m_min(m_max(ln, -lim), lim); } else ln = m_max(ln, T(0));
           T dl = ln - lam[r]; lam[r] = ln;
           for (int i = 0; i < NRW; i++) uu[i] += W[i * NRW + r] * dl;
         }
       }
     }
   }
-  for (int e = 0; e < 6; e++) lk[e] = lam[6 * k + e];
+  for (int e = 0; e < RPL; e++) lk[e] = lam[RPL * k + e];
   cm.sync();                                         // the scratch is reused by the next substep
 }
 
@@ -455,59 +459,100 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
     }
   }
 #undef FDA
-  T lk[3] = {T(0), T(0), T(0)};   // this lane's own impulses
-  T lkl[3] = {T(0), T(0), T(0)}, sl[3] = {T(1), T(1), T(1)}, Yl[3][6];   // joint-limit rows of this leg: impulse, side (+1 lower stop, -1 upper), Y
+  T lk[3] = {T(0), T(0), T(0)};   // this lane's own toe impulses
+  // extra rows of this leg in the FEAT variant: knee contact (n, t1, t2) and the three joint-limit rows: impulses, base-space Y rows, joint-space Jacobians
+  T lkx[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, Yx[6][6], Jx[6][3];
+#pragma unroll
+  for (int e = 0; e < 6; e++) {
+#pragma unroll
+    for (int c = 0; c < 6; c++) Yx[e][c] = T(0);
+    Jx[e][0] = Jx[e][1] = Jx[e][2] = T(0);
+  }
   bool general = false;
   if constexpr (FEAT != 0) {
     // A limit row can only bind when the joint is within JLIM_GAP of a stop (its target velocity is -gap/dt: 0.06 rad <=> 30 rad/s of
-    // approach); rows further away are dropped — identically in the oracle — and the general solve runs only for warps in which some
-    // robot has such a row (warp-uniform switch: the fast path's shuffles need the whole warp).
-    bool near = false;
+    // approach) and a knee row only when the knee sphere is within the contact margin; other rows are dropped — identically in the
+    // oracle — and the general solve runs only for warps in which some robot has such a row (warp-uniform switch: the fast path's
+    // shuffles need the whole warp).
+    bool need = false;
+    T kdist = T(1); V3<T> kn_w = mk<T>(0, 0, 1);
     if (cf.jlim) {
 #pragma unroll
-      for (int j = 0; j < 3; j++) near = near || (s.q[j] - md.qlo[j] < JLIM_GAP) || (md.qhi[j] - s.q[j] < JLIM_GAP);
+      for (int j = 0; j < 3; j++) need = need || (s.q[j] - md.qlo[j] < JLIM_GAP) || (md.qhi[j] - s.q[j] < JLIM_GAP);
     }
-    if (cf.jlim && cm.any(near)) {
-      // one limit row per joint (a1.py:186-223), towards the nearer stop; Jacobian +-e_j in joint space, none on the base; same target-velocity
-      // rule as a contact (approach up to gap/dt, ERP on violation), Bullet btMultiBodyJointLimitConstraint style
-      T Y6[6][6], u6[6], targ6[6], warm6[6], blk[21]; bool actl[3];
+    if (cf.knee) {
+      V3<T> kw = s.pos + rot(R, K.p3);
+      kdist = kw.z - terrain_height(cf, kw.x, kw.y, kn_w) - md.knee_r;
+      need = need || (kdist < cf.margin);
+    }
+    if ((cf.jlim || cf.knee) && cm.any(need)) {
+      T Y9[RPL][6], u9[RPL], targ9[RPL], warm9[RPL], blk[45], Jall[RPL][3]; bool act9[RPL];
 #pragma unroll
       for (int e = 0; e < 3; e++) {
 #pragma unroll
-        for (int c = 0; c < 6; c++) Y6[e][c] = Y[e][c];
-        u6[e] = u[e]; targ6[e] = T(0); warm6[e] = T(0);
+        for (int c = 0; c < 6; c++) Y9[e][c] = Y[e][c];
+        u9[e] = u[e]; targ9[e] = T(0); warm9[e] = T(0); act9[e] = act;
+        Jall[e][0] = Jk[e][0]; Jall[e][1] = Jk[e][1]; Jall[e][2] = Jk[e][2];
       }
-      targ6[0] = dist > T(0) ? -dist * idt : cf.erp * (-dist) * idt; warm6[0] = cf.warm * s.lam_n;
+      targ9[0] = dist > T(0) ? -dist * idt : cf.erp * (-dist) * idt; warm9[0] = cf.warm * s.lam_n;
+      {
+        // knee sphere (calf-joint origin, radius knee_r) against the terrain: the same row construction as the toe's, no warm start
+        const bool kact = cf.knee && (kdist < cf.margin);
+        V3<T> t1k = mk<T>(1 - kn_w.x * kn_w.x, -kn_w.x * kn_w.y, -kn_w.x * kn_w.z);
+        t1k = t1k * m_rsqrt(dot(t1k, t1k));
+        V3<T> t2k = cross(kn_w, t1k);
+        V3<T> ek[3] = {rotT(R, kn_w), rotT(R, t1k), rotT(R, t2k)};
+        V3<T> xk = K.p3 - ek[0] * md.knee_r;
+        V3<T> r1 = cross(a1, xk - K.p1), r2 = cross(a2, xk - K.p2), r3 = cross(a2, xk - K.p3);
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+          T jr[3] = {dot(ek[e], r1), dot(ek[e], r2), dot(ek[e], r3)};
+          V6<T> Jb; Jb.a = cross(xk, ek[e]); Jb.l = ek[e];
+          u9[3 + e] = dot(Jb.a, wBs) + dot(Jb.l, vBs) + jr[0] * qds[0] + jr[1] * qds[1] + jr[2] * qds[2];
+#pragma unroll
+          for (int i = 0; i < 6; i++) Yx[e][i] = get6(Jb, i) - (get6(FD[0], i) * jr[0] + get6(FD[1], i) * jr[1] + get6(FD[2], i) * jr[2]);
+          fwd6(S, Li, Yx[e]);
+          Jx[e][0] = jr[0]; Jx[e][1] = jr[1]; Jx[e][2] = jr[2];
+          targ9[3 + e] = T(0); warm9[3 + e] = T(0); act9[3 + e] = kact;
+        }
+        targ9[3] = kdist > T(0) ? -kdist * idt : cf.erp * (-kdist) * idt;
+      }
 #pragma unroll
       for (int j = 0; j < 3; j++) {
-        T glo = s.q[j] - md.qlo[j], ghi = md.qhi[j] - s.q[j], gap = glo;
-        sl[j] = T(1); if (ghi < glo) { gap = ghi; sl[j] = T(-1); }
+        // limit row of joint j (a1.py:186-223) towards the nearer stop: Jacobian +-e_j in joint space, none on the base; the same
+        // target-velocity rule as a contact (approach up to gap/dt, ERP on violation), Bullet btMultiBodyJointLimitConstraint style
+        T glo = s.q[j] - md.qlo[j], ghi = md.qhi[j] - s.q[j], gap = glo, sj = T(1);
+        if (ghi < glo) { gap = ghi; sj = T(-1); }
 #pragma unroll
-        for (int i = 0; i < 6; i++) Yl[j][i] = -sl[j] * get6(FD[j], i);
-        fwd6(S, Li, Yl[j]);
-#pragma unroll
-        for (int c = 0; c < 6; c++) Y6[3 + j][c] = Yl[j][c];
-        u6[3 + j] = sl[j] * qds[j];
-        targ6[3 + j] = gap > T(0) ? -gap * idt : cf.erp * (-gap) * idt;
-        warm6[3 + j] = cf.warm * s.lam_lim[j];
-        actl[j] = gap < JLIM_GAP;
+        for (int i = 0; i < 6; i++) Yx[3 + j][i] = -sj * get6(FD[j], i);
+        fwd6(S, Li, Yx[3 + j]);
+        Jx[3 + j][0] = j == 0 ? sj : T(0); Jx[3 + j][1] = j == 1 ? sj : T(0); Jx[3 + j][2] = j == 2 ? sj : T(0);
+        u9[6 + j] = sj * qds[j];
+        targ9[6 + j] = gap > T(0) ? -gap * idt : cf.erp * (-gap) * idt;
+        warm9[6 + j] = cf.warm * s.lam_lim[j];
+        act9[6 + j] = cf.jlim && (gap < JLIM_GAP);
       }
-      // leg-local block J_leg D J_leg^T over the rows (n, t1, t2, lim0, lim1, lim2), packed lower
 #pragma unroll
-      for (int a = 0; a < 6; a++) {
+      for (int e = 0; e < 6; e++) {
 #pragma unroll
-        for (int b = 0; b <= a; b++) {
-          T v;
-          if (a < 3) v = Wl[a][b];
-          else if (b < 3) v = sl[a - 3] * (D[a - 3][0] * Jk[b][0] + D[a - 3][1] * Jk[b][1] + D[a - 3][2] * Jk[b][2]);
-          else v = sl[a - 3] * sl[b - 3] * D[a - 3][b - 3];
-          blk[a * (a + 1) / 2 + b] = v;
-        }
+        for (int c = 0; c < 6; c++) Y9[3 + e][c] = Yx[e][c];
+        Jall[3 + e][0] = Jx[e][0]; Jall[3 + e][1] = Jx[e][1]; Jall[3 + e][2] = Jx[e][2];
       }
-      T lk6[6];
-      solve_rows24<T>(cm, cf, pr.mu, Y6, u6, blk, targ6, act, actl, warm6, lk6);
+      // leg-local block J D J^T over the nine rows, packed lower
 #pragma unroll
-      for (int e = 0; e < 3; e++) { lk[e] = lk6[e]; lkl[e] = lk6[3 + e]; }
+      for (int a = 0; a < RPL; a++) {
+        T dj[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) dj[i] = D[i][0] * Jall[a][0] + D[i][1] * Jall[a][1] + D[i][2] * Jall[a][2];
+#pragma unroll
+        for (int b = 0; b <= a; b++) blk[a * (a + 1) / 2 + b] = Jall[b][0] * dj[0] + Jall[b][1] * dj[1] + Jall[b][2] * dj[2];
+      }
+      T lk9[RPL];
+      solve_rows36<T>(cm, cf, pr.mu, Y9, u9, blk, targ9, act9, warm9, lk9);
+#pragma unroll
+      for (int e = 0; e < 3; e++) lk[e] = lk9[e];
+#pragma unroll
+      for (int e = 0; e < 6; e++) lkx[e] = lk9[3 + e];
       general = true;
     }
   }
@@ -634,12 +679,12 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
 #pragma unroll
   for (int f = 0; f < 4; f++) if (f == k) { lk[0] = lam[3 * f]; lk[1] = lam[3 * f + 1]; lk[2] = lam[3 * f + 2]; }   // own impulses (no dynamic register indexing)
   }
-  s.lam_n = lk[0]; s.contact = lk[0] > T(0); s.lam_lim[0] = lkl[0]; s.lam_lim[1] = lkl[1]; s.lam_lim[2] = lkl[2];
+  s.lam_n = lk[0]; s.contact = lk[0] > T(0); s.lam_lim[0] = lkx[3]; s.lam_lim[1] = lkx[4]; s.lam_lim[2] = lkx[5];
   // --- apply impulses: sum over feet of Y_f lam_f by a 4-lane butterfly of each lane's own rows (keeps the gathered rows
   //     of the other feet dead after the Delassus matrix is built: 72 fewer live registers across the sweep)
   T z[6];
 #pragma unroll
-  for (int c = 0; c < 6; c++) z[c] = cm.sum4(Y[0][c] * lk[0] + Y[1][c] * lk[1] + Y[2][c] * lk[2] + (FEAT != 0 ? Yl[0][c] * lkl[0] + Yl[1][c] * lkl[1] + Yl[2][c] * lkl[2] : T(0)));
+  for (int c = 0; c < 6; c++) z[c] = cm.sum4(Y[0][c] * lk[0] + Y[1][c] * lk[1] + Y[2][c] * lk[2] + (FEAT != 0 ? Yx[0][c] * lkx[0] + Yx[1][c] * lkx[1] + Yx[2][c] * lkx[2] + Yx[3][c] * lkx[3] + Yx[4][c] * lkx[4] + Yx[5][c] * lkx[5] : T(0)));
   bwd6(S, Li, z);
   V6<T> dnu = arr_to_v6(z);
   {
@@ -647,7 +692,7 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       jl[i] = Jk[0][i] * lk[0] + Jk[1][i] * lk[1] + Jk[2][i] * lk[2];
-      if (FEAT != 0) jl[i] += sl[i] * lkl[i];
+      if (FEAT != 0) jl[i] += Jx[0][i] * lkx[0] + Jx[1][i] * lkx[1] + Jx[2][i] * lkx[2] + Jx[3][i] * lkx[3] + Jx[4][i] * lkx[4] + Jx[5][i] * lkx[5];
       t[i] = jl[i] - dot6(Fc[i], dnu);
     }
 #pragma unroll

@@ -248,7 +248,7 @@ class QuadrupedalEnv:
                    action_filter=int(bool(enable_action_filter)), motor_mode=_motor_mode(motor_control_mode),
                    sensor_dis=int(bool(sm["dis"])), sensor_contact=int(bool(sm["contact"])), sensor_imu=int(sm["imu"]), sensor_motor=int(sm["motor"]),
                    sensor_etg=int(bool(sm["ETG"])), obs_normal=int(bool(normal)), external_force=int(self._random_force),
-                   stuck_termination=1, body_collisions=1, joint_limits=1, noise_seed=int(seed))
+                   stuck_termination=1, body_collisions=1, joint_limits=1, knee_contacts=1, noise_seed=int(seed))
         if sm["noise"]:
             cfg["noise_stdev"] = SENSOR_NOISE_STDDEV
         if task == "balancebeam":

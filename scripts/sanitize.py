@@ -20,7 +20,7 @@ for kw in (dict(num_envs=13), dict(num_envs=16, precision="f64"), dict(num_envs=
            # round-2 paths: reduced sensor layout + noise + stuck / body-collision epilogue; the FEAT variant (joint-limit rows in shared
            # memory, TORQUE mode, base push, damping) in f32 and f64
            dict(num_envs=13, sensor_motor=2, sensor_imu=2, obs_normal=0, noise_stdev=(0.01, 0.05, 0.1, 0.02, 0.04), stuck_termination=1, body_collisions=1, auto_reset=True),
-           dict(num_envs=11, joint_limits=1, external_force=1, base_damping=(0.04, 0.02, 0.04, 0.01)), dict(num_envs=9, joint_limits=1, precision="f64"),
+           dict(num_envs=11, joint_limits=1, knee_contacts=1, external_force=1, base_damping=(0.04, 0.02, 0.04, 0.01)), dict(num_envs=9, joint_limits=1, precision="f64"),
            dict(num_envs=8, motor_mode=1)):
     env = VecQuadrupedalEnv(**kw)
     n = env.num_envs

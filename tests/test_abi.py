@@ -45,7 +45,7 @@ def test_config_struct_mirror_matches_header_defaults():
     assert c.clip_motor_commands == 0 and c.max_angle_change == 0.2  # a1.py:229,62
     assert (c.sensor_dis, c.sensor_contact, c.sensor_imu, c.sensor_motor, c.sensor_etg, c.obs_normal) == (1, 1, 1, 1, 1, 1)   # train.py:494-500,473
     assert list(c.noise_stdev) == [0.0] * 5 and c.stuck_termination == 0 and c.body_collisions == 0 and c.motor_mode == 0
-    assert c.joint_limits == 0 and c.external_force == 0 and list(c.base_damping) == [0.0] * 4 and c.etg_foot_y_inset == 0.0
+    assert c.joint_limits == 0 and c.external_force == 0 and list(c.base_damping) == [0.0] * 4 and c.etg_foot_y_inset == 0.0 and c.knee_contacts == 0
     c.threads_per_block = 256
     h = C.c_void_p()
     assert _lib.load().b2q_create(C.byref(c), C.byref(h)) == -1 and b"threads_per_block" in _lib.load().b2q_last_error(None)

@@ -175,3 +175,49 @@ def test_joint_limit_rows(etg_shipped):
             break
     assert out and np.array(o.e.lam_lim[:]).max() >= 0
     e.close(); e0.close()
+
+
+def test_knee_contact_rows(etg_default):
+    """Non-toe link contact response: with knee_contacts the knee spheres (calf-joint origin, r 0.02) carry load when a robot goes down
+    on its knees — they stay above the ground where they sink through it without the rows — and the device code's 36-row solve equals the
+    oracle's DoF-space PGS (joint limits on at the same time)."""
+    w, b = etg_default
+    e, o = _pair(w, b, knee_contacts=1, joint_limits=1, body_collisions=1, etg_enabled=0)
+    e0, o0 = _pair(w, b, body_collisions=1, etg_enabled=0)
+    kmin = kmin0 = 1.0
+    for k in range(30):
+        a = np.zeros(12); a[1::3] = 0.3 - 0.9; a[2::3] = -2.6 + 1.8   # thigh 0.3, calf -2.6: the toes fold up behind the knees and the robot comes down on its knees
+        ob, rw, dn, inf = o.step(a); ob2, rw2, dn2, inf2 = e.step(a)
+        assert np.abs(ob2[0] - ob).max() < 1e-7 and abs(rw2[0] - rw) < 1e-7 and bool(dn2[0]) == dn, k
+        assert np.abs(inf2[0] - inf).max() < 1e-7, k
+        o0.step(a)
+        kmin = min(kmin, _knee_height(o)); kmin0 = min(kmin0, _knee_height(o0))
+    assert kmin > 0.02 - 3e-3, kmin            # the knee spheres rest on the ground (penetration within the ERP slack)
+    assert kmin0 < 0.0, kmin0                  # without the rows the knees go through it
+    e.close(); e0.close()
+
+
+def _knee_height(o):
+    """lowest calf-joint origin above the plane, from the oracle's kinematics (foot_world gives the toes; the knee is l_low up the calf)."""
+    s = o.get_state()
+    import ctypes as C
+    feet = o.foot_world()
+    # knee = toe + R_calf * (0,0,l_low): recover it from two FK calls is overkill — use the reported info instead: joint angles + base pose
+    from paddlerobotics_b200 import etg as E
+    R = _quat_to_R(s[3:7])
+    zs = []
+    for leg in range(4):
+        q = s[13 + 3 * leg:16 + 3 * leg]
+        sgn = (-1) ** (leg + 1)
+        l_hip = 0.08505 * sgn
+        # thigh-joint origin then knee: hip frame -> base frame (a1.py:113-129 geometry with the calf removed)
+        up = np.array([-0.2 * np.sin(q[1]), 0.0, -0.2 * np.cos(q[1])])
+        p = np.array([up[0], np.cos(q[0]) * l_hip - np.sin(q[0]) * up[2], np.sin(q[0]) * l_hip + np.cos(q[0]) * up[2]]) + E.HIP_OFFSETS[leg]
+        zs.append((s[:3] + R @ p)[2])
+    return min(zs)
+
+
+def _quat_to_R(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])

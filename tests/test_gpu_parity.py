@@ -160,7 +160,8 @@ def test_env_features_f64_equal_oracle(torch_cuda, etg_stable):
     for kw, torque in ((dict(sensor_motor=2, sensor_imu=2, obs_normal=0, noise_stdev=(0.01, 0.05, 0.1, 0.02, 0.04), noise_seed=99), False),
                        (dict(motor_mode=1), True),
                        (dict(external_force=1, base_damping=(0.04, 0.02, 0.04, 0.01), body_collisions=1, stuck_termination=1), False),
-                       (dict(joint_limits=1), False)):
+                       (dict(joint_limits=1), False),
+                       (dict(knee_contacts=1, joint_limits=1, body_collisions=1, etg_enabled=0), False)):
         n = 3
         env = VecQuadrupedalEnv(n, precision="f64", **kw)
         os_ = [O.OracleEnv(O.default_config(**kw)) for _ in range(n)]
@@ -175,7 +176,9 @@ def test_env_features_f64_equal_oracle(torch_cuda, etg_stable):
                 o.set_force(f[i])
         for k in range(8 if torque else 20):     # open-loop torques diverge exponentially: compare before the rounding differences are amplified
             a = (np.array([0.0, 1.0, -6.0] * 4) + rng.uniform(-1, 1, (n, 12))) if torque else rng.uniform(-0.2, 0.2, (n, 12))
-            if kw.get("joint_limits"):             # drive the knees and hips into their stops (a1.py:186-223)
+            if kw.get("knee_contacts"):            # thigh 0.3, calf -2.6: the toes fold up and the robot comes down on its knee spheres
+                a = a * 0; a[:, 1::3] = 0.3 - 0.9; a[:, 2::3] = -2.6 + 1.8
+            elif kw.get("joint_limits"):           # drive the knees and hips into their stops (a1.py:186-223)
                 a = a * 0; a[:, 2::3] = 1.2 * np.sin(0.3 * k); a[:, 0::3] = 0.9 * np.cos(0.25 * k)
             ob, rw, dn, inf = env.step(a)
             for i, o in enumerate(os_):
@@ -184,7 +187,7 @@ def test_env_features_f64_equal_oracle(torch_cuda, etg_stable):
                 tol = 1e-6 if torque else 1e-7        # open-loop torques: no PD loop damps the rounding differences of the two formulations
                 assert np.abs(_np(ob)[i] - oo).max() < tol and abs(float(rw[i]) - ro) < tol and bool(dn[i]) == do, (kw, k, i)
                 assert np.abs(_np(inf)[i] - io).max() < tol
-                if kw.get("joint_limits"):
+                if kw.get("joint_limits") and not kw.get("knee_contacts"):
                     q = o.get_state()[13:25]
                     assert q[2::3].min() > -2.69653369433 - 2e-3 and q[2::3].max() < -0.916297857297 + 2e-3 and np.abs(q[0::3]).max() < 0.802851455917 + 2e-3
                 if do:
