@@ -213,37 +213,44 @@ B2Q_HD void solve_rows36(const Comm& cm, const Cfg<T>& cf, T mu, const T (*Y)[6]
   }
   for (int i = 0; i < 45; i++) blk[k * 45 + i] = blk45[i];
   cm.sync();
-  for (int e = 0; e < RPL; e++) {
-    const int r = RPL * k + e;
-    for (int c = 0; c < NRW; c++) {
+  // compact list of the ACTIVE rows in the order one iteration visits them (limits, toe normals, knee normals, toe friction, knee
+  // friction; legs 0..3 inside each group): typically 6-12 of the 36, so the matrix and the sweep are built on that subset only
+  const int grp_row[9] = {6, 7, 8, 0, 3, 1, 2, 4, 5}, grp_par[9] = {-1, -1, -1, -1, -1, 0, 0, 3, 3};
+  int idx[NRW], par[NRW], pos_of[NRW], n = 0;
+  for (int i = 0; i < NRW; i++) pos_of[i] = -1;
+  for (int seg = 0; seg < 5; seg++) {
+    const int g0 = seg == 0 ? 0 : seg == 1 ? 3 : seg == 2 ? 4 : seg == 3 ? 5 : 7, g1 = seg == 0 ? 3 : seg == 1 ? 4 : seg == 2 ? 5 : seg == 3 ? 7 : 9;
+    for (int f = 0; f < 4; f++)
+      for (int g = g0; g < g1; g++) {
+        const int r = RPL * f + grp_row[g];
+        if (!(vec[r * 4 + 2] > T(0))) continue;
+        idx[n] = r; par[n] = grp_par[g] >= 0 ? pos_of[RPL * f + grp_par[g]] : -1; pos_of[r] = n; n++;
+      }
+  }
+  for (int i = 0; i < n; i++) {                       // this lane fills the rows of its own leg
+    const int r = idx[i];
+    if (r / RPL != k) continue;
+    for (int j = 0; j < n; j++) {
+      const int c = idx[j];
       T acc = T(0);
-      for (int i = 0; i < 6; i++) acc += Ya[r * 6 + i] * Ya[c * 6 + i];
-      if (c / RPL == k) { const int a = e, b = c - RPL * k; acc += blk[k * 45 + (a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a)]; }
-      W[r * NRW + c] = acc;
+      for (int q = 0; q < 6; q++) acc += Ya[r * 6 + q] * Ya[c * 6 + q];
+      if (c / RPL == k) { const int a = r - RPL * k, b = c - RPL * k; acc += blk[k * 45 + (a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a)]; }
+      W[i * NRW + j] = acc;
     }
   }
   cm.sync();
   T lam[NRW], uu[NRW];
-  for (int i = 0; i < NRW; i++) lam[i] = vec[i * 4 + 2] > T(0) ? vec[i * 4 + 3] : T(0);
-  for (int i = 0; i < NRW; i++) { T a = vec[i * 4 + 0]; for (int j = 0; j < NRW; j++) a += W[i * NRW + j] * lam[j]; uu[i] = a; }
-  // row sequence of one iteration: (row-in-leg, parent normal row or -1) per group, each group visited for legs 0..3
-  const int grp_row[9] = {6, 7, 8, 0, 3, 1, 2, 4, 5}, grp_par[9] = {-1, -1, -1, -1, -1, 0, 0, 3, 3};
+  for (int i = 0; i < n; i++) lam[i] = vec[idx[i] * 4 + 3];
+  for (int i = 0; i < n; i++) { T a = vec[idx[i] * 4 + 0]; for (int j = 0; j < n; j++) a += W[i * NRW + j] * lam[j]; uu[i] = a; }
   for (int it = 0; it < cf.iters; it++) {
-    for (int seg = 0; seg < 5; seg++) {             // limits | toe normals | knee normals | toe friction | knee friction
-      const int g0 = seg == 0 ? 0 : seg == 1 ? 3 : seg == 2 ? 4 : seg == 3 ? 5 : 7, g1 = seg == 0 ? 3 : seg == 1 ? 4 : seg == 2 ? 5 : seg == 3 ? 7 : 9;
-      for (int f = 0; f < 4; f++) {
-        for (int g = g0; g < g1; g++) {
-          const int r = RPL * f + grp_row[g];
-          if (!(vec[r * 4 + 2] > T(0))) continue;
-          T ln = lam[r] + (vec[r * 4 + 1] - uu[r]) / W[r * NRW + r];
-          if (grp_par[g] >= 0) { T lim = mu * lam[RPL * f + grp_par[g]]; ln = m_min(m_max(ln, -lim), lim); } else ln = m_max(ln, T(0));
-          T dl = ln - lam[r]; lam[r] = ln;
-          for (int i = 0; i < NRW; i++) uu[i] += W[i * NRW + r] * dl;
-        }
-      }
+    for (int i = 0; i < n; i++) {
+      T ln = lam[i] + (vec[idx[i] * 4 + 1] - uu[i]) / W[i * NRW + i];
+      if (par[i] >= 0) { T lim = mu * lam[par[i]]; ln = m_min(m_max(ln, -lim), lim); } else ln = m_max(ln, T(0));
+      T dl = ln - lam[i]; lam[i] = ln;
+      for (int j = 0; j < n; j++) uu[j] += W[j * NRW + i] * dl;
     }
   }
-  for (int e = 0; e < RPL; e++) lk[e] = lam[RPL * k + e];
+  for (int e = 0; e < RPL; e++) { const int q = pos_of[RPL * k + e]; lk[e] = q >= 0 ? lam[q] : T(0); }
   cm.sync();                                         // the scratch is reused by the next substep
 }
 
