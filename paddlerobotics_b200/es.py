@@ -146,6 +146,15 @@ def all_gather_concat(local, world, rank, group=None):
     return out
 
 
+def gather_fitness_and_length(fl, world, rank, group=None):
+    """fl [2, pop_local] = this rank's [fitness | mean episode length] -> (fitness [pop], length [pop]) on every rank with ONE all-gather
+    (SURVEY §8e collective 1: the two vectors travel packed)."""
+    if world == 1:
+        return fl[0], fl[1]
+    g = all_gather_concat(fl.reshape(1, 2, fl.shape[1]), world, rank, group)     # [world, 2, pop_local]
+    return g[:, 0, :].reshape(-1), g[:, 1, :].reshape(-1)
+
+
 class PopulationEvaluator:
     """Evaluates this rank's shard of an ES population on its GPU and all-gathers the fitness vector."""
 
@@ -198,10 +207,7 @@ class PopulationEvaluator:
                                      self.pop_local, self.rollouts, es, stream)
         assert rc == 0
         self.es_launches += 1
-        if self.world == 1:
-            return self.fitness, self.mean_len
-        g = all_gather_concat(self._fl.reshape(1, 2, self.pop_local), self.world, self.rank)     # [world, 2, pop_local], one collective
-        return g[:, 0, :].reshape(-1), g[:, 1, :].reshape(-1)
+        return gather_fitness_and_length(self._fl, self.world, self.rank)
 
 
 class DynamicsEvaluator:

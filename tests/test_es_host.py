@@ -49,6 +49,11 @@ for gen in range(2):
     fit = all_gather_concat(local, world, rank).numpy()
     ref = np.array([-np.sum(s * s) + 0.01 * i for i, s in enumerate(sol)])
     assert np.array_equal(fit, ref), (fit, ref)
+    # the evaluator's packed form: [fitness | mean length] of the shard in ONE collective
+    from paddlerobotics_b200.es import gather_fitness_and_length
+    fl = torch.stack([local, torch.arange(lo, hi, dtype=torch.float64) + 100.0])
+    f2, l2 = gather_fitness_and_length(fl, world, rank)
+    assert np.array_equal(f2.numpy(), ref) and np.array_equal(l2.numpy(), np.arange(16) + 100.0)
     ga.tell(fit)
 out = torch.tensor(ga.best_param)
 gathered = [torch.zeros_like(out) for _ in range(world)]

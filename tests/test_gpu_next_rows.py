@@ -1,4 +1,6 @@
 """SURVEY §8f "next" rows: on-device ETG fit (f-1) and device replay memory feeding the SAC kernels (f-2)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -148,3 +150,22 @@ def test_bc_loop_clones_expert():
     a = np.array([l[1] for l in losses])
     assert len(a) >= 50 and np.isfinite(a).all() and a[-10:].mean() < a[:10].mean() - 0.05, (a[:10].mean(), a[-10:].mean())
     env.close()
+
+
+def test_train_loop_checkpoints_on_the_reference_cadence_and_restores(tmp_path):
+    """agent.save + np.savez(w, b, param) (ETGRL/train.py:386-390) and the --load path (:332-333, 439-441): the loop writes itr_<steps>.pt
+    with the reference's state-dict keys and itr_<steps>.npz{w,b,param}; a second run restores both."""
+    import torch
+    from paddlerobotics_b200 import train
+    args = ["--num_envs", "256", "--batch", "256", "--warmup_steps", "2048", "--log_every", "20", "--ES", "0", "--task_mode", "ground",
+            "--outdir", str(tmp_path), "--suffix", "t", "--eval_every_steps", "10240"]
+    train.main(args + ["--max_steps", "25600"])
+    files = sorted(os.listdir(tmp_path / "t"))
+    pts = [f for f in files if f.endswith(".pt")]
+    assert len(pts) >= 2 and all(f[:-3] + ".npz" in files for f in pts), files
+    sd = torch.load(tmp_path / "t" / pts[-1])
+    assert {"actor_model.l1.weight", "actor_model.mean_linear.bias", "critic_model.l6.weight"} <= set(sd) and sd["actor_model.l1.weight"].shape == (256, 49)
+    z = np.load(tmp_path / "t" / (pts[-1][:-3] + ".npz"))
+    assert z["w"].shape == (3, 20) and z["b"].shape == (3,) and z["param"].reshape(-1).shape == (12,)
+    log = train.main(args + ["--max_steps", "5120", "--load", str(tmp_path / "t" / pts[-1])])
+    assert len(log) >= 1 and np.isfinite(log[-1]["mean_step_reward"])
