@@ -58,12 +58,12 @@ __device__ __forceinline__ void emit_obs_block(const Model<T>& md, const T* stag
 template <typename T, int FEAT>
 __global__ void __launch_bounds__(128) b2q_step_kernel(Cfg<T> cf, const Model<T>* __restrict__ gm, Buffers<T> B, const T* __restrict__ action, int donef,
                                                        int auto_reset, T* __restrict__ obs, T* __restrict__ reward, uint8_t* __restrict__ done, T* __restrict__ info) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(32) unsigned char smem[];
   const Model<T>& md = stage_model(gm, smem);
   // the CTA's observation rows are contiguous in [N][OBS_DIM]: stage them in shared memory and store the block with
   // full-width coalesced stores (the lanes produce the row in 3-element pieces; `obs` may be pinned HOST memory, where
   // piecewise stores would each become a small PCIe write)
-  T* stage = reinterpret_cast<T*>(smem + ((sizeof(Model<T>) + 15) & ~size_t(15)));
+  T* stage = reinterpret_cast<T*>(smem + ((sizeof(Model<T>) + 31) & ~size_t(31)));
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = gid >> 2;
   const int env0 = (blockIdx.x * blockDim.x) >> 2, per_cta = blockDim.x >> 2;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) b2q_step_kernel(Cfg<T> cf, const Model<T>
   const int srow = env0 + (int)(threadIdx.x >> 2);
   if (!valid) env = B.N - 1;
   T* istage0 = stage + (size_t)per_cta * OBS_DIM;
-  WarpComm cm{(int)(threadIdx.x & 3), FEAT ? reinterpret_cast<unsigned char*>(istage0 + (size_t)per_cta * INFO_DIM + (size_t)(threadIdx.x >> 2) * SCRATCH_FLOATS) : nullptr};
+  WarpComm cm{(int)(threadIdx.x & 3), reinterpret_cast<unsigned char*>(istage0 + (size_t)per_cta * INFO_DIM + (size_t)(threadIdx.x >> 2) * (FEAT ? SCRATCH_FLOATS : SCRATCH_FAST))};
   // the info rows (56 floats per env, produced in 3-float pieces) are staged the same way: one coalesced block per CTA, so that `info`
   // too may be pinned HOST memory (train.py:150-157 reads info every step)
   T* istage = istage0;
@@ -87,24 +87,24 @@ __global__ void __launch_bounds__(128) b2q_step_kernel(Cfg<T> cf, const Model<T>
 
 template <typename T, int FEAT>
 __global__ void __launch_bounds__(128) b2q_settle_kernel(Cfg<T> cf, const Model<T>* __restrict__ gm, Buffers<T> B, const uint8_t* __restrict__ mask) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(32) unsigned char smem[];
   const Model<T>& md = stage_model(gm, smem);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = gid >> 2;
   bool valid = env < B.N;
   if (!valid) env = B.N - 1;
   if (mask && !mask[env]) valid = false;
-  T* scr0 = reinterpret_cast<T*>(smem + ((sizeof(Model<T>) + 15) & ~size_t(15))) + (size_t)(blockDim.x >> 2) * (OBS_DIM + INFO_DIM);
-  WarpComm cm{(int)(threadIdx.x & 3), FEAT ? reinterpret_cast<unsigned char*>(scr0 + (size_t)(threadIdx.x >> 2) * SCRATCH_FLOATS) : nullptr};
+  T* scr0 = reinterpret_cast<T*>(smem + ((sizeof(Model<T>) + 31) & ~size_t(31))) + (size_t)(blockDim.x >> 2) * (OBS_DIM + INFO_DIM);
+  WarpComm cm{(int)(threadIdx.x & 3), reinterpret_cast<unsigned char*>(scr0 + (size_t)(threadIdx.x >> 2) * (FEAT ? SCRATCH_FLOATS : SCRATCH_FAST))};
   settle_lane<T, FEAT>(cm, cf, md, B, env, valid);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(128) b2q_reset_kernel(Cfg<T> cf, const Model<T>* __restrict__ gm, Buffers<T> B, const uint8_t* __restrict__ mask, const T* __restrict__ xoff,
                                                         T* __restrict__ obs) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(32) unsigned char smem[];
   const Model<T>& md = stage_model(gm, smem);
-  T* stage = reinterpret_cast<T*>(smem + ((sizeof(Model<T>) + 15) & ~size_t(15)));
+  T* stage = reinterpret_cast<T*>(smem + ((sizeof(Model<T>) + 31) & ~size_t(31)));
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = gid >> 2;
   const int env0 = (blockIdx.x * blockDim.x) >> 2;
@@ -253,7 +253,7 @@ struct EnvT : EnvBase {
     return B2Q_OK;
   }
   size_t smem_bytes() const {   // model | obs stage | info stage | (FEAT) per-robot solver scratch
-    return ((sizeof(Model<T>) + 15) & ~size_t(15)) + (size_t)(tpb / 4) * (OBS_DIM + INFO_DIM + (feat ? SCRATCH_FLOATS : 0)) * sizeof(T);
+    return ((sizeof(Model<T>) + 31) & ~size_t(31)) + (size_t)(tpb / 4) * (OBS_DIM + INFO_DIM + (feat ? SCRATCH_FLOATS : SCRATCH_FAST)) * sizeof(T);
   }
 
   int set_dynamics(const uint8_t* mask, const void* dyn, cudaStream_t s) override {
@@ -282,7 +282,7 @@ struct EnvT : EnvBase {
     CK(cudaSetDevice(cfg.device));
     int N = B.N;
     if (w || b) { b2q_pack_etg_kernel<T><<<(N + 127) / 128, 128, 0, s>>>((const T*)w, (const T*)b, const_cast<P4<T>*>(B.etg), mask, N); launches++; }
-    const size_t smem_reset = ((sizeof(Model<T>) + 15) & ~size_t(15)) + (size_t)(tpb / 4) * OBS_DIM * sizeof(T);   // model + observation stage only
+    const size_t smem_reset = ((sizeof(Model<T>) + 31) & ~size_t(31)) + (size_t)(tpb / 4) * OBS_DIM * sizeof(T);   // model + observation stage only
     b2q_reset_kernel<T><<<grid_lanes(), tpb, smem_reset, s>>>(kc, d_model, B, mask, (const T*)xoff, (T*)obs);
     launches++;
     CK(cudaGetLastError());

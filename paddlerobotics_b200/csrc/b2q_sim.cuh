@@ -199,6 +199,7 @@ B2Q_HD void etg_act_leg(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, co
 // Scratch layout: Ya[36][6] | blk[4][45] | vec[36][4] | W[36][36].
 constexpr int RPL = 9, NRW = 4 * RPL;
 constexpr int SCRATCH_FLOATS = NRW * 6 + 4 * 45 + NRW * 4 + NRW * NRW;
+constexpr int SCRATCH_FAST = 272;   // the default body's exchange area: Y^T [6][12] | vectors [4][12] | active [4] (+pad) | W' [12][12]
 #define JLIM_GAP T(0.06)
 template <typename T, class Comm>
 B2Q_HD void solve_rows36(const Comm& cm, const Cfg<T>& cf, T mu, const T (*Y)[6] /*[9] rows of this leg*/, const T* u /*[9]*/, const T* blk45 /*leg-local 9x9 block, packed lower*/,
@@ -564,10 +565,117 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
     }
   }
   if (!general) {
+  P2<T> g2[6], Wc[12][6];
+  T lam[12];
+  if constexpr (sizeof(T) == 4) {
+  // --- the 12x12 contact problem of the robot, built ONCE by its four lanes together and then solved REDUNDANTLY in registers by all
+  //     of them (the Gauss-Seidel sweep below has no shuffle on its dependent chain).  Row index r = 3*foot + e (e: 0 normal, 1,2 friction).
+  //     Delassus matrix W = J M^-1 J^T: W_ij = Y_i . Y_j (+ the leg-local 3x3 block on the diagonal blocks).  The sweep consumes
+  //     W'_ir = W_ir / W_ii (zero diagonal) as PAIRS of adjacent target rows: Wc[r][p] = (W'[2p][r], W'[2p+1][r]).
+  //     Each lane publishes its foot's three Y rows (transposed, so that the others read them as target pairs), 1/W_ii, the unconstrained
+  //     velocities, target and warm start in the robot's shared scratch; after one exchange it builds the three COLUMNS of W' that belong
+  //     to its own source rows (108 packed FMAs instead of the 252 of a fully redundant build), publishes them, and after the second
+  //     exchange every lane loads the whole matrix with 128-bit loads.  (The substep body is instruction-FETCH bound — DESIGN.md §5 —
+  //     so instruction count is what matters; the two exchanges replace 120 shuffles.)
+  {
+    T* sh = cm.template scratch<T>();
+    T* YT = sh;            // [6][12]  YT[c][i] = component c of row i's Y
+    T* vecs = sh + 72;     // [4][12]  1/W_ii (0 = inactive row) | unconstrained velocity | target velocity | warm start
+    T* afs = sh + 120;     // [4]      foot active
+    T* Wp = sh + 128;      // [12][12] Wp[r][i] = W'_ir
+    const T targ_n = dist > T(0) ? -dist * idt : cf.erp * (-dist) * idt;
+    T invo[3];
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+      T d = Wl[e][e];
+#pragma unroll
+      for (int c = 0; c < 6; c++) d = m_fma(Y[e][c], Y[e][c], d);
+      invo[e] = act ? m_rcp(d) : T(0);
+      const int i = 3 * k + e;
+#pragma unroll
+      for (int c = 0; c < 6; c++) YT[c * 12 + i] = Y[e][c];
+      vecs[i] = invo[e]; vecs[12 + i] = u[e]; vecs[24 + i] = e == 0 ? targ_n : T(0);
+      vecs[36 + i] = (e == 0 && act) ? cf.warm * s.lam_n : T(0);   // warm start of the normal impulse (Bullet 0.85)
+    }
+    afs[k] = act ? T(1) : T(0);
+    cm.sync();
+    {
+      P2<T> YP[6][6], invp[6];   // YP[p][c] = (Y_2p[c], Y_2p+1[c])
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          const P4<T> v = *reinterpret_cast<const P4<T>*>(YT + c * 12 + 4 * q);
+          YP[2 * q][c] = p2mk(v.x, v.y); YP[2 * q + 1][c] = p2mk(v.z, v.w);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 3; q++) { const P4<T> v = *reinterpret_cast<const P4<T>*>(vecs + 4 * q); invp[2 * q] = p2mk(v.x, v.y); invp[2 * q + 1] = p2mk(v.z, v.w); }
+#pragma unroll
+      for (int e = 0; e < 3; e++) {          // column r = 3k + e of W': all twelve targets
+        const int r = 3 * k + e;
+        P2<T> col[6];
+#pragma unroll
+        for (int p = 0; p < 6; p++) {
+          P2<T> acc = p2mul(YP[p][0], p2s(Y[e][0]));
+#pragma unroll
+          for (int c = 1; c < 6; c++) acc = p2fma(YP[p][c], p2s(Y[e][c]), acc);
+          col[p] = p2mul(acc, invp[p]);
+        }
+#pragma unroll
+        for (int q = 0; q < 3; q++) { P4<T> v; v.x = col[2 * q].x; v.y = col[2 * q].y; v.z = col[2 * q + 1].x; v.w = col[2 * q + 1].y; *reinterpret_cast<P4<T>*>(Wp + r * 12 + 4 * q) = v; }
+        // the three targets of the lane's own foot also carry the leg-local block (and the zero diagonal): overwrite them
+#pragma unroll
+        for (int e2 = 0; e2 < 3; e2++) {
+          T w = Wl[e2][e];
+#pragma unroll
+          for (int c = 0; c < 6; c++) w = m_fma(Y[e2][c], Y[e][c], w);
+          Wp[r * 12 + 3 * k + e2] = (e2 == e) ? T(0) : w * invo[e2];
+        }
+      }
+    }
+    cm.sync();
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+#pragma unroll
+      for (int q = 0; q < 3; q++) { const P4<T> v = *reinterpret_cast<const P4<T>*>(Wp + r * 12 + 4 * q); Wc[r][2 * q] = p2mk(v.x, v.y); Wc[r][2 * q + 1] = p2mk(v.z, v.w); }
+    }
+    // g_i = lam_i + (target_i - u_i) / W_ii is the UNCLAMPED Gauss-Seidel candidate of row i.  A row update
+    // lam_j <- clamp(g_j) changes g_i (i != j) by -(W_ij / W_ii) * dlam_j and leaves g_j itself unchanged, so the sweep
+    // carries g instead of the contact velocities.  With the warm-started normal impulses lam_3f:
+    // g_i = (target_i - u0_i) / W_ii - sum_f W'_{i,3f} lam_3f  (the row's own lam cancels against its W_ii lam term).
+    // Inactive feet: zero scale (g frozen at 0), g_n = -BIG => lam stays 0.
+    {
+      const P4<T> af = *reinterpret_cast<const P4<T>*>(afs);
+      const T actf[4] = {af.x, af.y, af.z, af.w};
+      T lw[4];
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const P4<T> iv = *reinterpret_cast<const P4<T>*>(vecs + 4 * q), uv = *reinterpret_cast<const P4<T>*>(vecs + 12 + 4 * q);
+        const P4<T> tv = *reinterpret_cast<const P4<T>*>(vecs + 24 + 4 * q), lv = *reinterpret_cast<const P4<T>*>(vecs + 36 + 4 * q);
+        g2[2 * q] = p2mk((tv.x - uv.x) * iv.x, (tv.y - uv.y) * iv.y); g2[2 * q + 1] = p2mk((tv.z - uv.z) * iv.z, (tv.w - uv.w) * iv.w);
+        lam[4 * q] = lv.x; lam[4 * q + 1] = lv.y; lam[4 * q + 2] = lv.z; lam[4 * q + 3] = lv.w;
+      }
+#pragma unroll
+      for (int f = 0; f < 4; f++) lw[f] = lam[3 * f];
+#pragma unroll
+      for (int p = 0; p < 6; p++) {
+#pragma unroll
+        for (int f = 0; f < 4; f++) g2[p] = p2fma(Wc[3 * f][p], p2s(-lw[f]), g2[p]);
+        const int i0 = 2 * p, i1 = 2 * p + 1;
+        if (i0 % 3 == 0 && !(actf[i0 / 3] > T(0))) g2[p].x = T(-1e30);
+        if (i1 % 3 == 0 && !(actf[i1 / 3] > T(0))) g2[p].y = T(-1e30);
+      }
+    }
+  }
+  } else {
+  // float64 validation build: the fully redundant build (every lane gathers all rows with 4-lane broadcasts and forms the whole matrix);
+  // measured on B200 the shared-memory exchange above is 4.6 % faster in f32 but 1.8x slower in f64 (twice the shared-memory traffic
+  // next to a saturated FP64 pipe), so each precision keeps the variant that is faster for it
   // --- gather every foot's rows on every lane (4-lane broadcasts), then the whole 12x12 contact problem is solved
   //     REDUNDANTLY in registers by all four lanes: the Gauss-Seidel sweep below has no shuffle on its dependent chain.
   //     Row index r = 3*foot + e (e: 0 normal, 1,2 friction).
-  T Ya[12][6], Wd[4][6], u0[12], lam[12], targn[4], actf[4];
+  T Ya[12][6], Wd[4][6], u0[12], targn[4], actf[4];
 #pragma unroll
   for (int f = 0; f < 4; f++) {
 #pragma unroll
@@ -621,7 +729,7 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
   // g_i = lam_i + (target_i - u_i) / W_ii is the UNCLAMPED Gauss-Seidel candidate of row i.  A row update
   // lam_j <- clamp(g_j) changes g_i (i != j) by -(W_ij / W_ii) * dlam_j and leaves g_j itself unchanged, so the sweep
   // carries g instead of the contact velocities.  Inactive feet: zero scale (g frozen), g_n = -BIG => lam stays 0.
-  P2<T> g2[6], Wc[12][6];   // Wc[r][p] = (W'[2p][r], W'[2p+1][r]), W'_ij = W_ij / W_ii with a zero diagonal
+  // Wc[r][p] = (W'[2p][r], W'[2p+1][r]), W'_ij = W_ij / W_ii with a zero diagonal
   {
     P2<T> invd[6], uu[6];
 #pragma unroll
@@ -648,6 +756,7 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
         if (2 * p + 1 == r) Wc[r][p].y = T(0);
       }
     }
+  }
   }
   // --- projected Gauss-Seidel, Bullet row order: normals of feet 0..3, then (t1,t2) of feet 0..3.
   //     Row update = clamp -> delta -> 11 independent scalar FFMAs (W'_rr = 0: the row's own candidate is unchanged).
