@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) b2q_step_kernel(Cfg<T> cf, const Model<T>
   const int srow = env0 + (int)(threadIdx.x >> 2);
   if (!valid) env = B.N - 1;
   T* istage0 = stage + (size_t)per_cta * OBS_DIM;
-  WarpComm cm{(int)(threadIdx.x & 3), reinterpret_cast<unsigned char*>(istage0 + (size_t)per_cta * INFO_DIM + (size_t)(threadIdx.x >> 2) * (FEAT ? SCRATCH_FLOATS : SCRATCH_FAST))};
+  WarpComm cm{(int)(threadIdx.x & 3), reinterpret_cast<unsigned char*>(istage0 + (size_t)per_cta * INFO_DIM + (size_t)(threadIdx.x >> 2) * (FEAT ? SCRATCH_FLOATS : (sizeof(T) == 4 ? SCRATCH_FAST : 0)))};
   // the info rows (56 floats per env, produced in 3-float pieces) are staged the same way: one coalesced block per CTA, so that `info`
   // too may be pinned HOST memory (train.py:150-157 reads info every step)
   T* istage = istage0;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) b2q_settle_kernel(Cfg<T> cf, const Model<
   if (!valid) env = B.N - 1;
   if (mask && !mask[env]) valid = false;
   T* scr0 = reinterpret_cast<T*>(smem + ((sizeof(Model<T>) + 31) & ~size_t(31))) + (size_t)(blockDim.x >> 2) * (OBS_DIM + INFO_DIM);
-  WarpComm cm{(int)(threadIdx.x & 3), reinterpret_cast<unsigned char*>(scr0 + (size_t)(threadIdx.x >> 2) * (FEAT ? SCRATCH_FLOATS : SCRATCH_FAST))};
+  WarpComm cm{(int)(threadIdx.x & 3), reinterpret_cast<unsigned char*>(scr0 + (size_t)(threadIdx.x >> 2) * (FEAT ? SCRATCH_FLOATS : (sizeof(T) == 4 ? SCRATCH_FAST : 0)))};
   settle_lane<T, FEAT>(cm, cf, md, B, env, valid);
 }
 
@@ -253,7 +253,7 @@ struct EnvT : EnvBase {
     return B2Q_OK;
   }
   size_t smem_bytes() const {   // model | obs stage | info stage | (FEAT) per-robot solver scratch
-    return ((sizeof(Model<T>) + 31) & ~size_t(31)) + (size_t)(tpb / 4) * (OBS_DIM + INFO_DIM + (feat ? SCRATCH_FLOATS : SCRATCH_FAST)) * sizeof(T);
+    return ((sizeof(Model<T>) + 31) & ~size_t(31)) + (size_t)(tpb / 4) * (OBS_DIM + INFO_DIM + (feat ? SCRATCH_FLOATS : (sizeof(T) == 4 ? SCRATCH_FAST : 0))) * sizeof(T);   // the f64 build exchanges through shuffles: no scratch, so its spill traffic keeps the L1
   }
 
   int set_dynamics(const uint8_t* mask, const void* dyn, cudaStream_t s) override {
