@@ -223,10 +223,15 @@ struct EnvT : EnvBase {
     Model<T> hm; build_model_host(hm, c.foot_radius, c.etg_T, c.etg_amp, c.etg_phase0, c.etg_phase1, c.etg_foot_y_inset);
     build_obs_map(hm, c); obs_dim = hm.obs_dim;
     feat = config_feat(c);
-    if (feat) {   // the FEAT variant keeps a 24x24 solver scratch per robot in shared memory: one warp (8 robots) per CTA, opt-in size above 48 KB
-      tpb = 32;
-      CK(cudaFuncSetAttribute(b2q_step_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
-      CK(cudaFuncSetAttribute(b2q_settle_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    if (feat) tpb = 32;   // the FEAT variant keeps a 36x36 solver scratch per robot in shared memory: one warp (8 robots) per CTA
+    if (smem_bytes() > 48 * 1024) {   // opt-in dynamic shared memory above 48 KB (FEAT scratch, or the exchange areas of a 128-thread CTA)
+      if (feat) {
+        CK(cudaFuncSetAttribute(b2q_step_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+        CK(cudaFuncSetAttribute(b2q_settle_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+      } else {
+        CK(cudaFuncSetAttribute(b2q_step_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+        CK(cudaFuncSetAttribute(b2q_settle_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+      }
     }
     CK(cudaHostAlloc((void**)&h_flag, sizeof(int), cudaHostAllocDefault));
     CK(cudaMalloc(&d_model, sizeof(Model<T>)));
