@@ -314,9 +314,9 @@ __global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ dy /
       }
     }
 #pragma unroll
-    for (int oi = 0; oi < 3; oi++) {        // outputs -> warps
+    for (int oi = 0; oi < 3; oi++) {        // outputs -> warps (skipped when dW3 comes from the tensor-core GEMM)
       const int o = warp + 8 * oi;
-      if (o < od) {
+      if (dW3 && o < od) {
         for (int r = 0; r < nr; r++) {
           const float d = sdy[r][o];
           const uint4 hv = *reinterpret_cast<const uint4*>(&h2s[r][chunk * 8]);
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ dy /
 #pragma unroll
   for (int oi = 0; oi < 3; oi++) {
     const int o = warp + 8 * oi;
-    if (o < od) {
+    if (dW3 && o < od) {
 #pragma unroll
       for (int j = 0; j < 8; j++) atomicAdd(dW3 + o * H + chunk * 8 + j, accw[oi][j]);
     }
@@ -343,7 +343,8 @@ __global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ dy /
 }
 // actor head: from raw y=[mean|raw_ls], eps, da_c (critic gradient wrt action, already includes -1/B routing) build dy and the loss
 __global__ void k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const float* act /*[B][A] tanh(x)*/, const float* logp, const float* q /*[2][B]*/,
-                           const float* da_c /*[B][16] (cols 0..A-1)*/, const float* da_c2 /*second critic's part or null*/, float alpha, float* dy /*[B][2A]*/, float* loss, int B, int A) { pdl_sync();
+                           const float* da_c /*[B][16] (cols 0..A-1)*/, const float* da_c2 /*second critic's part or null*/, float alpha, float* dy /*[B][2A]*/,
+                           bf16* dy_t /*[2A][B]: K-major A operand of the dW3 GEMM*/, float* loss, int B, int A) { pdl_sync();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   float l = 0.f;
   if (b < B) {
@@ -354,15 +355,17 @@ __global__ void k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const
       float ga = da_c[(size_t)b * 16 + j] + (da_c2 ? da_c2[(size_t)b * 16 + j] : 0.f) + (alpha / (float)B) * (2.f * a / ((1.f - a * a) + 1e-6f));
       float gx = ga * (1.f - a * a);
       float gls = gx * sd * e - alpha / (float)B;
+      const float gl = (rl > -20.f && rl < 2.f) ? gls : 0.f;                       // torch.clamp gradient
       dy[(size_t)b * 2 * A + j] = gx;
-      dy[(size_t)b * 2 * A + A + j] = (rl > -20.f && rl < 2.f) ? gls : 0.f;        // torch.clamp gradient
+      dy[(size_t)b * 2 * A + A + j] = gl;
+      dy_t[(size_t)j * B + b] = __float2bfloat16(gx); dy_t[(size_t)(A + j) * B + b] = __float2bfloat16(gl);
     }
   }
   for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
   if ((threadIdx.x & 31) == 0) atomicAdd(loss, l);
 }
 // behaviour cloning head (alg/BC.py:53-59): loss = -mean_{b,j} log N(ref | mean, exp(ls)); dy = dloss/d[mean | raw_ls]
-__global__ void k_bc_dy(const float* raw /*[B][2A]*/, const float* ref /*[B][A]*/, float* dy, float* loss, int B, int A) { pdl_sync();
+__global__ void k_bc_dy(const float* raw /*[B][2A]*/, const float* ref /*[B][A]*/, float* dy, bf16* dy_t /*[2A][B]*/, float* loss, int B, int A) { pdl_sync();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   float l = 0.f;
   const float inv = 1.f / (float)(B * A);
@@ -371,8 +374,10 @@ __global__ void k_bc_dy(const float* raw /*[B][2A]*/, const float* ref /*[B][A]*
       float mu = raw[(size_t)b * 2 * A + j], rl = raw[(size_t)b * 2 * A + A + j], ls = fminf(fmaxf(rl, -20.f), 2.f);
       float d = ref[(size_t)b * A + j] - mu, iv = expf(-2.f * ls);
       l -= (-0.5f * d * d * iv - ls - 0.9189385332046727f) * inv;
-      dy[(size_t)b * 2 * A + j] = -(d * iv) * inv;
-      dy[(size_t)b * 2 * A + A + j] = (rl > -20.f && rl < 2.f) ? -(d * d * iv - 1.f) * inv : 0.f;
+      const float g0 = -(d * iv) * inv, g1 = (rl > -20.f && rl < 2.f) ? -(d * d * iv - 1.f) * inv : 0.f;
+      dy[(size_t)b * 2 * A + j] = g0;
+      dy[(size_t)b * 2 * A + A + j] = g1;
+      dy_t[(size_t)j * B + b] = __float2bfloat16(g0); dy_t[(size_t)(A + j) * B + b] = __float2bfloat16(g1);
     }
   }
   for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
@@ -487,7 +492,7 @@ bool make_tmap(CUtensorMap* tm, const bf16* base, int rows, int cols, int ld, in
 struct TmapCache { std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> m; };
 TmapCache& tmaps(B2QSac* s) { if (!s->tmap_cache) s->tmap_cache = new TmapCache(); return *static_cast<TmapCache*>(s->tmap_cache); }
 
-int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int ldb, float* C, int ldc, int M, int N, int K, bool splitk) {
+int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int ldb, float* C, int ldc, int M, int N, int K, bool splitk, int a_rows = 0) {
   GemmArgs g; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
   g.BN = ((N + 15) / 16) * 16;
   if (g.BN > 64) g.BN = 64;                              // N tiled by 64 (grid.y): more CTAs on these latency-bound shapes, 8 KB B panel per k-chunk
@@ -510,7 +515,7 @@ int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int
     }
     return &it->second;
   };
-  const CUtensorMap* ta = get(A, M, lda, 128);
+  const CUtensorMap* ta = get(A, a_rows > M ? a_rows : M, lda, 128);   // a_rows: the operand buffer holds that many (zero) rows, so the 128-row box stays inside it
   const CUtensorMap* tb = get(Bm, N, ldb, g.BN);
   if (!ta || !tb) { s->err = "cuTensorMapEncodeTiled failed"; return -2; }
   if (g.atomic) cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st);
@@ -588,9 +593,16 @@ int critic_backward(B2QSac* s, cudaStream_t st0, DqSrc src = DqSrc{DQ_ARRAY, 0, 
 int actor_backward(B2QSac* s, cudaStream_t st) {
   const int B = s->B, A = s->A; const Net& an = s->an;
   float* g = s->g_actor;
-  pdl_launch(k_head_bwd, dim3((B + 32 * SUBT - 1) / (32 * SUBT)), dim3(H), 0, st, s->dy, 2 * A, s->p_actor + an.oW3, s->ha2_rm, s->dh_rm, s->dh_t, g + an.oW3, g + an.ob3, g + an.ob2, B);
+  // dW3 = dy^T . h2 (contracted over the batch) is a split-K tensor-core GEMM on the helper stream — A = dy^T as bf16 [2A (padded to 128)][B] written
+  // by the dy kernel, B = the [width x batch] dump of h2 — beside the head backward, which keeps dh2, db3 and db2
+  cudaEventRecord(s->ev_aux[2], st); cudaStreamWaitEvent(s->aux[1], s->ev_aux[2], 0);
+  if (gemm(s, s->aux[1], s->dy_bf, B, s->ha2_t, B, g + an.oW3, H, 2 * A, H, B, true, 128)) return -2;
+  cudaEventRecord(s->ev_aux[3], s->aux[1]);
+  pdl_launch(k_head_bwd, dim3((B + 32 * SUBT - 1) / (32 * SUBT)), dim3(H), 0, st, s->dy, 2 * A, s->p_actor + an.oW3, s->ha2_rm, s->dh_rm, s->dh_t, (float*)nullptr, g + an.ob3, g + an.ob2, B);
   s->launches++;
-  return hidden_backward(s, st, 0, s->dh_rm, s->dh_t, s->G, s->ha1_rm, s->ha1_t, s->xa_t, s->W2T[0], g + an.oW2, g + an.ob1, g + an.oW1, an.in_dim);
+  const int rc = hidden_backward(s, st, 0, s->dh_rm, s->dh_t, s->G, s->ha1_rm, s->ha1_t, s->xa_t, s->W2T[0], g + an.oW2, g + an.ob1, g + an.oW1, an.in_dim);
+  cudaStreamWaitEvent(st, s->ev_aux[3], 0);
+  return rc;
 }
 }  // namespace
 
@@ -614,7 +626,7 @@ int b2q_sac_create(int device, int obs_dim, int act_dim, int batch, float gamma,
   for (int i = 0; i < 3 && ok; i++) ok = dalloc(s, &s->W2T[i], (size_t)H * H) && dalloc(s, &s->W3T[i], (size_t)H * 64) && dalloc(s, &s->W1A[i], (size_t)16 * H);
   ok = ok && dalloc(s, &s->xc_rm, Bz * 64) && dalloc(s, &s->xc_t, 64 * Bz) && dalloc(s, &s->hc1_rm, 2 * Bz * H) && dalloc(s, &s->hc1_t, 2 * Bz * H) && dalloc(s, &s->hc2_rm, 2 * Bz * H) &&
        dalloc(s, &s->hc2_t, 2 * Bz * H) && dalloc(s, &s->xa_rm, Bz * 64) && dalloc(s, &s->xa_t, 64 * Bz) && dalloc(s, &s->ha1_rm, Bz * H) && dalloc(s, &s->ha1_t, Bz * H) &&
-       dalloc(s, &s->ha2_rm, Bz * H) && dalloc(s, &s->ha2_t, Bz * H) && dalloc(s, &s->dh_rm, Bz * H) && dalloc(s, &s->dh_t, Bz * H) && dalloc(s, &s->dy_bf, Bz * 64) &&
+       dalloc(s, &s->ha2_rm, Bz * H) && dalloc(s, &s->ha2_t, Bz * H) && dalloc(s, &s->dh_rm, Bz * H) && dalloc(s, &s->dh_t, Bz * H) && dalloc(s, &s->dy_bf, Bz * 128) &&
        dalloc(s, &s->G, Bz * H) && dalloc(s, &s->tq, Bz) && dalloc(s, &s->q, 2 * Bz) && dalloc(s, &s->qn, 2 * Bz) && dalloc(s, &s->dq, 2 * Bz) && dalloc(s, &s->next_a, Bz * 12) &&
        dalloc(s, &s->next_logp, Bz) && dalloc(s, &s->cur_a, Bz * 12) && dalloc(s, &s->cur_logp, Bz) && dalloc(s, &s->raw_a, Bz * 24) && dalloc(s, &s->da_c, Bz * 16) &&
        dalloc(s, &s->dy, Bz * 24) && dalloc(s, &s->losses, 4) && dalloc(s, &s->d_step, 1) &&
@@ -743,7 +755,7 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     }
     join(s, st);
     if (!eps_cur) return -1;   // the explicit-noise path is required for the backward pass
-    pdl_launch(k_actor_dy, dim3(NB), dim3(TB), 0, st, s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->da_c2 /* da = da_1 + da_2 */, s->alpha, s->dy, s->losses + 1, B, A);
+    pdl_launch(k_actor_dy, dim3(NB), dim3(TB), 0, st, s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->da_c2 /* da = da_1 + da_2 */, s->alpha, s->dy, s->dy_bf, s->losses + 1, B, A);
     if (actor_backward(s, st)) return -2;
   } else {
     return -1;
@@ -777,7 +789,7 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   if (b2q_mlp_forward(expert_actor, ref_obs, ref_obs_dim, nullptr, B, B2Q_MLP_PREDICT, 0, nullptr, s->next_a /*ref action*/, nullptr, nullptr, st)) return -2;
   B2QMlpSaves sa = {s->xa_rm, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
   if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_RAW, 0, nullptr, s->raw_a, nullptr, nullptr, &sa, st)) return -2;
-  pdl_launch(k_bc_dy, dim3(NB), dim3(TB), 0, st, s->raw_a, s->next_a, s->dy, s->losses + 1, B, A);
+  pdl_launch(k_bc_dy, dim3(NB), dim3(TB), 0, st, s->raw_a, s->next_a, s->dy, s->dy_bf, s->losses + 1, B, A);
   if (actor_backward(s, st)) return -2;
   pdl_launch(k_adam, dim3(((int)an.n + 255) / 256), dim3(256), 0, st, s->p_actor, s->g_actor, s->m_a, s->v_a, (int)an.n, s->lr_a, 0.9f, 0.999f, 1e-8f, s->d_step);
   sync_net_weights(s, st, 1);
