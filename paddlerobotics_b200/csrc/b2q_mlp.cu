@@ -103,7 +103,6 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
         const int idx = tid + NTHR * (j0 + j), r = idx >> 6, k = idx & 63, gr = row0 + r;
         __nv_bfloat16 vb = __float2bfloat16(v[j]);
         *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + sw128_offset(r, k, TILE_M)) = vb;
-        if (a.save && net == 0 && gr < a.M) { a.sv.x_rm[(size_t)gr * 64 + k] = vb; a.sv.x_t[(size_t)k * a.M + gr] = vb; }
       }
     }
   }
@@ -114,6 +113,33 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
   const uint32_t tmem = *tmem_slot;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // a warp may touch TMEM lanes 32*(warp%4)..+31
 
+  // Activation dumps for the backward pass, written from the shared-memory tile the epilogue just produced (while the next layer's MMAs
+  // read the same tile): row-major [batch][256] with one full 512-byte row per warp instruction, and the [256][batch] copy as 16-byte
+  // runs of eight consecutive batch rows per column (the epilogue's own registers hold one ROW per thread: its stores would be 2-byte
+  // scatters for the transposed copy and half-used sectors for the row-major one).
+  auto dump_tile = [&](__nv_bfloat16* d_rm, __nv_bfloat16* d_t, int ncols /*256: hidden activations (per net), 64: the input tile (shared by the nets)*/) {
+    const int nrows = min(TILE_M, a.M - row0);
+    const size_t nbase = ncols == HID ? (size_t)net : 0;
+    if (d_rm) {
+      const int lane = tid & 31;
+      if (lane * 8 < ncols)
+        for (int r = warp; r < nrows; r += NTHR / 32) {
+          const uint4 v = *reinterpret_cast<const uint4*>(smem + OFF_A + sw128_offset(r, lane * 8, TILE_M));
+          *reinterpret_cast<uint4*>(d_rm + (nbase * a.M + row0 + r) * ncols + lane * 8) = v;
+        }
+    }
+    if (d_t && tid < ncols) {
+      const int c = tid;                                   // NTHR == HID: one column per thread
+      __nv_bfloat16* dst = d_t + (nbase * ncols + c) * a.M + row0;
+      for (int r0 = 0; r0 < TILE_M; r0 += 8) {
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = *reinterpret_cast<const __nv_bfloat16*>(smem + OFF_A + sw128_offset(r0 + i, c, TILE_M));
+        if (r0 + 8 <= nrows) *reinterpret_cast<uint4*>(dst + r0) = *reinterpret_cast<const uint4*>(v);
+        else for (int i = 0; i < 8; i++) if (r0 + i < nrows) dst[r0 + i] = v[i];
+      }
+    }
+  };
   // ---- layer 1: [128 x 64] x [256 x 64]^T -> TMEM cols 0..255
   if (tid == 0) {
     mbar_wait(bar_w1, 0);
@@ -124,13 +150,14 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
     umma_commit(bar_mma);
   }
   __syncwarp();
+  if (a.save && net == 0 && (a.sv.x_rm || a.sv.x_t)) { dump_tile(a.sv.x_rm, a.sv.x_t, 64); __syncthreads(); }   // the input tile (panel 0), before epilogue 1 overwrites it
   mbar_wait(bar_mma, 0);
   tc_fence_after();
   if (tid == 0) {  // W1 is consumed: reuse its region for W3
     mbar_expect_tx(bar_w3, SZ_W3);
     bulk_g2s(sW13, img + IMG_W3, SZ_W3, bar_w3);
   }
-  auto epilogue_hidden = [&](uint32_t col_base, const float* b, __nv_bfloat16* d_rm, __nv_bfloat16* d_t) {
+  auto epilogue_hidden = [&](uint32_t col_base, const float* b) {
 #pragma unroll 1
     for (int cc = 4 * chalf; cc < 4 * chalf + 4; cc++) {
       uint32_t r[32];
@@ -147,17 +174,10 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
           pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
         *reinterpret_cast<uint4*>(smem + OFF_A + sw128_offset(trow, cc * 32 + j0, TILE_M)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        if (d_rm && row < a.M) {
-          const int col = cc * 32 + j0;
-          *reinterpret_cast<uint4*>(d_rm + ((size_t)net * a.M + row) * HID + col) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(pk);
-#pragma unroll
-          for (int j = 0; j < 8; j++) d_t[((size_t)net * HID + col + j) * a.M + row] = hv[j];
-        }
       }
     }
   };
-  epilogue_hidden(0, bias, a.save ? a.sv.h1_rm : nullptr, a.save ? a.sv.h1_t : nullptr);
+  epilogue_hidden(0, bias);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -174,9 +194,10 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
     umma_commit(bar_mma);
   }
   __syncwarp();
+  if (a.save) { dump_tile(a.sv.h1_rm, a.sv.h1_t, HID); __syncthreads(); }   // reads of the h1 tile end before any thread's next epilogue overwrites it
   mbar_wait(bar_mma, 1);
   tc_fence_after();
-  epilogue_hidden(256, bias + HID, a.save ? a.sv.h2_rm : nullptr, a.save ? a.sv.h2_t : nullptr);
+  epilogue_hidden(256, bias + HID);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -193,6 +214,7 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
     umma_commit(bar_mma);
   }
   __syncwarp();
+  if (a.save) dump_tile(a.sv.h2_rm, a.sv.h2_t, HID);   // the head epilogue does not write the tile: no barrier needed
   mbar_wait(bar_mma, 0);
   tc_fence_after();
   if (chalf == 0) {

@@ -736,7 +736,8 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     // a ~ pi(obs) with dumps; Q(obs, a) with dumps (sac.py:102-106)
     B2QMlpSaves sa = {s->xa_rm, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
     if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2, eps_cur, s->cur_a, s->cur_logp, s->raw_a, &sa, st)) return -2;
-    B2QMlpSaves sv = {s->xc_rm, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
+    // only the row-major activations are needed here (ReLU masks and the dh GEMMs of d(-min q)/da): no weight gradient of the critics in this phase
+    B2QMlpSaves sv = {nullptr, nullptr, s->hc1_rm, nullptr, s->hc2_rm, nullptr};
     if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, st)) return -2;
     s->launches += 2;
     // d(-min q)/da through both critics (no critic weight gradients: only the actor optimiser steps here)
