@@ -40,6 +40,10 @@ constexpr int H = 256;
 struct GemmArgs {
   float* C; int ldc;
   int M, N, K, BN, chunks_per_split, atomic;
+  // ReLU-backward epilogue (mask_h != null; BN = 64, full 128-row tiles): instead of the f32 tile, write  dh = C . [h > 0]  as bf16 — row-major
+  // [M][N] (dh_rm) and / or [N][M] (dh_t), either may be null — and add its column sums to db: the product never makes the f32 round trip
+  // through HBM and the separate mask kernel drops out of the dependency chain
+  const bf16* mask_h; bf16 *dh_rm, *dh_t; float* db;
 };
 constexpr int G_NSTAGE = 4;
 constexpr uint32_t G_STAGE_A = 128 * 128, G_STAGE_B = 64 * 128, G_STAGE = G_STAGE_A + G_STAGE_B;   // bytes: 128 x 64 bf16 and BN(<=64) x 64 bf16
@@ -108,6 +112,53 @@ __global__ void __launch_bounds__(128) b2q_gemm_kernel(const __grid_constant__ C
     // ---- epilogue (all four warps): TMEM lane = tile row; stage the tile in shared memory, then coalesced stores / reductions
     mbar_wait(bar_done, 0);
     tc_fence_after();
+    if (g.mask_h) {
+      constexpr int LDR = 72, LDT = 136;                                  // bf16 elements per staged row: 16-byte aligned, conflict-free for the accesses below
+      bf16* t_rm = reinterpret_cast<bf16*>(smem);                          // [128][LDR]  rows x this CTA's 64 columns
+      bf16* t_t = reinterpret_cast<bf16*>(smem + 128 * LDR * 2);           // [64][LDT]   columns x 128 rows
+      const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+      const bf16* hrow = g.mask_h + (size_t)(row0 + tid) * g.N + n0;
+#pragma unroll
+      for (int cc = 0; cc < 2; cc++) {
+        uint32_t r[32];
+        uint4 hv[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) hv[q] = *reinterpret_cast<const uint4*>(hrow + cc * 32 + q * 8);
+        __syncwarp();
+        tmem_ld32(lane_addr + cc * 32, r);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const bf16* hb = reinterpret_cast<const bf16*>(&hv[q]);
+          __align__(16) bf16 o[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            o[j] = __float2bfloat16(__bfloat162float(hb[j]) > 0.f ? __uint_as_float(r[q * 8 + j]) : 0.f);
+            t_t[(cc * 32 + q * 8 + j) * LDT + tid] = o[j];
+          }
+          *reinterpret_cast<uint4*>(t_rm + tid * LDR + cc * 32 + q * 8) = *reinterpret_cast<const uint4*>(o);
+        }
+      }
+      __syncthreads();
+      if (g.dh_rm)
+        for (int i = tid; i < 128 * 8; i += 128) { const int r_ = i >> 3, sg = i & 7;
+          *reinterpret_cast<uint4*>(g.dh_rm + (size_t)(row0 + r_) * g.N + n0 + sg * 8) = *reinterpret_cast<const uint4*>(t_rm + r_ * LDR + sg * 8); }
+      if (g.dh_t)
+        for (int i = tid; i < 64 * 16; i += 128) { const int c_ = i >> 4, sg = i & 15;
+          *reinterpret_cast<uint4*>(g.dh_t + (size_t)(n0 + c_) * g.M + row0 + sg * 8) = *reinterpret_cast<const uint4*>(t_t + c_ * LDT + sg * 8); }
+      if (g.db) {                                                          // column sums of the rounded values (what the weight-gradient GEMMs see)
+        const int c_ = tid >> 1, hf = tid & 1;
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const uint4 v = *reinterpret_cast<const uint4*>(t_t + c_ * LDT + hf * 64 + k * 8);
+          const bf16* vb = reinterpret_cast<const bf16*>(&v);
+#pragma unroll
+          for (int j = 0; j < 8; j++) sum += __bfloat162float(vb[j]);
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        if (hf == 0) atomicAdd(g.db + n0 + c_, sum);
+      }
+    } else {
     float* stile = reinterpret_cast<float*>(smem);                      // [128][BN + 1] floats: the operand ring is drained by now
     const int ldt = g.BN + 1;
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
@@ -125,6 +176,7 @@ __global__ void __launch_bounds__(128) b2q_gemm_kernel(const __grid_constant__ C
       float* c = g.C + (size_t)(row0 + r_) * g.ldc + n0 + c_;
       const float v = stile[r_ * ldt + c_];
       if (g.atomic) atomicAdd(c, v); else *c = v;
+    }
     }
   }
   tc_fence_before();
@@ -163,39 +215,6 @@ __device__ __forceinline__ void colsum_flush(float (*csum)[H], const float* cs /
   __syncthreads();
   if (db) { float t = 0.f; for (int w = 0; w < 8; w++) t += csum[w][threadIdx.x]; atomicAdd(db + threadIdx.x, t); }
   __syncthreads();
-}
-// dh = G (f32 [B][256]) masked by h>0 -> bf16 row-major + transposed; db += column sums
-__global__ void __launch_bounds__(256) k_relu_mask(const float* __restrict__ G, const bf16* __restrict__ h, bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t,
-                                                   float* db /*[256] or null*/, int B) { pdl_sync();
-  __shared__ __align__(16) bf16 tile[32][H + 8];
-  __shared__ float csum[8][H];
-  const int chunk = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int sub = 0; sub < SUBT; sub++) {
-    const int b0 = (blockIdx.x * SUBT + sub) * 32, nr = min(32, B - b0);
-    if (nr <= 0) break;
-    uint4 hv[4]; float4 g0[4], g1[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {      // all loads of the thread's four rows in flight before the first use
-      const int r = warp + 8 * k; const size_t off = (size_t)(b0 + r) * H + chunk * 8;
-      if (r < nr) { hv[k] = *reinterpret_cast<const uint4*>(h + off); g0[k] = *reinterpret_cast<const float4*>(G + off); g1[k] = *reinterpret_cast<const float4*>(G + off + 4); }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int r = warp + 8 * k;
-      if (r < nr) {
-        const bf16* hb = reinterpret_cast<const bf16*>(&hv[k]);
-        const float gv[8] = {g0[k].x, g0[k].y, g0[k].z, g0[k].w, g1[k].x, g1[k].y, g1[k].z, g1[k].w};
-        __align__(16) bf16 o[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) { o[j] = __float2bfloat16(__bfloat162float(hb[j]) > 0.f ? gv[j] : 0.f); cs[j] += __bfloat162float(o[j]); }
-        *reinterpret_cast<uint4*>(dh_rm + (size_t)(b0 + r) * H + chunk * 8) = *reinterpret_cast<const uint4*>(o);
-        *reinterpret_cast<uint4*>(&tile[r][chunk * 8]) = *reinterpret_cast<const uint4*>(o);
-      }
-    }
-    tile_transpose_out(tile, dh_t, B, b0, nr);
-  }
-  colsum_flush(csum, cs, chunk, warp, db);
 }
 // critic head backward (out_dim = 1), same tiling: dh2[b,:] = dq[b] W3 masked by h2 > 0; dW3 += sum_b dq[b] h2[b,:]; db3 += sum_b dq; db2 += sum_b dh2
 // How a row's dq is obtained: from an array, or computed in place so that the tiny dq kernels drop out of the dependency chain
@@ -492,8 +511,15 @@ bool make_tmap(CUtensorMap* tm, const bf16* base, int rows, int cols, int ld, in
 struct TmapCache { std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> m; };
 TmapCache& tmaps(B2QSac* s) { if (!s->tmap_cache) s->tmap_cache = new TmapCache(); return *static_cast<TmapCache*>(s->tmap_cache); }
 
-int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int ldb, float* C, int ldc, int M, int N, int K, bool splitk, int a_rows = 0) {
+struct ReluEpi { const bf16* h; bf16 *dh_rm, *dh_t; float* db; };
+int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int ldb, float* C, int ldc, int M, int N, int K, bool splitk, int a_rows = 0,
+         const ReluEpi* epi = nullptr) {
   GemmArgs g; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  g.mask_h = nullptr; g.dh_rm = g.dh_t = nullptr; g.db = nullptr;
+  if (epi) {
+    if (splitk || (M % 128) || (N % 64)) { s->err = "relu epilogue needs full 128 x 64 tiles and no split-K"; return -2; }
+    g.mask_h = epi->h; g.dh_rm = epi->dh_rm; g.dh_t = epi->dh_t; g.db = epi->db;
+  }
   g.BN = ((N + 15) / 16) * 16;
   if (g.BN > 64) g.BN = 64;                              // N tiled by 64 (grid.y): more CTAs on these latency-bound shapes, 8 KB B panel per k-chunk
   const int ntiles = (N + g.BN - 1) / g.BN;
@@ -565,11 +591,11 @@ int hidden_backward(B2QSac* s, cudaStream_t st, int slot, const bf16* dh2_rm, co
   cudaEventRecord(s->ev_aux[2 * slot], st); cudaStreamWaitEvent(ax, s->ev_aux[2 * slot], 0);
   if (gemm(s, ax, dh2_t, B, h1_t, B, gW2, H, H, H, B, true)) return -2;
   cudaEventRecord(s->ev_aux[2 * slot + 1], ax);
-  if (gemm(s, st, dh2_rm, H, W2T, H, G, H, B, H, H, false)) return -2;
-  pdl_launch(k_relu_mask, dim3((B + 32 * SUBT - 1) / (32 * SUBT)), dim3(H), 0, st, G, h1_rm, s->dh1_rm[slot], s->dh1_t[slot], gb1, B);                                                      // dh1, db1
+  const ReluEpi epi{h1_rm, nullptr, s->dh1_t[slot], gb1};                                   // dh1 = (dh2 W2) . relu' and db1 in the GEMM's epilogue; only dW1 reads it: [width][batch] copy
+  if (gemm(s, st, dh2_rm, H, W2T, H, nullptr, H, B, H, H, false, 0, &epi)) return -2;
   if (gemm(s, st, s->dh1_t[slot], B, x_t, B, gW1, in_dim, H, in_dim, B, true)) return -2;
   cudaStreamWaitEvent(st, s->ev_aux[2 * slot + 1], 0);
-  s->launches += 4;
+  s->launches += 3;
   return 0;
 }
 // weight gradients of both critics from dq [2][B] and the activation dumps of the last critic forward
@@ -749,10 +775,10 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
       const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
       DqSrc src{DQ_MINQ, i, s->q, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr};
       pdl_launch(k_head_bwd1, dim3((B + 32 * SUBT - 1) / (32 * SUBT)), dim3(H), 0, sx, nullptr, src, p + cn.oW3, h2, dh_rm, dh_t, G /*scratch dW3*/, nullptr, nullptr, B);
-      if (gemm(s, sx, dh_rm, H, s->W2T[1 + i], H, G, H, B, H, H, false)) return -2;
-      pdl_launch(k_relu_mask, dim3((B + 32 * SUBT - 1) / (32 * SUBT)), dim3(H), 0, sx, G, h1, dh_rm, dh_t, nullptr, B);
-      if (gemm(s, sx, dh_rm, H, s->W1A[1 + i], H, da, 16, B, 16, H, false)) return -2;                    // da_i [B][16]
-      s->launches += 2;
+      const ReluEpi epi{h1, s->dh1_rm[i], nullptr, nullptr};                                               // dh1 (row-major only) straight out of the GEMM's epilogue
+      if (gemm(s, sx, dh_rm, H, s->W2T[1 + i], H, nullptr, H, B, H, H, false, 0, &epi)) return -2;
+      if (gemm(s, sx, s->dh1_rm[i], H, s->W1A[1 + i], H, da, 16, B, 16, H, false)) return -2;             // da_i [B][16]
+      s->launches += 1;
     }
     join(s, st);
     if (!eps_cur) return -1;   // the explicit-noise path is required for the backward pass
