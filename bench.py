@@ -408,7 +408,7 @@ def main():
                        "envs_per_gpu": n, "substeps_per_step": 13, "solver_iters": 23, "l2": "flushed between timed steps (256 MiB write outside the event pair)",
                        "timing": "per-step CUDA event pairs on the launching stream, max over ranks", "done_frac_last_step": done_frac},
             "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": env.h2d_bytes_per_step(), "d2h_bytes_per_step": env.d2h_bytes_per_step(info=True), "steps": Ke,
-                    "transport": "numpy action -> pinned buffer -> step kernel reads it over PCIe and stores obs|reward|done to pinned host memory (b2q_step_host, B2Q_HOST_IO=2); info rows [N,56] staged on the device + one D2H; stream sync every step"},
+                    "transport": "numpy action -> pinned buffer -> step kernel reads it over PCIe and stores obs|reward|done and the info rows [N,56] (staged in shared memory, one coalesced block per CTA) straight to pinned host memory (b2q_step_host, B2Q_HOST_IO=2); stream sync every step"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "b2q_step_kernel<float>", "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP, "issue": issue,
