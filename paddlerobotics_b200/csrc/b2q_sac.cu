@@ -276,94 +276,27 @@ __global__ void __launch_bounds__(256) k_head_bwd1(const float* __restrict__ dq 
   if (src.mode == DQ_CRITIC && chunk == 0) atomicAdd(src.loss, sloss);   // ... and its share of the critic loss
   colsum_flush(csum, cs, chunk, warp, db2);
 }
-// general head backward (actor: out_dim = 2A <= 24), same tiling, two mappings per 32-row sub-tile and no per-output barriers:
-//   rows -> warps:    dh2[b,:] = dy[b,:] . W3 masked by h2 > 0 (each warp four rows), written row-major + staged for the transposed copy
-//   outputs -> warps: dW3[o,:] += sum_b dy[b,o] h2[b,:] with warp w owning outputs o = w, w+8, w+16 over ALL rows of the sub-tile (h2 tile
-//                     in shared memory), so the partial sums stay in registers until one atomic flush per block
-__global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ dy /*[B][od]*/, int od, const float* __restrict__ W3 /*[od][256]*/,
-                                                  const bf16* __restrict__ h2 /*[B][256]*/, bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t,
-                                                  float* dW3 /*[od][256]*/, float* db3 /*[od] or null*/, float* db2 /*[256] or null*/, int B) { pdl_sync();
-  __shared__ __align__(16) unsigned char raw_tile[32 * (H + 8) * sizeof(bf16)];
-  bf16 (*tile)[H + 8] = reinterpret_cast<bf16 (*)[H + 8]>(raw_tile);
-  float (*csum)[H] = reinterpret_cast<float (*)[H]>(raw_tile);          // aliases the tile: only used after the last transpose-out
-  __shared__ __align__(16) bf16 h2s[32][H + 8];
-  __shared__ float sdy[32][24];
-  const int chunk = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, accw[3][8], accb = 0.f;
-#pragma unroll
-  for (int oi = 0; oi < 3; oi++)
-#pragma unroll
-    for (int j = 0; j < 8; j++) accw[oi][j] = 0.f;
-  for (int sub = 0; sub < SUBT; sub++) {
-    const int b0 = (blockIdx.x * SUBT + sub) * 32, nr = min(32, B - b0);
-    if (nr <= 0) break;
-    for (int i = threadIdx.x; i < 32 * od; i += 256) { int r = i / od, o = i % od; sdy[r][o] = r < nr ? dy[(size_t)(b0 + r) * od + o] : 0.f; }
-    float hf[4][8], g[4][8];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int r = warp + 8 * k;
-      uint4 hv = make_uint4(0, 0, 0, 0);
-      if (r < nr) hv = *reinterpret_cast<const uint4*>(h2 + (size_t)(b0 + r) * H + chunk * 8);
-      *reinterpret_cast<uint4*>(&h2s[r][chunk * 8]) = hv;
-      const bf16* hb = reinterpret_cast<const bf16*>(&hv);
-#pragma unroll
-      for (int j = 0; j < 8; j++) { hf[k][j] = __bfloat162float(hb[j]); g[k][j] = 0.f; }
-    }
-    __syncthreads();
-    for (int o = 0; o < od; o++) {          // rows -> warps
-      // 2 x 128-bit loads: the actor's W3 block starts at a multiple of four floats (256 * in_dim + 256 + 65536 + 256) of a 256-byte aligned base
-      const float4 wa = *reinterpret_cast<const float4*>(W3 + o * H + chunk * 8), wb = *reinterpret_cast<const float4*>(W3 + o * H + chunk * 8 + 4);
-      const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const float d = sdy[warp + 8 * k][o];
-#pragma unroll
-        for (int j = 0; j < 8; j++) g[k][j] += d * w8[j];
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int r = warp + 8 * k;
-      if (r < nr) {
-        __align__(16) bf16 o8[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) { o8[j] = __float2bfloat16(hf[k][j] > 0.f ? g[k][j] : 0.f); cs[j] += __bfloat162float(o8[j]); }
-        *reinterpret_cast<uint4*>(dh_rm + (size_t)(b0 + r) * H + chunk * 8) = *reinterpret_cast<const uint4*>(o8);
-        *reinterpret_cast<uint4*>(&tile[r][chunk * 8]) = *reinterpret_cast<const uint4*>(o8);
-      }
-    }
-#pragma unroll
-    for (int oi = 0; oi < 3; oi++) {        // outputs -> warps (skipped when dW3 comes from the tensor-core GEMM)
-      const int o = warp + 8 * oi;
-      if (dW3 && o < od) {
-        for (int r = 0; r < nr; r++) {
-          const float d = sdy[r][o];
-          const uint4 hv = *reinterpret_cast<const uint4*>(&h2s[r][chunk * 8]);
-          const bf16* hb = reinterpret_cast<const bf16*>(&hv);
-#pragma unroll
-          for (int j = 0; j < 8; j++) accw[oi][j] += d * __bfloat162float(hb[j]);
-        }
-      }
-    }
-    if (threadIdx.x < od) for (int r = 0; r < nr; r++) accb += sdy[r][threadIdx.x];
-    tile_transpose_out(tile, dh_t, B, b0, nr);
+// the head gradient dy = dloss/d[mean | raw_ls] of one row leaves the dy kernels as bf16 in the two operand layouts the tensor-core GEMMs
+// read (row-major [B][64] for dh2 = dy W3, [2A][B] for dW3 = dy^T h2); db3 = column sums of the rounded values, one atomic per warp and column
+__device__ __forceinline__ void dy_out(float g_mean, float g_ls, int b, int j, int B, int A, bf16* dy_rm, bf16* dy_t) {
+  const bf16 m = __float2bfloat16(g_mean), l = __float2bfloat16(g_ls);
+  dy_rm[(size_t)b * 64 + j] = m; dy_rm[(size_t)b * 64 + A + j] = l;
+  dy_t[(size_t)j * B + b] = m; dy_t[(size_t)(A + j) * B + b] = l;
+}
+__device__ __forceinline__ void dy_colsum(bool valid, int B, int A, const bf16* dy_rm, float* db3) {
+  if (!db3) return;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int o = 0; o < 2 * A; o++) {
+    float v = valid ? __bfloat162float(dy_rm[(size_t)b * 64 + o]) : 0.f;   // the thread's own stores above
+    for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+    if ((threadIdx.x & 31) == 0) atomicAdd(db3 + o, v);
   }
-#pragma unroll
-  for (int oi = 0; oi < 3; oi++) {
-    const int o = warp + 8 * oi;
-    if (dW3 && o < od) {
-#pragma unroll
-      for (int j = 0; j < 8; j++) atomicAdd(dW3 + o * H + chunk * 8 + j, accw[oi][j]);
-    }
-  }
-  if (db3 && threadIdx.x < od) atomicAdd(db3 + threadIdx.x, accb);
-  __syncthreads();
-  colsum_flush(csum, cs, chunk, warp, db2);
 }
 // actor head: from raw y=[mean|raw_ls], eps, da_c (critic gradient wrt action, already includes -1/B routing) build dy and the loss
 __global__ void k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const float* act /*[B][A] tanh(x)*/, const float* logp, const float* q /*[2][B]*/,
-                           const float* da_c /*[B][16] (cols 0..A-1)*/, const float* da_c2 /*second critic's part or null*/, float alpha, float* dy /*[B][2A]*/,
-                           bf16* dy_t /*[2A][B]: K-major A operand of the dW3 GEMM*/, float* loss, int B, int A) { pdl_sync();
+                           const float* da_c /*[B][16] (cols 0..A-1)*/, const float* da_c2 /*second critic's part or null*/, float alpha,
+                           bf16* dy_rm /*[B][64], cols >= 2A stay zero: A operand of the dh2 GEMM*/, bf16* dy_t /*[2A][B]: K-major A operand of the dW3 GEMM*/,
+                           float* db3 /*[2A] += column sums of dy*/, float* loss, int B, int A) { pdl_sync();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   float l = 0.f;
   if (b < B) {
@@ -375,16 +308,15 @@ __global__ void k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const
       float gx = ga * (1.f - a * a);
       float gls = gx * sd * e - alpha / (float)B;
       const float gl = (rl > -20.f && rl < 2.f) ? gls : 0.f;                       // torch.clamp gradient
-      dy[(size_t)b * 2 * A + j] = gx;
-      dy[(size_t)b * 2 * A + A + j] = gl;
-      dy_t[(size_t)j * B + b] = __float2bfloat16(gx); dy_t[(size_t)(A + j) * B + b] = __float2bfloat16(gl);
+      dy_out(gx, gl, b, j, B, A, dy_rm, dy_t);
     }
   }
+  dy_colsum(b < B, B, A, dy_rm, db3);
   for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
   if ((threadIdx.x & 31) == 0) atomicAdd(loss, l);
 }
 // behaviour cloning head (alg/BC.py:53-59): loss = -mean_{b,j} log N(ref | mean, exp(ls)); dy = dloss/d[mean | raw_ls]
-__global__ void k_bc_dy(const float* raw /*[B][2A]*/, const float* ref /*[B][A]*/, float* dy, bf16* dy_t /*[2A][B]*/, float* loss, int B, int A) { pdl_sync();
+__global__ void k_bc_dy(const float* raw /*[B][2A]*/, const float* ref /*[B][A]*/, bf16* dy_rm /*[B][64]*/, bf16* dy_t /*[2A][B]*/, float* db3, float* loss, int B, int A) { pdl_sync();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   float l = 0.f;
   const float inv = 1.f / (float)(B * A);
@@ -394,11 +326,10 @@ __global__ void k_bc_dy(const float* raw /*[B][2A]*/, const float* ref /*[B][A]*
       float d = ref[(size_t)b * A + j] - mu, iv = expf(-2.f * ls);
       l -= (-0.5f * d * d * iv - ls - 0.9189385332046727f) * inv;
       const float g0 = -(d * iv) * inv, g1 = (rl > -20.f && rl < 2.f) ? -(d * d * iv - 1.f) * inv : 0.f;
-      dy[(size_t)b * 2 * A + j] = g0;
-      dy[(size_t)b * 2 * A + A + j] = g1;
-      dy_t[(size_t)j * B + b] = __float2bfloat16(g0); dy_t[(size_t)(A + j) * B + b] = __float2bfloat16(g1);
+      dy_out(g0, g1, b, j, B, A, dy_rm, dy_t);
     }
   }
+  dy_colsum(b < B, B, A, dy_rm, db3);
   for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
   if ((threadIdx.x & 31) == 0) atomicAdd(loss, l);
 }
@@ -457,13 +388,13 @@ struct B2QSac {
   // activation dumps: critic (2 nets) and actor
   bf16 *xc_rm = nullptr, *xc_t = nullptr, *hc1_rm = nullptr, *hc1_t = nullptr, *hc2_rm = nullptr, *hc2_t = nullptr;
   bf16 *xa_rm = nullptr, *xa_t = nullptr, *ha1_rm = nullptr, *ha1_t = nullptr, *ha2_rm = nullptr, *ha2_t = nullptr;
-  bf16 *dh_rm = nullptr, *dh_t = nullptr, *dy_bf = nullptr;
+  bf16 *dh_rm = nullptr, *dh_t = nullptr, *dy_bf = nullptr, *dy_rm = nullptr;
   bf16 *dh_rm2 = nullptr, *dh_t2 = nullptr; float *G2 = nullptr, *da_c2 = nullptr;   // second scratch set: the twin critics' backward chains run on two streams
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t aux[2] = {nullptr, nullptr}; cudaEvent_t ev_aux[4] = {nullptr, nullptr, nullptr, nullptr};   // per-chain helper streams: dW2 GEMM beside the dh1 -> dW1 chain
   bf16 *dh1_rm[2] = {nullptr, nullptr}, *dh1_t[2] = {nullptr, nullptr};                                      // layer-1 gradients (separate from dh2 so both GEMM branches can run)
   float *G = nullptr, *tq = nullptr, *q = nullptr, *qn = nullptr, *dq = nullptr, *next_a = nullptr, *next_logp = nullptr, *cur_a = nullptr, *cur_logp = nullptr, *raw_a = nullptr,
-        *da_c = nullptr, *dy = nullptr, *losses = nullptr;
+        *da_c = nullptr, *losses = nullptr;
   std::vector<void*> allocs;
   void* tmap_cache = nullptr;   // TmapCache*: TMA tensor maps of the GEMM operands
   int* d_step = nullptr;
@@ -624,8 +555,9 @@ int actor_backward(B2QSac* s, cudaStream_t st) {
   cudaEventRecord(s->ev_aux[2], st); cudaStreamWaitEvent(s->aux[1], s->ev_aux[2], 0);
   if (gemm(s, s->aux[1], s->dy_bf, B, s->ha2_t, B, g + an.oW3, H, 2 * A, H, B, true, 128)) return -2;
   cudaEventRecord(s->ev_aux[3], s->aux[1]);
-  pdl_launch(k_head_bwd, dim3((B + 32 * SUBT - 1) / (32 * SUBT)), dim3(H), 0, st, s->dy, 2 * A, s->p_actor + an.oW3, s->ha2_rm, s->dh_rm, s->dh_t, (float*)nullptr, g + an.ob3, g + an.ob2, B);
-  s->launches++;
+  // dh2 = (dy W3) . relu'(h2), db2: a K = 64 tensor-core GEMM (A = dy row-major, zero-padded; B = W3^T [256][64]) with the masking epilogue
+  const ReluEpi epi{s->ha2_rm, s->dh_rm, s->dh_t, g + an.ob2};
+  if (gemm(s, st, s->dy_rm, 64, s->W3T[0], 64, nullptr, H, B, H, 64, false, 0, &epi)) return -2;
   const int rc = hidden_backward(s, st, 0, s->dh_rm, s->dh_t, s->G, s->ha1_rm, s->ha1_t, s->xa_t, s->W2T[0], g + an.oW2, g + an.ob1, g + an.oW1, an.in_dim);
   cudaStreamWaitEvent(st, s->ev_aux[3], 0);
   return rc;
@@ -652,10 +584,10 @@ int b2q_sac_create(int device, int obs_dim, int act_dim, int batch, float gamma,
   for (int i = 0; i < 3 && ok; i++) ok = dalloc(s, &s->W2T[i], (size_t)H * H) && dalloc(s, &s->W3T[i], (size_t)H * 64) && dalloc(s, &s->W1A[i], (size_t)16 * H);
   ok = ok && dalloc(s, &s->xc_rm, Bz * 64) && dalloc(s, &s->xc_t, 64 * Bz) && dalloc(s, &s->hc1_rm, 2 * Bz * H) && dalloc(s, &s->hc1_t, 2 * Bz * H) && dalloc(s, &s->hc2_rm, 2 * Bz * H) &&
        dalloc(s, &s->hc2_t, 2 * Bz * H) && dalloc(s, &s->xa_rm, Bz * 64) && dalloc(s, &s->xa_t, 64 * Bz) && dalloc(s, &s->ha1_rm, Bz * H) && dalloc(s, &s->ha1_t, Bz * H) &&
-       dalloc(s, &s->ha2_rm, Bz * H) && dalloc(s, &s->ha2_t, Bz * H) && dalloc(s, &s->dh_rm, Bz * H) && dalloc(s, &s->dh_t, Bz * H) && dalloc(s, &s->dy_bf, Bz * 128) &&
+       dalloc(s, &s->ha2_rm, Bz * H) && dalloc(s, &s->ha2_t, Bz * H) && dalloc(s, &s->dh_rm, Bz * H) && dalloc(s, &s->dh_t, Bz * H) && dalloc(s, &s->dy_bf, Bz * 128) && dalloc(s, &s->dy_rm, Bz * 64) &&
        dalloc(s, &s->G, Bz * H) && dalloc(s, &s->tq, Bz) && dalloc(s, &s->q, 2 * Bz) && dalloc(s, &s->qn, 2 * Bz) && dalloc(s, &s->dq, 2 * Bz) && dalloc(s, &s->next_a, Bz * 12) &&
        dalloc(s, &s->next_logp, Bz) && dalloc(s, &s->cur_a, Bz * 12) && dalloc(s, &s->cur_logp, Bz) && dalloc(s, &s->raw_a, Bz * 24) && dalloc(s, &s->da_c, Bz * 16) &&
-       dalloc(s, &s->dy, Bz * 24) && dalloc(s, &s->losses, 4) && dalloc(s, &s->d_step, 1) &&
+       dalloc(s, &s->losses, 4) && dalloc(s, &s->d_step, 1) &&
        dalloc(s, &s->dh_rm2, Bz * H) && dalloc(s, &s->dh_t2, Bz * H) && dalloc(s, &s->G2, Bz * H) && dalloc(s, &s->da_c2, Bz * 16) &&
        dalloc(s, &s->dh1_rm[0], Bz * H) && dalloc(s, &s->dh1_t[0], Bz * H) && dalloc(s, &s->dh1_rm[1], Bz * H) && dalloc(s, &s->dh1_t[1], Bz * H);
   for (int i = 0; i < 2 && ok; i++) ok = cudaStreamCreateWithFlags(&s->aux[i], cudaStreamNonBlocking) == cudaSuccess;
@@ -782,7 +714,7 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     }
     join(s, st);
     if (!eps_cur) return -1;   // the explicit-noise path is required for the backward pass
-    pdl_launch(k_actor_dy, dim3(NB), dim3(TB), 0, st, s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->da_c2 /* da = da_1 + da_2 */, s->alpha, s->dy, s->dy_bf, s->losses + 1, B, A);
+    pdl_launch(k_actor_dy, dim3(NB), dim3(TB), 0, st, s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->da_c2 /* da = da_1 + da_2 */, s->alpha, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A);
     if (actor_backward(s, st)) return -2;
   } else {
     return -1;
@@ -816,7 +748,7 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   if (b2q_mlp_forward(expert_actor, ref_obs, ref_obs_dim, nullptr, B, B2Q_MLP_PREDICT, 0, nullptr, s->next_a /*ref action*/, nullptr, nullptr, st)) return -2;
   B2QMlpSaves sa = {s->xa_rm, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
   if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_RAW, 0, nullptr, s->raw_a, nullptr, nullptr, &sa, st)) return -2;
-  pdl_launch(k_bc_dy, dim3(NB), dim3(TB), 0, st, s->raw_a, s->next_a, s->dy, s->dy_bf, s->losses + 1, B, A);
+  pdl_launch(k_bc_dy, dim3(NB), dim3(TB), 0, st, s->raw_a, s->next_a, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A);
   if (actor_backward(s, st)) return -2;
   pdl_launch(k_adam, dim3(((int)an.n + 255) / 256), dim3(256), 0, st, s->p_actor, s->g_actor, s->m_a, s->v_a, (int)an.n, s->lr_a, 0.9f, 0.999f, 1e-8f, s->d_step);
   sync_net_weights(s, st, 1);
