@@ -26,10 +26,11 @@ namespace {
 
 constexpr int HID = B2Q_MLP_HIDDEN;
 constexpr int TILE_M = 128;
-constexpr uint32_t SZ_A = 65536, SZ_W2 = 131072, SZ_W13 = 32768, SZ_W1 = 32768, SZ_W3 = 16384, SZ_BIAS = (HID + HID + 32) * 4;
+using b2q_mlp_img::IMG_W1; using b2q_mlp_img::IMG_W2; using b2q_mlp_img::IMG_W3; using b2q_mlp_img::IMG_BIAS; using b2q_mlp_img::IMG_BYTES;
+constexpr uint32_t SZ_A = 65536, SZ_W2 = (uint32_t)b2q_mlp_img::SZ_W2, SZ_W13 = 32768, SZ_W1 = (uint32_t)b2q_mlp_img::SZ_W1, SZ_W3 = (uint32_t)b2q_mlp_img::SZ_W3,
+                   SZ_BIAS = (uint32_t)b2q_mlp_img::SZ_BIAS;
 constexpr uint32_t OFF_A = 0, OFF_W2 = OFF_A + SZ_A, OFF_W13 = OFF_W2 + SZ_W2, OFF_BIAS = OFF_W13 + SZ_W13, OFF_BAR = OFF_BIAS + SZ_BIAS;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 64;
-constexpr size_t IMG_W1 = 0, IMG_W2 = SZ_W1, IMG_W3 = IMG_W2 + SZ_W2, IMG_BIAS = IMG_W3 + SZ_W3, IMG_BYTES = IMG_BIAS + SZ_BIAS;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
 
 // counter-based Gaussian (Philox-4x32-10 keyed by seed, counter = (row, col)) -> Box-Muller
@@ -311,6 +312,7 @@ int b2q_mlp_destroy(B2QMlpHandle h) {
 }
 const char* b2q_mlp_last_error(B2QMlpHandle h) { return h ? h->err.c_str() : "null handle / create failed"; }
 int64_t b2q_mlp_launch_count(B2QMlpHandle h) { return h ? h->launches : 0; }
+uint8_t* b2q_mlp_image(B2QMlpHandle h, int net) { return (h && net >= 0 && net < h->nets) ? h->img + (size_t)net * IMG_BYTES : nullptr; }
 
 int b2q_mlp_set_weights(B2QMlpHandle h, int net, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3, void* stream) {
   if (!h || net < 0 || net >= h->nets || !w1 || !b1 || !w2 || !b2 || !w3 || !b3) { if (h) h->err = "b2q_mlp_set_weights: bad argument"; return -1; }

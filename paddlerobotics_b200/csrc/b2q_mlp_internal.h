@@ -3,6 +3,7 @@
 // the backward GEMMs consume ([batch x width] and [width x batch]).  Not part of the public C ABI.
 #pragma once
 #include <cuda_bf16.h>
+#include <cstdint>
 #include "../../include/b2q_mlp.h"
 
 struct B2QMlpSaves {
@@ -15,3 +16,11 @@ struct B2QMlpSaves {
 };
 extern "C" int b2q_mlp_forward_ex(B2QMlpHandle h, const float* in1, int in1_dim, const float* in2, int M, int mode, uint64_t seed, const float* eps,
                                   float* out, float* logp, float* raw, const B2QMlpSaves* saves, void* stream);
+
+// Layout of one net's forward image in HBM (bf16 K-major SWIZZLE_128B operand images + f32 biases [b1 | b2 | b3 padded to 32]); the SAC
+// optimiser kernels write updated parameters straight into it (b2q_sac.cu: k_adam_pack / k_polyak_pack).
+namespace b2q_mlp_img {
+constexpr size_t SZ_W1 = 32768, SZ_W2 = 131072, SZ_W3 = 16384, SZ_BIAS = (B2Q_MLP_HIDDEN + B2Q_MLP_HIDDEN + 32) * 4;
+constexpr size_t IMG_W1 = 0, IMG_W2 = SZ_W1, IMG_W3 = IMG_W2 + SZ_W2, IMG_BIAS = IMG_W3 + SZ_W3, IMG_BYTES = IMG_BIAS + SZ_BIAS;
+}
+extern "C" uint8_t* b2q_mlp_image(B2QMlpHandle h, int net);   // device pointer of net's image (library-internal)

@@ -276,62 +276,59 @@ __global__ void __launch_bounds__(256) k_head_bwd1(const float* __restrict__ dq 
   if (src.mode == DQ_CRITIC && chunk == 0) atomicAdd(src.loss, sloss);   // ... and its share of the critic loss
   colsum_flush(csum, cs, chunk, warp, db2);
 }
-// the head gradient dy = dloss/d[mean | raw_ls] of one row leaves the dy kernels as bf16 in the two operand layouts the tensor-core GEMMs
-// read (row-major [B][64] for dh2 = dy W3, [2A][B] for dW3 = dy^T h2); db3 = column sums of the rounded values, one atomic per warp and column
-__device__ __forceinline__ void dy_out(float g_mean, float g_ls, int b, int j, int B, int A, bf16* dy_rm, bf16* dy_t) {
+// The head gradient dy = dloss/d[mean | raw_ls] leaves the dy kernels as bf16 in the two operand layouts the tensor-core GEMMs read
+// (row-major [B][64] for dh2 = dy W3, [2A][B] for dW3 = dy^T h2); db3 = column sums of the rounded values.  One thread per (row, action
+// dimension): the f32 inputs are read coalesced and a block's column sums meet in shared memory (one global atomic per column and block).
+__device__ __forceinline__ void dy_out(float g_mean, float g_ls, int b, int j, int B, int A, bf16* dy_rm, bf16* dy_t, float* sdb) {
   const bf16 m = __float2bfloat16(g_mean), l = __float2bfloat16(g_ls);
   dy_rm[(size_t)b * 64 + j] = m; dy_rm[(size_t)b * 64 + A + j] = l;
   dy_t[(size_t)j * B + b] = m; dy_t[(size_t)(A + j) * B + b] = l;
+  atomicAdd(sdb + j, __bfloat162float(m)); atomicAdd(sdb + A + j, __bfloat162float(l));
 }
-__device__ __forceinline__ void dy_colsum(bool valid, int B, int A, const bf16* dy_rm, float* db3) {
-  if (!db3) return;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int o = 0; o < 2 * A; o++) {
-    float v = valid ? __bfloat162float(dy_rm[(size_t)b * 64 + o]) : 0.f;   // the thread's own stores above
-    for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
-    if ((threadIdx.x & 31) == 0) atomicAdd(db3 + o, v);
-  }
+__device__ __forceinline__ void dy_finish(float l, const float* sdb, int A, float* db3, float* loss) {
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  if ((threadIdx.x & 31) == 0 && l != 0.f) atomicAdd(loss, l);
+  __syncthreads();
+  if (db3 && threadIdx.x < 2 * A) atomicAdd(db3 + threadIdx.x, sdb[threadIdx.x]);
 }
 // actor head: from raw y=[mean|raw_ls], eps, da_c (critic gradient wrt action, already includes -1/B routing) build dy and the loss
-__global__ void k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const float* act /*[B][A] tanh(x)*/, const float* logp, const float* q /*[2][B]*/,
+__global__ void __launch_bounds__(256) k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const float* act /*[B][A] tanh(x)*/, const float* logp, const float* q /*[2][B]*/,
                            const float* da_c /*[B][16] (cols 0..A-1)*/, const float* da_c2 /*second critic's part or null*/, float alpha,
                            bf16* dy_rm /*[B][64], cols >= 2A stay zero: A operand of the dh2 GEMM*/, bf16* dy_t /*[2A][B]: K-major A operand of the dW3 GEMM*/,
                            float* db3 /*[2A] += column sums of dy*/, float* loss, int B, int A) { pdl_sync();
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float sdb[32];
+  if (threadIdx.x < 32) sdb[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = i / A, j = i - b * A;
   float l = 0.f;
   if (b < B) {
-    l = (alpha * logp[b] - fminf(q[b], q[B + b])) / (float)B;                     // sac.py:105-106
-    for (int j = 0; j < A; j++) {
-      float a = act[(size_t)b * A + j], rl = raw[(size_t)b * 2 * A + A + j];
-      float ls = fminf(fmaxf(rl, -20.f), 2.f), sd = expf(ls), e = eps[(size_t)b * A + j];
-      float ga = da_c[(size_t)b * 16 + j] + (da_c2 ? da_c2[(size_t)b * 16 + j] : 0.f) + (alpha / (float)B) * (2.f * a / ((1.f - a * a) + 1e-6f));
-      float gx = ga * (1.f - a * a);
-      float gls = gx * sd * e - alpha / (float)B;
-      const float gl = (rl > -20.f && rl < 2.f) ? gls : 0.f;                       // torch.clamp gradient
-      dy_out(gx, gl, b, j, B, A, dy_rm, dy_t);
-    }
+    if (j == 0) l = (alpha * logp[b] - fminf(q[b], q[B + b])) / (float)B;         // sac.py:105-106
+    const float a = act[i], rl = raw[(size_t)b * 2 * A + A + j];
+    const float ls = fminf(fmaxf(rl, -20.f), 2.f), sd = expf(ls), e = eps[i];
+    const float ga = da_c[(size_t)b * 16 + j] + (da_c2 ? da_c2[(size_t)b * 16 + j] : 0.f) + (alpha / (float)B) * (2.f * a / ((1.f - a * a) + 1e-6f));
+    const float gx = ga * (1.f - a * a);
+    const float gls = gx * sd * e - alpha / (float)B;
+    const float gl = (rl > -20.f && rl < 2.f) ? gls : 0.f;                         // torch.clamp gradient
+    dy_out(gx, gl, b, j, B, A, dy_rm, dy_t, sdb);
   }
-  dy_colsum(b < B, B, A, dy_rm, db3);
-  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-  if ((threadIdx.x & 31) == 0) atomicAdd(loss, l);
+  dy_finish(l, sdb, A, db3, loss);
 }
 // behaviour cloning head (alg/BC.py:53-59): loss = -mean_{b,j} log N(ref | mean, exp(ls)); dy = dloss/d[mean | raw_ls]
-__global__ void k_bc_dy(const float* raw /*[B][2A]*/, const float* ref /*[B][A]*/, bf16* dy_rm /*[B][64]*/, bf16* dy_t /*[2A][B]*/, float* db3, float* loss, int B, int A) { pdl_sync();
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_bc_dy(const float* raw /*[B][2A]*/, const float* ref /*[B][A]*/, bf16* dy_rm /*[B][64]*/, bf16* dy_t /*[2A][B]*/, float* db3, float* loss, int B, int A) { pdl_sync();
+  __shared__ float sdb[32];
+  if (threadIdx.x < 32) sdb[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = i / A, j = i - b * A;
   float l = 0.f;
   const float inv = 1.f / (float)(B * A);
   if (b < B) {
-    for (int j = 0; j < A; j++) {
-      float mu = raw[(size_t)b * 2 * A + j], rl = raw[(size_t)b * 2 * A + A + j], ls = fminf(fmaxf(rl, -20.f), 2.f);
-      float d = ref[(size_t)b * A + j] - mu, iv = expf(-2.f * ls);
-      l -= (-0.5f * d * d * iv - ls - 0.9189385332046727f) * inv;
-      const float g0 = -(d * iv) * inv, g1 = (rl > -20.f && rl < 2.f) ? -(d * d * iv - 1.f) * inv : 0.f;
-      dy_out(g0, g1, b, j, B, A, dy_rm, dy_t);
-    }
+    const float mu = raw[(size_t)b * 2 * A + j], rl = raw[(size_t)b * 2 * A + A + j], ls = fminf(fmaxf(rl, -20.f), 2.f);
+    const float d = ref[i] - mu, iv = expf(-2.f * ls);
+    l = -(-0.5f * d * d * iv - ls - 0.9189385332046727f) * inv;
+    const float g0 = -(d * iv) * inv, g1 = (rl > -20.f && rl < 2.f) ? -(d * d * iv - 1.f) * inv : 0.f;
+    dy_out(g0, g1, b, j, B, A, dy_rm, dy_t, sdb);
   }
-  dy_colsum(b < B, B, A, dy_rm, db3);
-  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-  if ((threadIdx.x & 31) == 0) atomicAdd(loss, l);
+  dy_finish(l, sdb, A, db3, loss);
 }
 // dq routing for the actor loss: d(-min(q1,q2))/dq_i /B
 __global__ void k_minq_dq(const float* q /*[2][B]*/, float* dq /*[2][B]*/, int B) { pdl_sync();
@@ -343,7 +340,7 @@ __global__ void k_add_f32(float* dst, const float* src, int n) { pdl_sync(); int
 __global__ void k_step_inc(int* step) { pdl_sync(); *step += 1; }
 // the step counter lives on the device so that the whole learn() can be replayed from a CUDA graph
 // `step` holds the number of COMPLETED optimiser steps; both Adam kernels of a learn use step + 1 and the last kernel of the learn
-// (k_polyak / k_step_inc) advances it — no separate increment kernel in front of the Adam on the dependency chain
+// (k_adam_pack's last block / k_step_inc) advances it — no separate increment kernel in front of the Adam on the dependency chain
 __global__ void k_adam(float* p, const float* g, float* m, float* v, int n, float lr, float b1, float b2, float eps, const int* step) { pdl_sync();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -353,10 +350,60 @@ __global__ void k_adam(float* p, const float* g, float* m, float* v, int n, floa
     p[i] -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
   }
 }
-__global__ void k_polyak(float* tgt, const float* src, int n, float tau, int* step) { pdl_sync();   // sync_target, sac.py:112-118: target = tau*param + (1-tau)*target
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) tgt[i] = tau * src[i] + (1.f - tau) * tgt[i];
-  if (i == 0 && step) *step += 1;
+// The optimiser kernels below also REPACK what they update: each thread converts its new parameter to bf16 and stores it where the tensor-core
+// kernels read it — the forward image of its net (K-major SWIZZLE_128B operand images + f32 biases, b2q_mlp_internal.h) and the backward copies
+// (W2^T, W3^T padded to 64, the action columns of W1) — so no pack / copy kernel follows an optimiser step on the dependency chain.
+// Padding entries of the images are zero from allocation and never change.
+struct PackDst { uint8_t* img; bf16 *W2T, *W3T, *W1A; int in_dim, od, a_off, a_dim; unsigned oW1, ob1, oW2, ob2, oW3, ob3, n; };
+struct PackDst2 { PackDst d[2]; };
+__device__ __forceinline__ void pack_one(const PackDst& d, unsigned i, float v) {
+  const bf16 vb = __float2bfloat16(v);
+  float* bias = reinterpret_cast<float*>(d.img + b2q_mlp_img::IMG_BIAS);
+  if (i < d.ob1) {                                   // W1 [256][in_dim]
+    const int n = (int)(i / (unsigned)d.in_dim), k = (int)i - n * d.in_dim;
+    *reinterpret_cast<bf16*>(d.img + b2q_mlp_img::IMG_W1 + sw128_offset(n, k, H)) = vb;
+    if (d.W1A && k >= d.a_off && k < d.a_off + d.a_dim) d.W1A[(size_t)(k - d.a_off) * H + n] = vb;
+  } else if (i < d.oW2) { bias[i - d.ob1] = v;
+  } else if (i < d.ob2) {                            // W2 [256][256]
+    const int j = (int)(i - d.oW2), n = j >> 8, k = j & 255;
+    *reinterpret_cast<bf16*>(d.img + b2q_mlp_img::IMG_W2 + sw128_offset(n, k, H)) = vb;
+    if (d.W2T) d.W2T[(size_t)k * H + n] = vb;
+  } else if (i < d.oW3) { bias[H + i - d.ob2] = v;
+  } else if (i < d.ob3) {                            // W3 [od][256]
+    const int j = (int)(i - d.oW3), n = j >> 8, k = j & 255;
+    *reinterpret_cast<bf16*>(d.img + b2q_mlp_img::IMG_W3 + sw128_offset(n, k, 32)) = vb;
+    if (d.W3T) d.W3T[(size_t)k * 64 + n] = vb;
+  } else { bias[2 * H + i - d.ob3] = v; }
+}
+// Adam over `nets` consecutive parameter blocks of dst.d[0].n floats each + repack.  `ticket` (optional): the last block to finish advances the
+// step counter, so the kernel can close a learn step while another stream runs the Polyak update beside it.
+__global__ void __launch_bounds__(256) k_adam_pack(float* p, const float* g, float* m, float* v, int n, float lr, float b1, float b2, float eps, int* step, int* ticket, PackDst2 dst) { pdl_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float t = (float)(*step + 1), bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+    const float gi = g[i], mi = b1 * m[i] + (1.f - b1) * gi, vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float pn = p[i] - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    p[i] = pn;
+    const unsigned per = dst.d[0].n, net = (unsigned)i / per;
+    pack_one(dst.d[net], (unsigned)i - net * per, pn);
+  }
+  if (ticket) {
+    __syncthreads();                                  // every thread of the block has read *step
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) { *ticket = 0; *step += 1; }
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_polyak_pack(float* tgt, const float* src, int n, float tau, PackDst2 dst) { pdl_sync();   // sync_target, sac.py:112-118
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float tn = tau * src[i] + (1.f - tau) * tgt[i];
+    tgt[i] = tn;
+    const unsigned per = dst.d[0].n, net = (unsigned)i / per;
+    pack_one(dst.d[net], (unsigned)i - net * per, tn);
+  }
 }
 // bf16 helper copies of one net's weights for the backward GEMMs: W2T [256][256], W3T64 [256][64] (k = output index, zero padded),
 // W1A [16][256] (rows = action columns of W1, for d/da)
@@ -587,7 +634,7 @@ int b2q_sac_create(int device, int obs_dim, int act_dim, int batch, float gamma,
        dalloc(s, &s->ha2_rm, Bz * H) && dalloc(s, &s->ha2_t, Bz * H) && dalloc(s, &s->dh_rm, Bz * H) && dalloc(s, &s->dh_t, Bz * H) && dalloc(s, &s->dy_bf, Bz * 128) && dalloc(s, &s->dy_rm, Bz * 64) &&
        dalloc(s, &s->G, Bz * H) && dalloc(s, &s->tq, Bz) && dalloc(s, &s->q, 2 * Bz) && dalloc(s, &s->qn, 2 * Bz) && dalloc(s, &s->dq, 2 * Bz) && dalloc(s, &s->next_a, Bz * 12) &&
        dalloc(s, &s->next_logp, Bz) && dalloc(s, &s->cur_a, Bz * 12) && dalloc(s, &s->cur_logp, Bz) && dalloc(s, &s->raw_a, Bz * 24) && dalloc(s, &s->da_c, Bz * 16) &&
-       dalloc(s, &s->losses, 4) && dalloc(s, &s->d_step, 1) &&
+       dalloc(s, &s->losses, 4) && dalloc(s, &s->d_step, 2 /*step | block ticket of the closing Adam*/) &&
        dalloc(s, &s->dh_rm2, Bz * H) && dalloc(s, &s->dh_t2, Bz * H) && dalloc(s, &s->G2, Bz * H) && dalloc(s, &s->da_c2, Bz * 16) &&
        dalloc(s, &s->dh1_rm[0], Bz * H) && dalloc(s, &s->dh1_t[0], Bz * H) && dalloc(s, &s->dh1_rm[1], Bz * H) && dalloc(s, &s->dh1_t[1], Bz * H);
   for (int i = 0; i < 2 && ok; i++) ok = cudaStreamCreateWithFlags(&s->aux[i], cudaStreamNonBlocking) == cudaSuccess;
@@ -677,17 +724,29 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     if (critic_backward(s, st, src)) return -2;
   } else if (phase == 1 || phase == 3) {
     const float b1 = 0.9f, b2 = 0.999f;
-    if (phase == 1) {
+    auto dst_of = [&](const Net& nt, B2QMlpHandle mlp, int net, int bw /*index of the backward copies or -1*/, int a_off, int a_dim) {
+      PackDst d;
+      d.img = b2q_mlp_image(mlp, net);
+      d.W2T = bw >= 0 ? s->W2T[bw] : nullptr; d.W3T = bw >= 0 ? s->W3T[bw] : nullptr; d.W1A = (bw >= 0 && a_dim > 0) ? s->W1A[bw] : nullptr;
+      d.in_dim = nt.in_dim; d.od = nt.od; d.a_off = a_off; d.a_dim = a_dim;
+      d.oW1 = (unsigned)nt.oW1; d.ob1 = (unsigned)nt.ob1; d.oW2 = (unsigned)nt.oW2; d.ob2 = (unsigned)nt.ob2; d.oW3 = (unsigned)nt.oW3; d.ob3 = (unsigned)nt.ob3; d.n = (unsigned)nt.n;
+      return d;
+    };
+    if (phase == 1) {                                 // critics: Adam + repack (forward images and backward copies) in one kernel
       int n = (int)(2 * cn.n);
-      pdl_launch(k_adam, dim3((n + 255) / 256), dim3(256), 0, st, s->p_critic, s->g_critic, s->m_c, s->v_c, n, s->lr_c, b1, b2, 1e-8f, s->d_step);
-    } else {
-      int n = (int)an.n, nc = (int)(2 * cn.n);
-      pdl_launch(k_adam, dim3((n + 255) / 256), dim3(256), 0, st, s->p_actor, s->g_actor, s->m_a, s->v_a, n, s->lr_a, b1, b2, 1e-8f, s->d_step);
-      pdl_launch(k_polyak, dim3((nc + 255) / 256), dim3(256), 0, st, s->p_target, s->p_critic, nc, s->tau, s->d_step);
+      PackDst2 dst; dst.d[0] = dst_of(cn, s->mlp_critic, 0, 1, D, A); dst.d[1] = dst_of(cn, s->mlp_critic, 1, 2, D, A);
+      pdl_launch(k_adam_pack, dim3((n + 255) / 256), dim3(256), 0, st, s->p_critic, s->g_critic, s->m_c, s->v_c, n, s->lr_c, b1, b2, 1e-8f, s->d_step, (int*)nullptr, dst);
       s->launches++;
+    } else {                                          // actor Adam + repack on the caller's stream, Polyak + repack of the targets beside it
+      int n = (int)an.n, nc = (int)(2 * cn.n);
+      fork(s, st);
+      PackDst2 dt; dt.d[0] = dst_of(cn, s->mlp_target, 0, -1, 0, 0); dt.d[1] = dst_of(cn, s->mlp_target, 1, -1, 0, 0);
+      pdl_launch(k_polyak_pack, dim3((nc + 255) / 256), dim3(256), 0, s->side, s->p_target, s->p_critic, nc, s->tau, dt);
+      PackDst2 da; da.d[0] = dst_of(an, s->mlp_actor, 0, 0, 0, 0); da.d[1] = da.d[0];
+      pdl_launch(k_adam_pack, dim3((n + 255) / 256), dim3(256), 0, st, s->p_actor, s->g_actor, s->m_a, s->v_a, n, s->lr_a, b1, b2, 1e-8f, s->d_step, s->d_step + 1, da);
+      join(s, st);
+      s->launches += 2;
     }
-    s->launches++;
-    sync_net_weights(s, st, phase == 1 ? 2 : (1 | 4));   // phase 1 changed the critics; phase 3 the actor and (Polyak) the targets
   } else if (phase == 2) {
     if (!obs) return -1;
     cudaMemsetAsync(s->g_actor, 0, an.n * sizeof(float), st);
@@ -714,7 +773,7 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     }
     join(s, st);
     if (!eps_cur) return -1;   // the explicit-noise path is required for the backward pass
-    pdl_launch(k_actor_dy, dim3(NB), dim3(TB), 0, st, s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->da_c2 /* da = da_1 + da_2 */, s->alpha, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A);
+    pdl_launch(k_actor_dy, dim3((B * A + TB - 1) / TB), dim3(TB), 0, st, s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->da_c2 /* da = da_1 + da_2 */, s->alpha, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A);
     if (actor_backward(s, st)) return -2;
   } else {
     return -1;
@@ -748,7 +807,7 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   if (b2q_mlp_forward(expert_actor, ref_obs, ref_obs_dim, nullptr, B, B2Q_MLP_PREDICT, 0, nullptr, s->next_a /*ref action*/, nullptr, nullptr, st)) return -2;
   B2QMlpSaves sa = {s->xa_rm, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
   if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_RAW, 0, nullptr, s->raw_a, nullptr, nullptr, &sa, st)) return -2;
-  pdl_launch(k_bc_dy, dim3(NB), dim3(TB), 0, st, s->raw_a, s->next_a, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A);
+  pdl_launch(k_bc_dy, dim3((B * A + TB - 1) / TB), dim3(TB), 0, st, s->raw_a, s->next_a, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A);
   if (actor_backward(s, st)) return -2;
   pdl_launch(k_adam, dim3(((int)an.n + 255) / 256), dim3(256), 0, st, s->p_actor, s->g_actor, s->m_a, s->v_a, (int)an.n, s->lr_a, 0.9f, 0.999f, 1e-8f, s->d_step);
   sync_net_weights(s, st, 1);

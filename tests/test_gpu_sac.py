@@ -79,6 +79,7 @@ def test_sac_gradients_and_losses_vs_torch(B):
     ga_d, gc_d = L.grads()
     losses = torch.as_tensor(__import__("paddlerobotics_b200.agent", fromlist=["_CudaBuf"])._CudaBuf(lib.b2q_sac_loss_ptr(h), 2), device=dev).clone()
     torch.cuda.synchronize()
+    cl, al = cl.detach(), al.detach()
     assert abs(float(losses[0]) - float(cl)) < 0.02 * abs(float(cl)) + 1e-3, (float(losses[0]), float(cl))
     assert abs(float(losses[1]) - float(al)) < 0.02 * abs(float(al)) + 2e-2, (float(losses[1]), float(al))
     for name, d, r in (("critic", gc_d, ref_c), ("actor", ga_d, ref_a)):
@@ -130,6 +131,43 @@ def test_sac_learn_three_steps_tracks_torch_adam():
     # agent.learn surface (numpy in, floats out)
     c_l, a_l = ag.learn(obs.cpu().numpy(), act.cpu().numpy(), rew.cpu().numpy(), nobs.cpu().numpy(), term.cpu().numpy())
     assert isinstance(c_l, float) and isinstance(a_l, float) and np.isfinite(c_l) and np.isfinite(a_l)
+
+
+def test_optimiser_kernels_repack_forward_images_and_backward_copies():
+    """The Adam / Polyak kernels write the updated parameters straight into the tensor-core operand images and the bf16 backward copies.
+    After three learns they must equal what the stand-alone pack kernels produce from the same f32 parameters: forward outputs bit-equal,
+    gradients equal up to the order of the split-K atomics (tau = 1 so that a fresh learner's targets equal the trained one's)."""
+    import copy
+    import torch
+    from paddlerobotics_b200.agent import MujocoAgent, SACLearner
+    B = 256
+    g = torch.Generator(device="cuda"); g.manual_seed(21)
+    r = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    ag = MujocoAgent(49, 12, seed=13)
+    L = SACLearner(ag, B, tau=1.0)
+    for _ in range(3):
+        L.learn(r(B, 49), torch.rand(B, 12, device="cuda", generator=g) * 2 - 1, r(B), r(B, 49), torch.ones(B, device="cuda"), eps_next=r(B, 12), eps_cur=r(B, 12))
+    obs, act = r(B, 49), torch.rand(B, 12, device="cuda", generator=g) * 2 - 1
+    # forward images: the learner's nets (written by k_adam_pack) vs the agent's own nets (pack kernel on the pulled parameters)
+    from paddlerobotics_b200.agent import PREDICT, RAW
+    assert torch.equal(L.actor.forward(obs, mode=PREDICT)[0][0], ag.predict_batch(obs))
+    q_l = L.critic.forward(obs, in2=act, mode=RAW)[0]
+    q_a = ag.q_values(obs, act)
+    assert torch.equal(q_l[0, :, 0], q_a[0]) and torch.equal(q_l[1, :, 0], q_a[1])
+    # backward copies and target images: gradient phases of the trained learner vs a fresh learner built from the pulled parameters
+    ag2 = MujocoAgent(49, 12, seed=99)
+    ag2.load_state_dict(copy.deepcopy(ag.state_dict()))
+    L2 = SACLearner(ag2, B, tau=1.0)
+    rew, nobs, term, e1, e2 = r(B), r(B, 49), torch.ones(B, device="cuda"), r(B, 12), r(B, 12)
+    out = []
+    for lr in (L, L2):
+        args = (obs.data_ptr(), act.data_ptr(), rew.data_ptr(), nobs.data_ptr(), term.data_ptr(), e1.data_ptr(), e2.data_ptr(), 1)
+        assert lr.lib.b2q_sac_phase(lr.h, 0, *args, lr._stream()) == 0
+        assert lr.lib.b2q_sac_phase(lr.h, 2, *args, lr._stream()) == 0
+        out.append([x.clone() for x in lr.grads()])
+    torch.cuda.synchronize()
+    for x, y in zip(out[0], out[1]):
+        assert float((x - y).abs().max()) <= 1e-5 * float(y.abs().max()) + 1e-9, float((x - y).abs().max())
 
 
 def test_sac_learn_cuda_graph_replay_equals_eager():
