@@ -27,6 +27,8 @@ namespace {
 constexpr int HID = B2Q_MLP_HIDDEN;
 constexpr int TILE_M = 128;
 using b2q_mlp_img::IMG_W1; using b2q_mlp_img::IMG_W2; using b2q_mlp_img::IMG_W3; using b2q_mlp_img::IMG_BIAS; using b2q_mlp_img::IMG_BYTES;
+using b2q_mlp_img::IMG_W2T; using b2q_mlp_img::IMG_W1A;
+constexpr uint32_t SZ_W1A = (uint32_t)b2q_mlp_img::SZ_W1A, OFF_W1A_IN_W13 = 16384;   // the W1A image sits behind W3 in the (32 KB) W1/W3 region
 constexpr uint32_t SZ_A = 65536, SZ_W2 = (uint32_t)b2q_mlp_img::SZ_W2, SZ_W13 = 32768, SZ_W1 = (uint32_t)b2q_mlp_img::SZ_W1, SZ_W3 = (uint32_t)b2q_mlp_img::SZ_W3,
                    SZ_BIAS = (uint32_t)b2q_mlp_img::SZ_BIAS;
 constexpr uint32_t OFF_A = 0, OFF_W2 = OFF_A + SZ_A, OFF_W13 = OFF_W2 + SZ_W2, OFF_BIAS = OFF_W13 + SZ_W13, OFF_BAR = OFF_BIAS + SZ_BIAS;
@@ -51,6 +53,7 @@ struct FwdArgs {
   const float* in1; const float* in2; int in1_dim, in_dim, out_dim, M, mode; uint64_t seed; const float* eps;
   float* out; float* logp; float* raw; const uint8_t* img; size_t img_stride;
   B2QMlpSaves sv; int save;
+  float* da;   // input-gradient pass (see b2q_mlp_internal.h) or null
 };
 
 constexpr int NTHR = 256;
@@ -62,13 +65,13 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0) __trap();   // SWIZZLE_128B operands need a 1024-byte aligned base
   const uint32_t sA = sbase + OFF_A, sW2 = sbase + OFF_W2, sW13 = sbase + OFF_W13;
-  const uint32_t bar_w1 = sbase + OFF_BAR, bar_w2 = bar_w1 + 8, bar_w3 = bar_w1 + 16, bar_mma = bar_w1 + 24;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 32);
+  const uint32_t bar_w1 = sbase + OFF_BAR, bar_w2 = bar_w1 + 8, bar_w3 = bar_w1 + 16, bar_mma = bar_w1 + 24, bar_w2t = bar_w1 + 32;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 40);
   const float* bias = reinterpret_cast<const float*>(smem + OFF_BIAS);
   const uint8_t* img = a.img + (size_t)net * a.img_stride;
 
   if (tid == 0) {
-    mbar_init(bar_w1, 1); mbar_init(bar_w2, 1); mbar_init(bar_w3, 1); mbar_init(bar_mma, 1);
+    mbar_init(bar_w1, 1); mbar_init(bar_w2, 1); mbar_init(bar_w3, 1); mbar_init(bar_mma, 1); mbar_init(bar_w2t, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // weights: W1 (+biases) first, then W2 in 32 KB pieces
     mbar_expect_tx(bar_w1, SZ_W1 + SZ_BIAS);
@@ -155,15 +158,20 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
   mbar_wait(bar_mma, 0);
   tc_fence_after();
   if (tid == 0) {  // W1 is consumed: reuse its region for W3
-    mbar_expect_tx(bar_w3, SZ_W3);
+    mbar_expect_tx(bar_w3, SZ_W3 + (a.da ? SZ_W1A : 0u));
     bulk_g2s(sW13, img + IMG_W3, SZ_W3, bar_w3);
+    if (a.da) bulk_g2s(sW13 + OFF_W1A_IN_W13, img + IMG_W1A, SZ_W1A, bar_w3);
   }
-  auto epilogue_hidden = [&](uint32_t col_base, const float* b) {
-#pragma unroll 1
-    for (int cc = 4 * chalf; cc < 4 * chalf + 4; cc++) {
+  // relu'(h1) of the thread's 128 columns (bit j of word cc: column 32 (4 chalf + cc) + j), kept for the input-gradient pass
+  uint32_t m1[4] = {0u, 0u, 0u, 0u};
+  auto epilogue_hidden = [&](uint32_t col_base, const float* b, bool keep_mask) {
+#pragma unroll
+    for (int c4 = 0; c4 < 4; c4++) {
+      const int cc = 4 * chalf + c4;
       uint32_t r[32];
       __syncwarp();
       tmem_ld32(lane_addr + col_base + cc * 32, r);
+      uint32_t mk = 0u;
 #pragma unroll
       for (int j0 = 0; j0 < 32; j0 += 8) {
         uint32_t pk[4];
@@ -171,14 +179,17 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
         for (int j = 0; j < 8; j += 2) {
           float v0 = fmaxf(__uint_as_float(r[j0 + j]) + b[cc * 32 + j0 + j], 0.f);
           float v1 = fmaxf(__uint_as_float(r[j0 + j + 1]) + b[cc * 32 + j0 + j + 1], 0.f);
+          mk |= (v0 > 0.f ? 1u : 0u) << (j0 + j);
+          mk |= (v1 > 0.f ? 1u : 0u) << (j0 + j + 1);
           __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
           pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
         *reinterpret_cast<uint4*>(smem + OFF_A + sw128_offset(trow, cc * 32 + j0, TILE_M)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
+      if (keep_mask) m1[c4] = mk;
     }
   };
-  epilogue_hidden(0, bias);
+  epilogue_hidden(0, bias, a.da != nullptr);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -198,7 +209,12 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
   if (a.save) { dump_tile(a.sv.h1_rm, a.sv.h1_t, HID); __syncthreads(); }   // reads of the h1 tile end before any thread's next epilogue overwrites it
   mbar_wait(bar_mma, 1);
   tc_fence_after();
-  epilogue_hidden(256, bias + HID);
+  if (a.da && tid == 0) {   // layer 2 has consumed W2: its region takes the W2^T image for the input-gradient pass
+    mbar_expect_tx(bar_w2t, SZ_W2);
+#pragma unroll
+    for (int i = 0; i < 4; i++) bulk_g2s(sW2 + i * 32768u, img + IMG_W2T + (size_t)i * 32768u, 32768u, bar_w2t);
+  }
+  epilogue_hidden(256, bias + HID, false);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -251,6 +267,83 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
       }
     }
   }
+  if (a.da) {
+    // ---- input-gradient pass (out_dim == 1): unit output gradient back to the action columns of the input, on the same tile.
+    // (a) dh2 = W3 . relu'(h2), in place over the h2 tile (layer 3's MMAs have completed: every thread waited on bar_mma above).  Row 0 of the
+    //     W3 operand image is W3 itself: 128 contiguous bytes per 64-column panel.
+#pragma unroll 4
+    for (int c0 = 128 * chalf; c0 < 128 * chalf + 128; c0 += 8) {
+      uint8_t* hp = smem + OFF_A + sw128_offset(trow, c0, TILE_M);
+      const uint4 hv = *reinterpret_cast<const uint4*>(hp);
+      const uint4 wv = *reinterpret_cast<const uint4*>(smem + OFF_W13 + (c0 >> 6) * (32 * 128) + (c0 & 63) * 2);
+      const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) o[j] = ((hw[j] & 0x7fffu) ? (ww[j] & 0xffffu) : 0u) | ((hw[j] & 0x7fff0000u) ? (ww[j] & 0xffff0000u) : 0u);   // h2 = relu(.) >= 0: nonzero <=> positive
+      *reinterpret_cast<uint4*>(hp) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // (b) dh1 pre-mask = dh2 . W2  -> TMEM cols 256..511 (B operand: the W2^T image)
+    if (tid == 0) {
+      mbar_wait(bar_w2t, 0);
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc(TILE_M, HID);
+#pragma unroll
+      for (int ks = 0; ks < 16; ks++)
+        umma_f16(tmem + 256, umma_desc(sA + (ks >> 2) * (TILE_M * 128) + (ks & 3) * 32), umma_desc(sW2 + (ks >> 2) * (HID * 128) + (ks & 3) * 32), idesc, ks > 0);
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(bar_mma, 1);
+    tc_fence_after();
+    // (c) dh1 = . relu'(h1) (bits kept from epilogue 1) -> bf16 over the tile
+#pragma unroll
+    for (int c4 = 0; c4 < 4; c4++) {
+      const int cc = 4 * chalf + c4;
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld32(lane_addr + 256 + cc * 32, r);
+#pragma unroll
+      for (int j0 = 0; j0 < 32; j0 += 8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const float v0 = ((m1[c4] >> (j0 + j)) & 1u) ? __uint_as_float(r[j0 + j]) : 0.f, v1 = ((m1[c4] >> (j0 + j + 1)) & 1u) ? __uint_as_float(r[j0 + j + 1]) : 0.f;
+          __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(smem + OFF_A + sw128_offset(trow, cc * 32 + j0, TILE_M)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // (d) da = dh1 . W1[:, action]  -> TMEM cols 0..15 (B operand: the W1A image, N = 16)
+    if (tid == 0) {
+      const uint32_t idesc = umma_idesc(TILE_M, 16);
+#pragma unroll
+      for (int ks = 0; ks < 16; ks++)
+        umma_f16(tmem, umma_desc(sA + (ks >> 2) * (TILE_M * 128) + (ks & 3) * 32), umma_desc(sW13 + OFF_W1A_IN_W13 + (ks >> 2) * (16 * 128) + (ks & 3) * 32), idesc, ks > 0);
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(bar_mma, 0);
+    tc_fence_after();
+    if (chalf == 0) {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld32(lane_addr, r);          // columns 16..31 are stale head outputs: not stored
+      if (row < a.M) {
+        float4* dst = reinterpret_cast<float4*>(a.da + ((size_t)net * a.M + row) * 16);
+#pragma unroll
+        for (int j = 0; j < 4; j++) dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
@@ -258,8 +351,16 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
 
 // f32 nn.Linear weights -> bf16 swizzled operand images (+ f32 biases) in the per-net image
 __global__ void b2q_mlp_pack_kernel(uint8_t* img, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
-                                    int in_dim, int out_dim) { pdl_sync();
+                                    int in_dim, int out_dim, int a_off, int a_dim) { pdl_sync();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < HID * HID) {   // W2^T image: B operand [N = in][K = out] of the input-gradient pass
+    int n = i >> 8, k = i & 255;
+    *reinterpret_cast<__nv_bfloat16*>(img + IMG_W2T + sw128_offset(n, k, HID)) = __float2bfloat16(w2[(size_t)k * HID + n]);
+  }
+  if (i < 16 * HID) {    // W1A image: [N = 16 action slots][K = hidden]
+    int n = i >> 8, k = i & 255;
+    *reinterpret_cast<__nv_bfloat16*>(img + IMG_W1A + sw128_offset(n, k, 16)) = __float2bfloat16(n < a_dim ? w1[(size_t)k * in_dim + a_off + n] : 0.f);
+  }
   if (i < HID * 64) {  // W1 [256 x 64 padded]
     int n = i >> 6, k = i & 63;
     *reinterpret_cast<__nv_bfloat16*>(img + IMG_W1 + sw128_offset(n, k, HID)) = __float2bfloat16(k < in_dim ? w1[(size_t)n * in_dim + k] : 0.f);
@@ -281,6 +382,7 @@ __global__ void b2q_mlp_pack_kernel(uint8_t* img, const float* w1, const float* 
 
 struct B2QMlp {
   int device, in_dim, out_dim, nets;
+  int a_off = 0, a_dim = 0;
   uint8_t* img = nullptr;
   std::string err;
   int64_t launches = 0;
@@ -312,11 +414,16 @@ int b2q_mlp_destroy(B2QMlpHandle h) {
 }
 const char* b2q_mlp_last_error(B2QMlpHandle h) { return h ? h->err.c_str() : "null handle / create failed"; }
 int64_t b2q_mlp_launch_count(B2QMlpHandle h) { return h ? h->launches : 0; }
+int b2q_mlp_set_action_slice(B2QMlpHandle h, int a_off, int a_dim) {
+  if (!h || a_off < 0 || a_dim < 0 || a_dim > 16 || a_off + a_dim > h->in_dim) return -1;
+  h->a_off = a_off; h->a_dim = a_dim;
+  return 0;
+}
 uint8_t* b2q_mlp_image(B2QMlpHandle h, int net) { return (h && net >= 0 && net < h->nets) ? h->img + (size_t)net * IMG_BYTES : nullptr; }
 
 int b2q_mlp_set_weights(B2QMlpHandle h, int net, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3, void* stream) {
   if (!h || net < 0 || net >= h->nets || !w1 || !b1 || !w2 || !b2 || !w3 || !b3) { if (h) h->err = "b2q_mlp_set_weights: bad argument"; return -1; }
-  pdl_launch(b2q_mlp_pack_kernel, dim3((HID * HID + 255) / 256), dim3(256), 0, (cudaStream_t)stream, h->img + (size_t)net * IMG_BYTES, w1, b1, w2, b2, w3, b3, h->in_dim, h->out_dim);
+  pdl_launch(b2q_mlp_pack_kernel, dim3((HID * HID + 255) / 256), dim3(256), 0, (cudaStream_t)stream, h->img + (size_t)net * IMG_BYTES, w1, b1, w2, b2, w3, b3, h->in_dim, h->out_dim, h->a_off, h->a_dim);
   h->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return -2; }
@@ -324,11 +431,11 @@ int b2q_mlp_set_weights(B2QMlpHandle h, int net, const float* w1, const float* b
 }
 
 int b2q_mlp_forward_ex(B2QMlpHandle h, const float* in1, int in1_dim, const float* in2, int M, int mode, uint64_t seed, const float* eps, float* out,
-                       float* logp, float* raw, const B2QMlpSaves* saves, void* stream) {
+                       float* logp, float* raw, const B2QMlpSaves* saves, float* da, void* stream) {
   if (!h || !in1 || !out || M < 1 || in1_dim < 1 || in1_dim > h->in_dim || (in1_dim < h->in_dim && !in2) || mode < 0 || mode > 2 ||
-      (mode != B2Q_MLP_RAW && (h->out_dim & 1))) { if (h) h->err = "b2q_mlp_forward: bad argument"; return -1; }
+      (mode != B2Q_MLP_RAW && (h->out_dim & 1)) || (da && (h->out_dim != 1 || h->a_dim < 1 || saves))) { if (h) h->err = "b2q_mlp_forward: bad argument"; return -1; }
   { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) cudaSetDevice(h->device); }   // handles are per GPU
-  FwdArgs a{in1, in2, in1_dim, h->in_dim, h->out_dim, M, mode, seed, eps, out, logp, raw, h->img, IMG_BYTES, B2QMlpSaves{}, 0};
+  FwdArgs a{in1, in2, in1_dim, h->in_dim, h->out_dim, M, mode, seed, eps, out, logp, raw, h->img, IMG_BYTES, B2QMlpSaves{}, 0, da};
   if (saves) { a.sv = *saves; a.save = 1; }
   dim3 grid((M + TILE_M - 1) / TILE_M, h->nets);
   pdl_launch(b2q_mlp_fwd_kernel, dim3(grid), dim3(NTHR), SMEM_BYTES, (cudaStream_t)stream, a);
@@ -339,7 +446,7 @@ int b2q_mlp_forward_ex(B2QMlpHandle h, const float* in1, int in1_dim, const floa
 }
 int b2q_mlp_forward(B2QMlpHandle h, const float* in1, int in1_dim, const float* in2, int M, int mode, uint64_t seed, const float* eps, float* out,
                     float* logp, float* raw, void* stream) {
-  return b2q_mlp_forward_ex(h, in1, in1_dim, in2, M, mode, seed, eps, out, logp, raw, nullptr, stream);
+  return b2q_mlp_forward_ex(h, in1, in1_dim, in2, M, mode, seed, eps, out, logp, raw, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

@@ -293,7 +293,7 @@ __device__ __forceinline__ void dy_finish(float l, const float* sdb, int A, floa
 }
 // actor head: from raw y=[mean|raw_ls], eps, da_c (critic gradient wrt action, already includes -1/B routing) build dy and the loss
 __global__ void __launch_bounds__(256) k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const float* act /*[B][A] tanh(x)*/, const float* logp, const float* q /*[2][B]*/,
-                           const float* da_c /*[B][16] (cols 0..A-1)*/, const float* da_c2 /*second critic's part or null*/, float alpha,
+                           const float* da_c /*[B][16] (cols 0..A-1): dQ1/da*/, const float* da_c2 /*dQ2/da*/, float alpha,
                            bf16* dy_rm /*[B][64], cols >= 2A stay zero: A operand of the dh2 GEMM*/, bf16* dy_t /*[2A][B]: K-major A operand of the dW3 GEMM*/,
                            float* db3 /*[2A] += column sums of dy*/, float* loss, int B, int A) { pdl_sync();
   __shared__ float sdb[32];
@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(256) k_actor_dy(const float* raw /*[B][2A]*/, 
     if (j == 0) l = (alpha * logp[b] - fminf(q[b], q[B + b])) / (float)B;         // sac.py:105-106
     const float a = act[i], rl = raw[(size_t)b * 2 * A + A + j];
     const float ls = fminf(fmaxf(rl, -20.f), 2.f), sd = expf(ls), e = eps[i];
-    const float ga = da_c[(size_t)b * 16 + j] + (da_c2 ? da_c2[(size_t)b * 16 + j] : 0.f) + (alpha / (float)B) * (2.f * a / ((1.f - a * a) + 1e-6f));
+    const float dqa = (q[b] <= q[B + b] ? da_c : da_c2)[(size_t)b * 16 + j];          // d min(q1, q2)/da: torch.min routes to the first on ties (sac.py:104-106)
+    const float ga = -dqa / (float)B + (alpha / (float)B) * (2.f * a / ((1.f - a * a) + 1e-6f));
     const float gx = ga * (1.f - a * a);
     const float gls = gx * sd * e - alpha / (float)B;
     const float gl = (rl > -20.f && rl < 2.f) ? gls : 0.f;                         // torch.clamp gradient
@@ -354,7 +355,7 @@ __global__ void k_adam(float* p, const float* g, float* m, float* v, int n, floa
 // kernels read it — the forward image of its net (K-major SWIZZLE_128B operand images + f32 biases, b2q_mlp_internal.h) and the backward copies
 // (W2^T, W3^T padded to 64, the action columns of W1) — so no pack / copy kernel follows an optimiser step on the dependency chain.
 // Padding entries of the images are zero from allocation and never change.
-struct PackDst { uint8_t* img; bf16 *W2T, *W3T, *W1A; int in_dim, od, a_off, a_dim; unsigned oW1, ob1, oW2, ob2, oW3, ob3, n; };
+struct PackDst { uint8_t* img; bf16 *W2T, *W3T, *W1A; int in_dim, od, a_off, a_dim, gradin /*also keep the W2^T / W1A operand images of the input-gradient pass*/; unsigned oW1, ob1, oW2, ob2, oW3, ob3, n; };
 struct PackDst2 { PackDst d[2]; };
 __device__ __forceinline__ void pack_one(const PackDst& d, unsigned i, float v) {
   const bf16 vb = __float2bfloat16(v);
@@ -362,12 +363,16 @@ __device__ __forceinline__ void pack_one(const PackDst& d, unsigned i, float v) 
   if (i < d.ob1) {                                   // W1 [256][in_dim]
     const int n = (int)(i / (unsigned)d.in_dim), k = (int)i - n * d.in_dim;
     *reinterpret_cast<bf16*>(d.img + b2q_mlp_img::IMG_W1 + sw128_offset(n, k, H)) = vb;
-    if (d.W1A && k >= d.a_off && k < d.a_off + d.a_dim) d.W1A[(size_t)(k - d.a_off) * H + n] = vb;
+    if (d.W1A && k >= d.a_off && k < d.a_off + d.a_dim) {
+      d.W1A[(size_t)(k - d.a_off) * H + n] = vb;
+      if (d.gradin) *reinterpret_cast<bf16*>(d.img + b2q_mlp_img::IMG_W1A + sw128_offset(k - d.a_off, n, 16)) = vb;
+    }
   } else if (i < d.oW2) { bias[i - d.ob1] = v;
   } else if (i < d.ob2) {                            // W2 [256][256]
     const int j = (int)(i - d.oW2), n = j >> 8, k = j & 255;
     *reinterpret_cast<bf16*>(d.img + b2q_mlp_img::IMG_W2 + sw128_offset(n, k, H)) = vb;
     if (d.W2T) d.W2T[(size_t)k * H + n] = vb;
+    if (d.gradin) *reinterpret_cast<bf16*>(d.img + b2q_mlp_img::IMG_W2T + sw128_offset(k, n, H)) = vb;
   } else if (i < d.oW3) { bias[H + i - d.ob2] = v;
   } else if (i < d.ob3) {                            // W3 [od][256]
     const int j = (int)(i - d.oW3), n = j >> 8, k = j & 255;
@@ -633,7 +638,7 @@ int b2q_sac_create(int device, int obs_dim, int act_dim, int batch, float gamma,
        dalloc(s, &s->hc2_t, 2 * Bz * H) && dalloc(s, &s->xa_rm, Bz * 64) && dalloc(s, &s->xa_t, 64 * Bz) && dalloc(s, &s->ha1_rm, Bz * H) && dalloc(s, &s->ha1_t, Bz * H) &&
        dalloc(s, &s->ha2_rm, Bz * H) && dalloc(s, &s->ha2_t, Bz * H) && dalloc(s, &s->dh_rm, Bz * H) && dalloc(s, &s->dh_t, Bz * H) && dalloc(s, &s->dy_bf, Bz * 128) && dalloc(s, &s->dy_rm, Bz * 64) &&
        dalloc(s, &s->G, Bz * H) && dalloc(s, &s->tq, Bz) && dalloc(s, &s->q, 2 * Bz) && dalloc(s, &s->qn, 2 * Bz) && dalloc(s, &s->dq, 2 * Bz) && dalloc(s, &s->next_a, Bz * 12) &&
-       dalloc(s, &s->next_logp, Bz) && dalloc(s, &s->cur_a, Bz * 12) && dalloc(s, &s->cur_logp, Bz) && dalloc(s, &s->raw_a, Bz * 24) && dalloc(s, &s->da_c, Bz * 16) &&
+       dalloc(s, &s->next_logp, Bz) && dalloc(s, &s->cur_a, Bz * 12) && dalloc(s, &s->cur_logp, Bz) && dalloc(s, &s->raw_a, Bz * 24) && dalloc(s, &s->da_c, 2 * Bz * 16) &&
        dalloc(s, &s->losses, 4) && dalloc(s, &s->d_step, 2 /*step | block ticket of the closing Adam*/) &&
        dalloc(s, &s->dh_rm2, Bz * H) && dalloc(s, &s->dh_t2, Bz * H) && dalloc(s, &s->G2, Bz * H) && dalloc(s, &s->da_c2, Bz * 16) &&
        dalloc(s, &s->dh1_rm[0], Bz * H) && dalloc(s, &s->dh1_t[0], Bz * H) && dalloc(s, &s->dh1_rm[1], Bz * H) && dalloc(s, &s->dh1_t[1], Bz * H);
@@ -642,7 +647,8 @@ int b2q_sac_create(int device, int obs_dim, int act_dim, int batch, float gamma,
   ok = ok && cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
        cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && b2q_mlp_create(device, obs_dim, 2 * act_dim, 1, &s->mlp_actor) == 0 && b2q_mlp_create(device, obs_dim + act_dim, 1, 2, &s->mlp_critic) == 0 &&
-       b2q_mlp_create(device, obs_dim + act_dim, 1, 2, &s->mlp_target) == 0;
+       b2q_mlp_create(device, obs_dim + act_dim, 1, 2, &s->mlp_target) == 0 &&
+       b2q_mlp_set_action_slice(s->mlp_critic, obs_dim, act_dim) == 0;
   ok = ok && cudaFuncSetAttribute(b2q_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM) == cudaSuccess;
   if (!ok) { b2q_sac_destroy(s); return -3; }
   *out = s;
@@ -717,7 +723,7 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     if (b2q_mlp_forward(s->mlp_target, next_obs, D, s->next_a, B, B2Q_MLP_RAW, 0, nullptr, s->qn, nullptr, nullptr, s->side)) return -2;
     // current Q with activation dumps (independent of the target chain: main stream)
     B2QMlpSaves sv = {s->xc_rm, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
-    if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, act, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, st)) return -2;
+    if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, act, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, nullptr, st)) return -2;
     join(s, st);
     s->launches += 3;
     DqSrc src{DQ_CRITIC, 0, s->q, rew, term, s->qn, s->next_logp, s->gamma, s->alpha, s->losses + 0};   // target Q and dq are computed inside the head backward
@@ -728,7 +734,7 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
       PackDst d;
       d.img = b2q_mlp_image(mlp, net);
       d.W2T = bw >= 0 ? s->W2T[bw] : nullptr; d.W3T = bw >= 0 ? s->W3T[bw] : nullptr; d.W1A = (bw >= 0 && a_dim > 0) ? s->W1A[bw] : nullptr;
-      d.in_dim = nt.in_dim; d.od = nt.od; d.a_off = a_off; d.a_dim = a_dim;
+      d.in_dim = nt.in_dim; d.od = nt.od; d.a_off = a_off; d.a_dim = a_dim; d.gradin = (bw >= 0 && a_dim > 0) ? 1 : 0;
       d.oW1 = (unsigned)nt.oW1; d.ob1 = (unsigned)nt.ob1; d.oW2 = (unsigned)nt.oW2; d.ob2 = (unsigned)nt.ob2; d.oW3 = (unsigned)nt.oW3; d.ob3 = (unsigned)nt.ob3; d.n = (unsigned)nt.n;
       return d;
     };
@@ -752,28 +758,13 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     cudaMemsetAsync(s->g_actor, 0, an.n * sizeof(float), st);
     // a ~ pi(obs) with dumps; Q(obs, a) with dumps (sac.py:102-106)
     B2QMlpSaves sa = {s->xa_rm, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
-    if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2, eps_cur, s->cur_a, s->cur_logp, s->raw_a, &sa, st)) return -2;
-    // only the row-major activations are needed here (ReLU masks and the dh GEMMs of d(-min q)/da): no weight gradient of the critics in this phase
-    B2QMlpSaves sv = {nullptr, nullptr, s->hc1_rm, nullptr, s->hc2_rm, nullptr};
-    if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, st)) return -2;
+    if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2, eps_cur, s->cur_a, s->cur_logp, s->raw_a, &sa, nullptr, st)) return -2;
+    // Q(obs, a) and, in the same kernel, dQ_i/da for both critics (unit output gradient; no critic weight gradients: only the actor
+    // optimiser steps here).  The routing of d(-min q)/da to the smaller critic and the 1/B happen in the dy kernel.
+    if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, nullptr, s->da_c, st)) return -2;
     s->launches += 2;
-    // d(-min q)/da through both critics (no critic weight gradients: only the actor optimiser steps here)
-    fork(s, st);
-    for (int i = 0; i < 2; i++) {
-      cudaStream_t sx = i ? s->side : st;
-      bf16 *dh_rm = i ? s->dh_rm2 : s->dh_rm, *dh_t = i ? s->dh_t2 : s->dh_t; float *G = i ? s->G2 : s->G, *da = i ? s->da_c2 : s->da_c;
-      const float* p = s->p_critic + (size_t)i * cn.n;
-      const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
-      DqSrc src{DQ_MINQ, i, s->q, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr};
-      pdl_launch(k_head_bwd1, dim3((B + 32 * SUBT - 1) / (32 * SUBT)), dim3(H), 0, sx, nullptr, src, p + cn.oW3, h2, dh_rm, dh_t, G /*scratch dW3*/, nullptr, nullptr, B);
-      const ReluEpi epi{h1, s->dh1_rm[i], nullptr, nullptr};                                               // dh1 (row-major only) straight out of the GEMM's epilogue
-      if (gemm(s, sx, dh_rm, H, s->W2T[1 + i], H, nullptr, H, B, H, H, false, 0, &epi)) return -2;
-      if (gemm(s, sx, s->dh1_rm[i], H, s->W1A[1 + i], H, da, 16, B, 16, H, false)) return -2;             // da_i [B][16]
-      s->launches += 1;
-    }
-    join(s, st);
     if (!eps_cur) return -1;   // the explicit-noise path is required for the backward pass
-    pdl_launch(k_actor_dy, dim3((B * A + TB - 1) / TB), dim3(TB), 0, st, s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->da_c2 /* da = da_1 + da_2 */, s->alpha, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A);
+    pdl_launch(k_actor_dy, dim3((B * A + TB - 1) / TB), dim3(TB), 0, st, s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->da_c + (size_t)B * 16, s->alpha, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A);
     if (actor_backward(s, st)) return -2;
   } else {
     return -1;
@@ -806,7 +797,7 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   // --- actor
   if (b2q_mlp_forward(expert_actor, ref_obs, ref_obs_dim, nullptr, B, B2Q_MLP_PREDICT, 0, nullptr, s->next_a /*ref action*/, nullptr, nullptr, st)) return -2;
   B2QMlpSaves sa = {s->xa_rm, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
-  if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_RAW, 0, nullptr, s->raw_a, nullptr, nullptr, &sa, st)) return -2;
+  if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_RAW, 0, nullptr, s->raw_a, nullptr, nullptr, &sa, nullptr, st)) return -2;
   pdl_launch(k_bc_dy, dim3((B * A + TB - 1) / TB), dim3(TB), 0, st, s->raw_a, s->next_a, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A);
   if (actor_backward(s, st)) return -2;
   pdl_launch(k_adam, dim3(((int)an.n + 255) / 256), dim3(256), 0, st, s->p_actor, s->g_actor, s->m_a, s->v_a, (int)an.n, s->lr_a, 0.9f, 0.999f, 1e-8f, s->d_step);
@@ -815,7 +806,7 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   if (b2q_mlp_forward(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_SAMPLE, 0, eps, s->cur_a, s->cur_logp, nullptr, st)) return -2;
   if (b2q_mlp_forward(expert_critic, ref_obs, ref_obs_dim, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->qn, nullptr, nullptr, st)) return -2;
   B2QMlpSaves sv = {s->xc_rm, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
-  if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, st)) return -2;
+  if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, nullptr, st)) return -2;
   pdl_launch(k_critic_dq, dim3(dim3(NB, 2)), dim3(TB), 0, st, s->q, s->qn, B, s->dq, s->losses + 0, B);
   if (critic_backward(s, st)) return -2;
   pdl_launch(k_adam, dim3(((int)(2 * cn.n) + 255) / 256), dim3(256), 0, st, s->p_critic, s->g_critic, s->m_c, s->v_c, (int)(2 * cn.n), s->lr_c, 0.9f, 0.999f, 1e-8f, s->d_step);
