@@ -438,8 +438,8 @@ struct B2QSac {
   // bf16 backward weights per net (0 actor, 1 c1, 2 c2)
   bf16 *W2T[3] = {0, 0, 0}, *W3T[3] = {0, 0, 0}, *W1A[3] = {0, 0, 0};
   // activation dumps: critic (2 nets) and actor
-  bf16 *xc_rm = nullptr, *xc_t = nullptr, *hc1_rm = nullptr, *hc1_t = nullptr, *hc2_rm = nullptr, *hc2_t = nullptr;
-  bf16 *xa_rm = nullptr, *xa_t = nullptr, *ha1_rm = nullptr, *ha1_t = nullptr, *ha2_rm = nullptr, *ha2_t = nullptr;
+  bf16 *xc_t = nullptr, *hc1_rm = nullptr, *hc1_t = nullptr, *hc2_rm = nullptr, *hc2_t = nullptr;
+  bf16 *xa_t = nullptr, *ha1_rm = nullptr, *ha1_t = nullptr, *ha2_rm = nullptr, *ha2_t = nullptr;
   bf16 *dh_rm = nullptr, *dh_t = nullptr, *dy_bf = nullptr, *dy_rm = nullptr;
   bf16 *dh_rm2 = nullptr, *dh_t2 = nullptr; float *G2 = nullptr, *da_c2 = nullptr;   // second scratch set: the twin critics' backward chains run on two streams
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -451,6 +451,7 @@ struct B2QSac {
   void* tmap_cache = nullptr;   // TmapCache*: TMA tensor maps of the GEMM operands
   int* d_step = nullptr;
   int64_t launches = 0;
+  bool actor_grad_dirty = false;   // g_actor holds a gradient that no phase 0 has cleared yet
   std::string err;
 };
 
@@ -527,7 +528,7 @@ int gemm(B2QSac* s, cudaStream_t st, const bf16* A, int lda, const bf16* Bm, int
   const CUtensorMap* ta = get(A, a_rows > M ? a_rows : M, lda, 128);   // a_rows: the operand buffer holds that many (zero) rows, so the 128-row box stays inside it
   const CUtensorMap* tb = get(Bm, N, ldb, g.BN);
   if (!ta || !tb) { s->err = "cuTensorMapEncodeTiled failed"; return -2; }
-  if (g.atomic) cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st);
+  // split-K products accumulate with f32 atomics: C must be zero on entry (every caller targets the gradient bucket, cleared once per learn)
   dim3 grid((M + 127) / 128, ntiles, splits);
   pdl_launch(b2q_gemm_kernel, dim3(grid), dim3(128), G_SMEM, st, *ta, *tb, g);
   s->launches++;
@@ -634,8 +635,8 @@ int b2q_sac_create(int device, int obs_dim, int act_dim, int batch, float gamma,
             dalloc(s, &s->p_critic, 2 * s->cn.n) && dalloc(s, &s->p_target, 2 * s->cn.n) && dalloc(s, &s->m_c, 2 * s->cn.n) && dalloc(s, &s->v_c, 2 * s->cn.n);
   if (ok) s->g_critic = s->g_actor + s->an.n;
   for (int i = 0; i < 3 && ok; i++) ok = dalloc(s, &s->W2T[i], (size_t)H * H) && dalloc(s, &s->W3T[i], (size_t)H * 64) && dalloc(s, &s->W1A[i], (size_t)16 * H);
-  ok = ok && dalloc(s, &s->xc_rm, Bz * 64) && dalloc(s, &s->xc_t, 64 * Bz) && dalloc(s, &s->hc1_rm, 2 * Bz * H) && dalloc(s, &s->hc1_t, 2 * Bz * H) && dalloc(s, &s->hc2_rm, 2 * Bz * H) &&
-       dalloc(s, &s->hc2_t, 2 * Bz * H) && dalloc(s, &s->xa_rm, Bz * 64) && dalloc(s, &s->xa_t, 64 * Bz) && dalloc(s, &s->ha1_rm, Bz * H) && dalloc(s, &s->ha1_t, Bz * H) &&
+  ok = ok && dalloc(s, &s->xc_t, 64 * Bz) && dalloc(s, &s->hc1_rm, 2 * Bz * H) && dalloc(s, &s->hc1_t, 2 * Bz * H) && dalloc(s, &s->hc2_rm, 2 * Bz * H) &&
+       dalloc(s, &s->hc2_t, 2 * Bz * H) && dalloc(s, &s->xa_t, 64 * Bz) && dalloc(s, &s->ha1_rm, Bz * H) && dalloc(s, &s->ha1_t, Bz * H) &&
        dalloc(s, &s->ha2_rm, Bz * H) && dalloc(s, &s->ha2_t, Bz * H) && dalloc(s, &s->dh_rm, Bz * H) && dalloc(s, &s->dh_t, Bz * H) && dalloc(s, &s->dy_bf, Bz * 128) && dalloc(s, &s->dy_rm, Bz * 64) &&
        dalloc(s, &s->G, Bz * H) && dalloc(s, &s->tq, Bz) && dalloc(s, &s->q, 2 * Bz) && dalloc(s, &s->qn, 2 * Bz) && dalloc(s, &s->dq, 2 * Bz) && dalloc(s, &s->next_a, Bz * 12) &&
        dalloc(s, &s->next_logp, Bz) && dalloc(s, &s->cur_a, Bz * 12) && dalloc(s, &s->cur_logp, Bz) && dalloc(s, &s->raw_a, Bz * 24) && dalloc(s, &s->da_c, 2 * Bz * 16) &&
@@ -715,14 +716,17 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
   const int TB = 256, NB = (B + TB - 1) / TB;
   if (phase == 0) {
     if (!obs || !act || !rew || !next_obs || !term) return -1;
-    cudaMemsetAsync(s->losses, 0, 4 * sizeof(float), st);
-    cudaMemsetAsync(s->g_critic, 0, 2 * cn.n * sizeof(float), st);
     // target: next action ~ pi(next_obs), twin target Q (sac.py:85-91)
     fork(s, st);
+    // ONE clear of the whole flat bucket [actor | critics] and the loss accumulators, after the fork: the caller's stream has slack here (the
+    // side stream carries the longer chain), and phase 2 then starts without a memset node between the critics' Adam and the actor forward
+    cudaMemsetAsync(s->losses, 0, 4 * sizeof(float), st);
+    cudaMemsetAsync(s->g_actor, 0, (an.n + 2 * cn.n) * sizeof(float), st);
+    s->actor_grad_dirty = false;
     if (b2q_mlp_forward(s->mlp_actor, next_obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2 + 1, eps_next, s->next_a, s->next_logp, nullptr, s->side)) return -2;
     if (b2q_mlp_forward(s->mlp_target, next_obs, D, s->next_a, B, B2Q_MLP_RAW, 0, nullptr, s->qn, nullptr, nullptr, s->side)) return -2;
     // current Q with activation dumps (independent of the target chain: main stream)
-    B2QMlpSaves sv = {s->xc_rm, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
+    B2QMlpSaves sv = {nullptr /*x row-major: no consumer*/, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
     if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, act, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, nullptr, st)) return -2;
     join(s, st);
     s->launches += 3;
@@ -755,9 +759,10 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     }
   } else if (phase == 2) {
     if (!obs) return -1;
-    cudaMemsetAsync(s->g_actor, 0, an.n * sizeof(float), st);
+    if (s->actor_grad_dirty) cudaMemsetAsync(s->g_actor, 0, an.n * sizeof(float), st);   // only when no phase 0 cleared the bucket since the last actor gradient
+    s->actor_grad_dirty = true;
     // a ~ pi(obs) with dumps; Q(obs, a) with dumps (sac.py:102-106)
-    B2QMlpSaves sa = {s->xa_rm, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
+    B2QMlpSaves sa = {nullptr /*x row-major: no consumer*/, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
     if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2, eps_cur, s->cur_a, s->cur_logp, s->raw_a, &sa, nullptr, st)) return -2;
     // Q(obs, a) and, in the same kernel, dQ_i/da for both critics (unit output gradient; no critic weight gradients: only the actor
     // optimiser steps here).  The routing of d(-min q)/da to the smaller critic and the 1/B happen in the dy kernel.
@@ -792,11 +797,11 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   const int B = s->B, A = s->A, D = s->D, TB = 256, NB = (B + TB - 1) / TB;
   const Net& an = s->an; const Net& cn = s->cn;
   cudaMemsetAsync(s->losses, 0, 4 * sizeof(float), st);
-  cudaMemsetAsync(s->g_actor, 0, an.n * sizeof(float), st);
-  cudaMemsetAsync(s->g_critic, 0, 2 * cn.n * sizeof(float), st);
+  cudaMemsetAsync(s->g_actor, 0, (an.n + 2 * cn.n) * sizeof(float), st);
+  s->actor_grad_dirty = true;
   // --- actor
   if (b2q_mlp_forward(expert_actor, ref_obs, ref_obs_dim, nullptr, B, B2Q_MLP_PREDICT, 0, nullptr, s->next_a /*ref action*/, nullptr, nullptr, st)) return -2;
-  B2QMlpSaves sa = {s->xa_rm, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
+  B2QMlpSaves sa = {nullptr /*x row-major: no consumer*/, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
   if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_RAW, 0, nullptr, s->raw_a, nullptr, nullptr, &sa, nullptr, st)) return -2;
   pdl_launch(k_bc_dy, dim3((B * A + TB - 1) / TB), dim3(TB), 0, st, s->raw_a, s->next_a, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A);
   if (actor_backward(s, st)) return -2;
@@ -805,7 +810,7 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   // --- critic: a_now ~ pi_student(obs) (no grad); targets = expert Q(ref_obs, a_now)
   if (b2q_mlp_forward(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_SAMPLE, 0, eps, s->cur_a, s->cur_logp, nullptr, st)) return -2;
   if (b2q_mlp_forward(expert_critic, ref_obs, ref_obs_dim, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->qn, nullptr, nullptr, st)) return -2;
-  B2QMlpSaves sv = {s->xc_rm, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
+  B2QMlpSaves sv = {nullptr /*x row-major: no consumer*/, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
   if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, nullptr, st)) return -2;
   pdl_launch(k_critic_dq, dim3(dim3(NB, 2)), dim3(TB), 0, st, s->q, s->qn, B, s->dq, s->losses + 0, B);
   if (critic_backward(s, st)) return -2;
