@@ -277,6 +277,23 @@ def run_extras(args, rank, world, local, dev, w, b):
     l0 = int(L.lib.b2q_sac_launch_count(L.h)); L.learn(o, ac, r, no, t, eps_next=e1_, eps_cur=e2_, pull=False)
     out["sac_learn"]["launches_per_learn"] = int(L.lib.b2q_sac_launch_count(L.h)) - l0
     L.close()
+    if world == 1:
+        # single-GPU production path: the reference's update order (sac.py:77-118) replayed from ONE CUDA graph, batch gathered straight into
+        # the graph's static inputs, rsample() noise from the counter RNG inside the kernels (no per-step torch kernels at all)
+        L = SACLearner(MujocoAgent(49, 12, device=local, seed=3), B)
+        for x, sx in zip((o, ac, r, no, t), L.static_batch()):
+            sx.copy_(x)
+        sb = L.static_batch()
+        for _ in range(5):
+            L.learn(*sb, graph=True, pull=False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            L.learn(*sb, graph=True, pull=False)
+        e1.record(); torch.cuda.synchronize()
+        out["sac_learn"]["us_per_learn_cuda_graph"] = e0.elapsed_time(e1) / 50 * 1e3
+        L.close()
     return out
 
 

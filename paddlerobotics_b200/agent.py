@@ -229,6 +229,8 @@ class SACLearner:
         self.losses = torch.zeros(2, device=agent.device)
         self.steps = 0
         self._graph = None
+        self._static = None
+        self._static_eps = [None, None]
         self.push()
         # forward objects that always see the parameters being trained (no weight copies during a rollout)
         self.actor = FusedMLP(agent.obs_dim, 2 * agent.act_dim, 1, agent.device.index or 0, borrowed=self.lib.b2q_sac_mlp(self.h, 0))
@@ -259,34 +261,49 @@ class SACLearner:
         # wrap the device bucket without copying (for in-place NCCL all-reduce)
         return torch.as_tensor(_CudaBuf(self.lib.b2q_sac_grad_ptr(self.h, which), n), device=self.agent.device)
 
+    def static_batch(self):
+        """The learner's static input tensors (obs, act, rew, next_obs, term) of the CUDA-graph path.  Fill them in place (e.g.
+        ReplayMemory.sample_batch(n, out=learner.static_batch())) and pass them to learn(graph=True): no per-step input copies."""
+        if self._static is None:
+            dev, B, D, A = self.agent.device, self.batch, self.agent.obs_dim, self.agent.act_dim
+            z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+            self._static = [z(B, D), z(B, A), z(B), z(B, D), z(B)]
+        return tuple(self._static[:5])
+
     def learn(self, obs, act, rew, next_obs, term, eps_next=None, eps_cur=None, pull=True, graph=False):
+        """SAC.learn (alg/sac.py:77-118).  eps_next / eps_cur: the N(0,1) draws of the two rsample() calls; None (the production path) = drawn
+        inside the kernels from a counter RNG keyed by (step seed, the learner's device-side step counter) — no noise tensors, and a CUDA-graph
+        replay still draws fresh noise every step."""
         dev = self.agent.device
         t = lambda x: torch.as_tensor(x, dtype=torch.float32, device=dev).contiguous()
         obs, act, rew, next_obs, term = t(obs), t(act), t(rew).reshape(-1), t(next_obs), t(term).reshape(-1)
         assert obs.shape[0] == self.batch
-        if eps_next is None:
-            eps_next = torch.randn(self.batch, self.agent.act_dim, device=dev)
-        if eps_cur is None:
-            eps_cur = torch.randn(self.batch, self.agent.act_dim, device=dev)
-        eps_next, eps_cur = t(eps_next), t(eps_cur)
+        eps_next = None if eps_next is None else t(eps_next)
+        eps_cur = None if eps_cur is None else t(eps_cur)
+        pe = lambda x: None if x is None else x.data_ptr()
         self.steps += 1
-        args = (obs.data_ptr(), act.data_ptr(), rew.data_ptr(), next_obs.data_ptr(), term.data_ptr(), eps_next.data_ptr(), eps_cur.data_ptr(), C.c_uint64(self.steps))
+        args = (obs.data_ptr(), act.data_ptr(), rew.data_ptr(), next_obs.data_ptr(), term.data_ptr(), pe(eps_next), pe(eps_cur), C.c_uint64(self.steps))
         if self.world == 1 and graph:
-            # the ~70 launches of one learner step replayed from a CUDA graph (static input buffers)
-            ins = (obs, act, rew, next_obs, term, eps_next, eps_cur)
+            # one learner step replayed from a CUDA graph (static input buffers; inputs that already ARE the static buffers are not copied)
+            ins = [obs, act, rew, next_obs, term]
             if self._graph is None:
-                self._static = [torch.empty_like(x) for x in ins]
-                sargs = tuple(x.data_ptr() for x in self._static) + (C.c_uint64(0),)
-                for x, sx in zip(ins, self._static):
-                    sx.copy_(x)
+                self.static_batch()
+                self._static_eps = [None if e is None else torch.empty_like(e) for e in (eps_next, eps_cur)]
+                sargs = tuple(x.data_ptr() for x in self._static[:5]) + tuple(pe(e) for e in self._static_eps) + (C.c_uint64(0),)
+                for x, sx in zip(ins + [eps_next, eps_cur], self._static[:5] + self._static_eps):
+                    if x is not None and x.data_ptr() != sx.data_ptr():
+                        sx.copy_(x)
                 side = torch.cuda.Stream(device=dev)
                 side.wait_stream(torch.cuda.current_stream(dev))
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph, stream=side):
                     rc = self.lib.b2q_sac_learn(self.h, *sargs, self.losses.data_ptr(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
                     assert rc == 0, rc
-            for x, sx in zip(ins, self._static):
-                sx.copy_(x)
+            if (eps_next is None) != (self._static_eps[0] is None) or (eps_cur is None) != (self._static_eps[1] is None):
+                raise ValueError("learn(graph=True): explicit eps must be given either on every call or on none (the graph was captured with the other choice)")
+            for x, sx in zip(ins + [eps_next, eps_cur], self._static[:5] + self._static_eps):
+                if x is not None and x.data_ptr() != sx.data_ptr():
+                    sx.copy_(x)
             self._graph.replay()
         elif self.sync == "flat":
             import torch.distributed as dist

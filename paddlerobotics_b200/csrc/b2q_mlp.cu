@@ -19,6 +19,7 @@
 #include "../../include/b2q_mlp.h"
 #include "b2q_tc.cuh"
 #include "b2q_mlp_internal.h"
+#include "b2q_philox.cuh"
 
 using namespace b2q_tc;
 
@@ -35,25 +36,14 @@ constexpr uint32_t OFF_A = 0, OFF_W2 = OFF_A + SZ_A, OFF_W13 = OFF_W2 + SZ_W2, O
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 64;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
 
-// counter-based Gaussian (Philox-4x32-10 keyed by seed, counter = (row, col)) -> Box-Muller
-__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
-  uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0, h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-  uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
-  c0 = n0; c1 = l1; c2 = n2; c3 = l0;
-}
-__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t row, uint32_t col) {
-  uint32_t c0 = row, c1 = col, c2 = 0x9E3779B9u, c3 = 0, k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-  for (int i = 0; i < 10; i++) { philox_round(c0, c1, c2, c3, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
-  float u1 = ((float)(c0 >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(c1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
-}
+using b2q_philox::philox_normal;
 
 struct FwdArgs {
   const float* in1; const float* in2; int in1_dim, in_dim, out_dim, M, mode; uint64_t seed; const float* eps;
   float* out; float* logp; float* raw; const uint8_t* img; size_t img_stride;
   B2QMlpSaves sv; int save;
   float* da;   // input-gradient pass (see b2q_mlp_internal.h) or null
+  const int* seed_ctr;   // device-side counter folded into the sampling key (b2q_philox.cuh) or null
 };
 
 constexpr int NTHR = 256;
@@ -248,6 +238,7 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
         for (int j = 0; j < a.out_dim; j++) a.out[((size_t)net * a.M + row) * a.out_dim + j] = y[j];
       } else {
         const int A = a.out_dim >> 1;
+        const uint64_t seed_eff = b2q_philox::effective_seed(a.seed, a.seed_ctr);
         float lp = 0.f;
         for (int j = 0; j < A; j++) {
           float mean = y[j], act;
@@ -255,7 +246,7 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
             act = tanhf(mean);                                                     // sac.py:60-63
           } else {
             float ls = fminf(fmaxf(y[A + j], -20.f), 2.f), sd = expf(ls);         // mujoco_model.py:21-22,59
-            float e = a.eps ? a.eps[(size_t)row * A + j] : philox_normal(a.seed, (uint32_t)row, (uint32_t)j);
+            float e = a.eps ? a.eps[(size_t)row * A + j] : philox_normal(seed_eff, (uint32_t)row, (uint32_t)j);
             float x = mean + sd * e;                                               // rsample
             act = tanhf(x);
             lp += -0.5f * e * e - ls - 0.9189385332046727f;                        // Normal.log_prob(x)
@@ -431,11 +422,11 @@ int b2q_mlp_set_weights(B2QMlpHandle h, int net, const float* w1, const float* b
 }
 
 int b2q_mlp_forward_ex(B2QMlpHandle h, const float* in1, int in1_dim, const float* in2, int M, int mode, uint64_t seed, const float* eps, float* out,
-                       float* logp, float* raw, const B2QMlpSaves* saves, float* da, void* stream) {
+                       float* logp, float* raw, const B2QMlpSaves* saves, float* da, const int* seed_ctr, void* stream) {
   if (!h || !in1 || !out || M < 1 || in1_dim < 1 || in1_dim > h->in_dim || (in1_dim < h->in_dim && !in2) || mode < 0 || mode > 2 ||
       (mode != B2Q_MLP_RAW && (h->out_dim & 1)) || (da && (h->out_dim != 1 || h->a_dim < 1 || saves))) { if (h) h->err = "b2q_mlp_forward: bad argument"; return -1; }
   { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) cudaSetDevice(h->device); }   // handles are per GPU
-  FwdArgs a{in1, in2, in1_dim, h->in_dim, h->out_dim, M, mode, seed, eps, out, logp, raw, h->img, IMG_BYTES, B2QMlpSaves{}, 0, da};
+  FwdArgs a{in1, in2, in1_dim, h->in_dim, h->out_dim, M, mode, seed, eps, out, logp, raw, h->img, IMG_BYTES, B2QMlpSaves{}, 0, da, seed_ctr};
   if (saves) { a.sv = *saves; a.save = 1; }
   dim3 grid((M + TILE_M - 1) / TILE_M, h->nets);
   pdl_launch(b2q_mlp_fwd_kernel, dim3(grid), dim3(NTHR), SMEM_BYTES, (cudaStream_t)stream, a);
@@ -446,7 +437,7 @@ int b2q_mlp_forward_ex(B2QMlpHandle h, const float* in1, int in1_dim, const floa
 }
 int b2q_mlp_forward(B2QMlpHandle h, const float* in1, int in1_dim, const float* in2, int M, int mode, uint64_t seed, const float* eps, float* out,
                     float* logp, float* raw, void* stream) {
-  return b2q_mlp_forward_ex(h, in1, in1_dim, in2, M, mode, seed, eps, out, logp, raw, nullptr, nullptr, stream);
+  return b2q_mlp_forward_ex(h, in1, in1_dim, in2, M, mode, seed, eps, out, logp, raw, nullptr, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

@@ -14,10 +14,11 @@ struct B2QMlpSaves {
   __nv_bfloat16* h2_rm;  // [nets][M][256]     relu(layer 2)
   __nv_bfloat16* h2_t;   // [nets][256][M]
 };
+// `seed_ctr` (optional): device-side counter folded into the sampling key when eps == NULL (b2q_philox.cuh), for CUDA-graph replays.
 // `da` (optional, out_dim == 1 nets): f32 [nets][M][16] — the gradient of each net's output wrt the action columns of its input, computed in the
 // same kernel right after the forward (dh2 = W3 . relu'(h2), dh1 = (dh2 W2) . relu'(h1), da = dh1 W1[:, action]), activations never leaving the SM
 extern "C" int b2q_mlp_forward_ex(B2QMlpHandle h, const float* in1, int in1_dim, const float* in2, int M, int mode, uint64_t seed, const float* eps,
-                                  float* out, float* logp, float* raw, const B2QMlpSaves* saves, float* da, void* stream);
+                                  float* out, float* logp, float* raw, const B2QMlpSaves* saves, float* da, const int* seed_ctr, void* stream);
 
 // Layout of one net's forward image in HBM (bf16 K-major SWIZZLE_128B operand images + f32 biases [b1 | b2 | b3 padded to 32]); the SAC
 // optimiser kernels write updated parameters straight into it (b2q_sac.cu: k_adam_pack / k_polyak_pack).

@@ -20,6 +20,7 @@
 #include <vector>
 #include "../../include/b2q_sac.h"
 #include "b2q_mlp_internal.h"
+#include "b2q_philox.cuh"
 #include "b2q_tc.cuh"
 
 using namespace b2q_tc;
@@ -295,7 +296,7 @@ __device__ __forceinline__ void dy_finish(float l, const float* sdb, int A, floa
 __global__ void __launch_bounds__(256) k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const float* act /*[B][A] tanh(x)*/, const float* logp, const float* q /*[2][B]*/,
                            const float* da_c /*[B][16] (cols 0..A-1): dQ1/da*/, const float* da_c2 /*dQ2/da*/, float alpha,
                            bf16* dy_rm /*[B][64], cols >= 2A stay zero: A operand of the dh2 GEMM*/, bf16* dy_t /*[2A][B]: K-major A operand of the dW3 GEMM*/,
-                           float* db3 /*[2A] += column sums of dy*/, float* loss, int B, int A) { pdl_sync();
+                           float* db3 /*[2A] += column sums of dy*/, float* loss, int B, int A, uint64_t seed, const int* seed_ctr /*eps == null: the forward's counter RNG draw*/) { pdl_sync();
   __shared__ float sdb[32];
   if (threadIdx.x < 32) sdb[threadIdx.x] = 0.f;
   __syncthreads();
@@ -304,7 +305,8 @@ __global__ void __launch_bounds__(256) k_actor_dy(const float* raw /*[B][2A]*/, 
   if (b < B) {
     if (j == 0) l = (alpha * logp[b] - fminf(q[b], q[B + b])) / (float)B;         // sac.py:105-106
     const float a = act[i], rl = raw[(size_t)b * 2 * A + A + j];
-    const float ls = fminf(fmaxf(rl, -20.f), 2.f), sd = expf(ls), e = eps[i];
+    const float ls = fminf(fmaxf(rl, -20.f), 2.f), sd = expf(ls);
+    const float e = eps ? eps[i] : b2q_philox::philox_normal(b2q_philox::effective_seed(seed, seed_ctr), (uint32_t)b, (uint32_t)j);
     const float dqa = (q[b] <= q[B + b] ? da_c : da_c2)[(size_t)b * 16 + j];          // d min(q1, q2)/da: torch.min routes to the first on ties (sac.py:104-106)
     const float ga = -dqa / (float)B + (alpha / (float)B) * (2.f * a / ((1.f - a * a) + 1e-6f));
     const float gx = ga * (1.f - a * a);
@@ -451,6 +453,7 @@ struct B2QSac {
   void* tmap_cache = nullptr;   // TmapCache*: TMA tensor maps of the GEMM operands
   int* d_step = nullptr;
   int64_t launches = 0;
+  bool overlap_p1 = false;         // set by b2q_sac_learn: phase 2 launches phase 1 on the side stream beside its actor forward
   bool actor_grad_dirty = false;   // g_actor holds a gradient that no phase 0 has cleared yet
   std::string err;
 };
@@ -708,7 +711,7 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
                   const float* eps_next, const float* eps_cur, uint64_t seed, void* stream) {
   if (!s) return -1;
   if (phase < 0 || phase > 3) return -1;
-  if (phase == 2 && (!obs || !eps_cur)) return -1;   // the explicit-noise path is required for the actor's backward pass: refuse before launching anything
+  if (phase == 2 && !obs) return -1;
   cudaSetDevice(s->device);                          // handles are per GPU
   cudaStream_t st = (cudaStream_t)stream;
   const int B = s->B, A = s->A, D = s->D;
@@ -723,11 +726,11 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     cudaMemsetAsync(s->losses, 0, 4 * sizeof(float), st);
     cudaMemsetAsync(s->g_actor, 0, (an.n + 2 * cn.n) * sizeof(float), st);
     s->actor_grad_dirty = false;
-    if (b2q_mlp_forward(s->mlp_actor, next_obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2 + 1, eps_next, s->next_a, s->next_logp, nullptr, s->side)) return -2;
+    if (b2q_mlp_forward_ex(s->mlp_actor, next_obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2 + 1, eps_next, s->next_a, s->next_logp, nullptr, nullptr, nullptr, s->d_step, s->side)) return -2;
     if (b2q_mlp_forward(s->mlp_target, next_obs, D, s->next_a, B, B2Q_MLP_RAW, 0, nullptr, s->qn, nullptr, nullptr, s->side)) return -2;
     // current Q with activation dumps (independent of the target chain: main stream)
     B2QMlpSaves sv = {nullptr /*x row-major: no consumer*/, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
-    if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, act, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, nullptr, st)) return -2;
+    if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, act, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, nullptr, nullptr, st)) return -2;
     join(s, st);
     s->launches += 3;
     DqSrc src{DQ_CRITIC, 0, s->q, rew, term, s->qn, s->next_logp, s->gamma, s->alpha, s->losses + 0};   // target Q and dq are computed inside the head backward
@@ -761,15 +764,21 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     if (!obs) return -1;
     if (s->actor_grad_dirty) cudaMemsetAsync(s->g_actor, 0, an.n * sizeof(float), st);   // only when no phase 0 cleared the bucket since the last actor gradient
     s->actor_grad_dirty = true;
+    // b2q_sac_learn: the critics' Adam + repack (phase 1) runs on the side stream beside the actor forward, which does not read the critics
+    if (s->overlap_p1) {
+      fork(s, st);
+      const int rc1 = b2q_sac_phase(s, 1, obs, act, rew, next_obs, term, eps_next, eps_cur, seed, (void*)s->side);
+      if (rc1) return rc1;
+    }
     // a ~ pi(obs) with dumps; Q(obs, a) with dumps (sac.py:102-106)
     B2QMlpSaves sa = {nullptr /*x row-major: no consumer*/, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
-    if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2, eps_cur, s->cur_a, s->cur_logp, s->raw_a, &sa, nullptr, st)) return -2;
+    if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2, eps_cur, s->cur_a, s->cur_logp, s->raw_a, &sa, nullptr, s->d_step, st)) return -2;
+    if (s->overlap_p1) join(s, st);
     // Q(obs, a) and, in the same kernel, dQ_i/da for both critics (unit output gradient; no critic weight gradients: only the actor
     // optimiser steps here).  The routing of d(-min q)/da to the smaller critic and the 1/B happen in the dy kernel.
-    if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, nullptr, s->da_c, st)) return -2;
+    if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, nullptr, s->da_c, nullptr, st)) return -2;
     s->launches += 2;
-    if (!eps_cur) return -1;   // the explicit-noise path is required for the backward pass
-    pdl_launch(k_actor_dy, dim3((B * A + TB - 1) / TB), dim3(TB), 0, st, s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->da_c + (size_t)B * 16, s->alpha, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A);
+    pdl_launch(k_actor_dy, dim3((B * A + TB - 1) / TB), dim3(TB), 0, st, s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->da_c + (size_t)B * 16, s->alpha, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A, seed * 2, s->d_step);
     if (actor_backward(s, st)) return -2;
   } else {
     return -1;
@@ -781,10 +790,14 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
 
 int b2q_sac_learn(B2QSacHandle s, const float* obs, const float* act, const float* rew, const float* next_obs, const float* term, const float* eps_next,
                   const float* eps_cur, uint64_t seed, float* losses_out /*device [2]: critic, actor*/, void* stream) {
+  if (!s) return -1;
+  s->overlap_p1 = true;                       // phase 1 is launched from inside phase 2 (side stream)
   for (int ph = 0; ph < 4; ph++) {
+    if (ph == 1) continue;
     int rc = b2q_sac_phase(s, ph, obs, act, rew, next_obs, term, eps_next, eps_cur, seed, stream);
-    if (rc) return rc;
+    if (rc) { s->overlap_p1 = false; return rc; }
   }
+  s->overlap_p1 = false;
   if (losses_out) cudaMemcpyAsync(losses_out, s->losses, 2 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
   return 0;
 }
@@ -802,7 +815,7 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   // --- actor
   if (b2q_mlp_forward(expert_actor, ref_obs, ref_obs_dim, nullptr, B, B2Q_MLP_PREDICT, 0, nullptr, s->next_a /*ref action*/, nullptr, nullptr, st)) return -2;
   B2QMlpSaves sa = {nullptr /*x row-major: no consumer*/, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
-  if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_RAW, 0, nullptr, s->raw_a, nullptr, nullptr, &sa, nullptr, st)) return -2;
+  if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_RAW, 0, nullptr, s->raw_a, nullptr, nullptr, &sa, nullptr, nullptr, st)) return -2;
   pdl_launch(k_bc_dy, dim3((B * A + TB - 1) / TB), dim3(TB), 0, st, s->raw_a, s->next_a, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A);
   if (actor_backward(s, st)) return -2;
   pdl_launch(k_adam, dim3(((int)an.n + 255) / 256), dim3(256), 0, st, s->p_actor, s->g_actor, s->m_a, s->v_a, (int)an.n, s->lr_a, 0.9f, 0.999f, 1e-8f, s->d_step);
@@ -811,7 +824,7 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   if (b2q_mlp_forward(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_SAMPLE, 0, eps, s->cur_a, s->cur_logp, nullptr, st)) return -2;
   if (b2q_mlp_forward(expert_critic, ref_obs, ref_obs_dim, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->qn, nullptr, nullptr, st)) return -2;
   B2QMlpSaves sv = {nullptr /*x row-major: no consumer*/, s->xc_t, s->hc1_rm, s->hc1_t, s->hc2_rm, s->hc2_t};
-  if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, nullptr, st)) return -2;
+  if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, &sv, nullptr, nullptr, st)) return -2;
   pdl_launch(k_critic_dq, dim3(dim3(NB, 2)), dim3(TB), 0, st, s->q, s->qn, B, s->dq, s->losses + 0, B);
   if (critic_backward(s, st)) return -2;
   pdl_launch(k_adam, dim3(((int)(2 * cn.n) + 255) / 256), dim3(256), 0, st, s->p_critic, s->g_critic, s->m_c, s->v_c, (int)(2 * cn.n), s->lr_c, 0.9f, 0.999f, 1e-8f, s->d_step);

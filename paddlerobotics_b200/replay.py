@@ -38,10 +38,16 @@ class ReplayMemory:
         self._curr_pos = (self._curr_pos + n) % self.max_size
         self._curr_size = min(self._curr_size + n, self.max_size)
 
-    def sample_batch(self, batch_size, seed=None):
+    def sample_batch(self, batch_size, seed=None, out=None):
+        """Uniform sample (replay_memory.py sample_batch).  out = (obs, act, rew, next_obs, term) float32 device tensors to gather into
+        (e.g. SACLearner.static_batch(): the learner's CUDA-graph inputs are then filled in place, with no copy in between)."""
         self._samples += 1
-        z = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
-        obs, nobs, act, rew, term = z(batch_size, self.obs_dim), z(batch_size, self.obs_dim), z(batch_size, self.act_dim), z(batch_size), z(batch_size)
+        if out is not None:
+            obs, act, rew, nobs, term = out
+            assert obs.shape == (batch_size, self.obs_dim) and act.shape == (batch_size, self.act_dim) and all(x.is_contiguous() and x.dtype == torch.float32 for x in out)
+        else:
+            z = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
+            obs, nobs, act, rew, term = z(batch_size, self.obs_dim), z(batch_size, self.obs_dim), z(batch_size, self.act_dim), z(batch_size), z(batch_size)
         rc = self.lib.b2q_rpm_sample(self.obs.data_ptr(), self.action.data_ptr(), self.reward.data_ptr(), self.next_obs.data_ptr(), self.terminal.data_ptr(),
                                      obs.data_ptr(), act.data_ptr(), rew.data_ptr(), nobs.data_ptr(), term.data_ptr(), batch_size, self.obs_dim, self.act_dim,
                                      self._curr_size, C.c_uint64(self._samples if seed is None else seed), self._stream())

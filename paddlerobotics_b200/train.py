@@ -97,7 +97,7 @@ def main(argv=None):
             # the learner step (latency-bound small kernels) runs on its own stream NEXT TO the env step (one warp per scheduler):
             # it samples transitions up to t-1 and its new weights are first used by the policy forward of step t+1, exactly as
             # in the sequential order, except that transition t itself joins the replay one update later
-            batch_t = rpm.sample_batch(args.batch)
+            batch_t = rpm.sample_batch(args.batch, out=learner.static_batch())
             s_learn.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s_learn):
                 for x in batch_t:
@@ -115,7 +115,7 @@ def main(argv=None):
         obs.copy_(nobs)
         total += n; it += 1
         if rpm.size() >= args.warmup_steps and not (learning and args.overlap):
-            losses = learner.learn(*rpm.sample_batch(args.batch), graph=True, pull=False)   # one update per control step, train.py:163-169
+            losses = learner.learn(*rpm.sample_batch(args.batch, out=learner.static_batch()), graph=True, pull=False)   # one update per control step, train.py:163-169
         if it % args.log_every == 0:
             torch.cuda.synchronize()
             el = time.perf_counter() - t0

