@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
       }
 #pragma unroll
       for (int j = 0; j < 16; j++) {
-        const int idx = tid + NTHR * (j0 + j), r = idx >> 6, k = idx & 63, gr = row0 + r;
+        const int idx = tid + NTHR * (j0 + j), r = idx >> 6, k = idx & 63;
         __nv_bfloat16 vb = __float2bfloat16(v[j]);
         *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + sw128_offset(r, k, TILE_M)) = vb;
       }

@@ -187,10 +187,6 @@ __global__ void __launch_bounds__(128) b2q_gemm_kernel(const __grid_constant__ C
 
 // ---------------------------------------------------------------------------------------------------------------------
 // elementwise / reduction kernels
-__global__ void k_target_q(const float* rew, const float* term, const float* q1n, const float* q2n, const float* logpn, float gamma, float alpha, float* tq, int B) { pdl_sync();
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) tq[b] = rew[b] + gamma * term[b] * (fminf(q1n[b], q2n[b]) - alpha * logpn[b]);   // sac.py:88-91
-}
 // critic head backward for both nets: dq = 2 (q - tq)/B; loss += (q-tq)^2/B; db3 += dq   (mse_loss mean reduction, sac.py:94-95)
 __global__ void k_critic_dq(const float* q /*[2][B]*/, const float* tq /*[B] or [2][B]*/, int tq_stride, float* dq /*[2][B]*/, float* loss, int B) { pdl_sync();
   int b = blockIdx.x * blockDim.x + threadIdx.x, net = blockIdx.y;
@@ -220,19 +216,14 @@ __device__ __forceinline__ void colsum_flush(float (*csum)[H], const float* cs /
 // critic head backward (out_dim = 1), same tiling: dh2[b,:] = dq[b] W3 masked by h2 > 0; dW3 += sum_b dq[b] h2[b,:]; db3 += sum_b dq; db2 += sum_b dh2
 // How a row's dq is obtained: from an array, or computed in place so that the tiny dq kernels drop out of the dependency chain
 //   DQ_CRITIC: dq = 2 (q - tq)/B with tq = r + gamma * term * (min(q1', q2') - alpha * logp')  (sac.py:85-95; loss += (q - tq)^2 / B)
-//   DQ_MINQ:   d(-min(q1, q2))/dq_i / B for the actor loss (torch.min picks the first on ties; sac.py:104-106)
-enum { DQ_ARRAY = 0, DQ_CRITIC = 1, DQ_MINQ = 2 };
+enum { DQ_ARRAY = 0, DQ_CRITIC = 1 };
 struct DqSrc { int mode, net; const float *q /*[2][B]*/, *rew, *term, *qn /*[2][B]*/, *logpn; float gamma, alpha; float* loss; };
 __device__ __forceinline__ float dq_of_row(const DqSrc& d, const float* dq, int b, int B, float& loss_acc) {
   if (d.mode == DQ_ARRAY) return dq[b];
-  if (d.mode == DQ_CRITIC) {
-    const float tq = d.rew[b] + d.gamma * d.term[b] * (fminf(d.qn[b], d.qn[B + b]) - d.alpha * d.logpn[b]);
-    const float e = d.q[d.net * B + b] - tq;
-    loss_acc += e * e / (float)B;
-    return 2.f * e / (float)B;
-  }
-  const bool first = d.q[b] <= d.q[B + b];
-  return ((d.net == 0) == first) ? -1.f / (float)B : 0.f;
+  const float tq = d.rew[b] + d.gamma * d.term[b] * (fminf(d.qn[b], d.qn[B + b]) - d.alpha * d.logpn[b]);
+  const float e = d.q[d.net * B + b] - tq;
+  loss_acc += e * e / (float)B;
+  return 2.f * e / (float)B;
 }
 __global__ void __launch_bounds__(256) k_head_bwd1(const float* __restrict__ dq /*[B]*/, DqSrc src, const float* __restrict__ W3 /*[256]*/, const bf16* __restrict__ h2,
                                                    bf16* __restrict__ dh_rm, bf16* __restrict__ dh_t, float* dW3 /*[256]*/, float* db3 /*[1] or null*/, float* db2 /*[256] or null*/, int B) { pdl_sync();
@@ -333,12 +324,6 @@ __global__ void __launch_bounds__(256) k_bc_dy(const float* raw /*[B][2A]*/, con
   }
   dy_finish(l, sdb, A, db3, loss);
 }
-// dq routing for the actor loss: d(-min(q1,q2))/dq_i /B
-__global__ void k_minq_dq(const float* q /*[2][B]*/, float* dq /*[2][B]*/, int B) { pdl_sync();
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) { bool first = q[b] <= q[B + b]; dq[b] = first ? -1.f / (float)B : 0.f; dq[B + b] = first ? 0.f : -1.f / (float)B; }   // torch.min picks the first on ties
-}
-__global__ void k_add_f32(float* dst, const float* src, int n) { pdl_sync(); int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) dst[i] += src[i]; }
 // Adam (torch.optim.Adam defaults: betas 0.9/0.999, eps 1e-8, no weight decay), sac.py:55-58
 __global__ void k_step_inc(int* step) { pdl_sync(); *step += 1; }
 // the step counter lives on the device so that the whole learn() can be replayed from a CUDA graph
@@ -443,11 +428,11 @@ struct B2QSac {
   bf16 *xc_t = nullptr, *hc1_rm = nullptr, *hc1_t = nullptr, *hc2_rm = nullptr, *hc2_t = nullptr;
   bf16 *xa_t = nullptr, *ha1_rm = nullptr, *ha1_t = nullptr, *ha2_rm = nullptr, *ha2_t = nullptr;
   bf16 *dh_rm = nullptr, *dh_t = nullptr, *dy_bf = nullptr, *dy_rm = nullptr;
-  bf16 *dh_rm2 = nullptr, *dh_t2 = nullptr; float *G2 = nullptr, *da_c2 = nullptr;   // second scratch set: the twin critics' backward chains run on two streams
+  bf16 *dh_rm2 = nullptr, *dh_t2 = nullptr; float *G2 = nullptr;   // second scratch set: the twin critics' backward chains run on two streams
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t aux[2] = {nullptr, nullptr}; cudaEvent_t ev_aux[4] = {nullptr, nullptr, nullptr, nullptr};   // per-chain helper streams: dW2 GEMM beside the dh1 -> dW1 chain
   bf16 *dh1_rm[2] = {nullptr, nullptr}, *dh1_t[2] = {nullptr, nullptr};                                      // layer-1 gradients (separate from dh2 so both GEMM branches can run)
-  float *G = nullptr, *tq = nullptr, *q = nullptr, *qn = nullptr, *dq = nullptr, *next_a = nullptr, *next_logp = nullptr, *cur_a = nullptr, *cur_logp = nullptr, *raw_a = nullptr,
+  float *G = nullptr, *q = nullptr, *qn = nullptr, *dq = nullptr, *next_a = nullptr, *next_logp = nullptr, *cur_a = nullptr, *cur_logp = nullptr, *raw_a = nullptr,
         *da_c = nullptr, *losses = nullptr;
   std::vector<void*> allocs;
   void* tmap_cache = nullptr;   // TmapCache*: TMA tensor maps of the GEMM operands
@@ -641,10 +626,10 @@ int b2q_sac_create(int device, int obs_dim, int act_dim, int batch, float gamma,
   ok = ok && dalloc(s, &s->xc_t, 64 * Bz) && dalloc(s, &s->hc1_rm, 2 * Bz * H) && dalloc(s, &s->hc1_t, 2 * Bz * H) && dalloc(s, &s->hc2_rm, 2 * Bz * H) &&
        dalloc(s, &s->hc2_t, 2 * Bz * H) && dalloc(s, &s->xa_t, 64 * Bz) && dalloc(s, &s->ha1_rm, Bz * H) && dalloc(s, &s->ha1_t, Bz * H) &&
        dalloc(s, &s->ha2_rm, Bz * H) && dalloc(s, &s->ha2_t, Bz * H) && dalloc(s, &s->dh_rm, Bz * H) && dalloc(s, &s->dh_t, Bz * H) && dalloc(s, &s->dy_bf, Bz * 128) && dalloc(s, &s->dy_rm, Bz * 64) &&
-       dalloc(s, &s->G, Bz * H) && dalloc(s, &s->tq, Bz) && dalloc(s, &s->q, 2 * Bz) && dalloc(s, &s->qn, 2 * Bz) && dalloc(s, &s->dq, 2 * Bz) && dalloc(s, &s->next_a, Bz * 12) &&
+       dalloc(s, &s->G, Bz * H) && dalloc(s, &s->q, 2 * Bz) && dalloc(s, &s->qn, 2 * Bz) && dalloc(s, &s->dq, 2 * Bz) && dalloc(s, &s->next_a, Bz * 12) &&
        dalloc(s, &s->next_logp, Bz) && dalloc(s, &s->cur_a, Bz * 12) && dalloc(s, &s->cur_logp, Bz) && dalloc(s, &s->raw_a, Bz * 24) && dalloc(s, &s->da_c, 2 * Bz * 16) &&
        dalloc(s, &s->losses, 4) && dalloc(s, &s->d_step, 2 /*step | block ticket of the closing Adam*/) &&
-       dalloc(s, &s->dh_rm2, Bz * H) && dalloc(s, &s->dh_t2, Bz * H) && dalloc(s, &s->G2, Bz * H) && dalloc(s, &s->da_c2, Bz * 16) &&
+       dalloc(s, &s->dh_rm2, Bz * H) && dalloc(s, &s->dh_t2, Bz * H) && dalloc(s, &s->G2, Bz * H) &&
        dalloc(s, &s->dh1_rm[0], Bz * H) && dalloc(s, &s->dh1_t[0], Bz * H) && dalloc(s, &s->dh1_rm[1], Bz * H) && dalloc(s, &s->dh1_t[1], Bz * H);
   for (int i = 0; i < 2 && ok; i++) ok = cudaStreamCreateWithFlags(&s->aux[i], cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreateWithFlags(&s->ev_aux[i], cudaEventDisableTiming) == cudaSuccess;
@@ -716,7 +701,7 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
   cudaStream_t st = (cudaStream_t)stream;
   const int B = s->B, A = s->A, D = s->D;
   const Net& an = s->an; const Net& cn = s->cn;
-  const int TB = 256, NB = (B + TB - 1) / TB;
+  const int TB = 256;
   if (phase == 0) {
     if (!obs || !act || !rew || !next_obs || !term) return -1;
     // target: next action ~ pi(next_obs), twin target Q (sac.py:85-91)
