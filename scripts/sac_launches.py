@@ -10,7 +10,7 @@ g = torch.Generator(device="cuda").manual_seed(0)
 obs = torch.randn(B, 49, device="cuda", generator=g); act = torch.rand(B, 12, device="cuda", generator=g) * 2 - 1
 rew = torch.randn(B, device="cuda", generator=g); nobs = torch.randn(B, 49, device="cuda", generator=g); term = torch.ones(B, device="cuda")
 for _ in range(4):
-    learner.learn(obs, act, rew, nobs, term, graph=False)
+    learner.learn(obs, act, rew, nobs, term, graph=False, pull=False)
 torch.cuda.synchronize()
 # production path: the batch is gathered straight into the learner's static graph inputs, noise comes from the counter RNG in the kernels
 for x, sx in zip((obs, act, rew, nobs, term), learner.static_batch()):

@@ -51,6 +51,13 @@ for _ in range(2):
     learner.learn(*rpm.sample_batch(256), graph=False)
 flat = SACLearner(agent, 256, sync="flat")
 flat.learn(*rpm.sample_batch(256), graph=False)
+# explicit-noise path, the graph path on the learner's static inputs (counter-RNG noise), behaviour cloning (given-target critic head, plain Adam)
+learner.learn(*rpm.sample_batch(256), eps_next=torch.randn(256, 12, device="cuda"), eps_cur=torch.randn(256, 12, device="cuda"), graph=False)
+g2 = SACLearner(MujocoAgent(49, 12, seed=1), 256)
+for _ in range(2):
+    g2.learn(*rpm.sample_batch(256, out=g2.static_batch()), graph=True, pull=False)
+expert = MujocoAgent(49, 12, seed=2)
+learner.bc_learn(torch.randn(256, 49, device="cuda"), torch.randn(256, 49, device="cuda"), expert)
 ev = PopulationEvaluator(4, 2, max_steps=5)
 ev.evaluate(np.repeat(w[None], 4, 0), np.repeat(b[None], 4, 0))
 torch.cuda.synchronize()
