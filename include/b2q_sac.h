@@ -28,11 +28,15 @@ int b2q_sac_set_params(B2QSacHandle h, const float* actor, const float* critic, 
 int b2q_sac_get_params(B2QSacHandle h, float* actor, float* critic, float* target, void* stream);
 int b2q_sac_get_grads(B2QSacHandle h, float* actor, float* critic, void* stream);
 /* obs [B,obs_dim], act [B,act_dim], rew [B], next_obs [B,obs_dim], term [B] (1 - terminal as train.py:148-149);
- * eps_next / eps_cur [B,act_dim]: the N(0,1) draws of the two rsample() calls (eps_next may be NULL -> counter RNG from seed).
- * losses_out: device float[2] = {critic_loss, actor_loss}. */
+ * eps_next / eps_cur [B,act_dim]: the N(0,1) draws of the two rsample() calls.  Either may be NULL: that draw then comes from a counter
+ * RNG inside the kernels (Philox-4x32-10 keyed by `seed` and the learner's device-side step counter, counter = (row, action)), the backward
+ * recomputing exactly the forward's draw — no noise tensors, and a CUDA-graph replay of the call draws fresh noise every step.
+ * losses_out: device float[2] = {critic_loss, actor_loss}.
+ * b2q_sac_learn == phases 0, 1, 2, 3 of b2q_sac_phase (with the critics' optimiser step overlapped on an internal stream). */
 int b2q_sac_learn(B2QSacHandle h, const float* obs, const float* act, const float* rew, const float* next_obs, const float* term,
                   const float* eps_next, const float* eps_cur, uint64_t seed, float* losses_out, void* stream);
-/* phase 0: critic grads; 1: Adam(critic); 2: actor grads; 3: Adam(actor) + Polyak. */
+/* phase 0: critic grads (clears the whole gradient bucket first); 1: Adam(critic); 2: actor grads; 3: Adam(actor) + Polyak.
+ * The optimiser phases also rewrite the bf16 tensor-core operand images of the nets they update. */
 int b2q_sac_phase(B2QSacHandle h, int phase, const float* obs, const float* act, const float* rew, const float* next_obs, const float* term,
                   const float* eps_next, const float* eps_cur, uint64_t seed, void* stream);
 /* Behaviour cloning step (BC.BClearn, alg/BC.py:53-72; BCtrain.py:123-138): the student (this handle, obs_dim may be
