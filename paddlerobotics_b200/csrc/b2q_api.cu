@@ -38,12 +38,34 @@ template <typename T>
 __device__ __forceinline__ const Model<T>& stage_model(const Model<T>* g, unsigned char* smem) {
   // model constants (~1 KB) staged once per CTA in shared memory: lanes of different legs read different
   // LegModel rows, which a __constant__ bank would serialise
+  // 128-bit loads, four per thread in flight before the first store: one memory latency instead of a 13-deep chain of dependent 4-byte
+  // load -> store pairs per 32-thread CTA (2 us of the 115 us step in the round-2 profile).  The device copy is padded to a multiple of 16 bytes.
   Model<T>* s = reinterpret_cast<Model<T>*>(smem);
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(g);
-  uint32_t* dst = reinterpret_cast<uint32_t*>(s);
-  for (int i = threadIdx.x; i < (int)(sizeof(Model<T>) / 4); i += blockDim.x) dst[i] = src[i];
+  const uint4* src = reinterpret_cast<const uint4*>(g);
+  uint4* dst = reinterpret_cast<uint4*>(s);
+  constexpr int NV = (int)((sizeof(Model<T>) + 15) / 16);
+  for (int i0 = threadIdx.x; i0 < NV; i0 += 4 * blockDim.x) {
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int i = i0 + k * (int)blockDim.x; if (i < NV) v[k] = __ldg(src + i); }
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int i = i0 + k * (int)blockDim.x; if (i < NV) dst[i] = v[k]; }
+  }
   __syncthreads();
   return *s;
+}
+
+// staged block (shared memory) -> global / pinned host memory: 128-bit stores when both ends are 16-byte aligned (full CTAs always are:
+// 8 rows x 49 or 56 floats), scalar otherwise
+template <typename T>
+__device__ __forceinline__ void copy_block(T* __restrict__ dst, const T* stage, int n) {
+  constexpr int PER = 16 / (int)sizeof(T);
+  if ((((size_t)dst | (size_t)stage) & 15) == 0 && n % PER == 0) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst); const uint4* s4 = reinterpret_cast<const uint4*>(stage);
+    for (int i = threadIdx.x; i < n / PER; i += blockDim.x) d4[i] = s4[i];
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = stage[i];
+  }
 }
 
 // the CTA's staged 49-wide rows -> the caller's [N][obs_dim] array (sensor_mode selection applied), coalesced
@@ -51,7 +73,7 @@ template <typename T>
 __device__ __forceinline__ void emit_obs_block(const Model<T>& md, const T* stage, T* __restrict__ obs, int env0, int rows) {
   const int od = md.obs_dim;
   T* dst = obs + (size_t)env0 * od;
-  if (md.obs_identity) { for (int i = threadIdx.x; i < rows * OBS_DIM; i += blockDim.x) dst[i] = stage[i]; return; }
+  if (md.obs_identity) { copy_block(dst, stage, rows * OBS_DIM); return; }
   for (int i = threadIdx.x; i < rows * od; i += blockDim.x) { int r = i / od, j = i - r * od; dst[i] = obs_out_elem(md, stage + r * OBS_DIM, j); }
 }
 
@@ -81,8 +103,7 @@ __global__ void __launch_bounds__(128) b2q_step_kernel(Cfg<T> cf, const Model<T>
   __syncthreads();
   const int rows = min(per_cta, B.N - env0);
   emit_obs_block(md, stage, obs, env0, rows);
-  T* idst = info + (size_t)env0 * INFO_DIM;
-  for (int i = threadIdx.x; i < rows * INFO_DIM; i += blockDim.x) idst[i] = istage[i];
+  copy_block(info + (size_t)env0 * INFO_DIM, istage, rows * INFO_DIM);
 }
 
 template <typename T, int FEAT>
@@ -234,7 +255,8 @@ struct EnvT : EnvBase {
       }
     }
     CK(cudaHostAlloc((void**)&h_flag, sizeof(int), cudaHostAllocDefault));
-    CK(cudaMalloc(&d_model, sizeof(Model<T>)));
+    CK(cudaMalloc((void**)&d_model, (sizeof(Model<T>) + 15) / 16 * 16));      // padded: the kernels stage it with 16-byte loads
+    CK(cudaMemset(d_model, 0, (sizeof(Model<T>) + 15) / 16 * 16));
     CK(cudaMemcpy(d_model, &hm, sizeof(Model<T>), cudaMemcpyHostToDevice));
     double d48[48]; default_dyn_row(d48); T t48[48]; for (int i = 0; i < 48; i++) t48[i] = (T)d48[i];
     CK(cudaMalloc(&d_def48, sizeof(t48)));
