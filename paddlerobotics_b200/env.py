@@ -137,18 +137,21 @@ class VecQuadrupedalEnv:
             self._h_rew = self._h_out[n * od * es: n * (od + 1) * es].view(npdt)
             self._h_done = self._h_out[n * (od + 1) * es:]
             self._np_act, self._np_obs, self._np_rew, self._np_done = self._h_act.numpy(), self._h_obs.numpy(), self._h_rew.numpy(), self._h_done.numpy()
+            self._h_ptrs = (self._h_act.data_ptr(), self._h_obs.data_ptr(), self._h_rew.data_ptr(), self._h_done.data_ptr())   # fixed for the env's lifetime
 
     def step_host(self, action_np, donef=False, info=False):
         """The reference-facing call with HOST buffers (numpy in / numpy out), one C call and one stream sync: the step kernel
         reads the actions from and stores obs / reward / done to pinned host memory (b2q_step_host).  info=True also returns
         the [N,56] info rows.  The returned arrays are views of the pinned buffers (overwritten by the next call)."""
-        self._host_bufs()
+        if self._h_act is None:
+            self._host_bufs()
         np.copyto(self._np_act, np.asarray(action_np).reshape(self.num_envs, ACT_DIM), casting="same_kind")
         if info and self._h_info is None:
             self._h_info = torch.empty(self.num_envs, INFO_DIM, dtype=self.dtype).pin_memory()
             self._np_info = self._h_info.numpy()
-        rc = self.lib.b2q_step_host(self.h, self._h_act.data_ptr(), int(bool(donef)), self._h_obs.data_ptr(), self._h_rew.data_ptr(),
-                                    self._h_done.data_ptr(), self._h_info.data_ptr() if info else None, self._stream())
+            self._h_info_ptr = self._h_info.data_ptr()
+        pa, po, pr, pd = self._h_ptrs
+        rc = self.lib.b2q_step_host(self.h, pa, 1 if donef else 0, po, pr, pd, self._h_info_ptr if info else None, self._stream())
         if rc != 0:
             _check(self.lib, self.h, rc, "b2q_step_host")
         if info:
