@@ -269,60 +269,58 @@ __global__ void __launch_bounds__(256) k_head_bwd1(const float* __restrict__ dq 
   colsum_flush(csum, cs, chunk, warp, db2);
 }
 // The head gradient dy = dloss/d[mean | raw_ls] leaves the dy kernels as bf16 in the two operand layouts the tensor-core GEMMs read
-// (row-major [B][64] for dh2 = dy W3, [2A][B] for dW3 = dy^T h2); db3 = column sums of the rounded values.  One thread per (row, action
-// dimension): the f32 inputs are read coalesced and a block's column sums meet in shared memory (one global atomic per column and block).
-__device__ __forceinline__ void dy_out(float g_mean, float g_ls, int b, int j, int B, int A, bf16* dy_rm, bf16* dy_t, float* sdb) {
-  const bf16 m = __float2bfloat16(g_mean), l = __float2bfloat16(g_ls);
-  dy_rm[(size_t)b * 64 + j] = m; dy_rm[(size_t)b * 64 + A + j] = l;
-  dy_t[(size_t)j * B + b] = m; dy_t[(size_t)(A + j) * B + b] = l;
-  atomicAdd(sdb + j, __bfloat162float(m)); atomicAdd(sdb + A + j, __bfloat162float(l));
-}
-__device__ __forceinline__ void dy_finish(float l, const float* sdb, int A, float* db3, float* loss) {
+// (row-major [B][64] for dh2 = dy W3, [2A][B] for dW3 = dy^T h2); db3 = column sums of the rounded values.  A block = 32 batch rows x A
+// action dimensions, one thread per element (coalesced f32 reads); the results meet in a shared-memory tile [2A][32] and leave as 64-byte
+// runs per output row of the [2A][B] copy and contiguous 4A-byte rows of the row-major copy (no 2-byte scatters, no shared-memory atomics).
+constexpr int DY_ROWS = 32;
+__device__ __forceinline__ void dy_store_block(bf16 (*sT)[DY_ROWS], float l, int b0, int B, int A, bf16* dy_rm, bf16* dy_t, float* db3, float* loss) {
   for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
   if ((threadIdx.x & 31) == 0 && l != 0.f) atomicAdd(loss, l);
   __syncthreads();
-  if (db3 && threadIdx.x < 2 * A) atomicAdd(db3 + threadIdx.x, sdb[threadIdx.x]);
+  const int t = threadIdx.x;
+  if (t < 2 * A * 4) { const int row = t >> 2, seg = t & 3; *reinterpret_cast<uint4*>(dy_t + (size_t)row * B + b0 + seg * 8) = *reinterpret_cast<const uint4*>(&sT[row][seg * 8]); }
+  for (int i = t; i < DY_ROWS * 2 * A; i += blockDim.x) { const int r = i / (2 * A), c = i - r * 2 * A; dy_rm[(size_t)(b0 + r) * 64 + c] = sT[c][r]; }
+  if (db3 && t < 2 * A) {
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < DY_ROWS; r++) sum += __bfloat162float(sT[t][r]);
+    atomicAdd(db3 + t, sum);
+  }
 }
-// actor head: from raw y=[mean|raw_ls], eps, da_c (critic gradient wrt action, already includes -1/B routing) build dy and the loss
-__global__ void __launch_bounds__(256) k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const float* act /*[B][A] tanh(x)*/, const float* logp, const float* q /*[2][B]*/,
+// actor head: from raw y=[mean|raw_ls], eps, the critics' dQ_i/da (unit gradients) build dy and the loss   (B % 32 == 0; blockDim = 32 A)
+__global__ void __launch_bounds__(384) k_actor_dy(const float* raw /*[B][2A]*/, const float* eps, const float* act /*[B][A] tanh(x)*/, const float* logp, const float* q /*[2][B]*/,
                            const float* da_c /*[B][16] (cols 0..A-1): dQ1/da*/, const float* da_c2 /*dQ2/da*/, float alpha,
                            bf16* dy_rm /*[B][64], cols >= 2A stay zero: A operand of the dh2 GEMM*/, bf16* dy_t /*[2A][B]: K-major A operand of the dW3 GEMM*/,
                            float* db3 /*[2A] += column sums of dy*/, float* loss, int B, int A, uint64_t seed, const int* seed_ctr /*eps == null: the forward's counter RNG draw*/) { pdl_sync();
-  __shared__ float sdb[32];
-  if (threadIdx.x < 32) sdb[threadIdx.x] = 0.f;
-  __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = i / A, j = i - b * A;
+  __shared__ __align__(16) bf16 sT[24][DY_ROWS];
+  const int b0 = blockIdx.x * DY_ROWS, r = threadIdx.x / A, j = threadIdx.x - r * A, b = b0 + r, i = b * A + j;
   float l = 0.f;
-  if (b < B) {
-    if (j == 0) l = (alpha * logp[b] - fminf(q[b], q[B + b])) / (float)B;         // sac.py:105-106
+  {
+    const float q0 = q[b], q1 = q[B + b];
+    if (j == 0) l = (alpha * logp[b] - fminf(q0, q1)) / (float)B;                  // sac.py:105-106
     const float a = act[i], rl = raw[(size_t)b * 2 * A + A + j];
     const float ls = fminf(fmaxf(rl, -20.f), 2.f), sd = expf(ls);
     const float e = eps ? eps[i] : b2q_philox::philox_normal(b2q_philox::effective_seed(seed, seed_ctr), (uint32_t)b, (uint32_t)j);
-    const float dqa = (q[b] <= q[B + b] ? da_c : da_c2)[(size_t)b * 16 + j];          // d min(q1, q2)/da: torch.min routes to the first on ties (sac.py:104-106)
+    const float dqa = (q0 <= q1 ? da_c : da_c2)[(size_t)b * 16 + j];              // d min(q1, q2)/da: torch.min routes to the first on ties (sac.py:104-106)
     const float ga = -dqa / (float)B + (alpha / (float)B) * (2.f * a / ((1.f - a * a) + 1e-6f));
     const float gx = ga * (1.f - a * a);
     const float gls = gx * sd * e - alpha / (float)B;
     const float gl = (rl > -20.f && rl < 2.f) ? gls : 0.f;                         // torch.clamp gradient
-    dy_out(gx, gl, b, j, B, A, dy_rm, dy_t, sdb);
+    sT[j][r] = __float2bfloat16(gx); sT[A + j][r] = __float2bfloat16(gl);
   }
-  dy_finish(l, sdb, A, db3, loss);
+  dy_store_block(sT, l, b0, B, A, dy_rm, dy_t, db3, loss);
 }
 // behaviour cloning head (alg/BC.py:53-59): loss = -mean_{b,j} log N(ref | mean, exp(ls)); dy = dloss/d[mean | raw_ls]
-__global__ void __launch_bounds__(256) k_bc_dy(const float* raw /*[B][2A]*/, const float* ref /*[B][A]*/, bf16* dy_rm /*[B][64]*/, bf16* dy_t /*[2A][B]*/, float* db3, float* loss, int B, int A) { pdl_sync();
-  __shared__ float sdb[32];
-  if (threadIdx.x < 32) sdb[threadIdx.x] = 0.f;
-  __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = i / A, j = i - b * A;
-  float l = 0.f;
+__global__ void __launch_bounds__(384) k_bc_dy(const float* raw /*[B][2A]*/, const float* ref /*[B][A]*/, bf16* dy_rm /*[B][64]*/, bf16* dy_t /*[2A][B]*/, float* db3, float* loss, int B, int A) { pdl_sync();
+  __shared__ __align__(16) bf16 sT[24][DY_ROWS];
+  const int b0 = blockIdx.x * DY_ROWS, r = threadIdx.x / A, j = threadIdx.x - r * A, b = b0 + r, i = b * A + j;
   const float inv = 1.f / (float)(B * A);
-  if (b < B) {
-    const float mu = raw[(size_t)b * 2 * A + j], rl = raw[(size_t)b * 2 * A + A + j], ls = fminf(fmaxf(rl, -20.f), 2.f);
-    const float d = ref[i] - mu, iv = expf(-2.f * ls);
-    l = -(-0.5f * d * d * iv - ls - 0.9189385332046727f) * inv;
-    const float g0 = -(d * iv) * inv, g1 = (rl > -20.f && rl < 2.f) ? -(d * d * iv - 1.f) * inv : 0.f;
-    dy_out(g0, g1, b, j, B, A, dy_rm, dy_t, sdb);
-  }
-  dy_finish(l, sdb, A, db3, loss);
+  const float mu = raw[(size_t)b * 2 * A + j], rl = raw[(size_t)b * 2 * A + A + j], ls = fminf(fmaxf(rl, -20.f), 2.f);
+  const float d = ref[i] - mu, iv = expf(-2.f * ls);
+  const float l = -(-0.5f * d * d * iv - ls - 0.9189385332046727f) * inv;
+  const float g0 = -(d * iv) * inv, g1 = (rl > -20.f && rl < 2.f) ? -(d * d * iv - 1.f) * inv : 0.f;
+  sT[j][r] = __float2bfloat16(g0); sT[A + j][r] = __float2bfloat16(g1);
+  dy_store_block(sT, l, b0, B, A, dy_rm, dy_t, db3, loss);
 }
 // Adam (torch.optim.Adam defaults: betas 0.9/0.999, eps 1e-8, no weight decay), sac.py:55-58
 __global__ void k_step_inc(int* step) { pdl_sync(); *step += 1; }
@@ -701,7 +699,6 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
   cudaStream_t st = (cudaStream_t)stream;
   const int B = s->B, A = s->A, D = s->D;
   const Net& an = s->an; const Net& cn = s->cn;
-  const int TB = 256;
   if (phase == 0) {
     if (!obs || !act || !rew || !next_obs || !term) return -1;
     // target: next action ~ pi(next_obs), twin target Q (sac.py:85-91)
@@ -763,7 +760,7 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     // optimiser steps here).  The routing of d(-min q)/da to the smaller critic and the 1/B happen in the dy kernel.
     if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, nullptr, s->da_c, nullptr, st)) return -2;
     s->launches += 2;
-    pdl_launch(k_actor_dy, dim3((B * A + TB - 1) / TB), dim3(TB), 0, st, s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->da_c + (size_t)B * 16, s->alpha, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A, seed * 2, s->d_step);
+    pdl_launch(k_actor_dy, dim3(B / DY_ROWS), dim3(DY_ROWS * A), 0, st, s->raw_a, eps_cur, s->cur_a, s->cur_logp, s->q, s->da_c, s->da_c + (size_t)B * 16, s->alpha, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A, seed * 2, s->d_step);
     if (actor_backward(s, st)) return -2;
   } else {
     return -1;
@@ -801,7 +798,7 @@ int b2q_sac_bc_learn(B2QSacHandle s, const float* obs, const float* ref_obs, int
   if (b2q_mlp_forward(expert_actor, ref_obs, ref_obs_dim, nullptr, B, B2Q_MLP_PREDICT, 0, nullptr, s->next_a /*ref action*/, nullptr, nullptr, st)) return -2;
   B2QMlpSaves sa = {nullptr /*x row-major: no consumer*/, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
   if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_RAW, 0, nullptr, s->raw_a, nullptr, nullptr, &sa, nullptr, nullptr, st)) return -2;
-  pdl_launch(k_bc_dy, dim3((B * A + TB - 1) / TB), dim3(TB), 0, st, s->raw_a, s->next_a, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A);
+  pdl_launch(k_bc_dy, dim3(B / DY_ROWS), dim3(DY_ROWS * A), 0, st, s->raw_a, s->next_a, s->dy_rm, s->dy_bf, s->g_actor + an.ob3, s->losses + 1, B, A);
   if (actor_backward(s, st)) return -2;
   pdl_launch(k_adam, dim3(((int)an.n + 255) / 256), dim3(256), 0, st, s->p_actor, s->g_actor, s->m_a, s->v_a, (int)an.n, s->lr_a, 0.9f, 0.999f, 1e-8f, s->d_step);
   sync_net_weights(s, st, 1);
