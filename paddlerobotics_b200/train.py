@@ -45,6 +45,8 @@ def main(argv=None):
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--log_every", type=int, default=50)
     p.add_argument("--overlap", type=int, default=1, help="run the SAC update on a second stream beside the env step")
+    p.add_argument("--graph_iter", type=int, default=1, help="capture one whole training iteration (policy forward, env step, replay append + sample, SAC update) "
+                   "in ONE CUDA graph and replay it per control step (needs --overlap 1)")
     p.add_argument("--torso", type=float, default=1.5); p.add_argument("--feet", type=float, default=0.3); p.add_argument("--up", type=float, default=0.6)
     p.add_argument("--tau", type=float, default=0.07); p.add_argument("--badfoot", type=float, default=0.1); p.add_argument("--footcontact", type=float, default=0.1)
     p.add_argument("--task_mode", type=str, default="stairstair")      # train.py:462
@@ -77,7 +79,7 @@ def main(argv=None):
     ckpt_every = args.eval_every_steps or int(1e4) * n
     next_ckpt = ckpt_every
     learner = SACLearner(agent, args.batch, gamma=GAMMA, tau=TAU, alpha=ALPHA, actor_lr=ACTOR_LR, critic_lr=CRITIC_LR)
-    rpm = ReplayMemory(args.memory, 49, 12)
+    rpm = ReplayMemory(args.memory, 49, 12, device_cursor=bool(args.graph_iter and args.overlap))
     solver = SimpleGA(12, sigma_init=args.sigma, sigma_decay=args.sigma_decay, sigma_limit=0.005, elite_ratio=0.1, weight_decay=0.005,
                       popsize=args.popsize, param=ETG_best_param.copy())                                                          # train.py:288-295
     evaluator = PopulationEvaluator(args.popsize, args.es_rollouts, max_steps=args.e_step, policy=lambda o: learner.actor.forward(o)[0][0],
@@ -87,35 +89,74 @@ def main(argv=None):
     s_learn = torch.cuda.Stream(device=env.device)
     ret_acc = torch.zeros(n, device=env.device); ep_rets = []; last_log = (0, 0.0)
     log = []
-    while total < args.max_steps:
-        if rpm.size() < args.warmup_steps:
-            act = torch.rand(n, 12, device=env.device) * 2 - 1                         # train.py:141-142
-        else:
-            act = learner.actor.forward(obs, mode=1, seed=it + 1)[0][0]               # agent.sample(obs)
-        learning = rpm.size() >= args.warmup_steps
-        if learning and args.overlap:
-            # the learner step (latency-bound small kernels) runs on its own stream NEXT TO the env step (one warp per scheduler):
-            # it samples transitions up to t-1 and its new weights are first used by the policy forward of step t+1, exactly as
-            # in the sequential order, except that transition t itself joins the replay one update later
-            batch_t = rpm.sample_batch(args.batch, out=learner.static_batch())
-            s_learn.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s_learn):
-                for x in batch_t:
-                    x.record_stream(s_learn)
-                losses = learner.learn(*batch_t, graph=True, pull=False)
-        nobs, rew, done, info = env.step(act * args.act_bound)
-        rpm.append(obs, act, rew, nobs, 1.0 - done.float())                            # terminal = 1 - done, train.py:148-149,159
-        if learning and args.overlap:
-            torch.cuda.current_stream().wait_stream(s_learn)
-        ret_acc += rew
-        fin = done.bool()
-        if it % args.log_every == 0 and bool(fin.any()):
-            ep_rets.append(float(ret_acc[fin].mean()))
-        ret_acc = torch.where(fin, torch.zeros_like(ret_acc), ret_acc)
+    # ---- one whole iteration as ONE CUDA graph (--graph_iter): everything step-dependent lives in device memory — the replay cursor, the learner's
+    #      step counter (which also keys the rsample() noise), torch's graph-safe generator for the exploration noise — so the captured launches are
+    #      valid for every later step.  The learner runs on its own stream inside the graph, beside the env step, exactly as in the eager loop below.
+    iter_graph = None
+    ep_sum = torch.zeros((), device=env.device); ep_cnt = torch.zeros((), device=env.device)
+    def graph_iteration():
+        cur = torch.cuda.current_stream()
+        act = learner.actor.forward(obs, mode=1, eps=torch.randn(n, 12, device=env.device))[0][0]     # agent.sample(obs)
+        batch_t = rpm.sample_batch(args.batch, out=learner.static_batch())
+        s_learn.wait_stream(cur)
+        with torch.cuda.stream(s_learn):
+            learner.learn(*batch_t, graph=False, pull=False)
+        nobs, rew, done, _ = env.step(act * args.act_bound)
+        rpm.append(obs, act, rew, nobs, 1.0 - done.float())
+        cur.wait_stream(s_learn)
+        fin = done.float()
+        ret_acc.add_(rew)
+        ep_sum.add_((ret_acc * fin).sum()); ep_cnt.add_(fin.sum())
+        ret_acc.mul_(1.0 - fin)
         obs.copy_(nobs)
-        total += n; it += 1
-        if rpm.size() >= args.warmup_steps and not (learning and args.overlap):
-            losses = learner.learn(*rpm.sample_batch(args.batch, out=learner.static_batch()), graph=True, pull=False)   # one update per control step, train.py:163-169
+    while total < args.max_steps:
+        if iter_graph is not None:
+            iter_graph.replay()
+            rpm.advance(n)
+            rew, done, losses = env.reward, env.done, learner.losses
+            total += n; it += 1
+            if it % args.log_every == 0 and float(ep_cnt) > 0:
+                ep_rets.append(float(ep_sum / ep_cnt)); ep_sum.zero_(); ep_cnt.zero_()
+        else:
+            if rpm.size() < args.warmup_steps:
+                act = torch.rand(n, 12, device=env.device) * 2 - 1                         # train.py:141-142
+            else:
+                act = learner.actor.forward(obs, mode=1, seed=it + 1)[0][0]               # agent.sample(obs)
+            learning = rpm.size() >= args.warmup_steps
+            if learning and args.overlap:
+                # the learner step (latency-bound small kernels) runs on its own stream NEXT TO the env step (one warp per scheduler):
+                # it samples transitions up to t-1 and its new weights are first used by the policy forward of step t+1, exactly as
+                # in the sequential order, except that transition t itself joins the replay one update later
+                batch_t = rpm.sample_batch(args.batch, out=learner.static_batch())
+                s_learn.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s_learn):
+                    for x in batch_t:
+                        x.record_stream(s_learn)
+                    losses = learner.learn(*batch_t, graph=True, pull=False)
+            nobs, rew, done, info = env.step(act * args.act_bound)
+            rpm.append(obs, act, rew, nobs, 1.0 - done.float())                            # terminal = 1 - done, train.py:148-149,159
+            if learning and args.overlap:
+                torch.cuda.current_stream().wait_stream(s_learn)
+            ret_acc += rew
+            fin = done.bool()
+            if it % args.log_every == 0 and bool(fin.any()):
+                ep_rets.append(float(ret_acc[fin].mean()))
+            ret_acc = torch.where(fin, torch.zeros_like(ret_acc), ret_acc)
+            obs.copy_(nobs)
+            total += n; it += 1
+            if rpm.size() >= args.warmup_steps and not (learning and args.overlap):
+                losses = learner.learn(*rpm.sample_batch(args.batch, out=learner.static_batch()), graph=True, pull=False)   # one update per control step, train.py:163-169
+            if args.graph_iter and args.overlap and learning and it % args.log_every != 0:
+                # warm-up is over and one eager learning iteration has run: capture the iteration once
+                torch.cuda.synchronize()
+                cap = torch.cuda.Stream(device=env.device)
+                cap.wait_stream(torch.cuda.current_stream())
+                iter_graph = torch.cuda.CUDAGraph()
+                mirrors = (rpm._curr_pos, rpm._curr_size, rpm._samples)
+                with torch.cuda.graph(iter_graph, stream=cap):
+                    graph_iteration()
+                rpm._curr_pos, rpm._curr_size, rpm._samples = mirrors     # capture records launches, it does not run them: the ring has not moved
+                torch.cuda.current_stream().wait_stream(cap)
         if it % args.log_every == 0:
             torch.cuda.synchronize()
             el = time.perf_counter() - t0
@@ -150,7 +191,7 @@ def main(argv=None):
             pts = prior_points + ETG_best_param.reshape(-1, 2)                          # train.py:433-437
             w, b, _ = Opt_with_points(ETG=layer, ETG_T=args.ETG_T, w0=w0, b0=b0, points=pts)
             solver.reset(ETG_best_param)
-            obs = env.reset(w, b).clone(); ret_acc.zero_()
+            obs.copy_(env.reset(w, b)); ret_acc.zero_()      # in place: the captured iteration graph reads and writes these tensors
     torch.cuda.synchronize()
     learner.pull()
     return log
