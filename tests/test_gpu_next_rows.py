@@ -169,3 +169,40 @@ def test_train_loop_checkpoints_on_the_reference_cadence_and_restores(tmp_path):
     assert z["w"].shape == (3, 20) and z["b"].shape == (3,) and z["param"].reshape(-1).shape == (12,)
     log = train.main(args + ["--max_steps", "5120", "--load", str(tmp_path / "t" / pts[-1])])
     assert len(log) >= 1 and np.isfinite(log[-1]["mean_step_reward"])
+
+
+def test_replay_memory_device_cursor_matches_host_cursor_and_replays_from_a_graph():
+    """b2q_rpm_*_cursor: ring position / fill level / sample counter in device memory.  Same contents as the host-cursor ring, across the wrap;
+    captured ONCE in a CUDA graph, every replay appends at the next position and draws a new sample."""
+    import torch
+    from paddlerobotics_b200.replay import ReplayMemory
+    dev = torch.device("cuda")
+    a, b = ReplayMemory(1000, 49, 12), ReplayMemory(1000, 49, 12, device_cursor=True)
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    obs, act, rew, nobs, term = (torch.empty(300, 49, device=dev), torch.empty(300, 12, device=dev), torch.empty(300, device=dev),
+                                 torch.empty(300, 49, device=dev), torch.empty(300, device=dev))
+    def fill(k):
+        obs.fill_(float(k)); nobs.fill_(float(k) + 0.5); act.fill_(float(-k)); rew.copy_(torch.arange(300, device=dev) + 1000.0 * k); term.fill_(float(k % 2))
+    fill(0); a.append(obs, act, rew, nobs, term); b.append(obs, act, rew, nobs, term)      # eager call of the cursor path
+    torch.cuda.synchronize()
+    out = tuple(torch.zeros_like(x[:64]) for x in (obs, act, rew, nobs, term))
+    gr = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+    mirrors = (b._curr_pos, b._curr_size, b._samples)
+    with torch.cuda.graph(gr, stream=side):
+        b.append(obs, act, rew, nobs, term)
+        b.sample_batch(64, out=out)
+    b._curr_pos, b._curr_size, b._samples = mirrors
+    torch.cuda.current_stream().wait_stream(side)
+    samples = []
+    for k in range(1, 5):                                                                  # 4 more blocks of 300: wraps the 1000-row ring
+        fill(k); a.append(obs, act, rew, nobs, term)
+        gr.replay(); b.advance(300)
+        torch.cuda.synchronize()
+        samples.append(out[2].clone())
+        assert bool(((out[0][:, 0] + 0.5) == out[3][:, 0]).all())                          # rows stay consistent (obs / next_obs of the same transition)
+    for x, y in ((a.obs, b.obs), (a.action, b.action), (a.reward, b.reward), (a.next_obs, b.next_obs), (a.terminal, b.terminal)):
+        assert torch.equal(x, y)
+    assert (a._curr_pos, a._curr_size) == (b._curr_pos, b._curr_size) == (500, 1000)
+    assert b.cursor.tolist() == [500, 1000, 4]
+    assert not torch.equal(samples[0], samples[1]) and not torch.equal(samples[2], samples[3])   # a new draw per replay
