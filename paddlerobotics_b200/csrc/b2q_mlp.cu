@@ -33,7 +33,7 @@ constexpr uint32_t SZ_W1A = (uint32_t)b2q_mlp_img::SZ_W1A, OFF_W1A_IN_W13 = 1638
 constexpr uint32_t SZ_A = 65536, SZ_W2 = (uint32_t)b2q_mlp_img::SZ_W2, SZ_W13 = 32768, SZ_W1 = (uint32_t)b2q_mlp_img::SZ_W1, SZ_W3 = (uint32_t)b2q_mlp_img::SZ_W3,
                    SZ_BIAS = (uint32_t)b2q_mlp_img::SZ_BIAS;
 constexpr uint32_t OFF_A = 0, OFF_W2 = OFF_A + SZ_A, OFF_W13 = OFF_W2 + SZ_W2, OFF_BIAS = OFF_W13 + SZ_W13, OFF_BAR = OFF_BIAS + SZ_BIAS;
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 64;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 64 + 512;   // + the head's log-prob exchange [128] f32
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
 
 using b2q_philox::philox_normal;
@@ -45,6 +45,36 @@ struct FwdArgs {
   float* da;   // input-gradient pass (see b2q_mlp_internal.h) or null
   const int* seed_ctr;   // device-side counter folded into the sampling key (b2q_philox.cuh) or null
 };
+
+// actor head of one row, actions j with (j & 1) == chalf: tanh(mean) or the rsample() + tanh-Gaussian log-prob; returns the row's log-prob share.
+// AC > 0: the action dimension as a compile-time constant (the TMEM register array stays statically indexed); AC == 0: runtime dimension.
+template <int AC>
+__device__ __forceinline__ float head_actions(const uint32_t (&r)[32], const float* b3, const FwdArgs& a, int row, size_t orow, int chalf) {
+  const int A = AC > 0 ? AC : (a.out_dim >> 1);
+  const uint64_t seed_eff = b2q_philox::effective_seed(a.seed, a.seed_ctr);
+  float y[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) y[j] = __uint_as_float(r[j]) + b3[j];
+  float lp = 0.f;
+#pragma unroll
+  for (int j = 0; j < (AC > 0 ? AC : 16); j++) {
+    if ((j & 1) != chalf || j >= A) continue;
+    const float mean = y[j];
+    float act;
+    if (a.mode == B2Q_MLP_PREDICT) {
+      act = tanhf(mean);                                                   // sac.py:60-63
+    } else {
+      const float ls = fminf(fmaxf(y[A + j], -20.f), 2.f), sd = expf(ls);  // mujoco_model.py:21-22,59
+      const float e = a.eps ? a.eps[(size_t)row * A + j] : philox_normal(seed_eff, (uint32_t)row, (uint32_t)j);
+      const float x = mean + sd * e;                                       // rsample
+      act = tanhf(x);
+      lp += -0.5f * e * e - ls - 0.9189385332046727f;                      // Normal.log_prob(x)
+      lp -= logf((1.f - act * act) + 1e-6f);                               // sac.py:72
+    }
+    a.out[orow * A + j] = act;
+  }
+  return lp;
+}
 
 constexpr int NTHR = 256;
 __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_sync();
@@ -78,27 +108,20 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
   // input tile: f32 [rows, in_dim] (two sources concatenated) -> bf16 swizzled panel 0 (K padded to 64 with zeros)
   {
     const int in2_dim = a.in_dim - a.in1_dim;
-    // 64 elements per thread in batches of 16 independent loads (all loads of a batch are in flight before the first use)
-#pragma unroll 1
-    for (int j0 = 0; j0 < 64 * TILE_M / NTHR; j0 += 16) {
-      float v[16];
+    // 32 elements per thread (one column k = tid & 63, rows (tid >> 6) + 4 j), ALL loads in flight before the first use
+    constexpr int PER = 64 * TILE_M / NTHR;
+    const int k = tid & 63;
+    const float* src = k < a.in1_dim ? a.in1 + k : (k < a.in_dim ? a.in2 + (k - a.in1_dim) : nullptr);
+    const int ld = k < a.in1_dim ? a.in1_dim : in2_dim;
+    float v[PER];
 #pragma unroll
-      for (int j = 0; j < 16; j++) {
-        const int idx = tid + NTHR * (j0 + j), r = idx >> 6, k = idx & 63, gr = row0 + r;
-        float x = 0.f;
-        if (gr < a.M) {
-          if (k < a.in1_dim) x = __ldg(a.in1 + (size_t)gr * a.in1_dim + k);
-          else if (k < a.in_dim) x = __ldg(a.in2 + (size_t)gr * in2_dim + (k - a.in1_dim));
-        }
-        v[j] = x;
-      }
-#pragma unroll
-      for (int j = 0; j < 16; j++) {
-        const int idx = tid + NTHR * (j0 + j), r = idx >> 6, k = idx & 63;
-        __nv_bfloat16 vb = __float2bfloat16(v[j]);
-        *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + sw128_offset(r, k, TILE_M)) = vb;
-      }
+    for (int j = 0; j < PER; j++) {
+      const int gr = row0 + (tid >> 6) + 4 * j;
+      v[j] = (src && gr < a.M) ? __ldg(src + (size_t)gr * ld) : 0.f;
     }
+#pragma unroll
+    for (int j = 0; j < PER; j++)
+      *reinterpret_cast<__nv_bfloat16*>(smem + OFF_A + sw128_offset((tid >> 6) + 4 * j, k, TILE_M)) = __float2bfloat16(v[j]);
   }
   fence_async_smem();
   tc_fence_before();
@@ -125,12 +148,21 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
     if (d_t && tid < ncols) {
       const int c = tid;                                   // NTHR == HID: one column per thread
       __nv_bfloat16* dst = d_t + (nbase * ncols + c) * a.M + row0;
+#pragma unroll 4
       for (int r0 = 0; r0 < TILE_M; r0 += 8) {
-        __align__(16) __nv_bfloat16 v[8];
+        uint32_t w[4];                                     // packed in registers (a local bf16[8] would live in local memory)
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = *reinterpret_cast<const __nv_bfloat16*>(smem + OFF_A + sw128_offset(r0 + i, c, TILE_M));
-        if (r0 + 8 <= nrows) *reinterpret_cast<uint4*>(dst + r0) = *reinterpret_cast<const uint4*>(v);
-        else for (int i = 0; i < 8; i++) if (r0 + i < nrows) dst[r0 + i] = v[i];
+        for (int i = 0; i < 4; i++) {
+          const uint32_t lo = *reinterpret_cast<const uint16_t*>(smem + OFF_A + sw128_offset(r0 + 2 * i, c, TILE_M));
+          const uint32_t hi = *reinterpret_cast<const uint16_t*>(smem + OFF_A + sw128_offset(r0 + 2 * i + 1, c, TILE_M));
+          w[i] = lo | (hi << 16);
+        }
+        if (r0 + 8 <= nrows) *reinterpret_cast<uint4*>(dst + r0) = make_uint4(w[0], w[1], w[2], w[3]);
+        else {
+          uint16_t* d16 = reinterpret_cast<uint16_t*>(dst + r0);
+#pragma unroll
+          for (int i = 0; i < 8; i++) if (r0 + i < nrows) d16[i] = (uint16_t)(w[i >> 1] >> (16 * (i & 1)));
+        }
       }
     }
   };
@@ -224,37 +256,37 @@ __global__ void __launch_bounds__(NTHR, 1) b2q_mlp_fwd_kernel(FwdArgs a) { pdl_s
   if (a.save) dump_tile(a.sv.h2_rm, a.sv.h2_t, HID);   // the head epilogue does not write the tile: no barrier needed
   mbar_wait(bar_mma, 0);
   tc_fence_after();
-  if (chalf == 0) {
+  // Head epilogue.  RAW (critics, BC): the row's thread of column half 0 stores its outputs.  PREDICT / SAMPLE (actor): BOTH threads of a row
+  // (the two column halves read the same 32 TMEM columns) take every second action — the per-action tanh / exp / log / counter-RNG work is the
+  // longest stretch of the actor forward — and the log-prob halves meet in shared memory.  All indices are compile-time (no local arrays).
+  {
     uint32_t r[32];
     __syncwarp();
     tmem_ld32(lane_addr, r);
-    if (row < a.M) {
-      const float* b3 = bias + 2 * HID;
-      float y[32];
+    const float* b3 = bias + 2 * HID;
+    float* slp = reinterpret_cast<float*>(smem + OFF_BAR + 64);            // [128] log-prob share of column half 1
+    const int od = a.out_dim, A = od >> 1;
+    const size_t orow = (size_t)net * a.M + row;
+    if (chalf == 0 && row < a.M && (a.raw || a.mode == B2Q_MLP_RAW)) {
 #pragma unroll
-      for (int j = 0; j < 32; j++) y[j] = __uint_as_float(r[j]) + b3[j];
-      if (a.raw) for (int j = 0; j < a.out_dim; j++) a.raw[((size_t)net * a.M + row) * a.out_dim + j] = y[j];
-      if (a.mode == B2Q_MLP_RAW) {
-        for (int j = 0; j < a.out_dim; j++) a.out[((size_t)net * a.M + row) * a.out_dim + j] = y[j];
-      } else {
-        const int A = a.out_dim >> 1;
-        const uint64_t seed_eff = b2q_philox::effective_seed(a.seed, a.seed_ctr);
-        float lp = 0.f;
-        for (int j = 0; j < A; j++) {
-          float mean = y[j], act;
-          if (a.mode == B2Q_MLP_PREDICT) {
-            act = tanhf(mean);                                                     // sac.py:60-63
-          } else {
-            float ls = fminf(fmaxf(y[A + j], -20.f), 2.f), sd = expf(ls);         // mujoco_model.py:21-22,59
-            float e = a.eps ? a.eps[(size_t)row * A + j] : philox_normal(seed_eff, (uint32_t)row, (uint32_t)j);
-            float x = mean + sd * e;                                               // rsample
-            act = tanhf(x);
-            lp += -0.5f * e * e - ls - 0.9189385332046727f;                        // Normal.log_prob(x)
-            lp -= logf((1.f - act * act) + 1e-6f);                                 // sac.py:72
-          }
-          a.out[((size_t)net * a.M + row) * A + j] = act;
+      for (int j = 0; j < 32; j++) {
+        if (j < od) {
+          const float y = __uint_as_float(r[j]) + b3[j];
+          if (a.raw) a.raw[orow * od + j] = y;
+          if (a.mode == B2Q_MLP_RAW) a.out[orow * od + j] = y;
         }
-        if (a.mode == B2Q_MLP_SAMPLE && a.logp) a.logp[(size_t)net * a.M + row] = lp;
+      }
+    }
+    if (a.mode != B2Q_MLP_RAW) {
+      float lp = 0.f;
+      if (row < a.M) {
+        if (A == 12) lp = head_actions<12>(r, b3, a, row, orow, chalf);        // the A1's action dimension: every index compile-time
+        else lp = head_actions<0>(r, b3, a, row, orow, chalf);
+      }
+      if (a.mode == B2Q_MLP_SAMPLE && a.logp) {
+        if (chalf == 1) slp[trow] = lp;
+        __syncthreads();
+        if (chalf == 0 && row < a.M) a.logp[orow] = lp + slp[trow];
       }
     }
   }
