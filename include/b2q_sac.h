@@ -32,7 +32,7 @@ int b2q_sac_get_grads(B2QSacHandle h, float* actor, float* critic, void* stream)
  * RNG inside the kernels (Philox-4x32-10 keyed by `seed` and the learner's device-side step counter, counter = (row, action)), the backward
  * recomputing exactly the forward's draw — no noise tensors, and a CUDA-graph replay of the call draws fresh noise every step.
  * losses_out: device float[2] = {critic_loss, actor_loss}.
- * b2q_sac_learn == phases 0, 1, 2, 3 of b2q_sac_phase (with the critics' optimiser step overlapped on an internal stream). */
+ * b2q_sac_learn == phases 0, 1, 2, 3 of b2q_sac_phase in stream order. */
 int b2q_sac_learn(B2QSacHandle h, const float* obs, const float* act, const float* rew, const float* next_obs, const float* term,
                   const float* eps_next, const float* eps_cur, uint64_t seed, float* losses_out, void* stream);
 /* phase 0: critic grads (clears the whole gradient bucket first); 1: Adam(critic); 2: actor grads; 3: Adam(actor) + Polyak.

@@ -226,7 +226,9 @@ class SACLearner:
         if rc != 0:
             raise RuntimeError("b2q_sac_create failed (%d)" % rc)
         self.na, self.nc = self.lib.b2q_sac_param_count(self.h, 0), self.lib.b2q_sac_param_count(self.h, 1)
-        self.losses = torch.zeros(2, device=agent.device)
+        # (critic_loss, actor_loss) of the last learn: a view of the learner's own accumulators (no copy node at the end of a learn); valid until the
+        # next learn / bc_learn call starts
+        self.losses = torch.as_tensor(_CudaBuf(self.lib.b2q_sac_loss_ptr(self.h), 2), device=agent.device)
         self.steps = 0
         self._graph = None
         self._static = None
@@ -297,7 +299,7 @@ class SACLearner:
                 side.wait_stream(torch.cuda.current_stream(dev))
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph, stream=side):
-                    rc = self.lib.b2q_sac_learn(self.h, *sargs, self.losses.data_ptr(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+                    rc = self.lib.b2q_sac_learn(self.h, *sargs, None, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
                     assert rc == 0, rc
             if (eps_next is None) != (self._static_eps[0] is None) or (eps_cur is None) != (self._static_eps[1] is None):
                 raise ValueError("learn(graph=True): explicit eps must be given either on every call or on none (the graph was captured with the other choice)")
@@ -322,9 +324,8 @@ class SACLearner:
                 rc = self.lib.b2q_sac_phase(self.h, ph, *args, self._stream())
                 if rc != 0:
                     raise RuntimeError("b2q_sac_phase %d: %d" % (ph, rc))
-            self.losses.copy_(torch.as_tensor(_CudaBuf(self.lib.b2q_sac_loss_ptr(self.h), 2), device=dev))
         elif self.world == 1:
-            rc = self.lib.b2q_sac_learn(self.h, *args, self.losses.data_ptr(), self._stream())
+            rc = self.lib.b2q_sac_learn(self.h, *args, None, self._stream())
             if rc != 0:
                 raise RuntimeError("b2q_sac_learn: %d %s" % (rc, self.lib.b2q_sac_last_error(self.h).decode()))
         else:
@@ -336,7 +337,6 @@ class SACLearner:
                 if ph in (0, 2):   # one flat bucket per optimiser: all-reduce(mean) then the fused Adam kernel consumes it
                     g = self._grad_view(0 if ph == 2 else 1, self.na if ph == 2 else self.nc)
                     dist.all_reduce(g, op=dist.ReduceOp.AVG)
-            self.losses.copy_(torch.as_tensor(_CudaBuf(self.lib.b2q_sac_loss_ptr(self.h), 2), device=dev))
         if pull:
             self.pull()
         return self.losses
@@ -348,7 +348,7 @@ class SACLearner:
         obs, ref_obs = t(obs), t(ref_obs)
         eps = torch.randn(self.batch, self.agent.act_dim, device=dev) if eps is None else t(eps)
         rc = self.lib.b2q_sac_bc_learn(self.h, obs.data_ptr(), ref_obs.data_ptr(), ref_obs.shape[1], ref_agent.actor.h, ref_agent.critic.h, eps.data_ptr(),
-                                       self.losses.data_ptr(), self._stream())
+                                       None, self._stream())
         if rc != 0:
             raise RuntimeError("b2q_sac_bc_learn: %d" % rc)
         if pull:

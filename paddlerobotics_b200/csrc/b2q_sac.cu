@@ -436,7 +436,6 @@ struct B2QSac {
   void* tmap_cache = nullptr;   // TmapCache*: TMA tensor maps of the GEMM operands
   int* d_step = nullptr;
   int64_t launches = 0;
-  bool overlap_p1 = false;         // set by b2q_sac_learn: phase 2 launches phase 1 on the side stream beside its actor forward
   bool actor_grad_dirty = false;   // g_actor holds a gradient that no phase 0 has cleared yet
   std::string err;
 };
@@ -746,16 +745,9 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
     if (!obs) return -1;
     if (s->actor_grad_dirty) cudaMemsetAsync(s->g_actor, 0, an.n * sizeof(float), st);   // only when no phase 0 cleared the bucket since the last actor gradient
     s->actor_grad_dirty = true;
-    // b2q_sac_learn: the critics' Adam + repack (phase 1) runs on the side stream beside the actor forward, which does not read the critics
-    if (s->overlap_p1) {
-      fork(s, st);
-      const int rc1 = b2q_sac_phase(s, 1, obs, act, rew, next_obs, term, eps_next, eps_cur, seed, (void*)s->side);
-      if (rc1) return rc1;
-    }
     // a ~ pi(obs) with dumps; Q(obs, a) with dumps (sac.py:102-106)
     B2QMlpSaves sa = {nullptr /*x row-major: no consumer*/, s->xa_t, s->ha1_rm, s->ha1_t, s->ha2_rm, s->ha2_t};
     if (b2q_mlp_forward_ex(s->mlp_actor, obs, D, nullptr, B, B2Q_MLP_SAMPLE, seed * 2, eps_cur, s->cur_a, s->cur_logp, s->raw_a, &sa, nullptr, s->d_step, st)) return -2;
-    if (s->overlap_p1) join(s, st);
     // Q(obs, a) and, in the same kernel, dQ_i/da for both critics (unit output gradient; no critic weight gradients: only the actor
     // optimiser steps here).  The routing of d(-min q)/da to the smaller critic and the 1/B happen in the dy kernel.
     if (b2q_mlp_forward_ex(s->mlp_critic, obs, D, s->cur_a, B, B2Q_MLP_RAW, 0, nullptr, s->q, nullptr, nullptr, nullptr, s->da_c, nullptr, st)) return -2;
@@ -773,13 +765,12 @@ int b2q_sac_phase(B2QSacHandle s, int phase, const float* obs, const float* act,
 int b2q_sac_learn(B2QSacHandle s, const float* obs, const float* act, const float* rew, const float* next_obs, const float* term, const float* eps_next,
                   const float* eps_cur, uint64_t seed, float* losses_out /*device [2]: critic, actor*/, void* stream) {
   if (!s) return -1;
-  s->overlap_p1 = true;                       // phase 1 is launched from inside phase 2 (side stream)
+  // the four phases in stream order.  (Running the critics' optimiser step on the side stream beside the actor forward was measured: the two
+  // extra cross-stream graph edges cost 7 us more than the 8 us kernel they hide.)
   for (int ph = 0; ph < 4; ph++) {
-    if (ph == 1) continue;
     int rc = b2q_sac_phase(s, ph, obs, act, rew, next_obs, term, eps_next, eps_cur, seed, stream);
-    if (rc) { s->overlap_p1 = false; return rc; }
+    if (rc) return rc;
   }
-  s->overlap_p1 = false;
   if (losses_out) cudaMemcpyAsync(losses_out, s->losses, 2 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
   return 0;
 }

@@ -16,15 +16,23 @@ torch.cuda.synchronize()
 args = (obs.data_ptr(), act.data_ptr(), rew.data_ptr(), nobs.data_ptr(), term.data_ptr(), e1.data_ptr(), e2.data_ptr(), 1)
 stream = torch.cuda.Stream()
 tot = 0.0
-for phases in ((0,), (1,), (2,), (3,), (0, 1, 2, 3)):
-    with torch.cuda.stream(stream):
+import ctypes as C
+noeps = args[:5] + (None, None, 1)
+def run(phases):
+    if phases == "learn":        # the fused entry point (critics' Adam beside the actor forward), explicit noise
+        assert L.lib.b2q_sac_learn(L.h, *args[:7], C.c_uint64(1), L.losses.data_ptr(), L._stream()) == 0
+    elif phases == "learn, counter-RNG noise":
+        assert L.lib.b2q_sac_learn(L.h, *noeps[:7], C.c_uint64(1), L.losses.data_ptr(), L._stream()) == 0
+    else:
         for ph in phases:
             assert L.lib.b2q_sac_phase(L.h, ph, *args, L._stream()) == 0
+for phases in ((0,), (1,), (2,), (3,), (0, 1, 2, 3), "learn", "learn, counter-RNG noise"):
+    with torch.cuda.stream(stream):
+        run(phases)
         torch.cuda.synchronize()
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr, stream=stream):
-            for ph in phases:
-                assert L.lib.b2q_sac_phase(L.h, ph, *args, L._stream()) == 0
+            run(phases)
         for _ in range(5):
             gr.replay()
         torch.cuda.synchronize()
