@@ -96,7 +96,9 @@ typedef struct B2QConfig {
   uint64_t noise_seed;       /* counter-based RNG key (Philox4x32-10 over (seed, env, step)) */
   int32_t stuck_termination; /* 1: done when the base position std over the last 10 control steps <= 2e-4 after step 10 (rlschool [EXT]) */
   int32_t body_collisions;   /* 1: `badfoot` counts non-toe leg links / trunk corners touching the terrain (not only low knees) */
-  int32_t motor_mode;        /* 0 POSITION (laikago_motor.py:139-145), 1 TORQUE (laikago_motor.py:131-134: the action IS the torque) */
+  int32_t motor_mode;        /* 0 POSITION (laikago_motor.py:139-145), 1 TORQUE (laikago_motor.py:131-134: the action IS the torque),
+                              * 2 HYBRID (laikago_motor.py:152-164): the action is [N][12][5] = per motor (q*, kp, qd*, kd, tau_ff), b2q_act_dim = 60,
+                              * tau = -kp (q - q*) - kd (qd - qd*) + tau_ff; taken as commanded (no ETG / pose offset, interpolation or filter) */
   int32_t joint_limits;      /* 1: URDF joint limits (a1.py:186-223) as unilateral rows of the contact solve (one slot per leg) */
   int32_t external_force;    /* 1: per-env base push set with b2q_set_external_force (random_param['random_force'], train.py:254) */
   double base_damping[4];    /* Bullet btMultiBody base damping: linear k1,k2, angular k1,k2 (force = m v (k1 + k2 |v|)); 0 = off */

@@ -562,6 +562,11 @@ void orc_substep(const OrcConfig* c, OrcEnv* e, const double target[12]) {
     double t = target[j]; if (c->torque_limit > 0) { if (t > c->torque_limit) t = c->torque_limit; if (t < -c->torque_limit) t = -c->torque_limit; }
     tau[j] = t;
   }
+  if (c->motor_mode == 2) for (int j = 0; j < 12; j++) { /* MotorControlMode.HYBRID, laikago_motor.py:162-164 (+ the torque clip :166-172) */
+    double t = -1.0 * (e->hyb[0][j] * (e->q[j] - cmd[j])) - e->hyb[2][j] * (e->qd[j] - e->hyb[1][j]) + e->hyb[3][j];
+    if (c->torque_limit > 0) { if (t > c->torque_limit) t = c->torque_limit; if (t < -c->torque_limit) t = -c->torque_limit; }
+    tau[j] = t;
+  }
   memcpy(e->last_tau, tau, sizeof tau);
   memcpy(D->damp, c->base_damping, sizeof D->damp);
   if (c->external_force) m3tv(D->R0, e->ext_force, D->fext_b);
@@ -816,13 +821,16 @@ void orc_env_reset_ex(const OrcConfig* c, OrcEnv* e, const double* w, const doub
 
 static double c_prec(double v, double t, double m) { double w = (v - t) * atanh(sqrt(0.95)) / m; return tanh(w * w); }
 
-void orc_env_step(const OrcConfig* c, OrcEnv* e, const double action[12], int donef,
+void orc_env_step(const OrcConfig* c, OrcEnv* e, const double* action, int donef,
                   double* obs, double* reward, int* done, double* info) {
   const int R = c->action_repeat; const double dtc = c->sim_dt * R;
   double target[12], start_pos[3], feet0[4][3], feet1[4][3];
   for (int j = 0; j < 12; j++) target[j] = POSE_ORI[j] + e->etg_act[j] + action[j]; /* deployment/test.py:95-99 */
   if (c->motor_mode == 1) memcpy(target, action, sizeof target);                     /* TORQUE mode: the action is the torque */
-  if (c->action_filter) { /* Minitaur.Step: action = _FilterAction(action), minitaur.py:250-251 */
+  if (c->motor_mode == 2) for (int j = 0; j < 12; j++) {   /* HYBRID: per motor (q*, kp, qd*, kd, tau_ff), laikago_motor.py:27-33,152-161; taken as commanded */
+    target[j] = action[5 * j]; e->hyb[0][j] = action[5 * j + 1]; e->hyb[1][j] = action[5 * j + 2]; e->hyb[2][j] = action[5 * j + 3]; e->hyb[3][j] = action[5 * j + 4];
+  }
+  if (c->action_filter && c->motor_mode != 2) { /* Minitaur.Step: action = _FilterAction(action), minitaur.py:250-251 */
     double fb[3], fa[3]; orc_butter2(c->filter_highcut, 1.0 / dtc, fb, fa);
     for (int j = 0; j < 12; j++) orc_filter_step(fb, fa, target[j], &e->fx1[j], &e->fx2[j], &e->fy1[j], &e->fy2[j], &target[j]);
   }
@@ -830,7 +838,7 @@ void orc_env_step(const OrcConfig* c, OrcEnv* e, const double action[12], int do
   orc_foot_world(e, feet0);
   for (int i = 0; i < R; i++) { /* minitaur.py:248-260 */
     double proc[12];
-    if (c->action_interp && e->has_last) { double lerp = (double)(i + 1) / R; for (int j = 0; j < 12; j++) proc[j] = e->last_action[j] + lerp * (target[j] - e->last_action[j]); }
+    if (c->action_interp && e->has_last && c->motor_mode != 2) { double lerp = (double)(i + 1) / R; for (int j = 0; j < 12; j++) proc[j] = e->last_action[j] + lerp * (target[j] - e->last_action[j]); }
     else memcpy(proc, target, sizeof proc);
     orc_substep(c, e, proc);
   }
@@ -908,7 +916,7 @@ static void* job_run(void* p) {
   Job* j = (Job*)p;
   for (int i = j->lo; i < j->hi; i++) {
     double info[ORC_INFO_DIM];
-    orc_env_step(j->c, &j->envs[i], j->act + 12 * i, j->donef, j->obs + ORC_OBS_DIM * i, j->rew + i, j->done + i, j->info ? j->info + ORC_INFO_DIM * i : info);
+    orc_env_step(j->c, &j->envs[i], j->act + (size_t)(j->c->motor_mode == 2 ? 60 : 12) * i, j->donef, j->obs + ORC_OBS_DIM * i, j->rew + i, j->done + i, j->info ? j->info + ORC_INFO_DIM * i : info);
     if (j->auto_reset && j->done[i]) orc_env_reset(j->c, &j->envs[i], NULL, NULL, j->obs + ORC_OBS_DIM * i);
   }
   return NULL;
@@ -932,7 +940,7 @@ static void* rjob_run(void* p) {
   for (int i = j->lo; i < j->hi; i++) {
     double info[ORC_INFO_DIM], rew; int done; j->ret[i] = 0; j->ndone[i] = 0;
     for (int k = 0; k < j->K; k++) {
-      orc_env_step(j->c, &j->envs[i], j->act + ((size_t)k * j->n + i) * 12, 0, j->obs + ORC_OBS_DIM * i, &rew, &done, info);
+      orc_env_step(j->c, &j->envs[i], j->act + ((size_t)k * j->n + i) * (j->c->motor_mode == 2 ? 60 : 12), 0, j->obs + ORC_OBS_DIM * i, &rew, &done, info);
       j->ret[i] += rew; j->ndone[i] += done;
       if (j->auto_reset && done) orc_env_reset(j->c, &j->envs[i], NULL, NULL, j->obs + ORC_OBS_DIM * i);
     }

@@ -91,6 +91,7 @@ typedef struct {
   double ext_force[3];         /* world-frame push at the base COM */
   double lam_lim[12];          /* warm starts of the joint-limit rows */
   int env_id;                  /* index of this env in its batch: the sensor-noise counter */
+  double hyb[4][12];           /* HYBRID command of the current control step: kp | qd* | kd | tau_ff (laikago_motor.py:152-161) */
 } OrcEnv;
 
 void orc_default_config(OrcConfig* c);
@@ -118,7 +119,8 @@ void orc_env_reset_ex(const OrcConfig* c, OrcEnv* e, const double* etg_w, const 
 int orc_obs_dim(const OrcConfig* c);
 void orc_normal4(unsigned long long seed, unsigned c0, unsigned c1, unsigned c2, double n[4]);   /* Philox4x32-10 + Box-Muller */
 void orc_substep(const OrcConfig* c, OrcEnv* e, const double target[12]);
-void orc_env_step(const OrcConfig* c, OrcEnv* e, const double action[12], int donef,
+/* action: 12 values, or 60 = [12 motors][q*, kp, qd*, kd, tau_ff] when c->motor_mode == 2 (HYBRID) */
+void orc_env_step(const OrcConfig* c, OrcEnv* e, const double* action, int donef,
                   double* obs, double* reward, int* done, double* info);
 /* batch helpers (cpu baseline): nthreads pthreads over envs */
 void orc_batch_step(const OrcConfig* c, OrcEnv* envs, int n, const double* actions, int donef, int auto_reset,

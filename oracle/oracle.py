@@ -54,7 +54,7 @@ class Env(C.Structure):
         ("contact", C.c_int * 4), ("last_tau", C.c_double * 12),
         ("fx1", C.c_double * 12), ("fx2", C.c_double * 12), ("fy1", C.c_double * 12), ("fy2", C.c_double * 12),
         ("snap", C.c_double * 37), ("snap_obs", C.c_double * HIST_W), ("snap_lam", C.c_double * 4),
-        ("pos_hist", (C.c_double * 3) * 10), ("ext_force", C.c_double * 3), ("lam_lim", C.c_double * 12), ("env_id", C.c_int),
+        ("pos_hist", (C.c_double * 3) * 10), ("ext_force", C.c_double * 3), ("lam_lim", C.c_double * 12), ("env_id", C.c_int), ("hyb", (C.c_double * 12) * 4),
     ]
 
 
@@ -292,7 +292,7 @@ class OracleBatch:
         self.info = np.zeros((n, INFO_DIM))
 
     def step(self, actions, donef=False, auto_reset=True, nthreads=1):
-        a, ap = _d(np.asarray(actions).reshape(self.n, 12))
+        a, ap = _d(np.asarray(actions).reshape(self.n, 60 if self.cfg.motor_mode == 2 else 12))
         dp = C.POINTER(C.c_double)
         lib().orc_batch_step(C.byref(self.cfg), self.envs, C.c_int(self.n), ap, C.c_int(int(donef)), C.c_int(int(auto_reset)),
                              self.obs.ctypes.data_as(dp), self.rew.ctypes.data_as(dp),
@@ -301,7 +301,7 @@ class OracleBatch:
 
     def rollout(self, actions, auto_reset=True, nthreads=1):
         """actions [K,n,12]: K control steps per env, envs distributed over pthreads (no per-step barrier)."""
-        a, ap = _d(np.asarray(actions).reshape(-1, self.n, 12))
+        a, ap = _d(np.asarray(actions).reshape(-1, self.n, 60 if self.cfg.motor_mode == 2 else 12))
         K = a.shape[0]
         ret = np.zeros(self.n)
         nd = np.zeros(self.n, dtype=np.int32)

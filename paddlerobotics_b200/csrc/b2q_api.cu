@@ -187,6 +187,7 @@ struct EnvBase {
   virtual int reset(const uint8_t* mask, const void* w, const void* b, const void* xoff, void* obs, cudaStream_t s) = 0;
   virtual int set_force(const void* f, cudaStream_t s) = 0;
   int obs_dim = B2Q_OBS_DIM;
+  int act_dim() const { return cfg.motor_mode == 2 ? 5 * B2Q_ACT_DIM : B2Q_ACT_DIM; }   // HYBRID: a 5-tuple per motor
   virtual int step(const void* action, int donef, void* obs, void* rew, uint8_t* done, void* info, cudaStream_t s) = 0;
   virtual int step_host(const void* a, int donef, void* obs, void* rew, uint8_t* done, void* info, cudaStream_t s) = 0;
   virtual int get_state(void* out, cudaStream_t s) = 0;
@@ -340,12 +341,12 @@ struct EnvT : EnvBase {
     CK(cudaSetDevice(cfg.device));
     const size_t N = (size_t)B.N;
     if (!st_act) {
-      size_t bytes = N * (12 + OBS_DIM + 1 + INFO_DIM) * sizeof(T) + N + 512;
+      size_t bytes = N * ((size_t)act_dim() + OBS_DIM + 1 + INFO_DIM) * sizeof(T) + N + 512;
       void* p = nullptr;
       CK(cudaMalloc(&p, bytes));
       // layout: act | obs | rew | done (bytes) | pad | info  — obs/rew/done contiguous so one D2H can serve all three
-      st_act = (T*)p; st_obs = st_act + N * 12; st_rew = st_obs + N * OBS_DIM; st_done = (uint8_t*)(st_rew + N);
-      st_info = (T*)((uint8_t*)p + ((N * (12 + OBS_DIM + 1) * sizeof(T) + N + 255) / 256) * 256);
+      st_act = (T*)p; st_obs = st_act + N * (size_t)act_dim(); st_rew = st_obs + N * OBS_DIM; st_done = (uint8_t*)(st_rew + N);
+      st_info = (T*)((uint8_t*)p + ((N * ((size_t)act_dim() + OBS_DIM + 1) * sizeof(T) + N + 255) / 256) * 256);
     }
     // Pinned (page-locked) host buffers are device-addressable under unified addressing: the kernel then reads the actions
     // straight from host memory (one coalesced 12-float row per robot, read once) instead of waiting for a separate H2D copy,
@@ -353,7 +354,7 @@ struct EnvT : EnvBase {
     // Pageable buffers, and the scattered info rows, go through the device staging area and cudaMemcpyAsync.
     const T* act_dev = st_act;
     if (host_io >= 1 && (act_dev = (const T*)mapped(a)) == nullptr) act_dev = st_act;
-    if (act_dev == st_act) CK(cudaMemcpyAsync(st_act, a, N * 12 * sizeof(T), cudaMemcpyHostToDevice, s));
+    if (act_dev == st_act) CK(cudaMemcpyAsync(st_act, a, N * (size_t)act_dim() * sizeof(T), cudaMemcpyHostToDevice, s));
     T* obs_dev = nullptr; T* rew_dev = nullptr; uint8_t* done_dev = nullptr;
     if (host_io >= 2) { obs_dev = (T*)mapped(obs); rew_dev = (T*)mapped(rew); done_dev = (uint8_t*)mapped(done); }
     const bool direct = obs_dev && rew_dev && done_dev;
@@ -437,7 +438,7 @@ int b2q_destroy(B2QHandle h) { if (!h) return B2Q_EINVAL; delete h->impl; delete
 const char* b2q_last_error(B2QHandle h) { return h ? h->impl->err.c_str() : g_create_err.c_str(); }
 int b2q_num_envs(B2QHandle h) { return h ? h->impl->cfg.num_envs : B2Q_EINVAL; }
 int b2q_obs_dim(B2QHandle h) { return h ? h->impl->obs_dim : B2Q_EINVAL; }
-int b2q_act_dim(B2QHandle h) { return h ? B2Q_ACT_DIM : B2Q_EINVAL; }
+int b2q_act_dim(B2QHandle h) { return h ? h->impl->act_dim() : B2Q_EINVAL; }
 int b2q_info_dim(B2QHandle h) { return h ? B2Q_INFO_DIM : B2Q_EINVAL; }
 int b2q_elem_size(B2QHandle h) { return h ? (h->impl->prec ? 8 : 4) : B2Q_EINVAL; }
 int b2q_set_dynamics(B2QHandle h, const uint8_t* m, const void* dyn, void* s) { return h ? h->impl->set_dynamics(m, dyn, (cudaStream_t)s) : B2Q_EINVAL; }

@@ -81,7 +81,7 @@ inline const char* validate_config(const B2QConfig& c) {
   if (c.terrain_type != 0 && c.terrain_type != 1) return "terrain_type must be 0 or 1";
   if (c.sensor_imu < 0 || c.sensor_imu > 2 || c.sensor_motor < 0 || c.sensor_motor > 2) return "sensor_imu / sensor_motor must be 0, 1 or 2";
   if (config_obs_dim(c) < 1) return "sensor flags select an empty observation";
-  if (c.motor_mode != 0 && c.motor_mode != 1) return "motor_mode must be 0 (POSITION) or 1 (TORQUE); HYBRID is not provided";
+  if (c.motor_mode < 0 || c.motor_mode > 2) return "motor_mode must be 0 (POSITION), 1 (TORQUE) or 2 (HYBRID)";
   for (int i = 0; i < 5; i++) if (!(c.noise_stdev[i] >= 0)) return "noise_stdev must be >= 0";
   for (int i = 0; i < 4; i++) if (!(c.base_damping[i] >= 0)) return "base_damping must be >= 0";
   if (c.threads_per_block != 0 && (c.threads_per_block % 32 != 0 || c.threads_per_block > 128)) return "threads_per_block must be a multiple of 32, at most 128 (kernels are __launch_bounds__(128))";

@@ -261,7 +261,7 @@ B2Q_HD void solve_rows36(const Comm& cm, const Cfg<T>& cf, T mu, const T (*Y)[6]
 // small as it is (the body is instruction-fetch bound).
 template <typename T, int FEAT, class Comm>
 B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const LaneParam<T>& pr, LaneState<T>& s,
-                    const T* target, T* tau_out, V3<T> fext = V3<T>{0, 0, 0}) {
+                    const T* target, T* tau_out, V3<T> fext = V3<T>{0, 0, 0}, const T* hyb = nullptr /*HYBRID: kp[3] | qd*[3] | kd[3] | tau_ff[3]*/) {
   const int k = cm.leg();
   const LegModel<T>& lm = md.leg[k];
   const T dt = cf.dt, idt = cf.idt;
@@ -276,6 +276,7 @@ B2Q_HD void substep(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, const 
     if (cf.clip_cmd) cmd = m_min(m_max(cmd, s.q[j] - cf.max_dq), s.q[j] + cf.max_dq);   // a1.py:452-457 (off by default)
     T t = T(-1) * (pr.kp[j] * (s.q[j] - cmd)) - pr.kd[j] * (s.qd[j] - T(0));
     if (FEAT && cf.motor_mode == 1) t = target[j];   // MotorControlMode.TORQUE: the command is the torque (laikago_motor.py:131-134)
+    if (FEAT && cf.motor_mode == 2) t = T(-1) * (hyb[j] * (s.q[j] - cmd)) - hyb[6 + j] * (s.qd[j] - hyb[3 + j]) + hyb[9 + j];   // HYBRID: per-command gains, desired velocity, feed-forward torque (laikago_motor.py:152-164)
     if (cf.tau_limit > T(0)) t = m_min(m_max(t, -cf.tau_limit), cf.tau_limit);
     tau[j] = t; tau_out[j] = t;
   }
@@ -1010,7 +1011,15 @@ B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, cons
     }
     if (cf.extf) { P4<T> f = B.extf[env]; fext = mk<T>(f.x, f.y, f.z); }
   }
-  if (cf.filter) {  // Minitaur.Step: action = _FilterAction(action) (minitaur.py:250-251); y = b.x_hist - a.y_hist (action_filter.py:111-120)
+  T hyb[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (FEAT && cf.motor_mode == 2) {   // HYBRID: the action is [N][12 motors][q*, kp, qd*, kd, tau_ff] (laikago_motor.py:27-33,152-161), taken as commanded:
+#pragma unroll                        // no ETG / pose offset, no interpolation or filtering of the 5-tuples
+    for (int j = 0; j < 3; j++) {
+      const T* a5 = action + ((size_t)env * 12 + 3 * k + j) * 5;
+      target[j] = a5[0]; hyb[j] = a5[1]; hyb[3 + j] = a5[2]; hyb[6 + j] = a5[3]; hyb[9 + j] = a5[4];
+    }
+  }
+  if (cf.filter && !(FEAT && cf.motor_mode == 2)) {  // Minitaur.Step: action = _FilterAction(action) (minitaur.py:250-251); y = b.x_hist - a.y_hist (action_filter.py:111-120)
     P4<T> x1 = ldp(B.state, 21 + 4 * k, N, env), x2 = ldp(B.state, 22 + 4 * k, N, env), y1 = ldp(B.state, 23 + 4 * k, N, env), y2 = ldp(B.state, 24 + 4 * k, N, env);
     T ax1[3] = {x1.x, x1.y, x1.z}, ax2[3] = {x2.x, x2.y, x2.z}, ay1[3] = {y1.x, y1.y, y1.z}, ay2[3] = {y2.x, y2.y, y2.z}, yy[3];
 #pragma unroll
@@ -1040,7 +1049,7 @@ B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, cons
 #pragma unroll 1
   for (int i = 0; i < R; i++) {  // Minitaur.Step, minitaur.py:248-260
     T proc[3];
-    if (cf.interp && has_last) {  // ProcessAction, minitaur.py:1384-1401
+    if (cf.interp && has_last && !(FEAT && cf.motor_mode == 2)) {  // ProcessAction, minitaur.py:1384-1401
       T lerp = T(i + 1) / T(R);
 #pragma unroll
       for (int j = 0; j < 3; j++) proc[j] = last_action[j] + lerp * (target[j] - last_action[j]);
@@ -1048,7 +1057,7 @@ B2Q_HD void step_lane(const Comm& cm, const Cfg<T>& cf, const Model<T>& md, cons
 #pragma unroll
       for (int j = 0; j < 3; j++) proc[j] = target[j];
     }
-    substep<T, FEAT>(cm, cf, md, pr, s, proc, tau, fext);
+    substep<T, FEAT>(cm, cf, md, pr, s, proc, tau, fext, hyb);
     if (valid && i == ia) ring_write(B, slot, 0, k, env, s.q, s.qd, tau);
     if (valid && i == ib) ring_write(B, slot, 1, k, env, s.q, s.qd, tau);
   }

@@ -65,12 +65,12 @@ class VecQuadrupedalEnv:
             raise RuntimeError("b2q_create failed (%d): %s" % (rc, self.lib.b2q_last_error(None).decode()))
         n, dev, dt = self.num_envs, self.device, self.dtype
         self.observation_dim = int(self.lib.b2q_obs_dim(self.h))          # <= 49: the sensor flags select blocks of the full layout
+        self.action_dim = int(self.lib.b2q_act_dim(self.h))               # 12, or 60 in HYBRID mode (a 5-tuple per motor)
         self.obs = torch.zeros(n, self.observation_dim, device=dev, dtype=dt)
         self.reward = torch.zeros(n, device=dev, dtype=dt)
         self.done = torch.zeros(n, device=dev, dtype=torch.uint8)
         self.info = torch.zeros(n, INFO_DIM, device=dev, dtype=dt)
         self.control_dt = c.sim_dt * c.action_repeat
-        self.action_dim = ACT_DIM
         # host API staging (pinned) — allocated lazily
         self._h_act = self._h_obs = self._h_rew = self._h_done = self._d_act = self._h_info = None
 
@@ -106,7 +106,7 @@ class VecQuadrupedalEnv:
     def step(self, action, donef=False):
         """action: [N,12] device tensor (joint-space residual, already scaled by act_bound)."""
         a = action if (isinstance(action, torch.Tensor) and action.dtype == self.dtype and action.device == self.device and action.is_contiguous()) \
-            else self._t(action, (self.num_envs, ACT_DIM))
+            else self._t(action, (self.num_envs, self.action_dim))
         rc = self.lib.b2q_step(self.h, a.data_ptr(), int(bool(donef)), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
                                self.info.data_ptr(), self._stream())
         if rc != 0:
@@ -129,7 +129,7 @@ class VecQuadrupedalEnv:
     def _host_bufs(self):
         if self._h_act is None:
             n, npdt = self.num_envs, self.dtype
-            self._h_act = torch.empty(n, ACT_DIM, dtype=npdt).pin_memory()
+            self._h_act = torch.empty(n, self.action_dim, dtype=npdt).pin_memory()
             es = self.obs.element_size()
             od = self.observation_dim
             self._h_out = torch.empty(n * (od + 1) * es + n, dtype=torch.uint8).pin_memory()     # obs | rew | done contiguous: one D2H
@@ -145,7 +145,7 @@ class VecQuadrupedalEnv:
         the [N,56] info rows.  The returned arrays are views of the pinned buffers (overwritten by the next call)."""
         if self._h_act is None:
             self._host_bufs()
-        np.copyto(self._np_act, np.asarray(action_np).reshape(self.num_envs, ACT_DIM), casting="same_kind")
+        np.copyto(self._np_act, np.asarray(action_np).reshape(self.num_envs, self.action_dim), casting="same_kind")
         if info and self._h_info is None:
             self._h_info = torch.empty(self.num_envs, INFO_DIM, dtype=self.dtype).pin_memory()
             self._np_info = self._h_info.numpy()
@@ -159,7 +159,7 @@ class VecQuadrupedalEnv:
         return self._np_obs, self._np_rew, self._np_done
 
     def h2d_bytes_per_step(self):
-        return self.num_envs * ACT_DIM * self.obs.element_size()
+        return self.num_envs * self.action_dim * self.obs.element_size()
 
     def d2h_bytes_per_step(self, info=False):
         es = self.obs.element_size()
@@ -211,7 +211,9 @@ def _motor_mode(m):
         return 0
     if name == "TORQUE" or val in (2, "TORQUE", "torque"):
         return 1
-    raise NotImplementedError("motor_control_mode %r: only POSITION and TORQUE are provided (HYBRID / PWM are not on the ETGRL path)" % (m,))
+    if name == "HYBRID" or val in (3, "HYBRID", "hybrid"):
+        return 2
+    raise NotImplementedError("motor_control_mode %r: POSITION, TORQUE and HYBRID are provided (PWM raises in the reference's motor model too, laikago_motor.py:126-128)" % (m,))
 
 
 class QuadrupedalEnv:
@@ -270,7 +272,7 @@ class QuadrupedalEnv:
         self._dyn_row = dynamic_dict_to_row(dynamic_param) if dynamic_param else None
         if self._dyn_row is not None:
             self.vec.set_dynamics(self._dyn_row[None, :])
-        self.observation_space, self.action_space = _Space(self.vec.observation_dim), _Space(ACT_DIM)
+        self.observation_space, self.action_space = _Space(self.vec.observation_dim), _Space(self.vec.action_dim)
         layer = ETG_layer(ETG_T, 0.026, ETG_H, 0.04, np.array([-np.pi / 2, 0]), 0.2, ETG_T)
         if ETG_path not in (None, "None", "") and str(ETG_path).endswith(".npz"):
             z = np.load(ETG_path)
@@ -301,7 +303,7 @@ class QuadrupedalEnv:
 
     def step(self, action, donef=False):
         # one C call + one stream sync: actions in, obs / reward / done / info out through pinned host buffers
-        obs, rew, done, info = self.vec.step_host(np.asarray(action).reshape(1, ACT_DIM), donef, info=True)
+        obs, rew, done, info = self.vec.step_host(np.asarray(action).reshape(1, self.vec.action_dim), donef, info=True)
         return obs[0].astype(np.float64), float(rew[0]), bool(done[0]), info_dict(info[0])
 
     def close(self):

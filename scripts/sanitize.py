@@ -21,11 +21,13 @@ for kw in (dict(num_envs=13), dict(num_envs=16, precision="f64"), dict(num_envs=
            # memory, TORQUE mode, base push, damping) in f32 and f64
            dict(num_envs=13, sensor_motor=2, sensor_imu=2, obs_normal=0, noise_stdev=(0.01, 0.05, 0.1, 0.02, 0.04), stuck_termination=1, body_collisions=1, auto_reset=True),
            dict(num_envs=11, joint_limits=1, knee_contacts=1, external_force=1, base_damping=(0.04, 0.02, 0.04, 0.01)), dict(num_envs=9, joint_limits=1, precision="f64"),
-           dict(num_envs=8, motor_mode=1)):
+           dict(num_envs=8, motor_mode=1), dict(num_envs=8, motor_mode=2)):
     env = VecQuadrupedalEnv(**kw)
     n = env.num_envs
     env.reset(w, b)
     a = (rng.random((n, 12)) * 0.6 - 0.3)
+    if kw.get("motor_mode") == 2:                                # HYBRID: (q*, kp, qd*, kd, tau_ff) per motor
+        a5 = np.zeros((n, 12, 5)); a5[:, :, 0] = np.array([0.0, 0.9, -1.8] * 4) + a; a5[:, :, 1] = 100.0; a5[:, :, 3] = 1.5; a = a5.reshape(n, 60)
     if kw.get("joint_limits"):
         a[:, 2::3] = 1.2; a[:, 0::3] = 0.9                       # into the stops: the shared-memory 24-row solve runs
     if kw.get("external_force"):

@@ -79,7 +79,7 @@ class EmuEnv:
         return obs
 
     def step(self, action, donef=False):
-        a = self._a(action, (self.n, 12))
+        a = self._a(action, (self.n, 60 if int(getattr(self.cfg, 'motor_mode', 0)) == 2 else 12))
         obs = np.zeros((self.n, self.obs_dim()), dtype=self.dtype)
         rew = np.zeros(self.n, dtype=self.dtype)
         done = np.zeros(self.n, dtype=np.uint8)

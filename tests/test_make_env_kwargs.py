@@ -12,7 +12,7 @@ def _mk(**kw):
 @pytest.mark.parametrize("kw", [dict(render=True), dict(task="cave"), dict(task="gallop"), dict(sensor_mode={"footpose": 1}), dict(sensor_mode={"dynamic_vec": 1}),
                                 dict(sensor_mode={"force_vec": 1}), dict(sensor_mode={"ETG_obs": 1}), dict(sensor_mode={"lidar": 1}),
                                 dict(sensor_mode={"RNN": {"mode": "GRU", "time_steps": 5, "time_interval": 1}}),
-                                dict(motor_control_mode=3), dict(motor_control_mode="HYBRID"), dict(random_param={"random_terrain": 1}), dict(ETG_H=30),
+                                dict(motor_control_mode=4), dict(motor_control_mode="PWM"), dict(random_param={"random_terrain": 1}), dict(ETG_H=30),
                                 dict(reward_param={"stand": 0.5})])
 def test_unsupported_keywords_raise(kw):
     with pytest.raises(NotImplementedError):
