@@ -132,8 +132,8 @@ int b2q_step(B2QHandle h, const void* action, int donef, void* obs, void* reward
 /* The same step with HOST buffers (the reference-facing call: numpy in / numpy out), synchronous: on return obs / reward /
  * done (and info if non-NULL) hold this step's results.  With page-locked host memory (b2q_host_alloc, cudaHostAlloc,
  * torch pin_memory) the step kernel reads the action rows from and stores its coalesced observation block to the host
- * buffers directly over PCIe (no separate copies; info still goes through a device staging area + one D2H).  Pageable
- * buffers are staged through device memory with cudaMemcpyAsync.  Environment variable B2Q_HOST_IO (read at b2q_create)
+ * buffers directly over PCIe (no separate copies; the info rows are staged in shared memory and stored as one block per
+ * CTA like the observations).  Pageable buffers are staged through device memory with cudaMemcpyAsync.  Environment variable B2Q_HOST_IO (read at b2q_create)
  * selects 0 = always memcpy, 1 = zero-copy actions only, 2 = zero-copy actions and outputs (default). */
 int b2q_step_host(B2QHandle h, const void* action_host, int donef, void* obs_host, void* reward_host, uint8_t* done_host,
                   void* info_host, void* stream);

@@ -357,6 +357,9 @@ class SACLearner:
 
     def close(self):
         if getattr(self, "h", None):
+            self.losses = self.losses.clone()      # the view of the learner's accumulators dies with the handle
+            self._graph = None
+            self._static = None
             self.lib.b2q_sac_destroy(self.h)
             self.h = None
 
