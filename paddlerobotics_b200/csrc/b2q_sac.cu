@@ -426,11 +426,11 @@ struct B2QSac {
   bf16 *xc_t = nullptr, *hc1_rm = nullptr, *hc1_t = nullptr, *hc2_rm = nullptr, *hc2_t = nullptr;
   bf16 *xa_t = nullptr, *ha1_rm = nullptr, *ha1_t = nullptr, *ha2_rm = nullptr, *ha2_t = nullptr;
   bf16 *dh_rm = nullptr, *dh_t = nullptr, *dy_bf = nullptr, *dy_rm = nullptr;
-  bf16 *dh_rm2 = nullptr, *dh_t2 = nullptr; float *G2 = nullptr;   // second scratch set: the twin critics' backward chains run on two streams
+  bf16 *dh_rm2 = nullptr, *dh_t2 = nullptr;   // second scratch set: the twin critics' backward chains run on two streams
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t aux[2] = {nullptr, nullptr}; cudaEvent_t ev_aux[4] = {nullptr, nullptr, nullptr, nullptr};   // per-chain helper streams: dW2 GEMM beside the dh1 -> dW1 chain
   bf16 *dh1_rm[2] = {nullptr, nullptr}, *dh1_t[2] = {nullptr, nullptr};                                      // layer-1 gradients (separate from dh2 so both GEMM branches can run)
-  float *G = nullptr, *q = nullptr, *qn = nullptr, *dq = nullptr, *next_a = nullptr, *next_logp = nullptr, *cur_a = nullptr, *cur_logp = nullptr, *raw_a = nullptr,
+  float *q = nullptr, *qn = nullptr, *dq = nullptr, *next_a = nullptr, *next_logp = nullptr, *cur_a = nullptr, *cur_logp = nullptr, *raw_a = nullptr,
         *da_c = nullptr, *losses = nullptr;
   std::vector<void*> allocs;
   void* tmap_cache = nullptr;   // TmapCache*: TMA tensor maps of the GEMM operands
@@ -553,7 +553,7 @@ namespace {
 // weight gradients of both critics from dq [2][B] and the activation dumps of the last critic forward
 // one MLP's weight-gradient chain after its head backward: dW2 (split-K GEMM over the batch) runs on the helper stream `ax`
 // beside  dh1 = (dh2 W2) . relu'  ->  dW1  on `st`
-int hidden_backward(B2QSac* s, cudaStream_t st, int slot, const bf16* dh2_rm, const bf16* dh2_t, float* G, const bf16* h1_rm, const bf16* h1_t, const bf16* x_t,
+int hidden_backward(B2QSac* s, cudaStream_t st, int slot, const bf16* dh2_rm, const bf16* dh2_t, const bf16* h1_rm, const bf16* h1_t, const bf16* x_t,
                     const bf16* W2T, float* gW2, float* gb1, float* gW1, int in_dim) {
   const int B = s->B;
   cudaStream_t ax = s->aux[slot];
@@ -573,13 +573,13 @@ int critic_backward(B2QSac* s, cudaStream_t st0, DqSrc src = DqSrc{DQ_ARRAY, 0, 
   fork(s, st0);
   for (int i = 0; i < 2; i++) {
     cudaStream_t st = i ? s->side : st0;
-    bf16 *dh_rm = i ? s->dh_rm2 : s->dh_rm, *dh_t = i ? s->dh_t2 : s->dh_t; float* G = i ? s->G2 : s->G;
+    bf16 *dh_rm = i ? s->dh_rm2 : s->dh_rm, *dh_t = i ? s->dh_t2 : s->dh_t;
     float* g = s->g_critic + (size_t)i * cn.n; const float* p = s->p_critic + (size_t)i * cn.n;
     const bf16 *h1 = s->hc1_rm + (size_t)i * B * H, *h1t = s->hc1_t + (size_t)i * B * H, *h2 = s->hc2_rm + (size_t)i * B * H;
     src.net = i;
     pdl_launch(k_head_bwd1, dim3((B + 32 * SUBT - 1) / (32 * SUBT)), dim3(H), 0, st, s->dq + (size_t)i * B, src, p + cn.oW3, h2, dh_rm, dh_t, g + cn.oW3, g + cn.ob3, g + cn.ob2, B);   // (dq,) dh2, dW3, db3, db2
     s->launches++;
-    if (hidden_backward(s, st, i, dh_rm, dh_t, G, h1, h1t, s->xc_t, s->W2T[1 + i], g + cn.oW2, g + cn.ob1, g + cn.oW1, cn.in_dim)) return -2;
+    if (hidden_backward(s, st, i, dh_rm, dh_t, h1, h1t, s->xc_t, s->W2T[1 + i], g + cn.oW2, g + cn.ob1, g + cn.oW1, cn.in_dim)) return -2;
   }
   join(s, st0);
   return 0;
@@ -596,7 +596,7 @@ int actor_backward(B2QSac* s, cudaStream_t st) {
   // dh2 = (dy W3) . relu'(h2), db2: a K = 64 tensor-core GEMM (A = dy row-major, zero-padded; B = W3^T [256][64]) with the masking epilogue
   const ReluEpi epi{s->ha2_rm, s->dh_rm, s->dh_t, g + an.ob2};
   if (gemm(s, st, s->dy_rm, 64, s->W3T[0], 64, nullptr, H, B, H, 64, false, 0, &epi)) return -2;
-  const int rc = hidden_backward(s, st, 0, s->dh_rm, s->dh_t, s->G, s->ha1_rm, s->ha1_t, s->xa_t, s->W2T[0], g + an.oW2, g + an.ob1, g + an.oW1, an.in_dim);
+  const int rc = hidden_backward(s, st, 0, s->dh_rm, s->dh_t, s->ha1_rm, s->ha1_t, s->xa_t, s->W2T[0], g + an.oW2, g + an.ob1, g + an.oW1, an.in_dim);
   cudaStreamWaitEvent(st, s->ev_aux[3], 0);
   return rc;
 }
@@ -623,10 +623,10 @@ int b2q_sac_create(int device, int obs_dim, int act_dim, int batch, float gamma,
   ok = ok && dalloc(s, &s->xc_t, 64 * Bz) && dalloc(s, &s->hc1_rm, 2 * Bz * H) && dalloc(s, &s->hc1_t, 2 * Bz * H) && dalloc(s, &s->hc2_rm, 2 * Bz * H) &&
        dalloc(s, &s->hc2_t, 2 * Bz * H) && dalloc(s, &s->xa_t, 64 * Bz) && dalloc(s, &s->ha1_rm, Bz * H) && dalloc(s, &s->ha1_t, Bz * H) &&
        dalloc(s, &s->ha2_rm, Bz * H) && dalloc(s, &s->ha2_t, Bz * H) && dalloc(s, &s->dh_rm, Bz * H) && dalloc(s, &s->dh_t, Bz * H) && dalloc(s, &s->dy_bf, Bz * 128) && dalloc(s, &s->dy_rm, Bz * 64) &&
-       dalloc(s, &s->G, Bz * H) && dalloc(s, &s->q, 2 * Bz) && dalloc(s, &s->qn, 2 * Bz) && dalloc(s, &s->dq, 2 * Bz) && dalloc(s, &s->next_a, Bz * 12) &&
+       dalloc(s, &s->q, 2 * Bz) && dalloc(s, &s->qn, 2 * Bz) && dalloc(s, &s->dq, 2 * Bz) && dalloc(s, &s->next_a, Bz * 12) &&
        dalloc(s, &s->next_logp, Bz) && dalloc(s, &s->cur_a, Bz * 12) && dalloc(s, &s->cur_logp, Bz) && dalloc(s, &s->raw_a, Bz * 24) && dalloc(s, &s->da_c, 2 * Bz * 16) &&
        dalloc(s, &s->losses, 4) && dalloc(s, &s->d_step, 2 /*step | block ticket of the closing Adam*/) &&
-       dalloc(s, &s->dh_rm2, Bz * H) && dalloc(s, &s->dh_t2, Bz * H) && dalloc(s, &s->G2, Bz * H) &&
+       dalloc(s, &s->dh_rm2, Bz * H) && dalloc(s, &s->dh_t2, Bz * H) &&
        dalloc(s, &s->dh1_rm[0], Bz * H) && dalloc(s, &s->dh1_t[0], Bz * H) && dalloc(s, &s->dh1_rm[1], Bz * H) && dalloc(s, &s->dh1_t[1], Bz * H);
   for (int i = 0; i < 2 && ok; i++) ok = cudaStreamCreateWithFlags(&s->aux[i], cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreateWithFlags(&s->ev_aux[i], cudaEventDisableTiming) == cudaSuccess;
