@@ -498,7 +498,7 @@ double orc_energy(const OrcConfig* c, const OrcEnv* e, double* kin, double* pot)
 static double terrain_height(const OrcConfig* c, double x, double y, double n[3]) {
   if (c->terrain_type == 0 || !c->hf) { n[0] = 0; n[1] = 0; n[2] = 1; return 0.0; }
   double fx = (x - c->hf_x0) / c->hf_cell, fy = (y - c->hf_y0) / c->hf_cell;
-  if (fx < 0) fx = 0; if (fy < 0) fy = 0;
+  if (!(fx >= 0)) fx = 0; if (!(fy >= 0)) fy = 0;   /* also catches NaN positions (a diverged state must end the episode, not index out of bounds) */
   if (fx > c->hf_nx - 1.000001) fx = c->hf_nx - 1.000001; if (fy > c->hf_ny - 1.000001) fy = c->hf_ny - 1.000001;
   int ix = (int)fx, iy = (int)fy; double tx = fx - ix, ty = fy - iy;
   const double* h = c->hf; int nx = c->hf_nx;
