@@ -58,3 +58,23 @@ def etg_shipped():
     """The gait the reference itself ships (ETGRL/gait_action_list_ETG_exp.npy, 600 samples of info['ETG_act'], sample k = t 0.026(k+1)),
     fitted back to W,b: it walks forward at ~0.48 m/s open loop in the oracle — the long-horizon parity workload."""
     return fit_etg_from_table(np.load(os.path.join(GOLDEN, "gait_action_list_ETG_exp.npy")), 0.026)
+
+
+def draw_feature_combo(rng):
+    """A random combination of the env's feature switches (+ an optional rough height field) for the randomised parity tests."""
+    kw = dict(sensor_dis=int(rng.integers(0, 2)), sensor_contact=int(rng.integers(0, 2)), sensor_imu=int(rng.integers(0, 3)), sensor_motor=int(rng.integers(0, 3)),
+              sensor_etg=int(rng.integers(0, 2)), obs_normal=int(rng.integers(0, 2)),
+              motor_mode=int(rng.choice([0, 0, 1, 2])), joint_limits=int(rng.integers(0, 2)), knee_contacts=int(rng.integers(0, 2)),
+              body_collisions=int(rng.integers(0, 2)), stuck_termination=int(rng.integers(0, 2)), external_force=int(rng.integers(0, 2)),
+              action_interp=int(rng.integers(0, 2)), action_filter=int(rng.integers(0, 2)), clip_motor_commands=int(rng.integers(0, 2)), max_angle_change=0.2)
+    if kw["sensor_dis"] + kw["sensor_contact"] + kw["sensor_imu"] + kw["sensor_motor"] + kw["sensor_etg"] == 0:
+        kw["sensor_motor"] = 1
+    if rng.integers(0, 2):
+        kw["noise_stdev"] = tuple(rng.uniform(0.0, 0.05, 5)); kw["noise_seed"] = int(rng.integers(1, 1000))
+    if rng.integers(0, 2):
+        kw["base_damping"] = tuple(rng.uniform(0.0, 0.05, 4))
+    hf = None
+    if rng.integers(0, 2):
+        z = rng.uniform(0, 0.03, (40, 40))
+        hf = (z, -1.0, -1.0, 0.05)
+    return kw, hf

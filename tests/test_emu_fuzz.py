@@ -14,23 +14,7 @@ from oracle import oracle as O  # noqa: E402
 _OKEYS = {f[0] for f in O.Config._fields_}
 
 
-def _draw(rng):
-    kw = dict(sensor_dis=int(rng.integers(0, 2)), sensor_contact=int(rng.integers(0, 2)), sensor_imu=int(rng.integers(0, 3)), sensor_motor=int(rng.integers(0, 3)),
-              sensor_etg=int(rng.integers(0, 2)), obs_normal=int(rng.integers(0, 2)),
-              motor_mode=int(rng.choice([0, 0, 1, 2])), joint_limits=int(rng.integers(0, 2)), knee_contacts=int(rng.integers(0, 2)),
-              body_collisions=int(rng.integers(0, 2)), stuck_termination=int(rng.integers(0, 2)), external_force=int(rng.integers(0, 2)),
-              action_interp=int(rng.integers(0, 2)), action_filter=int(rng.integers(0, 2)), clip_motor_commands=int(rng.integers(0, 2)), max_angle_change=0.2)
-    if kw["sensor_dis"] + kw["sensor_contact"] + kw["sensor_imu"] + kw["sensor_motor"] + kw["sensor_etg"] == 0:
-        kw["sensor_motor"] = 1
-    if rng.integers(0, 2):
-        kw["noise_stdev"] = tuple(rng.uniform(0.0, 0.05, 5)); kw["noise_seed"] = int(rng.integers(1, 1000))
-    if rng.integers(0, 2):
-        kw["base_damping"] = tuple(rng.uniform(0.0, 0.05, 4))
-    hf = None
-    if rng.integers(0, 2):
-        z = rng.uniform(0, 0.03, (40, 40))
-        hf = (z, -1.0, -1.0, 0.05)
-    return kw, hf
+from conftest import draw_feature_combo as _draw  # noqa: E402
 
 
 @pytest.mark.parametrize("case", range(24))

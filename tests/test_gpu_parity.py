@@ -203,6 +203,61 @@ def test_env_features_f64_equal_oracle(torch_cuda, etg_stable):
         env.close()
 
 
+@pytest.mark.parametrize("case", range(8))
+def test_random_feature_combinations_f64_equal_oracle(torch_cuda, etg_stable, case):
+    """Randomised interplay of the feature switches (sensor layout x noise x motor mode x limits / knee contacts x terrain x filter / interpolation /
+    command clip x the reference's dynamics randomisation) through the C ABI on the GPU, float64 build, three envs per handle == oracle."""
+    from conftest import draw_feature_combo
+    from oracle import oracle as O
+    from paddlerobotics_b200.env import VecQuadrupedalEnv
+    from paddlerobotics_b200.etg import dynamic_dict_to_row, param2dynamic_dict
+    w, b = etg_stable
+    rng = np.random.default_rng(2000 + case)
+    kw, hf = draw_feature_combo(rng)
+    n = 3
+    okeys = {f[0] for f in O.Config._fields_}
+    rows = np.stack([dynamic_dict_to_row(param2dynamic_dict(rng.uniform(-0.3, 0.3, 48))) for _ in range(n)])
+    ekw = dict(kw)
+    if hf is not None:
+        ekw["heightfield"] = hf
+    env = VecQuadrupedalEnv(n, precision="f64", **ekw)
+    env.set_dynamics(rows)
+    os_ = []
+    for i in range(n):
+        ocfg = O.default_config(**{k: v for k, v in kw.items() if k in okeys})
+        if hf is not None:
+            O.set_heightfield(ocfg, *hf)
+        o = O.OracleEnv(ocfg, rows[i]); o.e.env_id = i
+        os_.append(o)
+    xo = rng.uniform(-0.1, 0.1, n)
+    ob0 = _np(env.reset(w, b, x_offset=xo))
+    for i, o in enumerate(os_):
+        assert np.abs(ob0[i] - o.reset(w, b, x_offset=xo[i])).max() < 1e-8, (kw, i)
+    if kw["external_force"]:
+        f = rng.uniform(-15, 15, (n, 3)); env.set_external_force(f)
+        for i, o in enumerate(os_):
+            o.set_force(f[i])
+    pose = np.array([0.0, 0.9, -1.8] * 4)
+    alive = [True] * n
+    for k in range(6):
+        if kw["motor_mode"] == 2:
+            a = np.zeros((n, 12, 5)); a[:, :, 0] = pose + rng.uniform(-0.2, 0.2, (n, 12)); a[:, :, 1] = rng.uniform(60, 140, (n, 12)); a[:, :, 2] = rng.uniform(-1, 1, (n, 12))
+            a[:, :, 3] = rng.uniform(0.5, 3, (n, 12)); a[:, :, 4] = rng.uniform(-2, 2, (n, 12)); a = a.reshape(n, 60)
+        elif kw["motor_mode"] == 1:
+            a = np.array([0.0, 1.0, -6.0] * 4) + rng.uniform(-1, 1, (n, 12))
+        else:
+            a = rng.uniform(-0.3, 0.3, (n, 12))
+        ob, rw, dn, inf = env.step(a)
+        for i, o in enumerate(os_):
+            if not alive[i]:
+                continue
+            oo, ro, do, io = o.step(a[i])
+            assert np.abs(_np(ob)[i] - oo).max() < 1e-6 and abs(float(rw[i]) - ro) < 1e-6 and bool(dn[i]) == do, (kw, k, i)
+            assert np.abs(_np(inf)[i] - io).max() < 1e-6, (kw, k, i)
+            alive[i] = not do
+    env.close()
+
+
 def test_latency_beyond_the_ring_is_an_error(torch_cuda):
     """a control latency the observation ring cannot serve must be refused, not clamped."""
     from paddlerobotics_b200.env import VecQuadrupedalEnv
